@@ -1,0 +1,86 @@
+"""ctypes binding of libgat.so (include/gat.h).  Fails loudly when the CUDA library is
+missing -- there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgat.so")
+
+GAT_OK = 0
+GAT_ERR_INVALID, GAT_ERR_CUDA, GAT_ERR_UNSUPPORTED, GAT_ERR_ALIGNMENT = -1, -2, -3, -4
+GAT_ERR_NO_CODES, GAT_ERR_NO_SIGNAL, GAT_ERR_NO_DEVICE = -5, -6, -7
+GAT_ACCUMULATE = 1
+GAT_CODE_PHASE_F64 = 2
+GAT_GPSL1, GAT_GPSL5 = 0, 1
+GAT_MAX_TAPS = 11
+GAT_MAX_ANTS = 32
+
+
+class GatChannel(C.Structure):
+    _fields_ = [("system_id", C.c_int32), ("prn", C.c_int32), ("code_phase_chips", C.c_double),
+                ("code_freq_hz", C.c_double), ("carrier_phase_cycles", C.c_double),
+                ("carrier_freq_hz", C.c_double)]
+
+
+class GatLaunchInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "grid", "block", "smem_bytes", "ants_per_thread", "ant_groups", "sats_per_cta", "sample_slices",
+        "consumer_warps", "sat_groups", "chunks_per_job", "chunk_len", "tile_len", "stages", "items",
+        "kernels_launched")] + [("last_kernel_ms", C.c_float)]
+
+
+class GatError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"libgat status {status}: {text}")
+        self.status = status
+
+
+# every symbol include/gat.h declares: (restype, argtypes)
+_vp, _i, _d, _u = C.c_void_p, C.c_int, C.c_double, C.c_uint
+_f32p, _i32p, _i8p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int8)
+_chp = C.POINTER(GatChannel)
+SYMBOLS = {
+    "gat_version": (_i, []),
+    "gat_status_string": (C.c_char_p, [_i]),
+    "gat_device_count": (_i, []),
+    "gat_create": (_i, [C.POINTER(_vp), _i]),
+    "gat_destroy": (_i, [_vp]),
+    "gat_last_error": (C.c_char_p, [_vp]),
+    "gat_sync": (_i, [_vp]),
+    "gat_stream": (_vp, [_vp]),
+    "gat_set_stream": (_i, [_vp, _vp]),
+    "gat_gen_code": (_i, [_i, _i, _i8p, _i]),
+    "gat_set_codes": (_i, [_vp, _i, _i8p, _i, _i]),
+    "gat_upload_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i]),
+    "gat_bind_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
+    "gat_gen_signal": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _i, _i, _d, _d, C.c_uint64, _i]),
+    "gat_download_signal": (_i, [_vp, _i, _vp, _vp]),
+    "gat_correlate": (_i, [_vp, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _i, _u]),
+    "gat_correlate_batch": (_i, [_vp, _i, _i32p, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _i, _u]),
+    "gat_downconvert_and_correlate": (_i, [_vp, _vp, _vp, _i, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _u]),
+    "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
+    "gat_set_timing": (_i, [_vp, _i]),
+    "gat_kernel_launch_count": (C.c_uint64, [_vp]),
+    "gat_debug_chip_indices": (_i, [_vp, _chp, _d, _i, _i, _u, _i32p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libgat.so and bind every symbol.  Needs no GPU (used by the CPU test tier)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m gpuacceleratedtracking_b200.build` "
+                "(nvcc, sm_100a).  This package has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

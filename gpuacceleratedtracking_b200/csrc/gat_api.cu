@@ -1,0 +1,788 @@
+// gat_api.cu -- the C ABI of include/gat.h: contexts, chip tables, signal slots, launch
+// planning and the correlate entry points.  Host logic only; the kernels live in
+// gat_correlate.cu.  No CPU fallback exists: every entry point needs a live sm_100 device.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gat.h"
+#include "gat_internal.h"
+
+using namespace gat;
+
+namespace {
+
+struct SignalSlot {
+    float *re = nullptr, *im = nullptr;
+    int64_t ld = 0;
+    int n_samples = 0, n_ants = 0;
+    bool owned = false;
+    size_t cap_floats = 0;  // per plane, when owned
+};
+
+struct CodeTable {
+    int8_t *d_chips = nullptr;
+    int code_len = 0, n_prn = 0;
+};
+
+struct Staging {
+    unsigned char *h = nullptr;  // pinned
+    unsigned char *d = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+};
+
+constexpr int kStagingRing = 4;
+
+}  // namespace
+
+struct gat_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;      // the stream work is queued on
+    cudaStream_t own_stream = nullptr;  // created by gat_create
+    std::string err;
+    CodeTable codes[GAT_MAX_SYSTEMS];
+    std::vector<SignalSlot> slots;
+    Staging stg[kStagingRing];
+    int stg_next = 0;
+    float *d_partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int *d_counters = nullptr;
+    size_t counters_cap = 0;
+    float *d_out = nullptr;
+    size_t d_out_cap = 0;
+    float *h_out = nullptr;  // pinned
+    size_t h_out_cap = 0;
+    int32_t *d_dbg = nullptr;
+    size_t d_dbg_cap = 0;
+    gat_launch_info info{};
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(gat_ctx *ctx, int status, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return status;
+}
+
+int cuda_fail(gat_ctx *ctx, cudaError_t e, const char *what)
+{
+    return fail(ctx, GAT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define GAT_CUDA(ctx, call)                                          \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);   \
+    } while (0)
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+int pow2_ceil(int x)
+{
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+template <typename T>
+int ensure_device(gat_ctx *ctx, T *&ptr, size_t &cap, size_t need, bool zero)
+{
+    if (need <= cap) return GAT_OK;
+    // the old buffer may still be in use by work queued on the stream
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ptr) GAT_CUDA(ctx, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    const size_t grow = need + need / 2;
+    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ptr), grow * sizeof(T)));
+    if (zero) GAT_CUDA(ctx, cudaMemsetAsync(ptr, 0, grow * sizeof(T), ctx->stream));
+    cap = grow;
+    return GAT_OK;
+}
+
+// Host staging -> device for the per-call parameter block; ring of pinned buffers so a call
+// never overwrites a buffer whose H2D copy is still queued.
+int stage_params(gat_ctx *ctx, const void *src, size_t bytes, unsigned char **d_out)
+{
+    Staging &s = ctx->stg[ctx->stg_next];
+    ctx->stg_next = (ctx->stg_next + 1) % kStagingRing;
+    if (s.pending) {
+        GAT_CUDA(ctx, cudaEventSynchronize(s.done));
+        s.pending = false;
+    }
+    if (bytes > s.cap) {
+        if (s.h) GAT_CUDA(ctx, cudaFreeHost(s.h));
+        if (s.d) {
+            GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            GAT_CUDA(ctx, cudaFree(s.d));
+        }
+        s.h = s.d = nullptr;
+        s.cap = 0;
+        const size_t grow = std::max<size_t>(bytes * 2, 4096);
+        GAT_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&s.h), grow));
+        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&s.d), grow));
+        s.cap = grow;
+    }
+    if (!s.done) GAT_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    std::memcpy(s.h, src, bytes);
+    GAT_CUDA(ctx, cudaMemcpyAsync(s.d, s.h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GAT_CUDA(ctx, cudaEventRecord(s.done, ctx->stream));
+    s.pending = true;
+    *d_out = s.d;
+    return GAT_OK;
+}
+
+// Q0.64 fraction of a real number of cycles (two's complement wrap == mod 1)
+uint64_t cycles_to_q64(double x)
+{
+    double f = x - std::floor(x);  // [0, 1)
+    if (!(f >= 0.0) || f >= 1.0) f = 0.0;
+    return static_cast<uint64_t>(std::ldexp(f, 64));
+}
+
+int nco_fixed_point(int code_len)
+{
+    int bits = 0;
+    while ((1LL << bits) < static_cast<long long>(code_len)) ++bits;
+    return 63 - bits;
+}
+
+// Pre-digest one channel.  NCO constants follow Tracking.jl gen_code_replica! [upstream]:
+//   fixed_point = 63 - ceil(log2(code_length)); delta = floor(fc * 2^fp / fs);
+//   start = floor(mod(code_phase, code_length) * 2^fp)
+int fill_sat(gat_ctx *ctx, const gat_channel &ch, double fs, SatDev &sd)
+{
+    if (ch.system_id < 0 || ch.system_id >= GAT_MAX_SYSTEMS) return fail(ctx, GAT_ERR_INVALID, "system_id out of range");
+    const CodeTable &tab = ctx->codes[ch.system_id];
+    if (!tab.d_chips) return fail(ctx, GAT_ERR_NO_CODES, "no chip table set for system " + std::to_string(ch.system_id));
+    if (ch.prn < 1 || ch.prn > tab.n_prn) return fail(ctx, GAT_ERR_NO_CODES, "prn outside the chip table");
+    if (!(ch.code_freq_hz > 0.0) || !std::isfinite(ch.code_freq_hz) || !std::isfinite(ch.code_phase_chips) ||
+        !std::isfinite(ch.carrier_freq_hz) || !std::isfinite(ch.carrier_phase_cycles))
+        return fail(ctx, GAT_ERR_INVALID, "non-finite or non-positive channel parameter");
+    sd.code = tab.d_chips + static_cast<size_t>(ch.prn - 1) * tab.code_len;
+    sd.code_len = tab.code_len;
+    sd.nco_fp = nco_fixed_point(tab.code_len);
+    sd.nco_delta = static_cast<int64_t>(std::floor(ch.code_freq_hz * std::ldexp(1.0, sd.nco_fp) / fs));
+    double modded = std::fmod(ch.code_phase_chips, static_cast<double>(tab.code_len));
+    if (modded < 0) modded += static_cast<double>(tab.code_len);
+    sd.nco_start = static_cast<int64_t>(std::floor(modded * std::ldexp(1.0, sd.nco_fp)));
+    sd.car_phase = cycles_to_q64(ch.carrier_phase_cycles);
+    sd.car_delta = cycles_to_q64(ch.carrier_freq_hz / fs);
+    sd.code_ratio = ch.code_freq_hz / fs;
+    sd.code_phase = ch.code_phase_chips;
+    return GAT_OK;
+}
+
+struct Shape {
+    int P, K, M, L, start, n;
+    const int32_t *shifts;
+    double max_ratio;
+    int min_fp;
+    int64_t max_delta;
+    bool f64;
+};
+
+// Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
+int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
+{
+    const int L = sh.L, M = sh.M, K = sh.K;
+    // antennas per thread: keep 2*A*L accumulators per thread around <= 96 registers
+    int A = (L <= 3) ? 16 : (L <= 5 ? 8 : 4);
+    A = std::min(A, pow2_ceil(M));
+    A = std::max(1, std::min(A, env_int("GAT_TUNE_A", A)));
+    if (!kernel_available(A, L)) return fail(ctx, GAT_ERR_UNSUPPORTED, "no kernel for this (antennas, taps) shape");
+    const int AG = (M + A - 1) / A;
+    if (AG > kMaxConsumerWarps) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
+
+    const int w_target_multi = std::min(kMaxConsumerWarps, env_int("GAT_TUNE_WMAX", 11));
+    const int w_target_single = std::min(kMaxConsumerWarps, env_int("GAT_TUNE_W", 8));
+    int S = std::max(1, std::min(K, w_target_multi / AG));
+    S = std::max(1, std::min(S, env_int("GAT_TUNE_S", S)));
+    const int G = (K + S - 1) / S;
+    S = (K + G - 1) / G;  // balance the groups
+    int SL = std::max(1, w_target_single / (S * AG));
+    SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
+    const int W = S * AG * SL;
+    if (W > kMaxConsumerWarps || S > 12) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
+
+    const int aligned_start = sh.start & ~3;
+    const int aligned_end = (sh.start + sh.n + 3) & ~3;
+    const int aligned_len = aligned_end - aligned_start;
+    const int span = sh.shifts[L - 1] - sh.shifts[0];
+
+    const int jobs = sh.P * G;
+    int tile_len = kTileCap;
+    {
+        // small problems: shrink tiles so every SM gets one
+        const int64_t total = static_cast<int64_t>(jobs) * aligned_len;
+        const int64_t per_sm = (total + ctx->n_sm - 1) / ctx->n_sm;
+        const int quantum = 32 * SL;
+        int want = static_cast<int>(std::min<int64_t>(kTileCap, (per_sm + quantum - 1) / quantum * quantum));
+        tile_len = std::max(std::min(quantum, kTileCap), want);
+        tile_len = std::min(kTileCap, tile_len);
+        tile_len = env_int("GAT_TUNE_TILE", tile_len);
+        if (tile_len < 32 || tile_len > kTileCap || tile_len % 32) return fail(ctx, GAT_ERR_INVALID, "bad GAT_TUNE_TILE");
+    }
+    // per-tile relative NCO phase must fit 64 bits: (tile + span + 1) * delta + 2^fp < 2^64
+    if (!sh.f64) {
+        const long double need = static_cast<long double>(tile_len + span + 1) * static_cast<long double>(sh.max_delta) +
+                                 std::ldexp(1.0L, sh.min_fp);
+        if (need >= std::ldexp(1.0L, 64))
+            return fail(ctx, GAT_ERR_UNSUPPORTED, "code rate too high for the fixed-point window (code_freq/fs * tile too large)");
+    } else {
+        const double worst = sh.max_ratio * (static_cast<double>(sh.n) + std::abs(sh.shifts[0]) + std::abs(sh.shifts[L - 1]));
+        if (!(worst < 1.0e9)) return fail(ctx, GAT_ERR_UNSUPPORTED, "code phase range exceeds the f64 window arithmetic");
+    }
+    int win_stride = static_cast<int>(std::floor(sh.max_ratio * (tile_len + span + 1))) + 4;
+    win_stride = (win_stride + 3) & ~3;
+
+    const int tiles_per_job = (aligned_len + tile_len - 1) / tile_len;
+    const int64_t total_tiles = static_cast<int64_t>(jobs) * tiles_per_job;
+    const int RP = padded_acc(A, L);
+    const size_t tile_bytes = smem_tile_floats(AG, A) * sizeof(float);
+    const size_t win_bytes = static_cast<size_t>(S) * win_stride * sizeof(float);
+    const size_t part_bytes = static_cast<size_t>(W) * RP * sizeof(float);
+    const size_t budget = 227 * 1024;
+    if (kSmemHeaderBytes + part_bytes + tile_bytes + win_bytes > budget)
+        return fail(ctx, GAT_ERR_UNSUPPORTED, "shape does not fit shared memory (antennas x window)");
+    int stages = static_cast<int>((budget - kSmemHeaderBytes - part_bytes) / (tile_bytes + win_bytes));
+    stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 6)));
+    stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
+
+    const int ctas_per_sm = 1;
+    int grid = static_cast<int>(std::min<int64_t>(total_tiles, static_cast<int64_t>(ctx->n_sm) * ctas_per_sm));
+    grid = std::max(1, std::min(grid, env_int("GAT_TUNE_GRID", grid)));
+
+    plan.A = A;
+    plan.L = L;
+    plan.f64 = sh.f64;
+    plan.grid = grid;
+    plan.block = 32 * (W + 1);
+    plan.smem = kSmemHeaderBytes + stages * (tile_bytes + win_bytes) + part_bytes;
+    plan.RP = RP;
+    plan.jobs = jobs;
+
+    for (int l = 0; l < kMaxTaps; ++l) a.shifts[l] = l < L ? sh.shifts[l] : 0;
+    a.n_periods = sh.P;
+    a.n_sats = K;
+    a.n_ants = M;
+    a.n_taps = L;
+    a.start_sample = sh.start;
+    a.n_samples = sh.n;
+    a.aligned_start = aligned_start;
+    a.aligned_len = aligned_len;
+    a.tile_len = tile_len;
+    a.tiles_per_job = tiles_per_job;
+    a.S = S;
+    a.AG = AG;
+    a.SL = SL;
+    a.W = W;
+    a.G = G;
+    a.stages = stages;
+    a.win_stride = win_stride;
+    a.total_tiles = static_cast<int32_t>(total_tiles);
+
+    gat_launch_info &li = ctx->info;
+    li.grid = grid;
+    li.block = plan.block;
+    li.smem_bytes = static_cast<int32_t>(plan.smem);
+    li.ants_per_thread = A;
+    li.ant_groups = AG;
+    li.sats_per_cta = S;
+    li.sample_slices = SL;
+    li.consumer_warps = W;
+    li.sat_groups = G;
+    li.chunks_per_job = static_cast<int32_t>((grid + jobs - 1) / jobs);
+    li.chunk_len = static_cast<int32_t>(total_tiles / grid * tile_len);
+    li.tile_len = tile_len;
+    li.stages = stages;
+    li.items = static_cast<int32_t>(total_tiles);
+    return GAT_OK;
+}
+
+int check_ctx(gat_ctx *ctx)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    return GAT_OK;
+}
+
+int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats, const gat_channel *channels,
+                   double fs_hz, const int32_t *shifts, int n_taps, int start_sample, int n_samples,
+                   float *out_re, float *out_im, int out_is_device, unsigned flags)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!slots || !channels || !shifts || !out_re || !out_im) return fail(ctx, GAT_ERR_INVALID, "null pointer argument");
+    if (n_periods < 1 || n_sats < 1) return fail(ctx, GAT_ERR_INVALID, "n_periods and n_sats must be >= 1");
+    if (n_taps < 1 || n_taps > GAT_MAX_TAPS) return fail(ctx, GAT_ERR_UNSUPPORTED, "n_taps must be 1..11");
+    if (!(fs_hz > 0.0) || !std::isfinite(fs_hz)) return fail(ctx, GAT_ERR_INVALID, "sampling frequency must be positive");
+    if (start_sample < 0 || n_samples < 1) return fail(ctx, GAT_ERR_INVALID, "empty or negative sample range");
+    if ((flags & GAT_ACCUMULATE) && !out_is_device)
+        return fail(ctx, GAT_ERR_INVALID, "GAT_ACCUMULATE needs device outputs");
+    for (int l = 1; l < n_taps; ++l)
+        if (shifts[l] < shifts[l - 1]) return fail(ctx, GAT_ERR_INVALID, "sample shifts must be ascending");
+    if (static_cast<int64_t>(shifts[n_taps - 1]) - shifts[0] > 4096) return fail(ctx, GAT_ERR_UNSUPPORTED, "tap span > 4096 samples");
+
+    // even tap counts run on the next odd instantiation with the last shift repeated
+    int L = n_taps;
+    if (L > 1 && (L % 2) == 0) ++L;
+    int32_t sh_pad[kMaxTaps];
+    for (int l = 0; l < L; ++l) sh_pad[l] = shifts[std::min(l, n_taps - 1)];
+
+    // signal slots
+    std::vector<PeriodDev> periods(n_periods);
+    int M = -1;
+    for (int p = 0; p < n_periods; ++p) {
+        const int s = slots[p];
+        if (s < 0 || s >= static_cast<int>(ctx->slots.size()) || !ctx->slots[s].re)
+            return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(s) + " has no signal");
+        const SignalSlot &sl = ctx->slots[s];
+        if (M < 0) M = sl.n_ants;
+        if (sl.n_ants != M) return fail(ctx, GAT_ERR_INVALID, "all periods of a batch must have the same antenna count");
+        if (static_cast<int64_t>(start_sample) + n_samples > sl.n_samples)
+            return fail(ctx, GAT_ERR_INVALID, "sample range exceeds the signal in slot " + std::to_string(s));
+        periods[p] = PeriodDev{sl.re, sl.im, sl.ld};
+    }
+    if (M < 1 || M > kMaxAnts) return fail(ctx, GAT_ERR_UNSUPPORTED, "antenna count must be 1..32");
+
+    // channels
+    const size_t n_ch = static_cast<size_t>(n_periods) * n_sats;
+    std::vector<SatDev> sats(n_ch);
+    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0};
+    for (size_t i = 0; i < n_ch; ++i) {
+        rc = fill_sat(ctx, channels[i], fs_hz, sats[i]);
+        if (rc) return rc;
+        shape.max_ratio = std::max(shape.max_ratio, sats[i].code_ratio);
+        shape.min_fp = std::min(shape.min_fp, sats[i].nco_fp);
+        shape.max_delta = std::max(shape.max_delta, sats[i].nco_delta);
+    }
+
+    LaunchPlan plan{};
+    CorrArgs args{};
+    rc = make_plan(ctx, shape, plan, args);
+    if (rc) return rc;
+    args.flags = flags;
+
+    // parameter block: [PeriodDev x P][SatDev x P*K]
+    const size_t per_bytes = sizeof(PeriodDev) * n_periods;
+    const size_t sat_off = (per_bytes + 15) & ~static_cast<size_t>(15);
+    const size_t blk_bytes = sat_off + sizeof(SatDev) * n_ch;
+    std::vector<unsigned char> blk(blk_bytes);
+    std::memcpy(blk.data(), periods.data(), per_bytes);
+    std::memcpy(blk.data() + sat_off, sats.data(), sizeof(SatDev) * n_ch);
+    unsigned char *d_blk = nullptr;
+    rc = stage_params(ctx, blk.data(), blk_bytes, &d_blk);
+    if (rc) return rc;
+    args.periods = reinterpret_cast<const PeriodDev *>(d_blk);
+    args.sats = reinterpret_cast<const SatDev *>(d_blk + sat_off);
+
+    // scratch
+    const size_t roles_rp = static_cast<size_t>(args.S) * args.AG * plan.RP;
+    rc = ensure_device(ctx, ctx->d_partials, ctx->partials_cap, (static_cast<size_t>(plan.jobs) + plan.grid) * roles_rp, false);
+    if (rc) return rc;
+    rc = ensure_device(ctx, ctx->d_counters, ctx->counters_cap, static_cast<size_t>(plan.jobs), true);
+    if (rc) return rc;
+    args.partials = ctx->d_partials;
+    args.counters = ctx->d_counters;
+
+    const size_t out_elems = n_ch * n_taps * M;          // caller-visible
+    const size_t out_elems_k = n_ch * static_cast<size_t>(L) * M;  // kernel layout (padded taps)
+    const bool direct = out_is_device && L == n_taps;
+    if (direct) {
+        args.out_re = out_re;
+        args.out_im = out_im;
+    } else {
+        rc = ensure_device(ctx, ctx->d_out, ctx->d_out_cap, 2 * out_elems_k, false);
+        if (rc) return rc;
+        args.out_re = ctx->d_out;
+        args.out_im = ctx->d_out + out_elems_k;
+        if (flags & GAT_ACCUMULATE) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_ACCUMULATE with an even tap count");
+    }
+
+    if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = launch_correlate(plan, args, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "correlate kernel launch");
+    if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    ctx->info.kernels_launched = 1;
+
+    if (!direct) {
+        // strip padded taps / move to the caller: rows of L*M floats -> n_taps*M floats per channel
+        const size_t row_k = static_cast<size_t>(L) * M * sizeof(float), row_u = static_cast<size_t>(n_taps) * M * sizeof(float);
+        if (out_is_device) {
+            GAT_CUDA(ctx, cudaMemcpy2DAsync(out_re, row_u, args.out_re, row_k, row_u, n_ch, cudaMemcpyDeviceToDevice, ctx->stream));
+            GAT_CUDA(ctx, cudaMemcpy2DAsync(out_im, row_u, args.out_im, row_k, row_u, n_ch, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            if (2 * out_elems > ctx->h_out_cap) {
+                if (ctx->h_out) GAT_CUDA(ctx, cudaFreeHost(ctx->h_out));
+                ctx->h_out = nullptr;
+                ctx->h_out_cap = 0;
+                GAT_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_out), 4 * out_elems * sizeof(float)));
+                ctx->h_out_cap = 4 * out_elems;
+            }
+            GAT_CUDA(ctx, cudaMemcpy2DAsync(ctx->h_out, row_u, args.out_re, row_k, row_u, n_ch, cudaMemcpyDeviceToHost, ctx->stream));
+            GAT_CUDA(ctx, cudaMemcpy2DAsync(ctx->h_out + out_elems, row_u, args.out_im, row_k, row_u, n_ch, cudaMemcpyDeviceToHost, ctx->stream));
+            GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::memcpy(out_re, ctx->h_out, out_elems * sizeof(float));
+            std::memcpy(out_im, ctx->h_out + out_elems, out_elems * sizeof(float));
+        }
+    }
+    if (ctx->timing) {
+        GAT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        GAT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->info.last_kernel_ms = ms;
+    }
+    return GAT_OK;
+}
+
+SignalSlot *slot_for(gat_ctx *ctx, int slot)
+{
+    if (slot < 0 || slot >= 65536) return nullptr;
+    if (slot >= static_cast<int>(ctx->slots.size())) ctx->slots.resize(slot + 1);
+    return &ctx->slots[slot];
+}
+
+int release_slot(gat_ctx *ctx, SignalSlot &s)
+{
+    if (s.owned && s.re) {
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GAT_CUDA(ctx, cudaFree(s.re));
+    }
+    s = SignalSlot{};
+    return GAT_OK;
+}
+
+// make `s` an owned slot able to hold n_ants x ld floats per plane (one allocation: re then im)
+int own_slot(gat_ctx *ctx, SignalSlot &s, int n_samples, int n_ants, int64_t ld)
+{
+    const size_t need = static_cast<size_t>(ld) * n_ants;
+    if (!s.owned || s.cap_floats < need) {
+        int rc = release_slot(ctx, s);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&s.re), 2 * need * sizeof(float)));
+        s.cap_floats = need;
+        s.owned = true;
+    }
+    s.im = s.re + s.cap_floats;
+    s.ld = ld;
+    s.n_samples = n_samples;
+    s.n_ants = n_ants;
+    return GAT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// exported functions
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int gat_version(void) { return GAT_VERSION; }
+
+const char *gat_status_string(int status)
+{
+    switch (status) {
+    case GAT_OK: return "ok";
+    case GAT_ERR_INVALID: return "invalid argument";
+    case GAT_ERR_CUDA: return "CUDA error";
+    case GAT_ERR_UNSUPPORTED: return "unsupported shape";
+    case GAT_ERR_ALIGNMENT: return "misaligned device signal";
+    case GAT_ERR_NO_CODES: return "no chip table";
+    case GAT_ERR_NO_SIGNAL: return "no signal bound";
+    case GAT_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown status";
+    }
+}
+
+int gat_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return GAT_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+int gat_create(gat_ctx **out, int device_id)
+{
+    if (!out) return GAT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        return GAT_ERR_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= n) return GAT_ERR_INVALID;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return GAT_ERR_CUDA;
+    if (prop.major != 10) return GAT_ERR_NO_DEVICE;  // sm_100a cubin only; no fallback path exists
+    gat_ctx *ctx = new (std::nothrow) gat_ctx();
+    if (!ctx) return GAT_ERR_INVALID;
+    ctx->device = device_id;
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        configure_kernels() != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return GAT_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return GAT_OK;
+}
+
+int gat_set_stream(gat_ctx *ctx, void *cuda_stream)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return GAT_OK;
+}
+
+int gat_destroy(gat_ctx *ctx)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &s : ctx->slots)
+        if (s.owned && s.re) cudaFree(s.re);
+    for (auto &c : ctx->codes)
+        if (c.d_chips) cudaFree(c.d_chips);
+    for (auto &s : ctx->stg) {
+        if (s.h) cudaFreeHost(s.h);
+        if (s.d) cudaFree(s.d);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (ctx->d_partials) cudaFree(ctx->d_partials);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return GAT_OK;
+}
+
+const char *gat_last_error(gat_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gat_sync(gat_ctx *ctx)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GAT_OK;
+}
+
+void *gat_stream(gat_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+int gat_set_codes(gat_ctx *ctx, int system_id, const int8_t *chips, int code_len, int n_prn)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (system_id < 0 || system_id >= GAT_MAX_SYSTEMS || !chips || code_len < 1 || n_prn < 1)
+        return fail(ctx, GAT_ERR_INVALID, "bad chip table arguments");
+    const size_t n = static_cast<size_t>(code_len) * n_prn;
+    for (size_t i = 0; i < n; ++i)
+        if (chips[i] != 1 && chips[i] != -1) return fail(ctx, GAT_ERR_INVALID, "chips must be +1 or -1");
+    CodeTable &t = ctx->codes[system_id];
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (t.d_chips) GAT_CUDA(ctx, cudaFree(t.d_chips));
+    t = CodeTable{};
+    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&t.d_chips), n));
+    GAT_CUDA(ctx, cudaMemcpy(t.d_chips, chips, n, cudaMemcpyHostToDevice));
+    t.code_len = code_len;
+    t.n_prn = n_prn;
+    return GAT_OK;
+}
+
+int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, int n_samples, int n_ants, int ld,
+                      int src_is_device)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!re || !im || n_samples < 1 || n_ants < 1 || n_ants > kMaxAnts || ld < n_samples)
+        return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
+    SignalSlot *s = slot_for(ctx, slot);
+    if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
+    if (!s->owned && s->re) *s = SignalSlot{};  // drop a zero-copy binding
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (ld % 4 == 0) {
+        // same layout on both sides: one flat copy per plane
+        rc = own_slot(ctx, *s, n_samples, n_ants, ld);
+        if (rc) return rc;
+        const size_t bytes = (static_cast<size_t>(ld) * (n_ants - 1) + n_samples) * sizeof(float);
+        GAT_CUDA(ctx, cudaMemcpyAsync(s->re, re, bytes, kind, ctx->stream));
+        GAT_CUDA(ctx, cudaMemcpyAsync(s->im, im, bytes, kind, ctx->stream));
+    } else {
+        const int64_t dld = (static_cast<int64_t>(n_samples) + 3) & ~3LL;
+        rc = own_slot(ctx, *s, n_samples, n_ants, dld);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMemcpy2DAsync(s->re, dld * sizeof(float), re, static_cast<size_t>(ld) * sizeof(float),
+                                        static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, ctx->stream));
+        GAT_CUDA(ctx, cudaMemcpy2DAsync(s->im, dld * sizeof(float), im, static_cast<size_t>(ld) * sizeof(float),
+                                        static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, ctx->stream));
+    }
+    return GAT_OK;
+}
+
+int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im, int n_samples, int n_ants, int ld)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_re || !d_im || n_samples < 1 || n_ants < 1 || n_ants > kMaxAnts || ld < n_samples)
+        return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
+    if ((reinterpret_cast<uintptr_t>(d_re) & 15u) || (reinterpret_cast<uintptr_t>(d_im) & 15u) || (n_ants > 1 && ld % 4 != 0))
+        return fail(ctx, GAT_ERR_ALIGNMENT, "zero-copy planes must be 16-byte aligned with ld % 4 == 0 (use gat_upload_signal)");
+    // the bulk copies read whole 16-byte groups: the last group of the last row must exist
+    if (n_ants == 1 && ld % 4 != 0 && ((n_samples + 3) & ~3) > ld)
+        return fail(ctx, GAT_ERR_ALIGNMENT, "single-antenna zero-copy needs ld >= roundup4(n_samples)");
+    SignalSlot *s = slot_for(ctx, slot);
+    if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
+    rc = release_slot(ctx, *s);
+    if (rc) return rc;
+    s->re = const_cast<float *>(d_re);
+    s->im = const_cast<float *>(d_im);
+    s->ld = ld;
+    s->n_samples = n_samples;
+    s->n_ants = n_ants;
+    s->owned = false;
+    return GAT_OK;
+}
+
+int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrier_freq_hz, double fs_hz,
+                   double start_code_phase, double start_carrier_phase_rad, int n_samples, int n_ants,
+                   double ant_phase_step_rad, double noise_sigma, uint64_t seed, int superpose)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (system_id < 0 || system_id >= GAT_MAX_SYSTEMS || !ctx->codes[system_id].d_chips)
+        return fail(ctx, GAT_ERR_NO_CODES, "no chip table for gen_signal");
+    const CodeTable &t = ctx->codes[system_id];
+    if (prn < 1 || prn > t.n_prn || n_samples < 1 || n_ants < 1 || n_ants > kMaxAnts || !(fs_hz > 0.0))
+        return fail(ctx, GAT_ERR_INVALID, "bad gen_signal arguments");
+    SignalSlot *s = slot_for(ctx, slot);
+    if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
+    if (superpose) {
+        if (!s->re || s->n_samples != n_samples || s->n_ants != n_ants)
+            return fail(ctx, GAT_ERR_NO_SIGNAL, "superpose needs an existing slot of the same shape");
+    } else if (!(s->re && s->n_samples == n_samples && s->n_ants == n_ants)) {
+        // (a bound or owned slot of the right shape is generated into in place)
+        if (!s->owned && s->re) *s = SignalSlot{};
+        rc = own_slot(ctx, *s, n_samples, n_ants, (static_cast<int64_t>(n_samples) + 3) & ~3LL);
+        if (rc) return rc;
+    }
+    // code frequency of the system: the built-ins carry theirs; caller tables pass it via prn-independent ratio
+    const double code_freq = (system_id == GAT_GPSL5) ? 10.23e6 : 1.023e6;
+    cudaError_t e = launch_gen_signal(s->re, s->im, s->ld, t.d_chips + static_cast<size_t>(prn - 1) * t.code_len, t.code_len,
+                                      code_freq / fs_hz, carrier_freq_hz, fs_hz, start_code_phase, start_carrier_phase_rad,
+                                      n_samples, n_ants, ant_phase_step_rad, noise_sigma, seed, superpose, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "gen_signal launch");
+    ctx->launches += 1;
+    return GAT_OK;
+}
+
+int gat_download_signal(gat_ctx *ctx, int slot, float *re, float *im)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!re || !im || slot < 0 || slot >= static_cast<int>(ctx->slots.size()) || !ctx->slots[slot].re)
+        return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    const SignalSlot &s = ctx->slots[slot];
+    const size_t w = static_cast<size_t>(s.n_samples) * sizeof(float);
+    GAT_CUDA(ctx, cudaMemcpy2DAsync(re, w, s.re, s.ld * sizeof(float), w, s.n_ants, cudaMemcpyDeviceToHost, ctx->stream));
+    GAT_CUDA(ctx, cudaMemcpy2DAsync(im, w, s.im, s.ld * sizeof(float), w, s.n_ants, cudaMemcpyDeviceToHost, ctx->stream));
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GAT_OK;
+}
+
+int gat_correlate(gat_ctx *ctx, int slot, int n_sats, const gat_channel *channels, double fs_hz,
+                  const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples, float *out_re,
+                  float *out_im, int out_is_device, unsigned flags)
+{
+    const int32_t s = slot;
+    return correlate_impl(ctx, 1, &s, n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples, out_re,
+                          out_im, out_is_device, flags);
+}
+
+int gat_correlate_batch(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats, const gat_channel *channels,
+                        double fs_hz, const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples,
+                        float *out_re, float *out_im, int out_is_device, unsigned flags)
+{
+    return correlate_impl(ctx, n_periods, slots, n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples,
+                          out_re, out_im, out_is_device, flags);
+}
+
+int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *h_im, int ld, int n_ants, int n_sats,
+                                  const gat_channel *channels, double fs_hz, const int32_t *sample_shifts, int n_taps,
+                                  int start_sample, int n_samples, float *h_out_re, float *h_out_im, unsigned flags)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    const int scratch_slot = 65535;
+    int rc = gat_upload_signal(ctx, scratch_slot, h_re, h_im, start_sample + n_samples, n_ants, ld, 0);
+    if (rc) return rc;
+    return gat_correlate(ctx, scratch_slot, n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples,
+                         h_out_re, h_out_im, 0, flags);
+}
+
+int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out)
+{
+    if (!ctx || !out) return GAT_ERR_INVALID;
+    *out = ctx->info;
+    return GAT_OK;
+}
+
+int gat_set_timing(gat_ctx *ctx, int enable)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    ctx->timing = enable != 0;
+    return GAT_OK;
+}
+
+uint64_t gat_kernel_launch_count(gat_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift, int n_samples, unsigned flags,
+                           int32_t *out)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ch || !out || n_samples < 1 || !(fs_hz > 0.0)) return fail(ctx, GAT_ERR_INVALID, "bad arguments");
+    SatDev sd{};
+    rc = fill_sat(ctx, *ch, fs_hz, sd);
+    if (rc) return rc;
+    rc = ensure_device(ctx, ctx->d_dbg, ctx->d_dbg_cap, static_cast<size_t>(n_samples), false);
+    if (rc) return rc;
+    // the tile base is taken at the latest tap, exactly as the hot kernel does with shifts[0]
+    const int shift_first = std::min(shift, 0) - 3;
+    cudaError_t e = launch_chip_indices(sd, shift_first, shift, n_samples, kTileCap, (flags & GAT_CODE_PHASE_F64) != 0,
+                                        ctx->d_dbg, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "chip index launch");
+    ctx->launches += 1;
+    GAT_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_dbg, sizeof(int32_t) * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,651 @@
+// gat_correlate.cu -- the fused downconvert-and-correlate kernel family for sm_100a.
+//
+// Replaces, in ONE launch, what the reference spreads over 1-4 launches
+// (/root/reference/src/algorithms.jl:869-1545):
+//   code replica generation      (src/algorithms.jl:13-140, inline :179-186)
+//   carrier replica generation   (CUDA.sincos sites, e.g. :172, :484, :573)
+//   carrier wipe-off             (:175-176, :488-489)
+//   code wipe-off + accumulate   (:185-186, :494-495)
+//   in-block + cross-block reduce (:196-208, :521-533, :625-632, src/reduction.jl)
+//
+// Design (DESIGN.md has the long form):
+//   * persistent CTAs, one per SM; the flattened (period, sat-group, tile) space is split
+//     evenly over the grid ("stream-K"), so every SM streams the same number of bytes.
+//   * warp W is a producer: it moves [tile x antennas] signal tiles HBM -> smem with 1-D
+//     bulk async copies (TMA unit, UBLKCP) through a full/empty mbarrier ring, and builds the
+//     per-tile chip windows of every satellite batched on the CTA.
+//   * warps 0..W-1 are consumers.  A consumer warp owns (satellite s, antenna group ag,
+//     sample slice sl); all of them read the SAME staged signal tile, so one HBM/L2 read
+//     feeds every satellite on the SM.
+//   * carrier: 64-bit integer phase accumulator (exact wrap), top 32 bits -> FP32 -> MUFU
+//     sin/cos.  code: integer NCO (or IEEE-double formula) -> index into the smem window.
+//   * wipe-off and taps are packed FP32x2 FMAs (FFMA2), two antennas per instruction,
+//     accumulators in registers.
+//   * reduction: in-warp halving butterfly (reduce-scatter by shuffles) -> smem across
+//     slices -> per-CTA partial -> last-arriving CTA of a job sums partials in fixed order
+//     (single pass, deterministic, no float atomics, self-cleaning counters).
+#include "gat_internal.h"
+
+#include <cstdio>
+
+namespace gat {
+
+// --------------------------------------------------------------------------------------
+// PTX helpers
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync(int threads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+}
+
+typedef unsigned long long f32x2;  // two packed floats: lo = even antenna, hi = odd antenna
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// --------------------------------------------------------------------------------------
+// replica phase arithmetic (shared by the hot kernel and the debug chip-index kernel)
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t floormod64(int64_t a, int64_t m)
+{
+    int64_t r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+// Integer NCO, Tracking.jl gen_code_replica! [upstream]:
+//   idx(k) = (k * delta + start) >> fp         k = sample offset + tap shift (may be < 0)
+// Evaluated per tile as   base_idx + ((frac0 + kk * delta) >> fp),   kk >= 0 relative to the
+// tile's first (sample, latest tap): exact because the split is at a multiple of 2^fp.
+__device__ __forceinline__ void nco_tile_base(const SatDev &sd, int64_t u0, uint64_t &frac, uint32_t &bmod)
+{
+    const __int128 tot = (__int128)u0 * (__int128)sd.nco_delta + (__int128)sd.nco_start;
+    const int64_t base = (int64_t)(tot >> sd.nco_fp);
+    frac = (uint64_t)tot & ((1ull << sd.nco_fp) - 1ull);
+    bmod = (uint32_t)floormod64(base, sd.code_len);
+}
+__device__ __forceinline__ void nco_tile_advance(const SatDev &sd, int tile_len, uint64_t &frac, uint32_t &bmod)
+{
+    const unsigned __int128 nf = (unsigned __int128)frac + (unsigned __int128)(uint64_t)tile_len * (uint64_t)sd.nco_delta;
+    const uint64_t carry = (uint64_t)(nf >> sd.nco_fp);
+    frac = (uint64_t)nf & ((1ull << sd.nco_fp) - 1ull);
+    bmod = (uint32_t)((bmod + carry) % (uint64_t)sd.code_len);
+}
+// window slot of (tile-relative offset kk) -- consumer side; sh = fp - 32 (fp >= 32 always)
+__device__ __forceinline__ uint32_t nco_slot(uint64_t v, int sh) { return (uint32_t)(v >> 32) >> sh; }
+
+// IEEE-double form of the reference GPU kernels (src/algorithms.jl:179-182):
+//   floor(code_frequency / sampling_frequency * (n + shift) + start_code_phase)
+// separate multiply and add (Julia does not contract), then floor.
+__device__ __forceinline__ int32_t f64_chip_floor(double ratio, double phase, int32_t u)
+{
+    const double cp = __dadd_rn(__dmul_rn(ratio, (double)u), phase);
+    return __double2int_rd(cp);
+}
+
+// --------------------------------------------------------------------------------------
+// in-warp halving butterfly: N values per lane in, N/32 fully reduced values per lane out;
+// lane l ends up owning elements [l*N/32, (l+1)*N/32).
+// --------------------------------------------------------------------------------------
+template <int N, int MASK>
+__device__ __forceinline__ void reduce_scatter(float *v, int lane)
+{
+    const bool up = (lane & MASK) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float send = up ? v[i] : v[i + N / 2];
+        const float keep = up ? v[i + N / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+    if constexpr (MASK > 1) reduce_scatter<N / 2, MASK / 2>(v, lane);
+}
+
+// stream-K ownership: CTA b owns global tiles [b*TT/grid, (b+1)*TT/grid)
+__device__ __forceinline__ int tile_owner(int64_t x, int grid, int64_t total)
+{
+    return (int)(((x + 1) * grid - 1) / total);
+}
+
+// --------------------------------------------------------------------------------------
+// the kernel
+// --------------------------------------------------------------------------------------
+template <int A, int L, bool F64>
+__global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __grid_constant__ CorrArgs args)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int AP = (A >= 2) ? A / 2 : 1;
+    constexpr int R = 2 * A * L;
+    constexpr int RP = (R + 31) / 32 * 32;
+    constexpr int Q = RP / 32;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = args.W, S = args.S, AG = args.AG, SL = args.SL, G = args.G;
+    const int NR = S * AG;
+    const int MP = AG * A;
+    const int M = args.n_ants, K = args.n_sats;
+    const int stages = args.stages;
+    const int tile_len = args.tile_len;
+    const int TJ = args.tiles_per_job;
+
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty_bar = full_bar + kMaxStages;
+    volatile int *flag = reinterpret_cast<volatile int *>(smem + 128);
+    unsigned long long *meta = reinterpret_cast<unsigned long long *>(smem + 256);  // [stage][S]
+    float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
+    const int tile_floats = 2 * MP * kTileCap;
+    float *windows = tiles + (size_t)stages * tile_floats;
+    float *part = windows + (size_t)stages * S * args.win_stride;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 2);          // producer: expect_tx arrival + "windows built" arrival
+            mbar_init(&empty_bar[s], (uint32_t)W);  // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // antenna rows that pad M up to AG*A are never written by the copies: keep them zero
+    if (MP > M) {
+        const int pad_rows = MP - M;
+        for (int i = tid; i < stages * 2 * pad_rows * kTileCap; i += blockDim.x) {
+            const int col = i % kTileCap;
+            const int row = (i / kTileCap) % pad_rows;
+            const int plane = (i / (kTileCap * pad_rows)) % 2;
+            const int st = i / (kTileCap * pad_rows * 2);
+            tiles[(size_t)st * tile_floats + (size_t)(plane * MP + M + row) * kTileCap + col] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    const int64_t TT = args.total_tiles;
+    const int grid = gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * TT / grid;
+    const int64_t r1 = (int64_t)(blockIdx.x + 1) * TT / grid;
+    uint32_t q = 0;  // running tile counter of this CTA -> ring stage and parity
+
+    if (warp == W) {
+        // ============================ producer warp ============================
+        for (int64_t g = r0; g < r1;) {
+            const int job = (int)(g / TJ);
+            const int t_first = (int)(g - (int64_t)job * TJ);
+            const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
+            const int p = job / G, grp = job % G;
+            const PeriodDev per = args.periods[p];
+            const bool sat_ok = (lane < S) && (grp * S + lane < K);
+            SatDev sd;
+            sd.code = nullptr; sd.code_len = 1; sd.nco_fp = 32; sd.nco_delta = 0; sd.nco_start = 0;
+            sd.code_ratio = 0.0; sd.code_phase = 0.0;
+            if (sat_ok) sd = args.sats[(size_t)p * K + grp * S + lane];
+            uint64_t frac = 0;
+            uint32_t bmod = 0;
+            if (!F64 && sat_ok) {
+                const int64_t u0 = (int64_t)args.aligned_start + (int64_t)t_first * tile_len - args.start_sample + args.shifts[0];
+                nco_tile_base(sd, u0, frac, bmod);
+            }
+            for (int t = t_first; t < t_last; ++t, ++q) {
+                const int stage = q % stages;
+                const uint32_t par = (q / stages) & 1u;
+                mbar_wait(&empty_bar[stage], par ^ 1u);
+                const int ts_rel = t * tile_len;  // relative to aligned_start
+                const int len = min(tile_len, args.aligned_len - ts_rel);
+                if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * M * len * 4));
+                __syncwarp();
+                float *stage_tile = tiles + (size_t)stage * tile_floats;
+                for (int r = lane; r < 2 * M; r += 32) {
+                    const int plane = r >= M;
+                    const int m = plane ? r - M : r;
+                    const float *src = (plane ? per.im : per.re) + (int64_t)m * per.ld + args.aligned_start + ts_rel;
+                    bulk_g2s(stage_tile + (size_t)(plane * MP + m) * kTileCap, src, (uint32_t)len * 4u, &full_bar[stage]);
+                }
+                // chip windows for every satellite of this CTA
+                if (F64 && sat_ok) {
+                    const int32_t u0 = args.aligned_start + ts_rel - args.start_sample + args.shifts[0];
+                    const int32_t b = f64_chip_floor(sd.code_ratio, sd.code_phase, u0);
+                    bmod = (uint32_t)floormod64(b, sd.code_len);
+                    meta[stage * S + lane] = (unsigned long long)(long long)b;
+                } else if (sat_ok) {
+                    meta[stage * S + lane] = frac;
+                }
+                for (int s = 0; s < S; ++s) {
+                    const int ok = __shfl_sync(0xffffffffu, (int)sat_ok, s);
+                    if (!ok) continue;
+                    const uint32_t bm = __shfl_sync(0xffffffffu, bmod, s);
+                    const uint32_t lc = (uint32_t)__shfl_sync(0xffffffffu, sd.code_len, s);
+                    const int8_t *code = reinterpret_cast<const int8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)sd.code, s));
+                    float *win = windows + (size_t)(stage * S + s) * args.win_stride;
+                    for (int j = lane; j < args.win_stride; j += 32) {
+                        uint32_t idx = bm + (uint32_t)j;
+                        if (idx >= lc) idx %= lc;
+                        win[j] = (float)__ldg(code + idx);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (!F64 && sat_ok) nco_tile_advance(sd, tile_len, frac, bmod);
+            }
+            g += t_last - t_first;
+        }
+        return;
+    }
+
+    // ============================== consumer warps ==============================
+    const int role = warp % NR;
+    const int s_idx = role % S, ag = role / S;
+    const int sl = warp / NR;
+    const int consumer_threads = 32 * W;
+
+    for (int64_t g = r0; g < r1;) {
+        const int job = (int)(g / TJ);
+        const int t_first = (int)(g - (int64_t)job * TJ);
+        const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
+        const int p = job / G, grp = job % G;
+        const int k = grp * S + s_idx;
+        const bool active = k < K;
+
+        // per-satellite constants
+        uint64_t delta = 0, car_phase = 0, car_delta = 0;
+        int sh = 0;
+        double ratio = 0.0, cphase = 0.0;
+        if (active) {
+            const SatDev *sd = &args.sats[(size_t)p * K + k];
+            delta = (uint64_t)sd->nco_delta;
+            sh = sd->nco_fp - 32;
+            car_phase = sd->car_phase;
+            car_delta = sd->car_delta;
+            ratio = sd->code_ratio;
+            cphase = sd->code_phase;
+        }
+        uint64_t tapoff[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) tapoff[l] = (uint64_t)(int64_t)(args.shifts[l] - args.shifts[0]) * delta;
+        const uint64_t v_step = (uint64_t)(32 * SL) * delta;
+        const uint64_t ph_step = (uint64_t)(32 * SL) * car_delta;
+
+        f32x2 accRe[AP][L], accIm[AP][L];
+        float sRe[L], sIm[L];  // A == 1 path
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            sRe[l] = sIm[l] = 0.f;
+#pragma unroll
+            for (int a = 0; a < AP; ++a) accRe[a][l] = accIm[a][l] = 0ull;
+        }
+
+        for (int t = t_first; t < t_last; ++t, ++q) {
+            const int stage = q % stages;
+            const uint32_t par = (q / stages) & 1u;
+            mbar_wait(&full_bar[stage], par);
+            if (active) {
+                const int ts_rel = t * tile_len;
+                const int len = min(tile_len, args.aligned_len - ts_rel);
+                const int n0 = args.aligned_start + ts_rel - args.start_sample;  // relative index of tile sample 0
+                const float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
+                const float *tim = tre + (size_t)MP * kTileCap;
+                const float *win = windows + (size_t)(stage * S + s_idx) * args.win_stride;
+                const unsigned long long m0 = meta[stage * S + s_idx];
+                const int tt0 = sl * 32 + lane;
+                uint64_t v = m0 + (uint64_t)tt0 * delta;                       // NCO mode: frac0 + tt*delta
+                const int32_t b64 = (int32_t)(long long)m0;                    // F64 mode: base chip
+                uint64_t ph = car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta;
+                for (int tt = tt0; tt < len; tt += 32 * SL) {
+                    const int n = n0 + tt;
+                    if (n >= 0 && n < args.n_samples) {
+                        // ---- carrier replica: exp(j 2 pi phase) ----
+                        float cr, ci;
+                        const float x = (float)(int32_t)(ph >> 32) * 1.4629180792671596e-9f;  // 2 pi / 2^32
+                        __sincosf(x, &ci, &cr);
+                        // ---- code replica chips for every tap ----
+                        float chip[L];
+#pragma unroll
+                        for (int l = 0; l < L; ++l) {
+                            uint32_t slot;
+                            if constexpr (F64) {
+                                slot = (uint32_t)(f64_chip_floor(ratio, cphase, n + args.shifts[l]) - b64);
+                            } else {
+                                slot = nco_slot(v + tapoff[l], sh);
+                            }
+                            chip[l] = win[slot];
+                        }
+                        if constexpr (A >= 2) {
+                            const f32x2 CR = pack2(cr, cr), CI = pack2(ci, ci), NCI = pack2(-ci, -ci);
+#pragma unroll
+                            for (int a = 0; a < AP; ++a) {
+                                const f32x2 X = pack2(tre[(2 * a) * kTileCap + tt], tre[(2 * a + 1) * kTileCap + tt]);
+                                const f32x2 Y = pack2(tim[(2 * a) * kTileCap + tt], tim[(2 * a + 1) * kTileCap + tt]);
+                                // d = s * conj(c):  d_re = s_re c_re + s_im c_im ; d_im = s_im c_re - s_re c_im
+                                const f32x2 Dre = fma2(Y, CI, mul2(X, CR));
+                                const f32x2 Dim = fma2(X, NCI, mul2(Y, CR));
+#pragma unroll
+                                for (int l = 0; l < L; ++l) {
+                                    const f32x2 CH = pack2(chip[l], chip[l]);
+                                    accRe[a][l] = fma2(Dre, CH, accRe[a][l]);
+                                    accIm[a][l] = fma2(Dim, CH, accIm[a][l]);
+                                }
+                            }
+                        } else {
+                            const float xr = tre[tt], xi = tim[tt];
+                            const float dre = fmaf(xi, ci, xr * cr);
+                            const float dim = fmaf(-xr, ci, xi * cr);
+#pragma unroll
+                            for (int l = 0; l < L; ++l) {
+                                sRe[l] = fmaf(dre, chip[l], sRe[l]);
+                                sIm[l] = fmaf(dim, chip[l], sIm[l]);
+                            }
+                        }
+                    }
+                    v += v_step;
+                    ph += ph_step;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        }
+        g += t_last - t_first;
+
+        // ------------------------------ flush this segment ------------------------------
+        {
+            float vr[RP];
+#pragma unroll
+            for (int i = 0; i < RP; ++i) vr[i] = 0.f;
+            if constexpr (A >= 2) {
+#pragma unroll
+                for (int a = 0; a < AP; ++a)
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        unpack2(accRe[a][l], vr[(a * L + l) * 4 + 0], vr[(a * L + l) * 4 + 1]);
+                        unpack2(accIm[a][l], vr[(a * L + l) * 4 + 2], vr[(a * L + l) * 4 + 3]);
+                    }
+            } else {
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    vr[l * 2 + 0] = sRe[l];
+                    vr[l * 2 + 1] = sIm[l];
+                }
+            }
+            reduce_scatter<RP, 16>(vr, lane);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) part[warp * RP + lane * Q + i] = vr[i];
+        }
+        consumer_bar_sync(consumer_threads);
+
+        const int b_first = tile_owner((int64_t)job * TJ, grid, TT);
+        const int b_last = tile_owner((int64_t)(job + 1) * TJ - 1, grid, TT);
+        const int contributors = b_last - b_first + 1;
+        const int roles_rp = NR * RP;
+        float *my_partial = args.partials + (size_t)(job + (int)blockIdx.x) * roles_rp;
+
+        // decode an accumulator slot -> output element, then store (or accumulate)
+        auto emit = [&](int x, float val) {
+            const int r = x / RP, e = x % RP;
+            if (e >= R) return;
+            const int s2 = r % S, ag2 = r / S;
+            int ml, l, c;
+            if constexpr (A >= 2) {
+                ml = 2 * ((e >> 2) / L) + (e & 1);
+                l = (e >> 2) % L;
+                c = (e >> 1) & 1;
+            } else {
+                ml = 0;
+                l = e >> 1;
+                c = e & 1;
+            }
+            const int kk = grp * S + s2, m = ag2 * A + ml;
+            if (kk >= K || m >= M) return;
+            float *dst = (c ? args.out_im : args.out_re) + (((size_t)p * K + kk) * L + l) * M + m;
+            if (args.flags & 1u) val += *dst;   // GAT_ACCUMULATE
+            *dst = val;
+        };
+
+        if (contributors == 1) {
+            for (int x = tid; x < roles_rp; x += consumer_threads) {
+                const int r = x / RP, e = x % RP;
+                float acc = 0.f;
+                for (int i = 0; i < SL; ++i) acc += part[(i * NR + r) * RP + e];
+                emit(x, acc);
+            }
+            consumer_bar_sync(consumer_threads);
+        } else {
+            for (int x = tid; x < roles_rp; x += consumer_threads) {
+                const int r = x / RP, e = x % RP;
+                float acc = 0.f;
+                for (int i = 0; i < SL; ++i) acc += part[(i * NR + r) * RP + e];
+                __stcg(my_partial + x, acc);
+            }
+            __threadfence();
+            consumer_bar_sync(consumer_threads);
+            if (tid == 0) {
+                const unsigned old = atomicAdd(&args.counters[job], 1u);
+                *flag = (old == (unsigned)(contributors - 1));
+            }
+            consumer_bar_sync(consumer_threads);
+            if (*flag) {
+                __threadfence();
+                for (int x = tid; x < roles_rp; x += consumer_threads) {
+                    float acc = 0.f;
+                    for (int b = b_first; b <= b_last; ++b)
+                        acc += __ldcg(args.partials + (size_t)(job + b) * roles_rp + x);
+                    emit(x, acc);
+                }
+                if (tid == 0) args.counters[job] = 0u;  // self-cleaning for the next launch
+            }
+            consumer_bar_sync(consumer_threads);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// instantiation table + launcher
+// --------------------------------------------------------------------------------------
+typedef void (*KernelFn)(const CorrArgs);
+
+template <int A, int L>
+static KernelFn pick_mode(bool f64)
+{
+    return f64 ? (KernelFn)correlate_kernel<A, L, true> : (KernelFn)correlate_kernel<A, L, false>;
+}
+
+static KernelFn pick_kernel(int A, int L, bool f64)
+{
+#define GAT_CASE(a, l) \
+    if (A == a && L == l) return pick_mode<a, l>(f64);
+    GAT_CASE(1, 1) GAT_CASE(2, 1) GAT_CASE(4, 1) GAT_CASE(8, 1) GAT_CASE(16, 1)
+    GAT_CASE(1, 3) GAT_CASE(2, 3) GAT_CASE(4, 3) GAT_CASE(8, 3) GAT_CASE(16, 3)
+    GAT_CASE(1, 5) GAT_CASE(2, 5) GAT_CASE(4, 5) GAT_CASE(8, 5)
+    GAT_CASE(1, 7) GAT_CASE(2, 7) GAT_CASE(4, 7)
+    GAT_CASE(1, 9) GAT_CASE(2, 9) GAT_CASE(4, 9)
+    GAT_CASE(1, 11) GAT_CASE(2, 11) GAT_CASE(4, 11)
+#undef GAT_CASE
+    return nullptr;
+}
+
+bool kernel_available(int A, int L) { return pick_kernel(A, L, false) != nullptr; }
+
+cudaError_t configure_kernels()
+{
+    static const int As[] = {1, 2, 4, 8, 16};
+    static const int Ls[] = {1, 3, 5, 7, 9, 11};
+    for (int A : As)
+        for (int L : Ls)
+            for (int f = 0; f < 2; ++f) {
+                KernelFn fn = pick_kernel(A, L, f != 0);
+                if (!fn) continue;
+                cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e != cudaSuccess) return e;
+            }
+    return cudaSuccess;
+}
+
+cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream)
+{
+    KernelFn fn = pick_kernel(plan.A, plan.L, plan.f64);
+    if (!fn) return cudaErrorInvalidValue;
+    fn<<<plan.grid, plan.block, plan.smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// debug: replica chip indices through the very same tile-base / slot arithmetic
+// --------------------------------------------------------------------------------------
+__global__ void chip_index_kernel(const SatDev sd, int shift_first, int shift, int n_samples, int tile_len,
+                                  bool f64, int32_t *out)
+{
+    __shared__ unsigned long long s_meta;
+    __shared__ uint32_t s_bmod;
+    uint64_t frac = 0;
+    uint32_t bmod = 0;
+    const int tiles = (n_samples + tile_len - 1) / tile_len;
+    const uint64_t tapoff = (uint64_t)(int64_t)(shift - shift_first) * (uint64_t)sd.nco_delta;
+    for (int t = 0; t < tiles; ++t) {
+        if (threadIdx.x == 0) {
+            const int64_t u0 = (int64_t)t * tile_len + shift_first;
+            if (f64) {
+                const int32_t b = f64_chip_floor(sd.code_ratio, sd.code_phase, (int32_t)u0);
+                bmod = (uint32_t)floormod64(b, sd.code_len);
+                s_meta = (unsigned long long)(long long)b;
+            } else {
+                if (t == 0) nco_tile_base(sd, u0, frac, bmod);
+                s_meta = frac;
+            }
+            s_bmod = bmod;
+        }
+        __syncthreads();
+        for (int tt = threadIdx.x; tt < tile_len && t * tile_len + tt < n_samples; tt += blockDim.x) {
+            const int n = t * tile_len + tt;
+            uint32_t slot;
+            if (f64)
+                slot = (uint32_t)(f64_chip_floor(sd.code_ratio, sd.code_phase, n + shift) - (int32_t)(long long)s_meta);
+            else
+                slot = nco_slot(s_meta + (uint64_t)tt * (uint64_t)sd.nco_delta + tapoff, sd.nco_fp - 32);
+            out[n] = (int32_t)((s_bmod + slot) % (uint32_t)sd.code_len);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && !f64) nco_tile_advance(sd, tile_len, frac, bmod);
+    }
+}
+
+cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples, int tile_len,
+                                bool f64, int32_t *d_out, cudaStream_t stream)
+{
+    chip_index_kernel<<<1, 256, 0, stream>>>(sat, shift_first, shift, n_samples, tile_len, f64, d_out);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// synthetic signal generator, gen_signal semantics (src/gen_signal.jl:135-152)
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void gen_signal_kernel(float *re, float *im, int64_t ld, const int8_t *code, int code_len,
+                                  double code_ratio, double carrier_freq, double fs, double code_phase,
+                                  double carrier_phase_rad, int n_samples, int n_ants, double ant_phase_step,
+                                  double noise_sigma, uint64_t seed, int superpose)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) return;
+    // code_phases = fc/fs .* (0:N-1) .+ start_code_phase ; chips = codes[1 + mod(floor(Int, .), Lc)]
+    const double cp = __dadd_rn(__dmul_rn(code_ratio, (double)i), code_phase);
+    const int64_t idx = floormod64((int64_t)floor(cp), code_len);
+    const float chip = (float)code[idx];
+    // carrier_phases = Float32(2pi * i * f / fs + phase0)  (Float64, left to right, then cast)
+    const double two_pi = 6.283185307179586;
+    const double phd = __dadd_rn(__ddiv_rn(__dmul_rn(__dmul_rn(two_pi, (double)i), carrier_freq), fs), carrier_phase_rad);
+    for (int m = 0; m < n_ants; ++m) {
+        const float ph = (float)(phd + (double)m * ant_phase_step);
+        float vr = cosf(ph) * chip;
+        float vi = sinf(ph) * chip;
+        if (noise_sigma > 0.0) {
+            const uint64_t h = splitmix64(seed ^ splitmix64(((uint64_t)m << 32) | (uint32_t)i));
+            const float u1 = ((float)(uint32_t)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+            const float u2 = ((float)(uint32_t)((h >> 16) & 0xFFFFFFu) + 0.5f) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * logf(u1)) * (float)noise_sigma;
+            float sn, cs;
+            sincospif(2.0f * u2, &sn, &cs);
+            vr += rad * cs;
+            vi += rad * sn;
+        }
+        const int64_t o = (int64_t)m * ld + i;
+        if (superpose) {
+            re[o] += vr;
+            im[o] += vi;
+        } else {
+            re[o] = vr;
+            im[o] = vi;
+        }
+    }
+}
+
+cudaError_t launch_gen_signal(float *re, float *im, int64_t ld, const int8_t *code, int code_len,
+                              double code_ratio, double carrier_freq, double fs, double code_phase,
+                              double carrier_phase_rad, int n_samples, int n_ants, double ant_phase_step_rad,
+                              double noise_sigma, uint64_t seed, int superpose, cudaStream_t stream)
+{
+    const int threads = 256;
+    const int blocks = (n_samples + threads - 1) / threads;
+    gen_signal_kernel<<<blocks, threads, 0, stream>>>(re, im, ld, code, code_len, code_ratio, carrier_freq, fs,
+                                                      code_phase, carrier_phase_rad, n_samples, n_ants,
+                                                      ant_phase_step_rad, noise_sigma, seed, superpose);
+    return cudaGetLastError();
+}
+
+}  // namespace gat

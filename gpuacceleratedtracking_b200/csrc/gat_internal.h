@@ -1,0 +1,84 @@
+// gat_internal.h -- structures shared by the kernels (gat_correlate.cu) and the C-ABI host
+// layer (gat_api.cu).  Not part of the public interface (include/gat.h is).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gat {
+
+constexpr int kTileCap = 256;      // samples per staged smem row (row pitch, floats)
+constexpr int kMaxTaps = 11;       // GAT_MAX_TAPS
+constexpr int kMaxAnts = 32;       // rows per plane that fit the staging ring
+constexpr int kMaxConsumerWarps = 11;  // + 1 producer = 12 warps = 384 threads -> 168 registers/thread
+constexpr int kBlockThreadsMax = 32 * (kMaxConsumerWarps + 1);
+constexpr int kMaxStages = 8;
+constexpr int kSmemHeaderBytes = 1024;  // barriers + per-stage metadata
+
+// One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
+struct SatDev {
+    const int8_t *code;   // +-1 chips of (system, prn), length code_len
+    int32_t code_len;     // modulo length Lc
+    int32_t nco_fp;       // Q-format fractional bits: 63 - ceil(log2(Lc))   [Tracking.jl gen_code_replica!]
+    int64_t nco_delta;    // floor(fc * 2^fp / fs)
+    int64_t nco_start;    // floor(mod(phase, Lc) * 2^fp)
+    uint64_t car_phase;   // carrier phase at relative sample 0, Q0.64 cycles
+    uint64_t car_delta;   // carrier phase step per sample, Q0.64 cycles
+    double code_ratio;    // fc / fs                (GAT_CODE_PHASE_F64)
+    double code_phase;    // start code phase, chips (GAT_CODE_PHASE_F64)
+};
+
+struct PeriodDev {
+    const float *re;      // plane base (sample 0 of antenna 0)
+    const float *im;
+    int64_t ld;           // leading dimension in floats (multiple of 4)
+};
+
+struct CorrArgs {
+    const PeriodDev *periods;   // [n_periods]
+    const SatDev *sats;         // [n_periods * n_sats]
+    float *out_re, *out_im;     // [n_periods][n_sats][n_taps][n_ants]
+    float *partials;            // [(jobs + grid)][roles * RP]
+    unsigned int *counters;     // [jobs], zero between launches (self-cleaning)
+    int32_t shifts[kMaxTaps];
+    int32_t n_periods, n_sats, n_ants, n_taps;
+    int32_t start_sample, n_samples;   // integrated range [start, start + n)
+    int32_t aligned_start;             // start & ~3
+    int32_t aligned_len;               // roundup4(start + n) - aligned_start
+    int32_t tile_len;                  // <= kTileCap, multiple of 32
+    int32_t tiles_per_job;
+    int32_t S, AG, SL, W, G;           // sats/CTA, antenna groups, sample slices, consumer warps, sat groups
+    int32_t stages;
+    int32_t win_stride;                // floats per (stage, sat) chip window
+    int32_t total_tiles;               // jobs * tiles_per_job
+    uint32_t flags;
+};
+
+struct LaunchPlan {
+    int A;            // antennas per thread (template)
+    int L;            // taps (template)
+    bool f64;
+    int grid, block;
+    size_t smem;
+    int RP;           // padded accumulators per role
+    int jobs;
+};
+
+// smem carve-up, shared by host sizing and device addressing
+__host__ __device__ inline size_t smem_tile_floats(int AG, int A) { return (size_t)2 * AG * A * kTileCap; }
+__host__ __device__ inline int padded_acc(int A, int L) { return ((2 * A * L) + 31) / 32 * 32; }
+
+cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream);
+cudaError_t configure_kernels();   // opt-in to > 48 KB dynamic smem for every instantiation
+bool kernel_available(int A, int L);
+
+cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples,
+                                int tile_len, bool f64, int32_t *d_out, cudaStream_t stream);
+
+cudaError_t launch_gen_signal(float *re, float *im, int64_t ld, const int8_t *code, int code_len,
+                              double code_ratio, double carrier_freq_hz, double fs_hz, double code_phase,
+                              double carrier_phase_rad, int n_samples, int n_ants,
+                              double ant_phase_step_rad, double noise_sigma, uint64_t seed,
+                              int superpose, cudaStream_t stream);
+
+}  // namespace gat

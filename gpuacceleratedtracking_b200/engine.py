@@ -1,0 +1,236 @@
+"""Engine: a thin, typed Python face of one libgat context (one GPU, one stream).
+
+This is host-side plumbing only: it marshals numpy arrays / torch CUDA tensors into the
+plain-pointer C ABI of include/gat.h.  All arithmetic happens in libgat's CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import GatChannel, GatError, GatLaunchInfo
+from .gnss import GNSSSystem
+
+try:  # torch is optional plumbing (device memory + streams), never the compute path
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+@dataclass
+class Channel:
+    """One satellite channel of one integration period (the per-call scalars of
+    downconvert_and_correlate!, /root/reference/src/benchmarks.jl:63-79)."""
+    system: GNSSSystem
+    prn: int
+    code_phase: float = 0.0          # chips
+    carrier_frequency: float = 0.0   # Hz
+    carrier_phase: float = 0.0       # cycles
+    code_frequency: float | None = None  # Hz; default: nominal code rate of the system
+
+    def to_c(self) -> GatChannel:
+        fc = self.system.code_frequency if self.code_frequency is None else self.code_frequency
+        return GatChannel(self.system.system_id, int(self.prn), float(self.code_phase), float(fc),
+                          float(self.carrier_phase), float(self.carrier_frequency))
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _ptr(x) -> int:
+    return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+
+class Engine:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.gat_create(C.byref(h), int(device))
+        if rc != 0:
+            raise GatError(rc, self._lib.gat_status_string(rc).decode() +
+                           " (libgat needs a live sm_100 GPU; there is no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        self._systems: dict[int, GNSSSystem] = {}
+        self._keep: dict[int, tuple] = {}   # slot -> tensors kept alive while bound
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GatError(rc, self._lib.gat_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gat_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self._lib.gat_sync(self._h))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._lib.gat_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_timing(self, on: bool):
+        self._check(self._lib.gat_set_timing(self._h, int(on)))
+
+    def launch_info(self) -> dict:
+        li = GatLaunchInfo()
+        self._check(self._lib.gat_last_launch_info(self._h, C.byref(li)))
+        return {n: getattr(li, n) for n, _ in li._fields_}
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.gat_kernel_launch_count(self._h))
+
+    # -- chip tables ------------------------------------------------------------------------
+    def set_codes(self, system: GNSSSystem):
+        if self._systems.get(system.system_id) is system:
+            return
+        tab = np.ascontiguousarray(system.codes, np.int8)
+        self._check(self._lib.gat_set_codes(self._h, system.system_id,
+                                            tab.ctypes.data_as(C.POINTER(C.c_int8)), tab.shape[1], tab.shape[0]))
+        self._systems[system.system_id] = system
+
+    # -- signals ----------------------------------------------------------------------------
+    @staticmethod
+    def _planes(re, im):
+        if re.ndim == 1:
+            re, im = re[None, :], im[None, :]
+        if _is_torch(re):
+            assert re.dtype == torch.float32 and im.dtype == torch.float32
+            assert re.stride(-1) == 1 and im.stride(-1) == 1, "sample axis must be contiguous"
+            ld = re.stride(0) if re.shape[0] > 1 else re.shape[1]
+        else:
+            assert re.dtype == np.float32 and im.dtype == np.float32
+            assert re.strides[-1] == 4 and im.strides[-1] == 4, "sample axis must be contiguous"
+            ld = re.strides[0] // 4 if re.shape[0] > 1 else re.shape[1]
+        return re, im, int(re.shape[0]), int(re.shape[1]), int(ld)
+
+    def upload_signal(self, slot: int, re, im, n_samples: int | None = None):
+        """Copy [n_ants, ld] planes (numpy host or torch device) into engine-owned storage."""
+        re, im, m, n, ld = self._planes(re, im)
+        n = n if n_samples is None else n_samples
+        on_dev = _is_torch(re) and re.is_cuda
+        if _is_torch(re) and not on_dev:
+            re, im = re.numpy(), im.numpy()
+        self._check(self._lib.gat_upload_signal(self._h, slot, C.c_void_p(_ptr(re)), C.c_void_p(_ptr(im)),
+                                                n, m, ld, int(on_dev)))
+        self._keep.pop(slot, None)
+
+    def bind_signal(self, slot: int, re, im, n_samples: int | None = None):
+        """Zero-copy: register torch CUDA planes [n_ants, ld] as the signal of `slot`."""
+        if not (_is_torch(re) and re.is_cuda):
+            raise TypeError("bind_signal needs torch CUDA tensors (use upload_signal for host arrays)")
+        re, im, m, n, ld = self._planes(re, im)
+        n = n if n_samples is None else n_samples
+        self._check(self._lib.gat_bind_signal(self._h, slot, C.c_void_p(_ptr(re)), C.c_void_p(_ptr(im)), n, m, ld))
+        self._keep[slot] = (re, im)
+
+    def gen_signal(self, slot: int, system: GNSSSystem, prn: int, carrier_frequency: float, fs: float,
+                   n_samples: int, n_ants: int = 1, start_code_phase: float = 0.0,
+                   start_carrier_phase: float = 0.0, ant_phase_step: float = 0.0, noise_sigma: float = 0.0,
+                   seed: int = 0, superpose: bool = False):
+        self.set_codes(system)
+        self._check(self._lib.gat_gen_signal(self._h, slot, system.system_id, prn, carrier_frequency, fs,
+                                             start_code_phase, start_carrier_phase, n_samples, n_ants,
+                                             ant_phase_step, noise_sigma, seed, int(superpose)))
+
+    def download_signal(self, slot: int, n_samples: int, n_ants: int):
+        re = np.empty((n_ants, n_samples), np.float32)
+        im = np.empty_like(re)
+        self._check(self._lib.gat_download_signal(self._h, slot, C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data)))
+        return re, im
+
+    # -- the hot path -----------------------------------------------------------------------
+    def correlate_batch(self, slots: Sequence[int], channels: Sequence[Sequence[Channel]], fs: float,
+                        shifts: Sequence[int], n_ants: int, start_sample: int = 0, n_samples: int | None = None,
+                        out=None, accumulate: bool = False, code_phase_f64: bool = False):
+        """channels[p][k]; returns complex64 [P, K, L, M] (host) or fills `out=(re, im)` torch
+        CUDA tensors of that shape (asynchronous)."""
+        P = len(slots)
+        K = len(channels[0])
+        assert len(channels) == P and all(len(c) == K for c in channels)
+        for row in channels:
+            for ch in row:
+                self.set_codes(ch.system)
+        arr = (GatChannel * (P * K))(*[ch.to_c() for row in channels for ch in row])
+        sh = np.ascontiguousarray(shifts, np.int32)
+        L = sh.size
+        sl = np.ascontiguousarray(slots, np.int32)
+        if n_samples is None:
+            raise ValueError("n_samples is required")
+        flags = (_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0)
+        i32p = C.POINTER(C.c_int32)
+        if out is not None:
+            o_re, o_im = out
+            assert _is_torch(o_re) and o_re.is_cuda and o_re.is_contiguous() and o_im.is_contiguous()
+            assert o_re.numel() == P * K * L * n_ants and o_re.dtype == torch.float32
+            self._check(self._lib.gat_correlate_batch(self._h, P, sl.ctypes.data_as(i32p), K, arr, fs,
+                                                      sh.ctypes.data_as(i32p), L, start_sample, n_samples,
+                                                      C.c_void_p(o_re.data_ptr()), C.c_void_p(o_im.data_ptr()), 1, flags))
+            return out
+        o_re = np.empty((P, K, L, n_ants), np.float32)
+        o_im = np.empty_like(o_re)
+        self._check(self._lib.gat_correlate_batch(self._h, P, sl.ctypes.data_as(i32p), K, arr, fs,
+                                                  sh.ctypes.data_as(i32p), L, start_sample, n_samples,
+                                                  C.c_void_p(o_re.ctypes.data), C.c_void_p(o_im.ctypes.data), 0, flags))
+        return (o_re + 1j * o_im).astype(np.complex64)
+
+    def correlate(self, slot: int, channels: Sequence[Channel], fs: float, shifts: Sequence[int], n_ants: int,
+                  start_sample: int = 0, n_samples: int | None = None, out=None, accumulate: bool = False,
+                  code_phase_f64: bool = False):
+        """One period: returns complex64 [K, L, M]."""
+        res = self.correlate_batch([slot], [list(channels)], fs, shifts, n_ants, start_sample, n_samples,
+                                   out=out, accumulate=accumulate, code_phase_f64=code_phase_f64)
+        return res if out is not None else res[0]
+
+    def downconvert_and_correlate_host(self, re: np.ndarray, im: np.ndarray, channels: Sequence[Channel], fs: float,
+                                       shifts: Sequence[int], start_sample: int = 0, n_samples: int | None = None,
+                                       code_phase_f64: bool = False) -> np.ndarray:
+        """Host buffers in, host accumulators out, one C call (gat_downconvert_and_correlate)."""
+        re, im, m, n, ld = self._planes(re, im)
+        n_samples = n - start_sample if n_samples is None else n_samples
+        for ch in channels:
+            self.set_codes(ch.system)
+        K = len(channels)
+        arr = (GatChannel * K)(*[ch.to_c() for ch in channels])
+        sh = np.ascontiguousarray(shifts, np.int32)
+        o_re = np.empty((K, sh.size, m), np.float32)
+        o_im = np.empty_like(o_re)
+        flags = _lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0
+        self._check(self._lib.gat_downconvert_and_correlate(
+            self._h, C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data), ld, m, K, arr, fs,
+            sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size, start_sample, n_samples,
+            C.c_void_p(o_re.ctypes.data), C.c_void_p(o_im.ctypes.data), flags))
+        return (o_re + 1j * o_im).astype(np.complex64)
+
+    def chip_indices(self, channel: Channel, fs: float, shift: int, n_samples: int, code_phase_f64: bool = False):
+        self.set_codes(channel.system)
+        out = np.empty(n_samples, np.int32)
+        c = channel.to_c()
+        self._check(self._lib.gat_debug_chip_indices(self._h, C.byref(c), fs, shift, n_samples,
+                                                     _lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0,
+                                                     out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+
+_default: dict[int, Engine] = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]

@@ -1,0 +1,166 @@
+/*
+ * gat.h -- C ABI of libgat, the B200-native GNSS correlator engine.
+ *
+ * This is the drop-in boundary for the reference's correlate hot path
+ * (coezmaden/GPUAcceleratedTracking; citations relative to /root/reference):
+ *
+ *   GPU-style entry   kernel_algorithm(threads, blocks, shmem, code_replica, codes, code_frequency,
+ *                     sampling_frequency, start_code_phase, prn, num_samples, num_of_shifts,
+ *                     code_length, accum_re, accum_im, ..., signal_re, signal_im,
+ *                     correlator_sample_shifts, carrier_frequency, carrier_phase, num_ants,
+ *                     num_corrs, algorithm)                       src/algorithms.jl:1485-1545
+ *   CPU-style entry   Tracking.downconvert_and_correlate!(system, signal, correlator, code_replica,
+ *                     code_phase, carrier_replica, carrier_phase, downconverted_signal,
+ *                     code_frequency, correlator_sample_shifts, carrier_frequency,
+ *                     sampling_frequency, signal_start_sample, num_samples_left, prn)
+ *                                                                 src/benchmarks.jl:63-79
+ *
+ * A Julia method of either function forwards to gat_correlate() through `ccall`
+ * (julia/GATB200.jl).  Plain pointers and sizes only; no CUDA, torch or
+ * C++ types cross this boundary.  Every function returns GAT_OK (0) or a negative
+ * gat_status and never throws or aborts; gat_last_error() gives the text.
+ *
+ * Conventions (identical to the reference's):
+ *   - signal is SoA complex Float32: separate `re` and `im` planes, each column-major
+ *     [n_samples x n_ants] with leading dimension `ld` (sample index fastest)
+ *     (src/gen_signal.jl:181-184).
+ *   - code phase in chips, code/carrier/sampling frequency in Hz, carrier phase in CYCLES
+ *     (src/algorithms.jl:172), prn 1-based, sample shifts in samples, ascending
+ *     (late -> early), start_sample 0-BASED here (the Julia wrapper subtracts 1).
+ *   - outputs are [n_ants x n_taps x n_sats (x n_periods)] column-major (antenna fastest):
+ *     the accum[M, L, K] layout of src/algorithms.jl:712.
+ *   - chips are +-1 int8, table column-major [code_len x n_prn]  (GNSSSignals `system.codes`).
+ */
+#ifndef GAT_H
+#define GAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAT_VERSION 100 /* 0.1.0 */
+
+typedef enum gat_status {
+    GAT_OK = 0,
+    GAT_ERR_INVALID = -1,     /* bad argument (null pointer, size out of range, unsorted shifts ...) */
+    GAT_ERR_CUDA = -2,        /* CUDA runtime error; text in gat_last_error */
+    GAT_ERR_UNSUPPORTED = -3, /* shape outside the compiled kernel family (n_taps > 11, window too large) */
+    GAT_ERR_ALIGNMENT = -4,   /* zero-copy device signal not 16-byte aligned / ld % 4 != 0 */
+    GAT_ERR_NO_CODES = -5,    /* channel names a (system_id, prn) with no chip table set */
+    GAT_ERR_NO_SIGNAL = -6,   /* slot has no signal bound */
+    GAT_ERR_NO_DEVICE = -7    /* no CUDA device / wrong architecture (sm_100 required) */
+} gat_status;
+
+/* flags for gat_correlate* */
+#define GAT_ACCUMULATE 1u     /* out += result (device outputs only): the `+=` of src/algorithms.jl:207
+                                 and the atomic accumulate of :625-632.  Default overwrites.          */
+#define GAT_CODE_PHASE_F64 2u /* chip index = mod(floor(fc/fs*(n+shift)+phase), Lc) in IEEE double,
+                                 bit-exact with the reference's GPU kernels (src/algorithms.jl:179-182).
+                                 Default is the Int64 Q-format NCO of Tracking.jl's CPU path, bit-exact
+                                 with gen_code_replica! [upstream].                                   */
+
+/* built-in GNSS ids for gat_gen_code / the `system_id` of a channel.  Any other non-negative
+ * id may be used for caller-supplied tables (gat_set_codes). */
+#define GAT_GPSL1 0
+#define GAT_GPSL5 1
+#define GAT_MAX_SYSTEMS 8
+#define GAT_MAX_TAPS 11
+#define GAT_MAX_ANTS 32
+
+typedef struct gat_ctx gat_ctx;
+
+/* One satellite channel for one integration period.  Mirrors the per-call scalars of
+ * downconvert_and_correlate! (code_phase, code_frequency, carrier_phase, carrier_frequency, prn). */
+typedef struct gat_channel {
+    int32_t system_id;           /* which chip table (GAT_GPSL1, GAT_GPSL5, ...) */
+    int32_t prn;                 /* 1-based column of that table */
+    double code_phase_chips;     /* at the first integrated sample */
+    double code_freq_hz;         /* code frequency incl. code Doppler */
+    double carrier_phase_cycles; /* at the first integrated sample, cycles */
+    double carrier_freq_hz;      /* IF + carrier Doppler */
+} gat_channel;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+int gat_version(void);
+const char *gat_status_string(int status);
+int gat_device_count(void);                       /* visible CUDA devices, <0 on error */
+int gat_create(gat_ctx **out, int device_id);     /* one ctx = one device + one non-blocking stream */
+int gat_destroy(gat_ctx *ctx);
+const char *gat_last_error(gat_ctx *ctx);         /* valid until the next call on ctx */
+int gat_sync(gat_ctx *ctx);                       /* cudaStreamSynchronize; CUDA.@sync of src/benchmarks.jl:872 */
+void *gat_stream(gat_ctx *ctx);                   /* the ctx's cudaStream_t, for interop */
+/* Run on a caller-owned cudaStream_t (e.g. CUDA.jl's task stream, torch's current stream) so
+ * work is ordered with the caller's own kernels; NULL restores the ctx's private stream. */
+int gat_set_stream(gat_ctx *ctx, void *cuda_stream);
+
+/* ---- chip tables (replaces the CuTexture / gmem `codes` argument, src/benchmarks.jl:829-837) */
+/* Host helper: generate the +-1 chips of one PRN of a built-in system.  Returns code length
+ * (1023 / 10230) or <0.  (GNSSSignals.jl GPSL1()/GPSL5() `codes[:, prn]`.) */
+int gat_gen_code(int system_id, int prn, int8_t *out, int cap);
+/* Upload a table; chips is HOST memory, column-major [code_len x n_prn]. */
+int gat_set_codes(gat_ctx *ctx, int system_id, const int8_t *chips, int code_len, int n_prn);
+
+/* ---- signal blocks --------------------------------------------------------------------- */
+/* A ctx holds a ring of signal slots (one 1 ms block each).  Upload copies (H2D or D2D,
+ * asynchronously on the ctx stream, src may be pageable or pinned) into ctx-owned padded
+ * storage; bind registers caller-owned DEVICE planes zero-copy (CuArray / torch data_ptr). */
+int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im,
+                      int n_samples, int n_ants, int ld, int src_is_device);
+int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im,
+                    int n_samples, int n_ants, int ld);
+/* Device-side synthetic generator with gen_signal semantics (src/gen_signal.jl:135-152):
+ * code phase Float64 -> floor/mod, carrier phase Float64 -> Float32 -> cos/sin, every antenna
+ * identical.  Extensions (off when zero): per-antenna phase step [rad], AWGN sigma (seeded),
+ * additive superposition onto the existing slot contents. */
+int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrier_freq_hz,
+                   double fs_hz, double start_code_phase, double start_carrier_phase_rad,
+                   int n_samples, int n_ants, double ant_phase_step_rad, double noise_sigma,
+                   uint64_t seed, int superpose);
+/* Copy a slot's planes back (tests): host column-major [n_samples x n_ants], ld = n_samples. */
+int gat_download_signal(gat_ctx *ctx, int slot, float *re, float *im);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* One integration period: n_sats channels over the same signal block.
+ *   out_re/out_im: [n_ants x n_taps x n_sats].  out_is_device = 0: host pointers, the call
+ *   returns after the D2H copy (synchronous, like CUDA.@sync + Array()).  out_is_device = 1:
+ *   device pointers, the call is asynchronous on the ctx stream (call gat_sync). */
+int gat_correlate(gat_ctx *ctx, int slot, int n_sats, const gat_channel *channels, double fs_hz,
+                  const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples,
+                  float *out_re, float *out_im, int out_is_device, unsigned flags);
+
+/* A batch of integration periods in ONE launch: period p reads slots[p] with channels
+ * channels[p * n_sats + k].  All periods share fs, shifts, start_sample, n_samples and the
+ * antenna count.  out: [n_ants x n_taps x n_sats x n_periods]. */
+int gat_correlate_batch(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats,
+                        const gat_channel *channels, double fs_hz, const int32_t *sample_shifts,
+                        int n_taps, int start_sample, int n_samples, float *out_re, float *out_im,
+                        int out_is_device, unsigned flags);
+
+/* Host-buffer convenience = the CPU-style signature: upload + correlate + download. */
+int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *h_im, int ld,
+                                  int n_ants, int n_sats, const gat_channel *channels, double fs_hz,
+                                  const int32_t *sample_shifts, int n_taps, int start_sample,
+                                  int n_samples, float *h_out_re, float *h_out_im, unsigned flags);
+
+/* ---- introspection (bench / tests) ----------------------------------------------------- */
+typedef struct gat_launch_info {
+    int32_t grid, block, smem_bytes;
+    int32_t ants_per_thread, ant_groups, sats_per_cta, sample_slices, consumer_warps;
+    int32_t sat_groups, chunks_per_job, chunk_len, tile_len, stages, items;
+    int32_t kernels_launched;   /* kernels of OURS enqueued by the last correlate call */
+    float last_kernel_ms;       /* device time of the last correlate kernel if timing enabled */
+} gat_launch_info;
+int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out);
+int gat_set_timing(gat_ctx *ctx, int enable);  /* record cudaEvents around the correlate kernel */
+uint64_t gat_kernel_launch_count(gat_ctx *ctx); /* total kernels of ours launched on this ctx */
+/* Replica chip indices exactly as the kernel's code path computes them (device kernel),
+ * for the bit-exactness tests: out[n_samples] (host), sample i, one tap shift. */
+int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift,
+                           int n_samples, unsigned flags, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAT_H */
