@@ -22,11 +22,13 @@ struct SignalSlot {
     int n_samples = 0, n_ants = 0;
     bool owned = false;
     size_t cap_floats = 0;  // per plane, when owned
+    PeriodDev maps{};       // TMA descriptors of the two planes
+    bool maps_valid = false;
 };
 
 struct CodeTable {
-    int8_t *d_chips = nullptr;
-    int code_len = 0, n_prn = 0;
+    int8_t *d_chips = nullptr;   // [n_prn][col_stride], columns zero-padded to kCodeColAlign bytes
+    int code_len = 0, n_prn = 0, col_stride = 0;
 };
 
 struct Staging {
@@ -53,8 +55,8 @@ struct gat_ctx {
     int stg_next = 0;
     float *d_partials = nullptr;
     size_t partials_cap = 0;
-    unsigned int *d_counters = nullptr;
-    size_t counters_cap = 0;
+    unsigned int *d_barrier = nullptr;   // grid-barrier arrival counter (monotonic)
+    unsigned int barrier_count = 0;      // host mirror: value after all launches queued so far
     float *d_out = nullptr;
     size_t d_out_cap = 0;
     float *h_out = nullptr;  // pinned
@@ -174,7 +176,7 @@ int fill_sat(gat_ctx *ctx, const gat_channel &ch, double fs, SatDev &sd)
     if (!(ch.code_freq_hz > 0.0) || !std::isfinite(ch.code_freq_hz) || !std::isfinite(ch.code_phase_chips) ||
         !std::isfinite(ch.carrier_freq_hz) || !std::isfinite(ch.carrier_phase_cycles))
         return fail(ctx, GAT_ERR_INVALID, "non-finite or non-positive channel parameter");
-    sd.code = tab.d_chips + static_cast<size_t>(ch.prn - 1) * tab.code_len;
+    sd.code = tab.d_chips + static_cast<size_t>(ch.prn - 1) * tab.col_stride;
     sd.code_len = tab.code_len;
     sd.nco_fp = nco_fixed_point(tab.code_len);
     sd.nco_delta = static_cast<int64_t>(std::floor(ch.code_freq_hz * std::ldexp(1.0, sd.nco_fp) / fs));
@@ -195,6 +197,7 @@ struct Shape {
     int min_fp;
     int64_t max_delta;
     bool f64;
+    int max_code_len;
 };
 
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
@@ -211,18 +214,27 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
 
     const int w_target_multi = std::min(kMaxConsumerWarps, env_int("GAT_TUNE_WMAX", 11));
     const int w_target_single = std::min(kMaxConsumerWarps, env_int("GAT_TUNE_W", 8));
+    const int cache_stride = (sh.max_code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign;
+    const size_t smem_budget = 227 * 1024;
     int S = std::max(1, std::min(K, w_target_multi / AG));
     S = std::max(1, std::min(S, env_int("GAT_TUNE_S", S)));
+    // every satellite batched on a CTA keeps its chip table in smem: leave room for >= 2 stages
+    {
+        const size_t two_stages = kSmemHeaderBytes + 2 * smem_tile_floats(AG, A) * sizeof(float) + 8192;
+        if (two_stages + cache_stride > smem_budget)
+            return fail(ctx, GAT_ERR_UNSUPPORTED, "chip table too long for the shared-memory cache");
+        S = std::max(1, std::min<int>(S, static_cast<int>((smem_budget - two_stages) / cache_stride)));
+    }
     const int G = (K + S - 1) / S;
     S = (K + G - 1) / G;  // balance the groups
-    int SL = std::max(1, w_target_single / (S * AG));
-    SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
-    const int W = S * AG * SL;
-    if (W > kMaxConsumerWarps || S > 12) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
-
-    const int aligned_start = sh.start & ~3;
-    const int aligned_end = (sh.start + sh.n + 3) & ~3;
-    const int aligned_len = aligned_end - aligned_start;
+    const int RP = padded_acc(A, L);
+    const size_t tile_bytes = smem_tile_floats(AG, A) * sizeof(float);
+    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(kMaxConsumerWarps) * RP * sizeof(float) +
+                               static_cast<size_t>(S) * cache_stride;
+    // tile coordinates stay multiples of 4 samples (16 B); the TMA unit zero-fills past the block end,
+    // and the kernel masks the <= 3 samples staged before start_sample
+    const int aligned_start = env_int("GAT_TUNE_NOALIGN", 0) ? sh.start : (sh.start & ~3);
+    const int aligned_len = sh.start + sh.n - aligned_start;
     const int span = sh.shifts[L - 1] - sh.shifts[0];
 
     const int jobs = sh.P * G;
@@ -231,7 +243,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         // small problems: shrink tiles so every SM gets one
         const int64_t total = static_cast<int64_t>(jobs) * aligned_len;
         const int64_t per_sm = (total + ctx->n_sm - 1) / ctx->n_sm;
-        const int quantum = 32 * SL;
+        const int quantum = 32;
         int want = static_cast<int>(std::min<int64_t>(kTileCap, (per_sm + quantum - 1) / quantum * quantum));
         tile_len = std::max(std::min(quantum, kTileCap), want);
         tile_len = std::min(kTileCap, tile_len);
@@ -253,16 +265,17 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
 
     const int tiles_per_job = (aligned_len + tile_len - 1) / tile_len;
     const int64_t total_tiles = static_cast<int64_t>(jobs) * tiles_per_job;
-    const int RP = padded_acc(A, L);
-    const size_t tile_bytes = smem_tile_floats(AG, A) * sizeof(float);
     const size_t win_bytes = static_cast<size_t>(S) * win_stride * sizeof(float);
-    const size_t part_bytes = static_cast<size_t>(W) * RP * sizeof(float);
-    const size_t budget = 227 * 1024;
-    if (kSmemHeaderBytes + part_bytes + tile_bytes + win_bytes > budget)
+    if (fixed_bytes + tile_bytes + win_bytes > smem_budget)
         return fail(ctx, GAT_ERR_UNSUPPORTED, "shape does not fit shared memory (antennas x window)");
-    int stages = static_cast<int>((budget - kSmemHeaderBytes - part_bytes) / (tile_bytes + win_bytes));
+    int stages = static_cast<int>((smem_budget - fixed_bytes) / (tile_bytes + win_bytes));
     stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 6)));
     stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
+    // sample slices take whole tiles round-robin, so more slices than stages cannot all be fed
+    int SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
+    SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
+    const int W = S * AG * SL;
+    if (W > kMaxConsumerWarps || S > 12) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
 
     const int ctas_per_sm = 1;
     int grid = static_cast<int>(std::min<int64_t>(total_tiles, static_cast<int64_t>(ctx->n_sm) * ctas_per_sm));
@@ -273,7 +286,8 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     plan.f64 = sh.f64;
     plan.grid = grid;
     plan.block = 32 * (W + 1);
-    plan.smem = kSmemHeaderBytes + stages * (tile_bytes + win_bytes) + part_bytes;
+    plan.smem = kSmemHeaderBytes + stages * (tile_bytes + win_bytes) + static_cast<size_t>(W) * RP * sizeof(float) +
+                static_cast<size_t>(S) * cache_stride;
     plan.RP = RP;
     plan.jobs = jobs;
 
@@ -295,6 +309,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.G = G;
     a.stages = stages;
     a.win_stride = win_stride;
+    a.cache_stride = cache_stride;
     a.total_tiles = static_cast<int32_t>(total_tiles);
 
     gat_launch_info &li = ctx->info;
@@ -312,6 +327,47 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     li.tile_len = tile_len;
     li.stages = stages;
     li.items = static_cast<int32_t>(total_tiles);
+    return GAT_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// (re)build the two plane descriptors of a slot: dims {n_samples, n_ants}, box {kTileCap, n_ants}
+int encode_slot_maps(gat_ctx *ctx, SignalSlot &s)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(ctx, GAT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(s.n_samples), static_cast<cuuint64_t>(s.n_ants)};
+    cuuint64_t row_bytes = static_cast<cuuint64_t>(s.ld) * sizeof(float);
+    if (s.n_ants == 1) row_bytes = (static_cast<cuuint64_t>(s.n_samples) * sizeof(float) + 15) / 16 * 16;
+    const cuuint64_t strides[1] = {row_bytes};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileCap), static_cast<cuuint32_t>(s.n_ants)};
+    const cuuint32_t estr[2] = {1, 1};
+    float *planes[2] = {s.re, s.im};
+    CUtensorMap *maps[2] = {&s.maps.re, &s.maps.im};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, planes[i], dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(ctx, GAT_ERR_ALIGNMENT, "cuTensorMapEncodeTiled rejected the signal layout (CUresult " + std::to_string(r) + ")");
+    }
+    s.maps_valid = true;
     return GAT_OK;
 }
 
@@ -358,20 +414,22 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         if (sl.n_ants != M) return fail(ctx, GAT_ERR_INVALID, "all periods of a batch must have the same antenna count");
         if (static_cast<int64_t>(start_sample) + n_samples > sl.n_samples)
             return fail(ctx, GAT_ERR_INVALID, "sample range exceeds the signal in slot " + std::to_string(s));
-        periods[p] = PeriodDev{sl.re, sl.im, sl.ld};
+        if (!sl.maps_valid) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(s) + " has no TMA descriptor");
+        periods[p] = sl.maps;
     }
     if (M < 1 || M > kMaxAnts) return fail(ctx, GAT_ERR_UNSUPPORTED, "antenna count must be 1..32");
 
     // channels
     const size_t n_ch = static_cast<size_t>(n_periods) * n_sats;
     std::vector<SatDev> sats(n_ch);
-    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0};
+    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1};
     for (size_t i = 0; i < n_ch; ++i) {
         rc = fill_sat(ctx, channels[i], fs_hz, sats[i]);
         if (rc) return rc;
         shape.max_ratio = std::max(shape.max_ratio, sats[i].code_ratio);
         shape.min_fp = std::min(shape.min_fp, sats[i].nco_fp);
         shape.max_delta = std::max(shape.max_delta, sats[i].nco_delta);
+        shape.max_code_len = std::max(shape.max_code_len, sats[i].code_len);
     }
 
     LaunchPlan plan{};
@@ -382,7 +440,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
 
     // parameter block: [PeriodDev x P][SatDev x P*K]
     const size_t per_bytes = sizeof(PeriodDev) * n_periods;
-    const size_t sat_off = (per_bytes + 15) & ~static_cast<size_t>(15);
+    const size_t sat_off = (per_bytes + 63) & ~static_cast<size_t>(63);
     const size_t blk_bytes = sat_off + sizeof(SatDev) * n_ch;
     std::vector<unsigned char> blk(blk_bytes);
     std::memcpy(blk.data(), periods.data(), per_bytes);
@@ -397,10 +455,15 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     const size_t roles_rp = static_cast<size_t>(args.S) * args.AG * plan.RP;
     rc = ensure_device(ctx, ctx->d_partials, ctx->partials_cap, (static_cast<size_t>(plan.jobs) + plan.grid) * roles_rp, false);
     if (rc) return rc;
-    rc = ensure_device(ctx, ctx->d_counters, ctx->counters_cap, static_cast<size_t>(plan.jobs), true);
-    if (rc) return rc;
+    if (!ctx->d_barrier) {
+        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_barrier), sizeof(unsigned int)));
+        GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, sizeof(unsigned int), ctx->stream));
+        ctx->barrier_count = 0;
+    }
+    ctx->barrier_count += static_cast<unsigned int>(plan.grid);
     args.partials = ctx->d_partials;
-    args.counters = ctx->d_counters;
+    args.grid_barrier = ctx->d_barrier;
+    args.barrier_target = ctx->barrier_count;
 
     const size_t out_elems = n_ch * n_taps * M;          // caller-visible
     const size_t out_elems_k = n_ch * static_cast<size_t>(L) * M;  // kernel layout (padded taps)
@@ -482,10 +545,11 @@ int own_slot(gat_ctx *ctx, SignalSlot &s, int n_samples, int n_ants, int64_t ld)
         s.owned = true;
     }
     s.im = s.re + s.cap_floats;
+    const bool same = s.maps_valid && s.ld == ld && s.n_samples == n_samples && s.n_ants == n_ants;
     s.ld = ld;
     s.n_samples = n_samples;
     s.n_ants = n_ants;
-    return GAT_OK;
+    return same ? GAT_OK : encode_slot_maps(ctx, s);
 }
 
 }  // namespace
@@ -575,7 +639,7 @@ int gat_destroy(gat_ctx *ctx)
         if (s.done) cudaEventDestroy(s.done);
     }
     if (ctx->d_partials) cudaFree(ctx->d_partials);
-    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_barrier) cudaFree(ctx->d_barrier);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
@@ -611,10 +675,16 @@ int gat_set_codes(gat_ctx *ctx, int system_id, const int8_t *chips, int code_len
     GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (t.d_chips) GAT_CUDA(ctx, cudaFree(t.d_chips));
     t = CodeTable{};
-    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&t.d_chips), n));
-    GAT_CUDA(ctx, cudaMemcpy(t.d_chips, chips, n, cudaMemcpyHostToDevice));
+    // device layout: one zero-padded, 16-byte aligned column per PRN (vector loads into smem)
+    const int stride = (code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign;
+    std::vector<int8_t> padded(static_cast<size_t>(stride) * n_prn, 0);
+    for (int p = 0; p < n_prn; ++p)
+        std::memcpy(padded.data() + static_cast<size_t>(p) * stride, chips + static_cast<size_t>(p) * code_len, code_len);
+    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&t.d_chips), padded.size()));
+    GAT_CUDA(ctx, cudaMemcpy(t.d_chips, padded.data(), padded.size(), cudaMemcpyHostToDevice));
     t.code_len = code_len;
     t.n_prn = n_prn;
+    t.col_stride = stride;
     return GAT_OK;
 }
 
@@ -669,7 +739,7 @@ int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im
     s->n_samples = n_samples;
     s->n_ants = n_ants;
     s->owned = false;
-    return GAT_OK;
+    return encode_slot_maps(ctx, *s);
 }
 
 int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrier_freq_hz, double fs_hz,
@@ -696,7 +766,7 @@ int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrie
     }
     // code frequency of the system: the built-ins carry theirs; caller tables pass it via prn-independent ratio
     const double code_freq = (system_id == GAT_GPSL5) ? 10.23e6 : 1.023e6;
-    cudaError_t e = launch_gen_signal(s->re, s->im, s->ld, t.d_chips + static_cast<size_t>(prn - 1) * t.code_len, t.code_len,
+    cudaError_t e = launch_gen_signal(s->re, s->im, s->ld, t.d_chips + static_cast<size_t>(prn - 1) * t.col_stride, t.code_len,
                                       code_freq / fs_hz, carrier_freq_hz, fs_hz, start_code_phase, start_carrier_phase_rad,
                                       n_samples, n_ants, ant_phase_step_rad, noise_sigma, seed, superpose, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "gen_signal launch");

@@ -72,6 +72,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D tiled TMA load: one instruction moves a [box_rows x box_cols] tile (UTMALDG)
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void consumer_bar_sync(int threads)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
@@ -121,12 +130,15 @@ __device__ __forceinline__ void nco_tile_base(const SatDev &sd, int64_t u0, uint
     frac = (uint64_t)tot & ((1ull << sd.nco_fp) - 1ull);
     bmod = (uint32_t)floormod64(base, sd.code_len);
 }
+// host guarantees (tile_len + span + 1) * delta + 2^fp < 2^64, so 64-bit arithmetic is exact here
 __device__ __forceinline__ void nco_tile_advance(const SatDev &sd, int tile_len, uint64_t &frac, uint32_t &bmod)
 {
-    const unsigned __int128 nf = (unsigned __int128)frac + (unsigned __int128)(uint64_t)tile_len * (uint64_t)sd.nco_delta;
-    const uint64_t carry = (uint64_t)(nf >> sd.nco_fp);
-    frac = (uint64_t)nf & ((1ull << sd.nco_fp) - 1ull);
-    bmod = (uint32_t)((bmod + carry) % (uint64_t)sd.code_len);
+    const uint64_t nf = frac + (uint64_t)tile_len * (uint64_t)sd.nco_delta;
+    const uint32_t carry = (uint32_t)(nf >> sd.nco_fp);
+    frac = nf & ((1ull << sd.nco_fp) - 1ull);
+    uint32_t x = bmod + carry;
+    if (x >= (uint32_t)sd.code_len) x %= (uint32_t)sd.code_len;
+    bmod = x;
 }
 // window slot of (tile-relative offset kk) -- consumer side; sh = fp - 32 (fp >= 32 always)
 __device__ __forceinline__ uint32_t nco_slot(uint64_t v, int sh) { return (uint32_t)(v >> 32) >> sh; }
@@ -163,6 +175,35 @@ __device__ __forceinline__ int tile_owner(int64_t x, int grid, int64_t total)
     return (int)(((x + 1) * grid - 1) / total);
 }
 
+// accumulator slot x of a job -> output element.  Slot layout per role r = ag*S + s:
+//   A >= 2: e = ((antenna_pair * L + tap) * 2 + {re,im}) * 2 + {even,odd antenna};  A == 1: e = tap*2 + {re,im}
+template <int A, int L>
+__device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x, float val)
+{
+    constexpr int R = 2 * A * L;
+    constexpr int RP = (R + 31) / 32 * 32;
+    const int r = x / RP, e = x % RP;
+    if (e >= R) return;
+    const int S = args.S, K = args.n_sats, M = args.n_ants;
+    const int p = job / args.G, grp = job % args.G;
+    const int s2 = r % S, ag2 = r / S;
+    int ml, l, c;
+    if constexpr (A >= 2) {
+        ml = 2 * ((e >> 2) / L) + (e & 1);
+        l = (e >> 2) % L;
+        c = (e >> 1) & 1;
+    } else {
+        ml = 0;
+        l = e >> 1;
+        c = e & 1;
+    }
+    const int kk = grp * S + s2, m = ag2 * A + ml;
+    if (kk >= K || m >= M) return;
+    float *dst = (c ? args.out_im : args.out_re) + (((size_t)p * K + kk) * L + l) * M + m;
+    if (args.flags & 1u) val += *dst;  // GAT_ACCUMULATE
+    *dst = val;
+}
+
 // --------------------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------------------
@@ -186,17 +227,17 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
 
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxStages;
-    volatile int *flag = reinterpret_cast<volatile int *>(smem + 128);
-    unsigned long long *meta = reinterpret_cast<unsigned long long *>(smem + 256);  // [stage][S]
+    unsigned long long *meta = reinterpret_cast<unsigned long long *>(smem + 512);  // [stage][S], S <= 12
     float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
     const int tile_floats = 2 * MP * kTileCap;
     float *windows = tiles + (size_t)stages * tile_floats;
     float *part = windows + (size_t)stages * S * args.win_stride;
+    int8_t *code_cache = reinterpret_cast<int8_t *>(part + (size_t)W * RP);  // [S][cache_stride], producer-private
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 2);          // producer: expect_tx arrival + "windows built" arrival
-            mbar_init(&empty_bar[s], (uint32_t)W);  // one arrival per consumer warp
+            mbar_init(&empty_bar[s], (uint32_t)NR);  // one arrival per consumer warp of the owning slice
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -221,17 +262,30 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
 
     if (warp == W) {
         // ============================ producer warp ============================
+        const int8_t *cached_code = nullptr;  // lane s: which table sits in code_cache[s]
         for (int64_t g = r0; g < r1;) {
             const int job = (int)(g / TJ);
             const int t_first = (int)(g - (int64_t)job * TJ);
             const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
             const int p = job / G, grp = job % G;
-            const PeriodDev per = args.periods[p];
+            const PeriodDev *per = &args.periods[p];
             const bool sat_ok = (lane < S) && (grp * S + lane < K);
             SatDev sd;
             sd.code = nullptr; sd.code_len = 1; sd.nco_fp = 32; sd.nco_delta = 0; sd.nco_start = 0;
             sd.code_ratio = 0.0; sd.code_phase = 0.0;
             if (sat_ok) sd = args.sats[(size_t)p * K + grp * S + lane];
+            // (re)fill the smem chip-table cache of every satellite whose table changed
+            for (int s = 0; s < S; ++s) {
+                const int8_t *code = reinterpret_cast<const int8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)sd.code, s));
+                const int8_t *have = reinterpret_cast<const int8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)cached_code, s));
+                if (code == nullptr || code == have) continue;
+                const int n16 = (__shfl_sync(0xffffffffu, sd.code_len, s) + 15) >> 4;
+                const int4 *src = reinterpret_cast<const int4 *>(code);   // columns are padded to 16 B
+                int4 *dst = reinterpret_cast<int4 *>(code_cache + (size_t)s * args.cache_stride);
+                for (int c = lane; c < n16; c += 32) dst[c] = __ldg(src + c);
+            }
+            if (sat_ok) cached_code = sd.code;
+            __syncwarp();
             uint64_t frac = 0;
             uint32_t bmod = 0;
             if (!F64 && sat_ok) {
@@ -243,17 +297,14 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                 const uint32_t par = (q / stages) & 1u;
                 mbar_wait(&empty_bar[stage], par ^ 1u);
                 const int ts_rel = t * tile_len;  // relative to aligned_start
-                const int len = min(tile_len, args.aligned_len - ts_rel);
-                if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * M * len * 4));
-                __syncwarp();
-                float *stage_tile = tiles + (size_t)stage * tile_floats;
-                for (int r = lane; r < 2 * M; r += 32) {
-                    const int plane = r >= M;
-                    const int m = plane ? r - M : r;
-                    const float *src = (plane ? per.im : per.re) + (int64_t)m * per.ld + args.aligned_start + ts_rel;
-                    bulk_g2s(stage_tile + (size_t)(plane * MP + m) * kTileCap, src, (uint32_t)len * 4u, &full_bar[stage]);
+                if (lane == 0) {
+                    // full boxes always: samples past the block end arrive as zeros and still count
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * M * kTileCap * 4));
+                    float *stage_tile = tiles + (size_t)stage * tile_floats;
+                    tma_load_2d(stage_tile, &per->re, args.aligned_start + ts_rel, 0, &full_bar[stage]);
+                    tma_load_2d(stage_tile + (size_t)MP * kTileCap, &per->im, args.aligned_start + ts_rel, 0, &full_bar[stage]);
                 }
-                // chip windows for every satellite of this CTA
+                // chip windows for every satellite of this CTA, out of the smem table cache
                 if (F64 && sat_ok) {
                     const int32_t u0 = args.aligned_start + ts_rel - args.start_sample + args.shifts[0];
                     const int32_t b = f64_chip_floor(sd.code_ratio, sd.code_phase, u0);
@@ -262,17 +313,18 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                 } else if (sat_ok) {
                     meta[stage * S + lane] = frac;
                 }
+#pragma unroll 2
                 for (int s = 0; s < S; ++s) {
                     const int ok = __shfl_sync(0xffffffffu, (int)sat_ok, s);
                     if (!ok) continue;
                     const uint32_t bm = __shfl_sync(0xffffffffu, bmod, s);
                     const uint32_t lc = (uint32_t)__shfl_sync(0xffffffffu, sd.code_len, s);
-                    const int8_t *code = reinterpret_cast<const int8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)sd.code, s));
+                    const int8_t *tab = code_cache + (size_t)s * args.cache_stride;
                     float *win = windows + (size_t)(stage * S + s) * args.win_stride;
                     for (int j = lane; j < args.win_stride; j += 32) {
                         uint32_t idx = bm + (uint32_t)j;
                         if (idx >= lc) idx %= lc;
-                        win[j] = (float)__ldg(code + idx);
+                        win[j] = (float)tab[idx];
                     }
                 }
                 __syncwarp();
@@ -289,6 +341,7 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
     const int s_idx = role % S, ag = role / S;
     const int sl = warp / NR;
     const int consumer_threads = 32 * W;
+    const int roles_rp = NR * RP;
 
     for (int64_t g = r0; g < r1;) {
         const int job = (int)(g / TJ);
@@ -314,8 +367,8 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
         uint64_t tapoff[L];
 #pragma unroll
         for (int l = 0; l < L; ++l) tapoff[l] = (uint64_t)(int64_t)(args.shifts[l] - args.shifts[0]) * delta;
-        const uint64_t v_step = (uint64_t)(32 * SL) * delta;
-        const uint64_t ph_step = (uint64_t)(32 * SL) * car_delta;
+        const uint64_t v_step = 32ull * delta;
+        const uint64_t ph_step = 32ull * car_delta;
 
         f32x2 accRe[AP][L], accIm[AP][L];
         float sRe[L], sIm[L];  // A == 1 path
@@ -327,6 +380,7 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
         }
 
         for (int t = t_first; t < t_last; ++t, ++q) {
+            if ((int)(q % (uint32_t)SL) != sl) continue;  // tiles go round-robin over the sample slices
             const int stage = q % stages;
             const uint32_t par = (q / stages) & 1u;
             mbar_wait(&full_bar[stage], par);
@@ -338,11 +392,11 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                 const float *tim = tre + (size_t)MP * kTileCap;
                 const float *win = windows + (size_t)(stage * S + s_idx) * args.win_stride;
                 const unsigned long long m0 = meta[stage * S + s_idx];
-                const int tt0 = sl * 32 + lane;
+                const int tt0 = lane;
                 uint64_t v = m0 + (uint64_t)tt0 * delta;                       // NCO mode: frac0 + tt*delta
                 const int32_t b64 = (int32_t)(long long)m0;                    // F64 mode: base chip
                 uint64_t ph = car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta;
-                for (int tt = tt0; tt < len; tt += 32 * SL) {
+                for (int tt = tt0; tt < len; tt += 32) {
                     const int n = n0 + tt;
                     if (n >= 0 && n < args.n_samples) {
                         // ---- carrier replica: exp(j 2 pi phase) ----
@@ -425,65 +479,56 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
 
         const int b_first = tile_owner((int64_t)job * TJ, grid, TT);
         const int b_last = tile_owner((int64_t)(job + 1) * TJ - 1, grid, TT);
-        const int contributors = b_last - b_first + 1;
-        const int roles_rp = NR * RP;
-        float *my_partial = args.partials + (size_t)(job + (int)blockIdx.x) * roles_rp;
-
-        // decode an accumulator slot -> output element, then store (or accumulate)
-        auto emit = [&](int x, float val) {
-            const int r = x / RP, e = x % RP;
-            if (e >= R) return;
-            const int s2 = r % S, ag2 = r / S;
-            int ml, l, c;
-            if constexpr (A >= 2) {
-                ml = 2 * ((e >> 2) / L) + (e & 1);
-                l = (e >> 2) % L;
-                c = (e >> 1) & 1;
-            } else {
-                ml = 0;
-                l = e >> 1;
-                c = e & 1;
-            }
-            const int kk = grp * S + s2, m = ag2 * A + ml;
-            if (kk >= K || m >= M) return;
-            float *dst = (c ? args.out_im : args.out_re) + (((size_t)p * K + kk) * L + l) * M + m;
-            if (args.flags & 1u) val += *dst;   // GAT_ACCUMULATE
-            *dst = val;
-        };
-
-        if (contributors == 1) {
+        {
+            // a job that lives entirely on this CTA is written straight out; otherwise this
+            // CTA's share goes to its partial slot (job + b is unique along the stream-K staircase)
+            const bool sole = (b_first == b_last);
+            float *my_partial = args.partials + (size_t)(job + (int)blockIdx.x) * roles_rp;
             for (int x = tid; x < roles_rp; x += consumer_threads) {
                 const int r = x / RP, e = x % RP;
                 float acc = 0.f;
                 for (int i = 0; i < SL; ++i) acc += part[(i * NR + r) * RP + e];
-                emit(x, acc);
+                if (sole)
+                    emit_output<A, L>(args, job, x, acc);
+                else
+                    __stcg(my_partial + x, acc);
             }
-            consumer_bar_sync(consumer_threads);
-        } else {
-            for (int x = tid; x < roles_rp; x += consumer_threads) {
-                const int r = x / RP, e = x % RP;
-                float acc = 0.f;
-                for (int i = 0; i < SL; ++i) acc += part[(i * NR + r) * RP + e];
-                __stcg(my_partial + x, acc);
+        }
+        consumer_bar_sync(consumer_threads);  // `part` is free again
+    }
+
+    // ---------------- single-pass grid reduction: barrier, then every CTA finalises a share ----------------
+    // All CTAs are co-resident (grid <= number of SMs, one CTA per SM), so a counting barrier is safe.
+    __threadfence();
+    consumer_bar_sync(consumer_threads);
+    if (tid == 0) {
+        atomicAdd(args.grid_barrier, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(args.grid_barrier) : "memory");
+        } while ((int)(seen - args.barrier_target) < 0);
+    }
+    consumer_bar_sync(consumer_threads);
+    {
+        const int jobs = args.n_periods * G;
+        const int64_t E = (int64_t)jobs * roles_rp;
+        for (int64_t e = (int64_t)blockIdx.x * consumer_threads + tid; e < E; e += (int64_t)grid * consumer_threads) {
+            const int job = (int)(e / roles_rp), x = (int)(e % roles_rp);
+            const int b_first = tile_owner((int64_t)job * TJ, grid, TT);
+            const int b_last = tile_owner((int64_t)(job + 1) * TJ - 1, grid, TT);
+            if (b_first == b_last) continue;  // already written by its only owner
+            // fixed summation order -> bit-reproducible results
+            const float *src = args.partials + (size_t)(job + b_first) * roles_rp + x;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int b = b_first;
+            for (; b + 3 <= b_last; b += 4, src += 4 * (size_t)roles_rp) {
+                a0 += __ldcg(src);
+                a1 += __ldcg(src + roles_rp);
+                a2 += __ldcg(src + 2 * (size_t)roles_rp);
+                a3 += __ldcg(src + 3 * (size_t)roles_rp);
             }
-            __threadfence();
-            consumer_bar_sync(consumer_threads);
-            if (tid == 0) {
-                const unsigned old = atomicAdd(&args.counters[job], 1u);
-                *flag = (old == (unsigned)(contributors - 1));
-            }
-            consumer_bar_sync(consumer_threads);
-            if (*flag) {
-                __threadfence();
-                for (int x = tid; x < roles_rp; x += consumer_threads) {
-                    float acc = 0.f;
-                    for (int b = b_first; b <= b_last; ++b)
-                        acc += __ldcg(args.partials + (size_t)(job + b) * roles_rp + x);
-                    emit(x, acc);
-                }
-                if (tid == 0) args.counters[job] = 0u;  // self-cleaning for the next launch
-            }
-            consumer_bar_sync(consumer_threads);
+            for (; b <= b_last; ++b, src += roles_rp) a0 += __ldcg(src);
+            emit_output<A, L>(args, job, x, (a0 + a1) + (a2 + a3));
         }
     }
 }

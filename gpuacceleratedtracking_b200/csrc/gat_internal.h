@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace gat {
@@ -12,8 +13,9 @@ constexpr int kMaxTaps = 11;       // GAT_MAX_TAPS
 constexpr int kMaxAnts = 32;       // rows per plane that fit the staging ring
 constexpr int kMaxConsumerWarps = 11;  // + 1 producer = 12 warps = 384 threads -> 168 registers/thread
 constexpr int kBlockThreadsMax = 32 * (kMaxConsumerWarps + 1);
-constexpr int kMaxStages = 8;
-constexpr int kSmemHeaderBytes = 1024;  // barriers + per-stage metadata
+constexpr int kMaxStages = 16;
+constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
+constexpr int kSmemHeaderBytes = 2048;  // barriers (0..255), flag (256), per-stage metadata (512..)
 
 // One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
 struct SatDev {
@@ -28,10 +30,12 @@ struct SatDev {
     double code_phase;    // start code phase, chips (GAT_CODE_PHASE_F64)
 };
 
-struct PeriodDev {
-    const float *re;      // plane base (sample 0 of antenna 0)
-    const float *im;
-    int64_t ld;           // leading dimension in floats (multiple of 4)
+// One signal block: 2-D TMA descriptors of the re / im planes, dims {n_samples, n_ants},
+// row stride ld*4 bytes, box {kTileCap, n_ants}.  Out-of-range samples are zero-filled by the
+// TMA unit, so tiles may start at any sample and run past the end of the block.
+struct alignas(64) PeriodDev {
+    CUtensorMap re;
+    CUtensorMap im;
 };
 
 struct CorrArgs {
@@ -39,17 +43,19 @@ struct CorrArgs {
     const SatDev *sats;         // [n_periods * n_sats]
     float *out_re, *out_im;     // [n_periods][n_sats][n_taps][n_ants]
     float *partials;            // [(jobs + grid)][roles * RP]
-    unsigned int *counters;     // [jobs], zero between launches (self-cleaning)
+    unsigned int *grid_barrier; // monotonically increasing arrival counter (never reset)
+    unsigned int barrier_target;// value the counter reaches when every CTA of THIS launch arrived
     int32_t shifts[kMaxTaps];
     int32_t n_periods, n_sats, n_ants, n_taps;
     int32_t start_sample, n_samples;   // integrated range [start, start + n)
-    int32_t aligned_start;             // start & ~3
-    int32_t aligned_len;               // roundup4(start + n) - aligned_start
+    int32_t aligned_start;             // first staged sample (== start_sample with tensor-map TMA)
+    int32_t aligned_len;               // staged length (== n_samples)
     int32_t tile_len;                  // <= kTileCap, multiple of 32
     int32_t tiles_per_job;
     int32_t S, AG, SL, W, G;           // sats/CTA, antenna groups, sample slices, consumer warps, sat groups
     int32_t stages;
     int32_t win_stride;                // floats per (stage, sat) chip window
+    int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
     uint32_t flags;
 };

@@ -77,15 +77,17 @@ for p in range(P):
 chans = [[g.Channel(l1, 1, 0.0, 1500.0, 0.0)] for _ in range(P)]
 o_re = torch.zeros(P, 1, L, M, device="cuda"); o_im = torch.zeros_like(o_re)
 eng.set_timing(True)
-for it in range(5):
+for it in range(3):
     eng.correlate_batch(list(range(10, 10 + P)), chans, fs, shifts, M, 0, N, out=(o_re, o_im))
     eng.sync()
     ms = eng.launch_info()["last_kernel_ms"]
-    print(f"batch P={P}: kernel {ms*1e3:.1f} us -> {P*8*N*M/ms/1e6:.0f} GB/s  info={eng.launch_info()}")
+    li = eng.launch_info()
+    print(f"batch P={P}: kernel {ms*1e3:.1f} us -> {P*8*N*M/ms/1e6:.0f} GB/s  W={li['consumer_warps']} SL={li['sample_slices']} stages={li['stages']} tile={li['tile_len']}")
 for K in (1, 8, 32):
     chansK = [[g.Channel(l1, k + 1, 10.0 * k, 1500.0 + k, 0.0) for k in range(K)]]
     oK = (torch.zeros(1, K, L, M, device="cuda"), torch.zeros(1, K, L, M, device="cuda"))
     for it in range(3):
         eng.correlate_batch([10], chansK, fs, shifts, M, 0, N, out=oK); eng.sync()
     ms = eng.launch_info()["last_kernel_ms"]
-    print(f"single period K={K}: kernel {ms*1e3:.1f} us  ({K*N*M*(6+4*L)/ms/1e9:.2f} TFLOP/s) info={eng.launch_info()}")
+    li = eng.launch_info()
+    print(f"single period K={K}: kernel {ms*1e3:.1f} us  ({K*N*M*(6+4*L)/ms/1e9:.2f} TFLOP/s) S={li['sats_per_cta']} G={li['sat_groups']} W={li['consumer_warps']} stages={li['stages']} tiles={li['items']}")

@@ -1,0 +1,44 @@
+"""Profiling driver (run under ncu through gpurun): a few launches of the correlate kernel on the
+benchmark shapes.  argv[1] selects: batch | single1 | single32 | c4 | all."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import gpuacceleratedtracking_b200 as g
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+eng = g.Engine(0)
+l1, l5 = g.GPSL1(), g.GPSL5()
+N, M = 50000, 16
+fs = N / 1e-3
+torch.cuda.set_device(0)
+P = 64
+re = torch.randn(P, M, N, device="cuda"); im = torch.randn(P, M, N, device="cuda")
+torch.cuda.synchronize()
+for p in range(P):
+    eng.bind_signal(10 + p, re[p], im[p])
+
+
+def run(name, P_, K, L, pref, system=l1):
+    c = g.EarlyPromptLateCorrelator(g.NumAnts(M), g.NumAccumulators(L))
+    shifts = g.get_correlator_sample_shifts(system, c, fs, pref)
+    chans = [[g.Channel(system, k % 32 + 1, 10.0 * k, 1500.0 + k, 0.0) for k in range(K)] for _ in range(P_)]
+    out = (torch.zeros(P_, K, L, M, device="cuda"), torch.zeros(P_, K, L, M, device="cuda"))
+    for _ in range(reps):
+        eng.correlate_batch(list(range(10, 10 + P_)), chans, fs, shifts, M, 0, N, out=out)
+    eng.sync()
+    print(name, eng.launch_info())
+
+
+if which in ("batch", "all"):
+    run("batch P=64 K=1 L=3", 64, 1, 3, 0.5)
+if which in ("single1", "all"):
+    run("single K=1 L=3", 1, 1, 3, 0.5)
+if which in ("single32", "all"):
+    run("single K=32 L=3", 1, 32, 3, 0.5)
+if which in ("c4", "all"):
+    run("batch P=64 K=1 L=11", 64, 1, 11, 0.1)
+if which in ("c3", "all"):
+    run("batch P=64 K=1 L=3 L5", 64, 1, 3, 0.5, l5)
+if which in ("k32batch", "all"):
+    run("batch P=8 K=32 L=3", 8, 32, 3, 0.5)

@@ -1,0 +1,487 @@
+"""GPU tier (-m gpu): libgat's CUDA path against the oracle, through the C ABI.
+
+Bars (north_star): replica chip indices BIT-EXACT; correlator outputs within 1e-4 of the prompt
+magnitude (FP32 relative tolerance, written as TOL below); results reproducible run to run.
+/root/reference does not exist on the GPU box: everything here uses oracle/ and tests/golden/."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # of the prompt magnitude (BASELINE.json north_star)
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sysd(orc, system):
+    return orc.GPSL1 if system.name == "GPSL1" else orc.GPSL5
+
+
+def make_block(orc, gat, system, n, m, chans_spec, seed=0, noise=0.0, start=0, tail=0):
+    """chans_spec: list of (prn, code_phase, carrier_freq, carrier_phase[, code_freq]).  Returns planes + channels."""
+    fs = n / 1e-3
+    ld = start + n + tail
+    re = np.zeros((m, ld), np.float32)
+    im = np.zeros((m, ld), np.float32)
+    chans = []
+    for spec in chans_spec:
+        prn, cp, fd, ph = spec[:4]
+        fc = spec[4] if len(spec) > 4 else system.code_frequency
+        r, i = orc.gen_signal(system.codes[prn - 1], fc, fd, fs, n, m, cp, 2 * np.pi * ph)
+        re[:, start:start + n] += r
+        im[:, start:start + n] += i
+        chans.append(gat.Channel(system, prn, cp, fd, ph, fc))
+    if noise:
+        rng = np.random.default_rng(seed + 77)
+        re += rng.normal(0, noise, re.shape).astype(np.float32)
+        im += rng.normal(0, noise, im.shape).astype(np.float32)
+    return re, im, chans, fs
+
+
+def oracle_out(orc, re, im, chans, fs, shifts, start=0, n=None, mode="nco"):
+    return np.stack([orc.correlate_direct(re, im, c.system.codes[c.prn - 1], c.code_frequency or c.system.code_frequency,
+                                          c.code_phase, c.carrier_frequency, c.carrier_phase, fs, shifts,
+                                          start_sample=start, n_samples=n, code_mode=mode) for c in chans])
+
+
+def assert_close(got, ref):
+    L = ref.shape[1]
+    for k in range(ref.shape[0]):
+        prompt = np.abs(ref[k, (L - 1) // 2]).max()
+        err = np.abs(got[k] - ref[k]).max()
+        assert err <= TOL * prompt, f"sat {k}: err {err:.3e} vs prompt {prompt:.3e}"
+
+
+def random_specs(rng, system, k):
+    return [(int(rng.integers(1, 33)), float(rng.uniform(0, system.code_length)), float(rng.uniform(-5e3, 5e3)),
+             float(rng.uniform(-0.5, 0.5))) for _ in range(k)]
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own known answer, through both reference-facing entry points
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num_ants", [1, 4])
+def test_kernel_algorithm_known_answer(gat, engine, num_ants):
+    """test/algorithms.jl:1-88 (and :895-1027 for 4431) restated on KernelAlgorithm('b200')."""
+    import torch
+    num_samples, num_correlators = 2500, 3
+    system = gat.GPSL1(use_gpu=True)
+    codes = system.codes
+    code_frequency = gat.get_code_frequency(system)
+    code_length = gat.get_code_length(system)
+    start_code_phase, carrier_phase, carrier_frequency, prn = 0.0, 0.0, 1500.0, 1
+    signal, sampling_frequency = gat.gen_signal(system, prn, carrier_frequency, num_samples,
+                                                num_ants=gat.NumAnts(num_ants), start_code_phase=start_code_phase,
+                                                start_carrier_phase=carrier_phase, engine=engine)
+    correlator = gat.EarlyPromptLateCorrelator(gat.NumAnts(num_ants), gat.NumAccumulators(num_correlators))
+    shifts = gat.get_correlator_sample_shifts(system, correlator, sampling_frequency, 0.5)
+    num_of_shifts = int(shifts[-1] - shifts[0])
+    accum_re = torch.zeros(num_correlators, num_ants, device="cuda")
+    accum_im = torch.zeros(num_correlators, num_ants, device="cuda")
+    algorithm = gat.KernelAlgorithm("b200")
+    for _ in range(2):   # 4431 semantics: the result accumulates across calls (src/algorithms.jl:625-632)
+        gat.kernel_algorithm(256, 5, 0, None, codes, code_frequency, sampling_frequency, start_code_phase, prn,
+                             num_samples, num_of_shifts, code_length, accum_re, accum_im, None, None, None, None,
+                             signal.re, signal.im, shifts, carrier_frequency, carrier_phase, gat.NumAnts(num_ants),
+                             num_correlators, algorithm, system=system, engine=engine)
+    torch.cuda.synchronize()
+    acc = (accum_re.cpu().numpy() + 1j * accum_im.cpu().numpy()) / 2
+    truth = np.array([1476.0, 2500.0, 1476.0])
+    rtol = float(np.sqrt(np.finfo(np.float32).eps))       # Julia's default isapprox for Float32
+    assert np.allclose(acc, truth[:, None], rtol=rtol, atol=0)
+
+
+@pytest.mark.parametrize("use_gpu", [True, False])
+def test_downconvert_and_correlate_known_answer(gat, engine, use_gpu):
+    """The CPU-style 15-argument call of src/benchmarks.jl:63-79, host and device signals."""
+    system = gat.GPSL1(use_gpu=use_gpu)
+    signal, fs = gat.gen_signal(system, 1, 1500.0, 2500, num_ants=gat.NumAnts(4), engine=engine)
+    correlator = gat.EarlyPromptLateCorrelator(gat.NumAnts(4), gat.NumAccumulators(3))
+    shifts = gat.get_correlator_sample_shifts(system, correlator, fs, 0.5)
+    c1 = gat.downconvert_and_correlate(system, signal, correlator, None, 0.0, None, 0.0, None,
+                                       gat.get_code_frequency(system), shifts, 1500.0, fs, 1, 2500, 1, engine=engine)
+    assert c1 is not correlator and np.all(correlator.accumulators == 0)     # immutable, returns a new one
+    truth = np.array([1476.0, 2500.0, 1476.0])[:, None]
+    assert np.allclose(gat.get_accumulators(c1), truth, rtol=3.5e-4, atol=0)
+    c2 = gat.downconvert_and_correlate(system, signal, c1, None, 0.0, None, 0.0, None, gat.get_code_frequency(system),
+                                       shifts, 1500.0, fs, 1, 2500, 1, engine=engine)
+    assert np.allclose(gat.get_accumulators(c2), 2 * truth, rtol=3.5e-4, atol=0)  # old + new
+    assert np.allclose(gat.get_prompt(c2), 5000.0, rtol=3.5e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs
+# ------------------------------------------------------------------------------------------------
+CONFIGS = {
+    "C1": ("GPSL1", 1, 1, 3, 2500, 0.5),
+    "C2": ("GPSL1", 1, 16, 3, 50000, 0.5),
+    "C3": ("GPSL5", 1, 16, 3, 50000, 0.5),
+    "C4": ("GPSL1", 1, 16, 11, 50000, 0.1),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("mode", ["nco", "f64"])
+def test_baseline_configs(gat, orc, engine, name, mode):
+    sysname, k, m, taps, n, pref = CONFIGS[name]
+    system = gat.GNSSDICT[sysname]()
+    re, im, chans, fs = make_block(orc, gat, system, n, m, [(1, 0.0, 1500.0, 0.0)])
+    shifts = orc.sample_shifts(system.code_frequency, fs, pref, taps)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=n, code_phase_f64=(mode == "f64"))
+    assert got.shape == (k, taps, m) and got.dtype == np.complex64
+    assert_close(got, oracle_out(orc, re, im, chans, fs, shifts, mode=mode))
+    if mode == "f64":   # generator and replica share the formula: exact integer known answers
+        with open(os.path.join(GOLD, "kat.json")) as f:
+            rows = [r for r in json.load(f)["derived"] if r["system"] == sysname and r["n"] == n and len(r["shifts"]) == taps]
+        assert rows
+        assert np.allclose(got[0].real, np.array(rows[0]["expected_re"])[:, None], rtol=3.5e-4)
+
+
+def test_c5_mixed_l1_l5_32_sats(gat, orc, engine):
+    """C5 on one GPU: 16 L1 + 16 L5 channels, two bands = two signal blocks, 16 antennas."""
+    rng = np.random.default_rng(55)
+    n, m = 50000, 16
+    l1, l5 = gat.GPSL1(), gat.GPSL5()
+    out = {}
+    for slot, system in ((0, l1), (1, l5)):
+        specs = [(prn, float(rng.uniform(0, system.code_length)), float(rng.uniform(-5e3, 5e3)),
+                  float(rng.uniform(-0.5, 0.5))) for prn in range(1, 17)]
+        re, im, chans, fs = make_block(orc, gat, system, n, m, specs, noise=1.0, seed=slot)
+        shifts = orc.sample_shifts(system.code_frequency, fs, 0.5, 3)
+        engine.upload_signal(slot, re, im)
+        got = engine.correlate(slot, chans, fs, shifts, m, n_samples=n)
+        assert got.shape == (16, 3, 16)
+        assert_close(got, oracle_out(orc, re, im, chans, fs, shifts))
+        out[slot] = got
+    assert np.abs(out[0][:, 1]).mean() > 0.9 * n       # every satellite's prompt found its own signal
+
+
+def test_mixed_systems_in_one_launch(gat, orc, engine):
+    """L1 and L5 channels batched on the same CTA over one block (different chip tables per warp)."""
+    rng = np.random.default_rng(8)
+    n, m = 20000, 4
+    l1, l5 = gat.GPSL1(), gat.GPSL5()
+    re1, im1, ch1, fs = make_block(orc, gat, l1, n, m, random_specs(rng, l1, 3))
+    re5, im5, ch5, _ = make_block(orc, gat, l5, n, m, random_specs(rng, l5, 3))
+    re, im = re1 + re5, im1 + im5
+    chans = [ch1[0], ch5[0], ch1[1], ch5[1], ch1[2], ch5[2]]
+    shifts = np.array([-2, 0, 2], np.int32)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    assert_close(got, oracle_out(orc, re, im, chans, fs, shifts))
+
+
+# ------------------------------------------------------------------------------------------------
+# committed golden cases (inputs + outputs travel with the repo)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["nco", "f64"])
+def test_committed_golden_cases(gat, engine, mode):
+    z = np.load(os.path.join(GOLD, "cases.npz"))
+    for ci in range(int(z["n_cases"])):
+        system = gat.GNSSDICT[str(z[f"c{ci}_system"])]()
+        re, im = z[f"c{ci}_re"], z[f"c{ci}_im"]
+        fs, shifts = float(z[f"c{ci}_fs"]), z[f"c{ci}_shifts"]
+        chans = [gat.Channel(system, int(c[0]), float(c[1]), float(c[4]), float(c[3]), float(c[2])) for c in z[f"c{ci}_chans"]]
+        engine.upload_signal(0, re, im)
+        got = engine.correlate(0, chans, fs, shifts, re.shape[0], n_samples=re.shape[1], code_phase_f64=(mode == "f64"))
+        assert_close(got, z[f"c{ci}_out_{mode}"])
+
+
+# ------------------------------------------------------------------------------------------------
+# bit-exact replica chip indices
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["nco", "f64"])
+def test_chip_indices_bit_exact(gat, orc, engine, mode):
+    rng = np.random.default_rng(3)
+    l1, l5 = gat.GPSL1(), gat.GPSL5()
+    cases = [(l1, 5e7, 0.0, 1.023e6, s, 50000) for s in (-24, 0, 24)]          # incl. the exact-boundary sample
+    cases += [(l5, 5e7, 0.0, 10.23e6, s, 50000) for s in (-2, 0, 2)]
+    cases += [(l1, 2.5e6, 0.0, 1.023e6, s, 2500) for s in (-1, 0, 1)]
+    for _ in range(8):
+        system = l1 if rng.random() < 0.5 else l5
+        fs = float(rng.choice([4.0e6, 16.368e6, 2.5e7, 5e7, 1.0e8])) if system is l5 else float(rng.choice([2.5e6, 4.0e6, 16.368e6, 5e7]))
+        fc = system.code_frequency * (1 + float(rng.uniform(-2e-5, 2e-5)))
+        cases.append((system, fs, float(rng.uniform(-100, 3 * system.code_length)), fc, int(rng.integers(-40, 41)),
+                      int(rng.integers(1000, 60000))))
+    for system, fs, phase, fc, shift, n in cases:
+        ch = gat.Channel(system, 1, phase, 0.0, 0.0, fc)
+        got = engine.chip_indices(ch, fs, shift, n, code_phase_f64=(mode == "f64"))
+        want = orc.chip_index(fc, fs, phase, system.code_length, shift, n, mode)
+        assert np.array_equal(got, want), (system.name, fs, phase, shift, n, int((got != want).sum()))
+
+
+def test_nco_and_f64_modes_differ_exactly_where_the_reference_paths_do(gat, orc, engine):
+    """L1 at 50 MHz, early tap: sample 49976 sits on the code-period boundary (tests/test_oracle.py)."""
+    l1 = gat.GPSL1()
+    re, im, chans, fs = make_block(orc, gat, l1, 50000, 2, [(1, 0.0, 1500.0, 0.0)])
+    shifts = np.array([-24, 0, 24], np.int32)
+    engine.upload_signal(0, re, im)
+    a = engine.correlate(0, chans, fs, shifts, 2, n_samples=50000)
+    b = engine.correlate(0, chans, fs, shifts, 2, n_samples=50000, code_phase_f64=True)
+    assert np.allclose(b[0].real, np.array([25424, 50000, 25424])[:, None], rtol=1e-6)
+    assert np.allclose(a[0].real, np.array([25424, 50000, 25426])[:, None], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# ragged / edge shapes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [1, 2, 3, 5, 8, 12, 16, 24, 32])
+def test_antenna_counts(gat, orc, engine, m):
+    rng = np.random.default_rng(m)
+    l1 = gat.GPSL1()
+    re, im, chans, fs = make_block(orc, gat, l1, 6000, m, random_specs(rng, l1, 2), noise=0.3, seed=m)
+    # make antennas distinct so a swapped row would be caught
+    re *= (1 + 0.1 * np.arange(m, dtype=np.float32))[:, None]
+    im *= (1 - 0.02 * np.arange(m, dtype=np.float32))[:, None]
+    shifts = np.array([-1, 0, 1], np.int32)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=6000)
+    assert_close(got, oracle_out(orc, re, im, chans, fs, shifts))
+
+
+@pytest.mark.parametrize("taps", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
+def test_tap_counts(gat, orc, engine, taps):
+    rng = np.random.default_rng(100 + taps)
+    l1 = gat.GPSL1()
+    re, im, chans, fs = make_block(orc, gat, l1, 9000, 4, random_specs(rng, l1, 2), noise=0.2, seed=taps)
+    shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 3
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, 4, n_samples=9000)
+    assert got.shape == (2, taps, 4)
+    assert_close(got, oracle_out(orc, re, im, chans, fs, shifts))
+
+
+@pytest.mark.parametrize("n,start,tail", [(1, 0, 0), (31, 0, 0), (33, 5, 2), (255, 1, 0), (257, 3, 9), (1023, 2, 1),
+                                          (4001, 3, 9), (16367, 7, 0), (50001, 0, 0), (2 ** 18, 0, 0)])
+def test_ragged_lengths_and_start_offsets(gat, orc, engine, n, start, tail):
+    rng = np.random.default_rng(n)
+    l1 = gat.GPSL1()
+    m = 3 if n < 100000 else 2
+    re, im, chans, fs = make_block(orc, gat, l1, n, m, random_specs(rng, l1, 2), noise=0.1, seed=n, start=start, tail=tail)
+    fs = max(fs, 2.0e6)
+    # poison what lies outside the integrated range: it must not leak into the sums
+    re[:, :start] = 1e6
+    im[:, :start] = -1e6
+    if tail:
+        re[:, start + n:] = 1e6
+        im[:, start + n:] = 1e6
+    shifts = np.array([-2, 0, 2], np.int32)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, start_sample=start, n_samples=n)
+    ref = oracle_out(orc, re, im, chans, fs, shifts, start=start, n=n)
+    scale = max(np.abs(ref[:, 1]).max(), np.sqrt(n))
+    assert np.abs(got - ref).max() <= TOL * scale
+
+
+def test_phase_extremes(gat, orc, engine):
+    """Negative and beyond-one-period code phases, negative Doppler, MHz-class IF, phases > 1 cycle."""
+    l1 = gat.GPSL1()
+    n, m = 20000, 2
+    specs = [(3, -17.25, -4999.0, -3.75), (9, 1022.999, 4.092e6, 12.5), (11, 5 * 1023 + 0.5, -1.25e6, 0.49999),
+             (20, 0.0, 0.0, 0.0), (21, 511.5, 9.99e6, -0.5)]
+    re, im, chans, fs = make_block(orc, gat, l1, n, m, specs)
+    shifts = np.array([-9, 0, 9], np.int32)
+    engine.upload_signal(0, re, im)
+    for mode in ("nco", "f64"):
+        got = engine.correlate(0, chans, fs, shifts, m, n_samples=n, code_phase_f64=(mode == "f64"))
+        assert_close(got, oracle_out(orc, re, im, chans, fs, shifts, mode=mode))
+
+
+def test_low_sampling_rate_many_chips_per_tile(gat, orc, engine):
+    """fs barely above the chip rate: the per-tile chip window is long (ratio ~ 0.98 chips/sample)."""
+    l5 = gat.GPSL5()
+    n, m, fs = 10440, 2, 10.44e6
+    code = l5.codes[4]
+    re, im = orc.gen_signal(code, 10.23e6, 250.0, fs, n, m, 100.0, 0.0)
+    chans = [gat.Channel(l5, 5, 100.0, 250.0, 0.0)]
+    shifts = np.array([-1, 0, 1], np.int32)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    assert_close(got, oracle_out(orc, re, im, chans, fs, shifts))
+
+
+def test_many_satellites_exceeding_one_cta(gat, orc, engine):
+    rng = np.random.default_rng(64)
+    l1 = gat.GPSL1()
+    n, m, k = 12000, 4, 64
+    re, im, chans, fs = make_block(orc, gat, l1, n, m, random_specs(rng, l1, k), noise=0.5)
+    shifts = np.array([-3, 0, 3], np.int32)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    assert engine.launch_info()["sat_groups"] > 1
+    assert_close(got, oracle_out(orc, re, im, chans, fs, shifts))
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the benchmark's full size
+# ------------------------------------------------------------------------------------------------
+def test_linearity_and_determinism_full_size(gat, orc, engine):
+    import torch
+    n, m = 50000, 16
+    l1 = gat.GPSL1()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a_re, a_im, b_re, b_im = (torch.randn(m, n, device="cuda", generator=g) for _ in range(4))
+    chans = [gat.Channel(l1, 5, 321.0, 2500.0, 0.25), gat.Channel(l1, 6, 17.0, -1234.0, -0.4)]
+    shifts = np.array([-24, 0, 24], np.int32)
+    fs = n / 1e-3
+
+    def run(re, im):
+        engine.bind_signal(3, re, im)
+        return engine.correlate(3, chans, fs, shifts, m, n_samples=n).astype(np.complex128)
+
+    ya, yb = run(a_re, a_im), run(b_re, b_im)
+    yc = run(2.0 * a_re - 0.5 * b_re, 2.0 * a_im - 0.5 * b_im)
+    scale = np.sqrt(n) * 4
+    assert np.abs(yc - (2.0 * ya - 0.5 * yb)).max() < 1e-3 * scale          # linear in the signal
+    # deterministic single-pass reduction: repeated launches are bit-identical
+    y1 = engine.correlate(3, chans, fs, shifts, m, n_samples=n)
+    y2 = engine.correlate(3, chans, fs, shifts, m, n_samples=n)
+    assert np.array_equal(y1.view(np.uint64), y2.view(np.uint64))
+    # conjugate symmetry: conj(signal) with negated carrier gives conj(result)
+    engine.bind_signal(3, a_re, -a_im)
+    neg = [gat.Channel(l1, c.prn, c.code_phase, -c.carrier_frequency, -c.carrier_phase) for c in chans]
+    yn = engine.correlate(3, neg, fs, shifts, m, n_samples=n)
+    assert np.abs(yn - np.conj(ya)).max() < 1e-3 * scale
+
+
+def test_batch_equals_single_calls_and_splitting_adds_up(gat, orc, engine):
+    rng = np.random.default_rng(21)
+    l1 = gat.GPSL1()
+    n, m, P = 50000, 16, 6
+    shifts = np.array([-24, 0, 24], np.int32)
+    blocks, chans = [], []
+    for p in range(P):
+        re, im, ch, fs = make_block(orc, gat, l1, n, m, random_specs(rng, l1, 2), noise=0.5, seed=p)
+        engine.upload_signal(20 + p, re, im)
+        blocks.append((re, im))
+        chans.append(ch)
+    batch = engine.correlate_batch(list(range(20, 20 + P)), chans, fs, shifts, m, n_samples=n)
+    assert batch.shape == (P, 2, 3, m)
+    for p in range(P):
+        single = engine.correlate(20 + p, chans[p], fs, shifts, m, n_samples=n)
+        assert np.abs(batch[p] - single).max() <= 2e-6 * n
+    assert_close(batch[2], oracle_out(orc, *blocks[2], chans[2], fs, shifts))
+    # integrating [0, n1) and [n1, n) with handed-over phases sums to the whole (partial integrations)
+    n1 = 20001
+    c0 = chans[0]
+    whole = engine.correlate(20, c0, fs, shifts, m, n_samples=n).astype(np.complex128)
+    first = engine.correlate(20, c0, fs, shifts, m, start_sample=0, n_samples=n1).astype(np.complex128)
+    moved = [gat.Channel(l1, c.prn, c.code_phase + c.system.code_frequency / fs * n1, c.carrier_frequency,
+                         c.carrier_phase + c.carrier_frequency / fs * n1) for c in c0]
+    second = engine.correlate(20, moved, fs, shifts, m, start_sample=n1, n_samples=n - n1, code_phase_f64=True).astype(np.complex128)
+    assert np.abs(first + second - whole).max() <= 3e-4 * n      # (code index conventions differ by a few samples)
+
+
+def test_accumulate_flag_and_device_outputs(gat, orc, engine):
+    import torch
+    l1 = gat.GPSL1()
+    re, im, chans, fs = make_block(orc, gat, l1, 8000, 4, [(2, 10.0, 800.0, 0.1), (4, 700.0, -900.0, -0.2)])
+    shifts = np.array([-2, 0, 2], np.int32)
+    engine.upload_signal(0, re, im)
+    host = engine.correlate(0, chans, fs, shifts, 4, n_samples=8000)
+    o_re = torch.full((1, 2, 3, 4), 5.0, device="cuda")
+    o_im = torch.full((1, 2, 3, 4), -7.0, device="cuda")
+    engine.correlate(0, chans, fs, shifts, 4, n_samples=8000, out=(o_re, o_im))          # overwrite
+    engine.sync()
+    assert np.array_equal(o_re.cpu().numpy()[0], host.real) and np.array_equal(o_im.cpu().numpy()[0], host.imag)
+    engine.correlate(0, chans, fs, shifts, 4, n_samples=8000, out=(o_re, o_im), accumulate=True)
+    engine.sync()
+    assert np.allclose(o_re.cpu().numpy()[0], 2 * host.real, rtol=1e-6, atol=1e-3)
+
+
+def test_zero_copy_bind_equals_upload(gat, orc, engine):
+    import torch
+    l1 = gat.GPSL1()
+    re, im, chans, fs = make_block(orc, gat, l1, 10000, 8, [(7, 3.0, 100.0, 0.0)], noise=0.4)
+    shifts = np.array([-5, 0, 5], np.int32)
+    engine.upload_signal(0, re, im)
+    a = engine.correlate(0, chans, fs, shifts, 8, n_samples=10000)
+    t_re, t_im = torch.from_numpy(re).cuda(), torch.from_numpy(im).cuda()
+    engine.bind_signal(1, t_re, t_im)
+    b = engine.correlate(1, chans, fs, shifts, 8, n_samples=10000)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    c = engine.downconvert_and_correlate_host(re, im, chans, fs, shifts)         # one C call, host buffers
+    assert np.array_equal(a.view(np.uint64), c.view(np.uint64))
+
+
+def test_device_gen_signal_matches_oracle(gat, orc, engine):
+    for system, n, m, cp, fd, ph in ((gat.GPSL1(), 2500, 4, 0.0, 1500.0, 0.0), (gat.GPSL5(), 50000, 2, 1234.5, -777.0, 1.1),
+                                     (gat.GPSL1(), 16367, 1, 1000.9, 4000.0, -2.0)):
+        fs = n / 1e-3
+        engine.gen_signal(9, system, 3, fd, fs, n, m, cp, ph)
+        re, im = engine.download_signal(9, n, m)
+        r0, i0 = orc.gen_signal(system.codes[2], system.code_frequency, fd, fs, n, m, cp, ph)
+        assert np.abs(re - r0).max() < 5e-6 and np.abs(im - i0).max() < 5e-6      # cosf/sinf ulps only
+        assert np.array_equal(np.sign(re[0] ** 2 + im[0] ** 2), np.ones(n))
+
+
+def test_gen_signal_extensions(gat, engine):
+    l1 = gat.GPSL1()
+    n, m, fs = 20000, 4, 2.0e7
+    engine.gen_signal(9, l1, 1, 1000.0, fs, n, m, ant_phase_step=0.5)
+    re, im = engine.download_signal(9, n, m)
+    z = re + 1j * im
+    assert np.allclose(np.angle(z[1] / z[0]), 0.5, atol=1e-4) and np.allclose(np.angle(z[3] / z[0]), 1.5, atol=1e-4)
+    engine.gen_signal(9, l1, 2, -500.0, fs, n, m, superpose=True)                  # second satellite on top
+    re2, _ = engine.download_signal(9, n, m)
+    assert np.abs(re2 - re).max() > 0.5
+    engine.gen_signal(9, l1, 1, 0.0, fs, n, m, noise_sigma=1.0, seed=42)
+    a, _ = engine.download_signal(9, n, m)
+    engine.gen_signal(9, l1, 1, 0.0, fs, n, m, noise_sigma=1.0, seed=42)
+    b, _ = engine.download_signal(9, n, m)
+    assert np.array_equal(a, b) and 0.9 < (a - np.sign(a.mean()) * 0).std() < 1.6
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour of the C ABI
+# ------------------------------------------------------------------------------------------------
+def test_error_statuses(gat, orc):
+    import torch
+    from gpuacceleratedtracking_b200 import _lib
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    ch = [gat.Channel(l1, 1)]
+    shifts = np.array([-1, 0, 1], np.int32)
+
+    def status(fn):
+        with pytest.raises(gat.GatError) as e:
+            fn()
+        return e.value.status
+
+    assert status(lambda: eng.correlate(0, ch, 2.5e6, shifts, 1, n_samples=100)) == _lib.GAT_ERR_NO_SIGNAL
+    re, im = orc.gen_signal(l1.codes[0], 1.023e6, 0.0, 2.5e6, 2500, 2)
+    eng.upload_signal(0, re, im)
+    assert status(lambda: eng.correlate(0, ch, 2.5e6, shifts, 2, n_samples=2501)) == _lib.GAT_ERR_INVALID
+    assert status(lambda: eng.correlate(0, ch, 2.5e6, [1, 0, -1], 2, n_samples=2500)) == _lib.GAT_ERR_INVALID
+    assert status(lambda: eng.correlate(0, ch, 2.5e6, list(range(12)), 2, n_samples=2500)) == _lib.GAT_ERR_UNSUPPORTED
+    assert status(lambda: eng.correlate(0, ch, -1.0, shifts, 2, n_samples=2500)) == _lib.GAT_ERR_INVALID
+    assert status(lambda: eng.correlate(0, [gat.Channel(l1, 38)], 2.5e6, shifts, 2, n_samples=2500)) == _lib.GAT_ERR_NO_CODES
+    t = torch.zeros(2, 2501, device="cuda")                      # ld % 4 != 0 with two antennas
+    assert status(lambda: eng.bind_signal(1, t, t.clone())) == _lib.GAT_ERR_ALIGNMENT
+    bad = np.ones((1, 100), np.int8) * 3
+    lib = gat.load()
+    assert lib.gat_set_codes(eng._h, 3, bad.ctypes.data_as(C.POINTER(C.c_int8)), 100, 1) == _lib.GAT_ERR_INVALID
+    # the context is still usable after every failure
+    got = eng.correlate(0, ch, 2.5e6, shifts, 2, n_samples=2500)
+    assert np.allclose(got[0].real, np.array([1476, 2500, 1476])[:, None], rtol=3.5e-4)
+    eng.close()
+
+
+def test_caller_supplied_code_table(gat, orc, engine):
+    """gat_set_codes with an arbitrary +-1 table (the `codes` argument of kernel_algorithm)."""
+    rng = np.random.default_rng(2)
+    table = (1 - 2 * rng.integers(0, 2, size=(3, 511))).astype(np.int8)
+    system = gat.GNSSSystem("custom511", 4, 511, 0.511e6, 0.0, 1, True, table)
+    n, m, fs = 8000, 2, 4.0e6
+    re, im = orc.gen_signal(table[1], 0.511e6, 300.0, fs, n, m, 77.0, 0.0)
+    chans = [gat.Channel(system, 2, 77.0, 300.0, 0.0)]
+    shifts = np.array([-3, 0, 3], np.int32)
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    ref = np.stack([orc.correlate_direct(re, im, table[1], 0.511e6, 77.0, 300.0, 0.0, fs, shifts)])
+    assert_close(got, ref)
+    assert abs(got[0, 1, 0].real - n) < 1.0
