@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the correlate hot path (contract: task brief section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--periods P]
+
+Workload (BASELINE.json configs[1], "C2"): GPS L1 C/A, 1 satellite per GPU, 16 antennas,
+3 correlators (E/P/L), 50 000 samples per 1 ms period at 50 MHz.  A STEP is one pass of the hot
+path over a batch of P distinct 1 ms signal blocks (default P = 128 -> 819 MB per GPU, far larger
+than the 126 MB L2, so every step streams from HBM) = ONE fused kernel launch per GPU.
+
+  value   correlations/s = finished complex accumulators (periods x sats x taps x antennas) per
+          second, whole job, signal blocks already resident in HBM.
+  e2e     same metric through the C ABI with HOST buffers: every step copies its signal blocks
+          from pinned host memory (H2D, chunked and overlapped with compute on two streams) and
+          reads the accumulators back (D2H).
+  N > 1   one process per GPU (torchrun).  Satellite channels are independent given the signal
+          block, so they shard across ranks: rank r correlates its own satellite over the same
+          blocks (weak scaling, per-GPU work fixed), and the small accumulators are all-gathered
+          over NCCL every step.  In the e2e leg rank 0 owns the host buffers and the blocks reach
+          the other GPUs by NCCL broadcast over NVLink.
+
+  --impl reference   times the CPU restatement of the reference's Tracking.jl path (oracle/,
+          "port": Julia is not installed, the reference cannot run) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES, N_ANTS, N_TAPS = 50_000, 16, 3
+FS = N_SAMPLES / 1e-3
+CODE_FREQ = 1.023e6
+DOPPLER = 1500.0
+WORKLOAD = "GPS L1 C/A, 1 sat/GPU, 16 antennas, 3 correlators (E/P/L), 50000 samples/ms @ 50 MHz (BASELINE configs[1])"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        """Launch nvidia-smi and wait (<= 5 s) until its first sample lands, so the samples that
+        follow really fall inside the load window."""
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
+            self.skip = sum(1 for _ in open(self.path))      # idle samples taken before the load starts
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for li, line in enumerate(open(self.path)):
+                if li < getattr(self, "skip", 0):
+                    continue
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path, restated (oracle/), on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(periods: int, steps: int, warmup: int, budget_s: float | None = None):
+    """Returns (correlations/s, ms_per_step, cores, kind, sample description)."""
+    import ctypes as C
+    import oracle
+    native = True
+    try:
+        oracle.build(native=True)          # -march=native on THIS host (the box), falls back below
+        lib = oracle.lib(native=True)
+    except Exception:
+        native = False
+        lib = oracle.lib(native=False)
+    code = oracle.prn_code("GPSL1", 1)
+    shifts = oracle.sample_shifts(CODE_FREQ, FS, 0.5, N_TAPS)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    periods = max(periods, 1)
+    rng = np.random.default_rng(7)
+    base_re, base_im = oracle.gen_signal(code, CODE_FREQ, DOPPLER, FS, N_SAMPLES, N_ANTS)
+    re = np.empty((periods, N_ANTS, N_SAMPLES), np.float32)
+    im = np.empty_like(re)
+    pool = [rng.normal(0, 1, base_re.shape).astype(np.float32) for _ in range(4)]   # unit AWGN, reused cyclically
+    for p in range(periods):
+        re[p] = base_re + pool[p % 4]
+        im[p] = base_im + pool[(p + 1) % 4]
+    jobs = periods
+    codes = (C.POINTER(C.c_int8) * jobs)(*[code.ctypes.data_as(C.POINTER(C.c_int8))] * jobs)
+    lens = np.full(jobs, code.size, np.int32)
+    fc = np.full(jobs, CODE_FREQ)
+    cp = np.zeros(jobs)
+    fd = np.full(jobs, DOPPLER)
+    ph = np.zeros(jobs)
+    o_re = np.empty((jobs, N_TAPS, N_ANTS), np.float32)
+    o_im = np.empty_like(o_re)
+    f32p, f64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+    def step():
+        return lib.orc_correlate_tracking_batch(
+            re.ctypes.data_as(f32p), im.ctypes.data_as(f32p), N_ANTS * N_SAMPLES, N_SAMPLES, N_ANTS, N_SAMPLES,
+            periods, 1, codes, lens.ctypes.data_as(i32p), fc.ctypes.data_as(f64p), cp.ctypes.data_as(f64p),
+            fd.ctypes.data_as(f64p), ph.ctypes.data_as(f64p), FS, shifts.ctypes.data_as(i32p), N_TAPS, cores,
+            o_re.ctypes.data_as(f32p), o_im.ctypes.data_as(f32p))
+
+    used = 1
+    for _ in range(warmup):
+        used = step()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        used = step()
+        times.append(time.perf_counter() - t0)
+        if budget_s and time.perf_counter() - t_begin > budget_s:
+            break
+    assert abs(float(o_re[0, 1, 0]) - N_SAMPLES) < 0.02 * N_SAMPLES          # it really correlated
+    t = float(np.mean(times))
+    value = periods * N_TAPS * N_ANTS / t
+    sample = (f"{len(times)} steps x {periods} one-ms periods of the C2 shape, OpenMP over periods, "
+              f"{'-march=native' if native else 'x86-64-v3'} build of oracle/oracle.c")
+    return value, t * 1e3, int(used), "port", sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    periods = args.ref_periods or max(16, 2 * cores)
+    value, ms, used, kind, sample = cpu_arm(periods, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "correlations/sec", "value": value, "unit": "correlations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "periods_per_step": periods, "n_sats": 1, "n_ants": N_ANTS, "n_taps": N_TAPS,
+                   "n_samples": N_SAMPLES, "note": "CPU restatement of Tracking.downconvert_and_correlate! (Julia absent)"},
+        "cpu_baseline": {"value": value, "unit": "correlations/s", "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "correlations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "realtime_channels": periods / ms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import gpuacceleratedtracking_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: libgat has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    P, steps, warmup = args.periods, args.steps, args.warmup
+    eng = g.Engine(local)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)     # torch events see our kernels
+    l1 = g.GPSL1()
+    corr = g.EarlyPromptLateCorrelator(g.NumAnts(N_ANTS), g.NumAccumulators(N_TAPS))
+    shifts = g.get_correlator_sample_shifts(l1, corr, FS, 0.5)
+
+    # ---- synthetic input, resident in HBM: P distinct blocks (every visible PRN + unit AWGN) ----
+    re = torch.empty(P, N_ANTS, N_SAMPLES, device=dev)
+    im = torch.empty(P, N_ANTS, N_SAMPLES, device=dev)
+    for p in range(P):
+        eng.bind_signal(p, re[p], im[p])
+        for s in range(world):
+            eng.gen_signal(p, l1, s + 1, DOPPLER + 10.0 * s, FS, N_SAMPLES, N_ANTS, start_code_phase=3.0 * p,
+                           noise_sigma=(1.0 if s == 0 else 0.0), seed=1000 + p, superpose=(s > 0))
+    my_prn = rank % 32 + 1
+    chans = [[g.Channel(l1, my_prn, 3.0 * p, DOPPLER + 10.0 * rank, 0.0)] for p in range(P)]
+    slots = list(range(P))
+    o_re = torch.zeros(P, 1, N_TAPS, N_ANTS, device=dev)
+    o_im = torch.zeros_like(o_re)
+    if world > 1:
+        g_buf = torch.empty(world, 2, P, 1, N_TAPS, N_ANTS, device=dev)
+
+    def step():
+        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
+        if world > 1:   # the path's real exchange step: gather the (tiny) accumulators
+            dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    # sanity: the prompt found this rank's satellite in every block
+    prompt = o_re[:, 0, 1, :].mean().item()
+    assert prompt > 0.9 * N_SAMPLES, f"prompt {prompt}"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # The timed region lasts only a few ms (K x ~0.15 ms), shorter than nvidia-smi's sampling period,
+    # so the same step is first run untimed for ~0.6 s under the sampler; the timed steps follow
+    # immediately at the same load and the clock record covers both.
+    barrier()
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
+    launches0 = eng.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for a, b in ev:
+        a.record()
+        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
+        b.record()
+        if world > 1:
+            dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))
+    t1.record()
+    barrier()
+    gpu_launches = eng.kernel_launches - launches0
+    total_ms = t0.elapsed_time(t1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    clocks = sampler.stop() if rank == 0 else {}
+    tt = torch.tensor([total_ms, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = tt.tolist()
+    ms_per_step = total_ms / steps
+    corr_per_step = world * P * 1 * N_TAPS * N_ANTS
+    value = corr_per_step / (ms_per_step * 1e-3)
+    info = eng.launch_info()
+
+    # ---- e2e: host buffers -> H2D (-> NCCL broadcast) -> correlate -> gather -> D2H ----
+    e2e_steps = max(2, min(steps, args.e2e_steps))
+    CH = 16                                                       # periods per pipelined chunk
+    h_re = h_im = None
+    if rank == 0:
+        h_re = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
+        h_im = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
+        h_re.copy_(re)
+        h_im.copy_(im)
+    h_out = torch.empty(2, world, P, 1, N_TAPS, N_ANTS, pin_memory=True) if rank == 0 else None
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+
+    def e2e_step():
+        done = []
+        for c0 in range(0, P, CH):
+            c1 = min(P, c0 + CH)
+            with torch.cuda.stream(copy_stream):
+                if rank == 0:
+                    re[c0:c1].copy_(h_re[c0:c1], non_blocking=True)
+                    im[c0:c1].copy_(h_im[c0:c1], non_blocking=True)
+                if world > 1:
+                    dist.broadcast(re[c0:c1], src=0)
+                    dist.broadcast(im[c0:c1], src=0)
+                e = torch.cuda.Event()
+                e.record()
+            done.append((c0, c1, e))
+        for c0, c1, e in done:                                    # compute chunk i while chunk i+1 is in flight
+            main.wait_event(e)
+            eng.correlate_batch(slots[c0:c1], chans[c0:c1], FS, shifts, N_ANTS, 0, N_SAMPLES,
+                                out=(o_re[c0:c1], o_im[c0:c1]))
+        if world > 1:
+            dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))
+            if rank == 0:
+                h_out.copy_(g_buf.transpose(0, 1), non_blocking=True)
+        elif rank == 0:
+            h_out[:, 0].copy_(torch.stack([o_re, o_im]), non_blocking=True)
+        copy_stream.wait_stream(main)                            # next step's H2D must not overtake this compute
+        torch.cuda.current_stream().synchronize()                # the user sees the result (D2H read)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_wall_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
+    te = torch.tensor([max(e2e_ms, e2e_wall_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = te.item()
+    e2e_value = corr_per_step / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+        algo_bytes = P * (8 * N_SAMPLES * N_ANTS) + P * (8 * N_TAPS * N_ANTS) + 1023   # signal once + outputs + chip table
+        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("periods_per_step") == P:
+                    traffic = tj["dram_bytes_per_launch"]
+            except Exception:
+                pass
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, ms, used, kind, sample = cpu_arm(max(16, 2 * cores), 1000, 1, budget_s=args.cpu_seconds)
+            cpu = {"value": v, "unit": "correlations/s", "cores": used, "kind": kind, "sample": sample}
+        line = {
+            "metric": "correlations/sec", "value": value, "unit": "correlations/s", "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "periods_per_step": P, "n_sats_per_gpu": 1, "n_ants": N_ANTS,
+                       "n_taps": N_TAPS, "n_samples": N_SAMPLES, "parallelism": f"satellite-sharded x{world}",
+                       "l2_policy": f"inputs larger than L2 ({P * 8 * N_SAMPLES * N_ANTS / 1e6:.0f} MB of distinct signal blocks per step)",
+                       "launch": {k: info[k] for k in ("grid", "block", "smem_bytes", "stages", "tile_len", "consumer_warps")}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "correlations/s", "h2d_bytes_per_step": P * 8 * N_SAMPLES * N_ANTS,
+                    "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "path": "pinned host -> H2D" + (" -> NCCL broadcast" if world > 1 else "") + " -> gat_correlate_batch -> D2H"},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "cmacs_per_s": value * N_SAMPLES,
+            "realtime_channels": world * P / ms_per_step,      # 1 ms periods finished per ms of wall clock
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--periods", type=int, default=128, help="1 ms signal blocks per step (batch)")
+    ap.add_argument("--ref-periods", type=int, default=0, help="periods per CPU step (default 2 x cores)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,8 @@ SYMBOLS = {
     "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
     "gat_set_timing": (_i, [_vp, _i]),
     "gat_kernel_launch_count": (C.c_uint64, [_vp]),
+    "gat_set_timeline": (_i, [_vp, _i]),
+    "gat_get_timeline": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "gat_debug_chip_indices": (_i, [_vp, _chp, _d, _i, _i, _u, _i32p]),
 }
 

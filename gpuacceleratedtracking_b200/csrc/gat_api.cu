@@ -35,11 +35,12 @@ struct Staging {
     unsigned char *h = nullptr;  // pinned
     unsigned char *d = nullptr;
     size_t cap = 0;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;      // H2D copy finished (param stream)
+    cudaEvent_t consumed = nullptr;  // the kernel reading `d` was queued behind this (main stream)
     bool pending = false;
 };
 
-constexpr int kStagingRing = 4;
+constexpr int kStagingRing = 8;
 
 }  // namespace
 
@@ -48,6 +49,7 @@ struct gat_ctx {
     int n_sm = 0;
     cudaStream_t stream = nullptr;      // the stream work is queued on
     cudaStream_t own_stream = nullptr;  // created by gat_create
+    cudaStream_t param_stream = nullptr;  // parameter-block uploads, overlapping the previous kernel
     std::string err;
     CodeTable codes[GAT_MAX_SYSTEMS];
     std::vector<SignalSlot> slots;
@@ -63,6 +65,10 @@ struct gat_ctx {
     size_t h_out_cap = 0;
     int32_t *d_dbg = nullptr;
     size_t d_dbg_cap = 0;
+    unsigned long long *d_timeline = nullptr;
+    size_t timeline_cap = 0;
+    bool timeline_on = false;
+    int timeline_ctas = 0;
     gat_launch_info info{};
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -117,14 +123,15 @@ int ensure_device(gat_ctx *ctx, T *&ptr, size_t &cap, size_t need, bool zero)
     return GAT_OK;
 }
 
-// Host staging -> device for the per-call parameter block; ring of pinned buffers so a call
-// never overwrites a buffer whose H2D copy is still queued.
-int stage_params(gat_ctx *ctx, const void *src, size_t bytes, unsigned char **d_out)
+// Host staging -> device for the per-call parameter block.  The upload runs on a side stream so
+// that, with calls queued back to back, block i+1 is copied while kernel i runs; a ring of pinned
+// buffers with two events each keeps host and device copies from being overwritten while in use.
+int stage_params(gat_ctx *ctx, const void *src, size_t bytes, unsigned char **d_out, Staging **used)
 {
     Staging &s = ctx->stg[ctx->stg_next];
     ctx->stg_next = (ctx->stg_next + 1) % kStagingRing;
     if (s.pending) {
-        GAT_CUDA(ctx, cudaEventSynchronize(s.done));
+        GAT_CUDA(ctx, cudaEventSynchronize(s.done));   // pinned buffer free again
         s.pending = false;
     }
     if (bytes > s.cap) {
@@ -140,12 +147,19 @@ int stage_params(gat_ctx *ctx, const void *src, size_t bytes, unsigned char **d_
         GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&s.d), grow));
         s.cap = grow;
     }
-    if (!s.done) GAT_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (!s.done) {
+        GAT_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        GAT_CUDA(ctx, cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+        GAT_CUDA(ctx, cudaEventRecord(s.consumed, ctx->stream));
+    }
     std::memcpy(s.h, src, bytes);
-    GAT_CUDA(ctx, cudaMemcpyAsync(s.d, s.h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    GAT_CUDA(ctx, cudaEventRecord(s.done, ctx->stream));
+    GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->param_stream, s.consumed, 0));  // last reader of s.d is done
+    GAT_CUDA(ctx, cudaMemcpyAsync(s.d, s.h, bytes, cudaMemcpyHostToDevice, ctx->param_stream));
+    GAT_CUDA(ctx, cudaEventRecord(s.done, ctx->param_stream));
+    GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.done, 0));
     s.pending = true;
     *d_out = s.d;
+    *used = &s;
     return GAT_OK;
 }
 
@@ -242,11 +256,11 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     {
         // small problems: shrink tiles so every SM gets one
         const int64_t total = static_cast<int64_t>(jobs) * aligned_len;
-        const int64_t per_sm = (total + ctx->n_sm - 1) / ctx->n_sm;
+        // aim at >= 8 tiles per CTA so the +-1 tile quantisation of the even split stays small
+        const int64_t per_tile = (total + 8LL * ctx->n_sm - 1) / (8LL * ctx->n_sm);
         const int quantum = 32;
-        int want = static_cast<int>(std::min<int64_t>(kTileCap, (per_sm + quantum - 1) / quantum * quantum));
-        tile_len = std::max(std::min(quantum, kTileCap), want);
-        tile_len = std::min(kTileCap, tile_len);
+        int want = static_cast<int>(std::min<int64_t>(kTileCap, (per_tile + quantum - 1) / quantum * quantum));
+        tile_len = std::min(kTileCap, std::max(total >= 64LL * ctx->n_sm ? 64 : quantum, want));
         tile_len = env_int("GAT_TUNE_TILE", tile_len);
         if (tile_len < 32 || tile_len > kTileCap || tile_len % 32) return fail(ctx, GAT_ERR_INVALID, "bad GAT_TUNE_TILE");
     }
@@ -311,6 +325,15 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.win_stride = win_stride;
     a.cache_stride = cache_stride;
     a.total_tiles = static_cast<int32_t>(total_tiles);
+    {
+        // finalize: a job's tiles are spread over at most ceil(TJ / tiles-per-CTA) + 1 CTAs
+        const int64_t per_cta = std::max<int64_t>(1, total_tiles / grid);
+        const int64_t max_contrib = std::min<int64_t>(grid, (tiles_per_job + per_cta - 1) / per_cta + 1);
+        a.fin_group = max_contrib <= 8 ? 1 : 32;
+        // few tiles per CTA: let every slice work on every tile instead of taking turns
+        a.split_tiles = (SL > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid) ? 1 : 0;
+        a.split_tiles = env_int("GAT_TUNE_SPLIT", a.split_tiles);
+    }
 
     gat_launch_info &li = ctx->info;
     li.grid = grid;
@@ -446,7 +469,8 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     std::memcpy(blk.data(), periods.data(), per_bytes);
     std::memcpy(blk.data() + sat_off, sats.data(), sizeof(SatDev) * n_ch);
     unsigned char *d_blk = nullptr;
-    rc = stage_params(ctx, blk.data(), blk_bytes, &d_blk);
+    Staging *stg = nullptr;
+    rc = stage_params(ctx, blk.data(), blk_bytes, &d_blk, &stg);
     if (rc) return rc;
     args.periods = reinterpret_cast<const PeriodDev *>(d_blk);
     args.sats = reinterpret_cast<const SatDev *>(d_blk + sat_off);
@@ -479,9 +503,18 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         if (flags & GAT_ACCUMULATE) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_ACCUMULATE with an even tap count");
     }
 
+    args.timeline = nullptr;
+    if (ctx->timeline_on) {
+        rc = ensure_device(ctx, ctx->d_timeline, ctx->timeline_cap, static_cast<size_t>(plan.grid) * 16, false);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_timeline, 0, static_cast<size_t>(plan.grid) * 16 * sizeof(unsigned long long), ctx->stream));
+        args.timeline = ctx->d_timeline;
+        ctx->timeline_ctas = plan.grid;
+    }
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = launch_correlate(plan, args, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "correlate kernel launch");
+    GAT_CUDA(ctx, cudaEventRecord(stg->consumed, ctx->stream));
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     ctx->info.kernels_launched = 1;
@@ -604,6 +637,7 @@ int gat_create(gat_ctx **out, int device_id)
     ctx->device = device_id;
     ctx->n_sm = prop.multiProcessorCount;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->param_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         configure_kernels() != cudaSuccess) {
         cudaGetLastError();
@@ -637,15 +671,18 @@ int gat_destroy(gat_ctx *ctx)
         if (s.h) cudaFreeHost(s.h);
         if (s.d) cudaFree(s.d);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.consumed) cudaEventDestroy(s.consumed);
     }
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     if (ctx->d_barrier) cudaFree(ctx->d_barrier);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->d_timeline) cudaFree(ctx->d_timeline);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->param_stream) cudaStreamDestroy(ctx->param_stream);
     delete ctx;
     return GAT_OK;
 }
@@ -832,6 +869,24 @@ int gat_set_timing(gat_ctx *ctx, int enable)
 }
 
 uint64_t gat_kernel_launch_count(gat_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gat_set_timeline(gat_ctx *ctx, int enable)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    ctx->timeline_on = enable != 0;
+    return GAT_OK;
+}
+
+int gat_get_timeline(gat_ctx *ctx, uint64_t *out, int cap_ctas)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!out || !ctx->d_timeline || ctx->timeline_ctas < 1) return fail(ctx, GAT_ERR_INVALID, "no timeline recorded");
+    const int n = std::min(cap_ctas, ctx->timeline_ctas);
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GAT_CUDA(ctx, cudaMemcpy(out, ctx->d_timeline, static_cast<size_t>(n) * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return n;
+}
 
 int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift, int n_samples, unsigned flags,
                            int32_t *out)

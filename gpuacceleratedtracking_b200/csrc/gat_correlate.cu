@@ -86,6 +86,19 @@ __device__ __forceinline__ void consumer_bar_sync(int threads)
     asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// debug timeline: one thread per role stamps a slot (see gat_get_timeline in include/gat.h)
+#define GAT_STAMP(slot)                                                                        \
+    do {                                                                                       \
+        if (args.timeline && lane == 0 && (warp == 0 || warp == W))                            \
+            args.timeline[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns();                \
+    } while (0)
+
 typedef unsigned long long f32x2;  // two packed floats: lo = even antenna, hi = odd antenna
 __device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
@@ -228,17 +241,23 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxStages;
     unsigned long long *meta = reinterpret_cast<unsigned long long *>(smem + 512);  // [stage][S], S <= 12
+    uint32_t *p_lc = reinterpret_cast<uint32_t *>(smem + 2048 + 96);
+    uint32_t *p_bmod = reinterpret_cast<uint32_t *>(smem + 2048 + 144);
+    uint64_t *code_bar = reinterpret_cast<uint64_t *>(smem + 2048 + 192);                 // chip-table bulk copies
+    const bool split = args.split_tiles != 0;
     float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
     const int tile_floats = 2 * MP * kTileCap;
     float *windows = tiles + (size_t)stages * tile_floats;
     float *part = windows + (size_t)stages * S * args.win_stride;
     int8_t *code_cache = reinterpret_cast<int8_t *>(part + (size_t)W * RP);  // [S][cache_stride], producer-private
 
+    GAT_STAMP(warp == W ? 8 : 0);
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 2);          // producer: expect_tx arrival + "windows built" arrival
-            mbar_init(&empty_bar[s], (uint32_t)NR);  // one arrival per consumer warp of the owning slice
+            mbar_init(&empty_bar[s], (uint32_t)(split ? W : NR));  // one arrival per consumer warp that reads the stage
         }
+        mbar_init(code_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // antenna rows that pad M up to AG*A are never written by the copies: keep them zero
@@ -259,10 +278,12 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
     const int64_t r0 = (int64_t)blockIdx.x * TT / grid;
     const int64_t r1 = (int64_t)(blockIdx.x + 1) * TT / grid;
     uint32_t q = 0;  // running tile counter of this CTA -> ring stage and parity
+    GAT_STAMP(warp == W ? 9 : 1);
 
     if (warp == W) {
         // ============================ producer warp ============================
         const int8_t *cached_code = nullptr;  // lane s: which table sits in code_cache[s]
+        uint32_t code_phase = 0;
         for (int64_t g = r0; g < r1;) {
             const int job = (int)(g / TJ);
             const int t_first = (int)(g - (int64_t)job * TJ);
@@ -271,27 +292,10 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
             const PeriodDev *per = &args.periods[p];
             const bool sat_ok = (lane < S) && (grp * S + lane < K);
             SatDev sd;
-            sd.code = nullptr; sd.code_len = 1; sd.nco_fp = 32; sd.nco_delta = 0; sd.nco_start = 0;
+            sd.code = nullptr; sd.code_len = 0; sd.nco_fp = 32; sd.nco_delta = 0; sd.nco_start = 0;
             sd.code_ratio = 0.0; sd.code_phase = 0.0;
-            if (sat_ok) sd = args.sats[(size_t)p * K + grp * S + lane];
-            // (re)fill the smem chip-table cache of every satellite whose table changed
-            for (int s = 0; s < S; ++s) {
-                const int8_t *code = reinterpret_cast<const int8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)sd.code, s));
-                const int8_t *have = reinterpret_cast<const int8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)cached_code, s));
-                if (code == nullptr || code == have) continue;
-                const int n16 = (__shfl_sync(0xffffffffu, sd.code_len, s) + 15) >> 4;
-                const int4 *src = reinterpret_cast<const int4 *>(code);   // columns are padded to 16 B
-                int4 *dst = reinterpret_cast<int4 *>(code_cache + (size_t)s * args.cache_stride);
-                for (int c = lane; c < n16; c += 32) dst[c] = __ldg(src + c);
-            }
-            if (sat_ok) cached_code = sd.code;
-            __syncwarp();
             uint64_t frac = 0;
             uint32_t bmod = 0;
-            if (!F64 && sat_ok) {
-                const int64_t u0 = (int64_t)args.aligned_start + (int64_t)t_first * tile_len - args.start_sample + args.shifts[0];
-                nco_tile_base(sd, u0, frac, bmod);
-            }
             for (int t = t_first; t < t_last; ++t, ++q) {
                 const int stage = q % stages;
                 const uint32_t par = (q / stages) & 1u;
@@ -304,6 +308,29 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                     tma_load_2d(stage_tile, &per->re, args.aligned_start + ts_rel, 0, &full_bar[stage]);
                     tma_load_2d(stage_tile + (size_t)MP * kTileCap, &per->im, args.aligned_start + ts_rel, 0, &full_bar[stage]);
                 }
+                if (t == t_first) {
+                    // segment setup AFTER the first tile is in flight: satellite constants, chip-table
+                    // cache (all satellites' loads issued together), NCO base of the first tile
+                    if (sat_ok) sd = args.sats[(size_t)p * K + grp * S + lane];
+                    if (lane < S) p_lc[lane] = sat_ok ? (uint32_t)sd.code_len : 0u;
+                    // every satellite whose table changed pulls its (16 B padded) column with ONE bulk copy
+                    const bool reload = sat_ok && sd.code != cached_code;
+                    const uint32_t my_bytes = reload ? (uint32_t)((sd.code_len + 15) & ~15) : 0u;
+                    const uint32_t all_bytes = __reduce_add_sync(0xffffffffu, my_bytes);
+                    if (all_bytes != 0u) {
+                        if (lane == 0) mbar_arrive_expect_tx(code_bar, all_bytes);
+                        __syncwarp();
+                        if (reload) bulk_g2s(code_cache + (size_t)lane * args.cache_stride, sd.code, my_bytes, code_bar);
+                        mbar_wait(code_bar, code_phase);
+                        code_phase ^= 1u;
+                    }
+                    if (sat_ok) cached_code = sd.code;
+                    if (!F64 && sat_ok) {
+                        const int64_t u0 = (int64_t)args.aligned_start + (int64_t)t_first * tile_len - args.start_sample + args.shifts[0];
+                        nco_tile_base(sd, u0, frac, bmod);
+                    }
+                    if (q == 0) GAT_STAMP(10);
+                }
                 // chip windows for every satellite of this CTA, out of the smem table cache
                 if (F64 && sat_ok) {
                     const int32_t u0 = args.aligned_start + ts_rel - args.start_sample + args.shifts[0];
@@ -313,26 +340,30 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                 } else if (sat_ok) {
                     meta[stage * S + lane] = frac;
                 }
+                if (lane < S) p_bmod[lane] = bmod;
+                __syncwarp();
+                {
+                    float *win = windows + (size_t)stage * S * args.win_stride;
+                    const int total = S * args.win_stride;
 #pragma unroll 2
-                for (int s = 0; s < S; ++s) {
-                    const int ok = __shfl_sync(0xffffffffu, (int)sat_ok, s);
-                    if (!ok) continue;
-                    const uint32_t bm = __shfl_sync(0xffffffffu, bmod, s);
-                    const uint32_t lc = (uint32_t)__shfl_sync(0xffffffffu, sd.code_len, s);
-                    const int8_t *tab = code_cache + (size_t)s * args.cache_stride;
-                    float *win = windows + (size_t)(stage * S + s) * args.win_stride;
-                    for (int j = lane; j < args.win_stride; j += 32) {
-                        uint32_t idx = bm + (uint32_t)j;
-                        if (idx >= lc) idx %= lc;
-                        win[j] = (float)tab[idx];
+                    for (int e = lane; e < total; e += 32) {
+                        const int s = e / args.win_stride, j = e - s * args.win_stride;
+                        const uint32_t lc = p_lc[s];
+                        if (lc != 0u) {
+                            uint32_t idx = p_bmod[s] + (uint32_t)j;
+                            if (idx >= lc) idx %= lc;
+                            win[e] = (float)code_cache[(size_t)s * args.cache_stride + idx];
+                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (q == 0) GAT_STAMP(11);
                 if (!F64 && sat_ok) nco_tile_advance(sd, tile_len, frac, bmod);
             }
             g += t_last - t_first;
         }
+        GAT_STAMP(12);
         return;
     }
 
@@ -367,8 +398,9 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
         uint64_t tapoff[L];
 #pragma unroll
         for (int l = 0; l < L; ++l) tapoff[l] = (uint64_t)(int64_t)(args.shifts[l] - args.shifts[0]) * delta;
-        const uint64_t v_step = 32ull * delta;
-        const uint64_t ph_step = 32ull * car_delta;
+        const int tt_stride = split ? 32 * SL : 32;
+        const uint64_t v_step = (uint64_t)tt_stride * delta;
+        const uint64_t ph_step = (uint64_t)tt_stride * car_delta;
 
         f32x2 accRe[AP][L], accIm[AP][L];
         float sRe[L], sIm[L];  // A == 1 path
@@ -380,10 +412,11 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
         }
 
         for (int t = t_first; t < t_last; ++t, ++q) {
-            if ((int)(q % (uint32_t)SL) != sl) continue;  // tiles go round-robin over the sample slices
+            if (!split && (int)(q % (uint32_t)SL) != sl) continue;  // whole tiles go round-robin over the sample slices
             const int stage = q % stages;
             const uint32_t par = (q / stages) & 1u;
             mbar_wait(&full_bar[stage], par);
+            if (q == 0) GAT_STAMP(2);
             if (active) {
                 const int ts_rel = t * tile_len;
                 const int len = min(tile_len, args.aligned_len - ts_rel);
@@ -392,11 +425,11 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                 const float *tim = tre + (size_t)MP * kTileCap;
                 const float *win = windows + (size_t)(stage * S + s_idx) * args.win_stride;
                 const unsigned long long m0 = meta[stage * S + s_idx];
-                const int tt0 = lane;
+                const int tt0 = split ? sl * 32 + lane : lane;
                 uint64_t v = m0 + (uint64_t)tt0 * delta;                       // NCO mode: frac0 + tt*delta
                 const int32_t b64 = (int32_t)(long long)m0;                    // F64 mode: base chip
                 uint64_t ph = car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta;
-                for (int tt = tt0; tt < len; tt += 32) {
+                for (int tt = tt0; tt < len; tt += tt_stride) {
                     const int n = n0 + tt;
                     if (n >= 0 && n < args.n_samples) {
                         // ---- carrier replica: exp(j 2 pi phase) ----
@@ -451,6 +484,7 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
         }
         g += t_last - t_first;
 
+        if (g >= r1) GAT_STAMP(3);
         // ------------------------------ flush this segment ------------------------------
         {
             float vr[RP];
@@ -501,6 +535,7 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
     // All CTAs are co-resident (grid <= number of SMs, one CTA per SM), so a counting barrier is safe.
     __threadfence();
     consumer_bar_sync(consumer_threads);
+    GAT_STAMP(4);
     if (tid == 0) {
         atomicAdd(args.grid_barrier, 1u);
         unsigned int seen;
@@ -509,28 +544,48 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
         } while ((int)(seen - args.barrier_target) < 0);
     }
     consumer_bar_sync(consumer_threads);
+    GAT_STAMP(5);
     {
+        // GS lanes cooperate on one output element: lane j of the group sums contributors
+        // b_first + j, + GS, ... in order, then a fixed xor tree combines them -> bit-reproducible.
         const int jobs = args.n_periods * G;
         const int64_t E = (int64_t)jobs * roles_rp;
-        for (int64_t e = (int64_t)blockIdx.x * consumer_threads + tid; e < E; e += (int64_t)grid * consumer_threads) {
-            const int job = (int)(e / roles_rp), x = (int)(e % roles_rp);
-            const int b_first = tile_owner((int64_t)job * TJ, grid, TT);
-            const int b_last = tile_owner((int64_t)(job + 1) * TJ - 1, grid, TT);
-            if (b_first == b_last) continue;  // already written by its only owner
-            // fixed summation order -> bit-reproducible results
-            const float *src = args.partials + (size_t)(job + b_first) * roles_rp + x;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int b = b_first;
-            for (; b + 3 <= b_last; b += 4, src += 4 * (size_t)roles_rp) {
-                a0 += __ldcg(src);
-                a1 += __ldcg(src + roles_rp);
-                a2 += __ldcg(src + 2 * (size_t)roles_rp);
-                a3 += __ldcg(src + 3 * (size_t)roles_rp);
+        const int GS = args.fin_group;
+        const int groups_per_cta = consumer_threads / GS;
+        const int64_t n_groups = (int64_t)grid * groups_per_cta;
+        const int gl = tid & (GS - 1);
+        int64_t e = (int64_t)blockIdx.x * groups_per_cta + tid / GS;
+        int64_t warp_e = (int64_t)blockIdx.x * groups_per_cta + (tid & ~31) / GS;   // warp-uniform loop bound
+        for (; warp_e < E; warp_e += n_groups, e += n_groups) {
+            float acc = 0.f;
+            bool emit = false;
+            int job = 0, x = 0;
+            if (e < E) {
+                job = (int)(e / roles_rp);
+                x = (int)(e % roles_rp);
+                const int b_first = tile_owner((int64_t)job * TJ, grid, TT);
+                const int b_last = tile_owner((int64_t)(job + 1) * TJ - 1, grid, TT);
+                if (b_first != b_last) {  // otherwise already written by its only owner
+                    emit = true;
+                    const float *src = args.partials + (size_t)(job + b_first + gl) * roles_rp + x;
+                    const size_t step = (size_t)GS * roles_rp;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    int b = b_first + gl;
+                    for (; b + 3 * GS <= b_last; b += 4 * GS, src += 4 * step) {
+                        a0 += __ldcg(src);
+                        a1 += __ldcg(src + step);
+                        a2 += __ldcg(src + 2 * step);
+                        a3 += __ldcg(src + 3 * step);
+                    }
+                    for (; b <= b_last; b += GS, src += step) a0 += __ldcg(src);
+                    acc = (a0 + a1) + (a2 + a3);
+                }
             }
-            for (; b <= b_last; ++b, src += roles_rp) a0 += __ldcg(src);
-            emit_output<A, L>(args, job, x, (a0 + a1) + (a2 + a3));
+            for (int o = GS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (emit && gl == 0) emit_output<A, L>(args, job, x, acc);
         }
     }
+    GAT_STAMP(6);
 }
 
 // --------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ constexpr int kMaxConsumerWarps = 11;  // + 1 producer = 12 warps = 384 threads 
 constexpr int kBlockThreadsMax = 32 * (kMaxConsumerWarps + 1);
 constexpr int kMaxStages = 16;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
-constexpr int kSmemHeaderBytes = 2048;  // barriers (0..255), flag (256), per-stage metadata (512..)
+constexpr int kSmemHeaderBytes = 2304;  // barriers (0..255), per-stage metadata (512..2047), producer scratch (2048..)
 
 // One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
 struct SatDev {
@@ -57,7 +57,10 @@ struct CorrArgs {
     int32_t win_stride;                // floats per (stage, sat) chip window
     int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
+    int32_t fin_group;                 // lanes cooperating on one output element in the finalize (pow2 <= 32)
+    int32_t split_tiles;               // 1: every slice works on every tile (small problems); 0: whole tiles round-robin
     uint32_t flags;
+    unsigned long long *timeline;      // debug: [grid][16] globaltimer stamps, or nullptr
 };
 
 struct LaunchPlan {

@@ -91,6 +91,17 @@ class Engine:
         self._check(self._lib.gat_last_launch_info(self._h, C.byref(li)))
         return {n: getattr(li, n) for n, _ in li._fields_}
 
+    def set_timeline(self, on: bool):
+        self._check(self._lib.gat_set_timeline(self._h, int(on)))
+
+    def timeline(self, max_ctas: int = 1024) -> np.ndarray:
+        """[n_ctas, 16] %globaltimer stamps (ns) of the last launch (include/gat.h gat_get_timeline)."""
+        buf = np.zeros((max_ctas, 16), np.uint64)
+        n = self._lib.gat_get_timeline(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), max_ctas)
+        if n < 0:
+            self._check(n)
+        return buf[:n]
+
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.gat_kernel_launch_count(self._h))

@@ -155,6 +155,13 @@ typedef struct gat_launch_info {
 int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out);
 int gat_set_timing(gat_ctx *ctx, int enable);  /* record cudaEvents around the correlate kernel */
 uint64_t gat_kernel_launch_count(gat_ctx *ctx); /* total kernels of ours launched on this ctx */
+/* Debug timeline: when enabled, every CTA of the next correlate launches stamps %globaltimer (ns) into
+ * 16 slots: consumer warp 0 -> [0] kernel entry, [1] setup done, [2] first tile landed, [3] last tile
+ * consumed, [4] partials published, [5] grid barrier passed, [6] exit; producer warp -> [8] entry,
+ * [9] setup done, [10] chip tables cached, [11] first tile issued and windows built, [12] all tiles issued.
+ * gat_get_timeline syncs and copies [n_ctas x 16] stamps of the LAST launch; returns n_ctas or <0. */
+int gat_set_timeline(gat_ctx *ctx, int enable);
+int gat_get_timeline(gat_ctx *ctx, uint64_t *out, int cap_ctas);
 /* Replica chip indices exactly as the kernel's code path computes them (device kernel),
  * for the bit-exactness tests: out[n_samples] (host), sample i, one tap shift. */
 int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift,
