@@ -216,7 +216,11 @@ def run_gpu(args):
 
     P, steps, warmup = args.periods, args.steps, args.warmup
     eng = g.Engine(local)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)     # torch events see our kernels
+    # one explicit (non-default) stream for everything: libgat's kernels, torch's events and the
+    # NCCL hand-offs are all ordered on it, so torch.cuda.Event brackets exactly what libgat queued
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    eng.set_stream(work_stream.cuda_stream)
     l1 = g.GPSL1()
     corr = g.EarlyPromptLateCorrelator(g.NumAnts(N_ANTS), g.NumAccumulators(N_TAPS))
     shifts = g.get_correlator_sample_shifts(l1, corr, FS, 0.5)
@@ -230,8 +234,9 @@ def run_gpu(args):
             eng.gen_signal(p, l1, s + 1, DOPPLER + 10.0 * s, FS, N_SAMPLES, N_ANTS, start_code_phase=3.0 * p,
                            noise_sigma=(1.0 if s == 0 else 0.0), seed=1000 + p, superpose=(s > 0))
     my_prn = rank % 32 + 1
-    chans = [[g.Channel(l1, my_prn, 3.0 * p, DOPPLER + 10.0 * rank, 0.0)] for p in range(P)]
-    slots = list(range(P))
+    chan_list = [[g.Channel(l1, my_prn, 3.0 * p, DOPPLER + 10.0 * rank, 0.0)] for p in range(P)]
+    chans = eng.marshal(chan_list)                 # C array built once: the timed loop is pure launches
+    slots = np.arange(P, dtype=np.int32)
     o_re = torch.zeros(P, 1, N_TAPS, N_ANTS, device=dev)
     o_im = torch.zeros_like(o_re)
     if world > 1:
@@ -304,6 +309,7 @@ def run_gpu(args):
     h_out = torch.empty(2, world, P, 1, N_TAPS, N_ANTS, pin_memory=True) if rank == 0 else None
     copy_stream = torch.cuda.Stream()
     main = torch.cuda.current_stream()
+    chunk_chans = {c0: eng.marshal(chan_list[c0:min(P, c0 + CH)]) for c0 in range(0, P, CH)}
 
     def e2e_step():
         done = []
@@ -321,7 +327,7 @@ def run_gpu(args):
             done.append((c0, c1, e))
         for c0, c1, e in done:                                    # compute chunk i while chunk i+1 is in flight
             main.wait_event(e)
-            eng.correlate_batch(slots[c0:c1], chans[c0:c1], FS, shifts, N_ANTS, 0, N_SAMPLES,
+            eng.correlate_batch(slots[c0:c1], chunk_chans[c0], FS, shifts, N_ANTS, 0, N_SAMPLES,
                                 out=(o_re[c0:c1], o_im[c0:c1]))
         if world > 1:
             dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))

@@ -51,6 +51,7 @@ SYMBOLS = {
     "gat_sync": (_i, [_vp]),
     "gat_stream": (_vp, [_vp]),
     "gat_set_stream": (_i, [_vp, _vp]),
+    "gat_use_own_stream": (_i, [_vp]),
     "gat_gen_code": (_i, [_i, _i, _i8p, _i]),
     "gat_set_codes": (_i, [_vp, _i, _i8p, _i, _i]),
     "gat_upload_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i]),

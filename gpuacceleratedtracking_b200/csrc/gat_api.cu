@@ -232,9 +232,12 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     const size_t smem_budget = 227 * 1024;
     int S = std::max(1, std::min(K, w_target_multi / AG));
     S = std::max(1, std::min(S, env_int("GAT_TUNE_S", S)));
-    // every satellite batched on a CTA keeps its chip table in smem: leave room for >= 2 stages
+    const int span = sh.shifts[L - 1] - sh.shifts[0];
+    // every satellite batched on a CTA keeps its chip table in smem: leave room for >= 2 stages,
+    // the per-warp code replicas and the flush buffer
     {
-        const size_t two_stages = kSmemHeaderBytes + 2 * smem_tile_floats(AG, A) * sizeof(float) + 8192;
+        const size_t two_stages = kSmemHeaderBytes + 2 * smem_tile_floats(AG, A) * sizeof(float) +
+                                  static_cast<size_t>(kMaxConsumerWarps) * (padded_acc(A, L) + kTileCap + span + 128) * sizeof(float);
         if (two_stages + cache_stride > smem_budget)
             return fail(ctx, GAT_ERR_UNSUPPORTED, "chip table too long for the shared-memory cache");
         S = std::max(1, std::min<int>(S, static_cast<int>((smem_budget - two_stages) / cache_stride)));
@@ -243,13 +246,10 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     S = (K + G - 1) / G;  // balance the groups
     const int RP = padded_acc(A, L);
     const size_t tile_bytes = smem_tile_floats(AG, A) * sizeof(float);
-    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(kMaxConsumerWarps) * RP * sizeof(float) +
-                               static_cast<size_t>(S) * cache_stride;
     // tile coordinates stay multiples of 4 samples (16 B); the TMA unit zero-fills past the block end,
     // and the kernel masks the <= 3 samples staged before start_sample
     const int aligned_start = env_int("GAT_TUNE_NOALIGN", 0) ? sh.start : (sh.start & ~3);
     const int aligned_len = sh.start + sh.n - aligned_start;
-    const int span = sh.shifts[L - 1] - sh.shifts[0];
 
     const int jobs = sh.P * G;
     int tile_len = kTileCap;
@@ -266,7 +266,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     }
     // per-tile relative NCO phase must fit 64 bits: (tile + span + 1) * delta + 2^fp < 2^64
     if (!sh.f64) {
-        const long double need = static_cast<long double>(tile_len + span + 1) * static_cast<long double>(sh.max_delta) +
+        const long double need = static_cast<long double>(tile_len + span + 32) * static_cast<long double>(sh.max_delta) +
                                  std::ldexp(1.0L, sh.min_fp);
         if (need >= std::ldexp(1.0L, 64))
             return fail(ctx, GAT_ERR_UNSUPPORTED, "code rate too high for the fixed-point window (code_freq/fs * tile too large)");
@@ -274,15 +274,15 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         const double worst = sh.max_ratio * (static_cast<double>(sh.n) + std::abs(sh.shifts[0]) + std::abs(sh.shifts[L - 1]));
         if (!(worst < 1.0e9)) return fail(ctx, GAT_ERR_UNSUPPORTED, "code phase range exceeds the f64 window arithmetic");
     }
-    int win_stride = static_cast<int>(std::floor(sh.max_ratio * (tile_len + span + 1))) + 4;
-    win_stride = (win_stride + 3) & ~3;
+    const int rep_stride = (tile_len + span + 31) & ~31;   // generated in rows of 32 entries
+    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(kMaxConsumerWarps) * (RP + rep_stride) * sizeof(float) +
+                               static_cast<size_t>(S) * cache_stride;
 
     const int tiles_per_job = (aligned_len + tile_len - 1) / tile_len;
     const int64_t total_tiles = static_cast<int64_t>(jobs) * tiles_per_job;
-    const size_t win_bytes = static_cast<size_t>(S) * win_stride * sizeof(float);
-    if (fixed_bytes + tile_bytes + win_bytes > smem_budget)
-        return fail(ctx, GAT_ERR_UNSUPPORTED, "shape does not fit shared memory (antennas x window)");
-    int stages = static_cast<int>((smem_budget - fixed_bytes) / (tile_bytes + win_bytes));
+    if (fixed_bytes + tile_bytes > smem_budget)
+        return fail(ctx, GAT_ERR_UNSUPPORTED, "shape does not fit shared memory (antennas x tap span)");
+    int stages = static_cast<int>((smem_budget - fixed_bytes) / tile_bytes);
     stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 6)));
     stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
     // sample slices take whole tiles round-robin, so more slices than stages cannot all be fed
@@ -300,12 +300,13 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     plan.f64 = sh.f64;
     plan.grid = grid;
     plan.block = 32 * (W + 1);
-    plan.smem = kSmemHeaderBytes + stages * (tile_bytes + win_bytes) + static_cast<size_t>(W) * RP * sizeof(float) +
+    plan.smem = kSmemHeaderBytes + stages * tile_bytes + static_cast<size_t>(W) * (RP + rep_stride) * sizeof(float) +
                 static_cast<size_t>(S) * cache_stride;
     plan.RP = RP;
     plan.jobs = jobs;
 
     for (int l = 0; l < kMaxTaps; ++l) a.shifts[l] = l < L ? sh.shifts[l] : 0;
+    for (int l = 0; l < kMaxTaps; ++l) a.koff4[l] = l < L ? 4 * (sh.shifts[l] - sh.shifts[0]) : 0;
     a.n_periods = sh.P;
     a.n_sats = K;
     a.n_ants = M;
@@ -322,7 +323,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.W = W;
     a.G = G;
     a.stages = stages;
-    a.win_stride = win_stride;
+    a.rep_stride = rep_stride;
     a.cache_stride = cache_stride;
     a.total_tiles = static_cast<int32_t>(total_tiles);
     {
@@ -333,6 +334,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         // few tiles per CTA: let every slice work on every tile instead of taking turns
         a.split_tiles = (SL > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid) ? 1 : 0;
         a.split_tiles = env_int("GAT_TUNE_SPLIT", a.split_tiles);
+        a.tt_stride = a.split_tiles ? 32 * SL : 32;
     }
 
     gat_launch_info &li = ctx->info;
@@ -654,7 +656,16 @@ int gat_set_stream(gat_ctx *ctx, void *cuda_stream)
     int rc = check_ctx(ctx);
     if (rc) return rc;
     GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);   // NULL == legacy default stream
+    return GAT_OK;
+}
+
+int gat_use_own_stream(gat_ctx *ctx)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return GAT_OK;
 }
 

@@ -11,14 +11,16 @@
 // Design (DESIGN.md has the long form):
 //   * persistent CTAs, one per SM; the flattened (period, sat-group, tile) space is split
 //     evenly over the grid ("stream-K"), so every SM streams the same number of bytes.
-//   * warp W is a producer: it moves [tile x antennas] signal tiles HBM -> smem with 1-D
-//     bulk async copies (TMA unit, UBLKCP) through a full/empty mbarrier ring, and builds the
-//     per-tile chip windows of every satellite batched on the CTA.
+//   * warp W is a producer: it moves [tile x antennas] signal tiles HBM -> smem with 2-D tiled
+//     TMA loads (UTMALDG) through a full/empty mbarrier ring and keeps the chip table of every
+//     satellite batched on the CTA in shared memory.
 //   * warps 0..W-1 are consumers.  A consumer warp owns (satellite s, antenna group ag,
 //     sample slice sl); all of them read the SAME staged signal tile, so one HBM/L2 read
 //     feeds every satellite on the SM.
 //   * carrier: 64-bit integer phase accumulator (exact wrap), top 32 bits -> FP32 -> MUFU
-//     sin/cos.  code: integer NCO (or IEEE-double formula) -> index into the smem window.
+//     sin/cos.  code: each warp generates its tile's code replica (integer NCO or IEEE-double
+//     formula -> smem chip table) into a private smem buffer while the signal tile is in flight;
+//     every tap is then one shared-memory load.
 //   * wipe-off and taps are packed FP32x2 FMAs (FFMA2), two antennas per instruction,
 //     accumulators in registers.
 //   * reduction: in-warp halving butterfly (reduce-scatter by shuffles) -> smem across
@@ -81,6 +83,15 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *m
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// named barrier among the warps that share one code replica (ids 2..): id and count are warp-uniform
+__device__ __forceinline__ void group_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ float chip_to_float(int c)   // +-1 int8 -> +-1.0f without a conversion instruction
+{
+    return __uint_as_float(0x3f800000u | ((uint32_t)c & 0x80000000u));
+}
 __device__ __forceinline__ void consumer_bar_sync(int threads)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
@@ -98,6 +109,22 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
         if (args.timeline && lane == 0 && (warp == 0 || warp == W))                            \
             args.timeline[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns();                \
     } while (0)
+
+// Shared-memory load that ptxas may not move across loop iterations: without it the assembler
+// software-pipelines the sample loop and pays ~20 register-rotation moves per iteration (IMAD.MOV on
+// the FMA pipe) -- measured in the SASS of the 11-tap kernel.
+__device__ __forceinline__ float lds_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ float lds_f32_at(uint32_t smem_addr)
+{
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+    return v;
+}
 
 typedef unsigned long long f32x2;  // two packed floats: lo = even antenna, hi = odd antenna
 __device__ __forceinline__ f32x2 pack2(float lo, float hi)
@@ -143,19 +170,28 @@ __device__ __forceinline__ void nco_tile_base(const SatDev &sd, int64_t u0, uint
     frac = (uint64_t)tot & ((1ull << sd.nco_fp) - 1ull);
     bmod = (uint32_t)floormod64(base, sd.code_len);
 }
-// host guarantees (tile_len + span + 1) * delta + 2^fp < 2^64, so 64-bit arithmetic is exact here
-__device__ __forceinline__ void nco_tile_advance(const SatDev &sd, int tile_len, uint64_t &frac, uint32_t &bmod)
+// advance the tile base by n samples (n * delta may exceed 64 bits when several tiles are skipped)
+__device__ __forceinline__ void nco_advance(uint64_t delta, int fp, uint32_t lc, uint32_t n, uint64_t &frac, uint32_t &bmod)
 {
-    const uint64_t nf = frac + (uint64_t)tile_len * (uint64_t)sd.nco_delta;
-    const uint32_t carry = (uint32_t)(nf >> sd.nco_fp);
-    frac = nf & ((1ull << sd.nco_fp) - 1ull);
-    uint32_t x = bmod + carry;
-    if (x >= (uint32_t)sd.code_len) x %= (uint32_t)sd.code_len;
-    bmod = x;
+    const unsigned __int128 nf = (unsigned __int128)frac + (unsigned __int128)n * (unsigned __int128)delta;
+    const uint64_t carry = (uint64_t)(nf >> fp);
+    frac = (uint64_t)nf & ((1ull << fp) - 1ull);
+    uint64_t x = (uint64_t)bmod + carry;
+    if (x >= lc) x %= lc;
+    bmod = (uint32_t)x;
 }
-// window slot of (tile-relative offset kk) -- consumer side; sh = fp - 32 (fp >= 32 always)
-__device__ __forceinline__ uint32_t nco_slot(uint64_t v, int sh) { return (uint32_t)(v >> 32) >> sh; }
-
+// chip-table index of replica entry u (u = sample offset in the tile + tap offset from the latest tap).
+// host guarantees (tile_len + span + 1) * delta + 2^fp < 2^64, so v = frac + u * delta is exact in 64 bits;
+// fp >= 32 always, so only the high word is shifted (sh = fp - 32).
+__device__ __forceinline__ uint32_t rep_index_nco(uint64_t v, int sh, uint32_t bmod, uint32_t lc)
+{
+    uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
+    if (idx >= lc) {
+        idx -= lc;
+        if (idx >= lc) idx %= lc;
+    }
+    return idx;
+}
 // IEEE-double form of the reference GPU kernels (src/algorithms.jl:179-182):
 //   floor(code_frequency / sampling_frequency * (n + shift) + start_code_phase)
 // separate multiply and add (Julia does not contract), then floor.
@@ -163,6 +199,15 @@ __device__ __forceinline__ int32_t f64_chip_floor(double ratio, double phase, in
 {
     const double cp = __dadd_rn(__dmul_rn(ratio, (double)u), phase);
     return __double2int_rd(cp);
+}
+__device__ __forceinline__ uint32_t rep_index_f64(double ratio, double phase, int32_t u_abs, int32_t b, uint32_t bmod, uint32_t lc)
+{
+    uint32_t idx = bmod + (uint32_t)(f64_chip_floor(ratio, phase, u_abs) - b);   // floor() is monotone: >= 0
+    if (idx >= lc) {
+        idx -= lc;
+        if (idx >= lc) idx %= lc;
+    }
+    return idx;
 }
 
 // --------------------------------------------------------------------------------------
@@ -240,21 +285,18 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
 
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxStages;
-    unsigned long long *meta = reinterpret_cast<unsigned long long *>(smem + 512);  // [stage][S], S <= 12
-    uint32_t *p_lc = reinterpret_cast<uint32_t *>(smem + 2048 + 96);
-    uint32_t *p_bmod = reinterpret_cast<uint32_t *>(smem + 2048 + 144);
-    uint64_t *code_bar = reinterpret_cast<uint64_t *>(smem + 2048 + 192);                 // chip-table bulk copies
+    uint64_t *code_bar = reinterpret_cast<uint64_t *>(smem + 256);   // chip-table bulk copies, one phase per segment
     const bool split = args.split_tiles != 0;
     float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
     const int tile_floats = 2 * MP * kTileCap;
-    float *windows = tiles + (size_t)stages * tile_floats;
-    float *part = windows + (size_t)stages * S * args.win_stride;
-    int8_t *code_cache = reinterpret_cast<int8_t *>(part + (size_t)W * RP);  // [S][cache_stride], producer-private
+    float *part = tiles + (size_t)stages * tile_floats;                               // [W][RP]
+    float *rep_all = part + (size_t)W * RP;                                           // [W][rep_stride]
+    int8_t *code_cache = reinterpret_cast<int8_t *>(rep_all + (size_t)W * args.rep_stride);  // [S][cache_stride]
 
     GAT_STAMP(warp == W ? 8 : 0);
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 2);          // producer: expect_tx arrival + "windows built" arrival
+            mbar_init(&full_bar[s], 1);                            // producer's expect_tx arrival (+ TMA bytes)
             mbar_init(&empty_bar[s], (uint32_t)(split ? W : NR));  // one arrival per consumer warp that reads the stage
         }
         mbar_init(code_bar, 1);
@@ -277,25 +319,36 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
     const int grid = gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * TT / grid;
     const int64_t r1 = (int64_t)(blockIdx.x + 1) * TT / grid;
-    uint32_t q = 0;  // running tile counter of this CTA -> ring stage and parity
+    uint32_t q = 0;    // running tile counter of this CTA -> ring stage and parity
+    uint32_t seg = 0;  // running segment counter -> code_bar parity
     GAT_STAMP(warp == W ? 9 : 1);
 
     if (warp == W) {
         // ============================ producer warp ============================
+        // Moves signal tiles (two 2-D TMA loads per tile) and keeps the chip table of every
+        // satellite batched on this CTA in shared memory (one bulk copy per table change).
         const int8_t *cached_code = nullptr;  // lane s: which table sits in code_cache[s]
-        uint32_t code_phase = 0;
-        for (int64_t g = r0; g < r1;) {
+        for (int64_t g = r0; g < r1; ++seg) {
             const int job = (int)(g / TJ);
             const int t_first = (int)(g - (int64_t)job * TJ);
             const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
             const int p = job / G, grp = job % G;
             const PeriodDev *per = &args.periods[p];
             const bool sat_ok = (lane < S) && (grp * S + lane < K);
-            SatDev sd;
-            sd.code = nullptr; sd.code_len = 0; sd.nco_fp = 32; sd.nco_delta = 0; sd.nco_start = 0;
-            sd.code_ratio = 0.0; sd.code_phase = 0.0;
-            uint64_t frac = 0;
-            uint32_t bmod = 0;
+            const int8_t *code = nullptr;
+            int code_len = 0;
+            if (sat_ok) {
+                const SatDev *sd = &args.sats[(size_t)p * K + grp * S + lane];
+                code = sd->code;
+                code_len = sd->code_len;
+            }
+            const bool reload = sat_ok && code != cached_code;
+            if (__any_sync(0xffffffffu, reload) && q > 0) {
+                // the consumers still read the cached tables while they work on the previous
+                // segment: wait until every tile issued so far has been released
+                const int live = (int)min(q, (uint32_t)stages);
+                for (int st = 0; st < live; ++st) mbar_wait(&empty_bar[st], ((q - 1u - (uint32_t)st) / (uint32_t)stages) & 1u);
+            }
             for (int t = t_first; t < t_last; ++t, ++q) {
                 const int stage = q % stages;
                 const uint32_t par = (q / stages) & 1u;
@@ -309,57 +362,17 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                     tma_load_2d(stage_tile + (size_t)MP * kTileCap, &per->im, args.aligned_start + ts_rel, 0, &full_bar[stage]);
                 }
                 if (t == t_first) {
-                    // segment setup AFTER the first tile is in flight: satellite constants, chip-table
-                    // cache (all satellites' loads issued together), NCO base of the first tile
-                    if (sat_ok) sd = args.sats[(size_t)p * K + grp * S + lane];
-                    if (lane < S) p_lc[lane] = sat_ok ? (uint32_t)sd.code_len : 0u;
-                    // every satellite whose table changed pulls its (16 B padded) column with ONE bulk copy
-                    const bool reload = sat_ok && sd.code != cached_code;
-                    const uint32_t my_bytes = reload ? (uint32_t)((sd.code_len + 15) & ~15) : 0u;
+                    // chip tables AFTER the first tile is in flight; code_bar completes one phase per
+                    // segment (with zero bytes when nothing changed) and releases the consumers
+                    const uint32_t my_bytes = reload ? (uint32_t)((code_len + 15) & ~15) : 0u;
                     const uint32_t all_bytes = __reduce_add_sync(0xffffffffu, my_bytes);
-                    if (all_bytes != 0u) {
-                        if (lane == 0) mbar_arrive_expect_tx(code_bar, all_bytes);
-                        __syncwarp();
-                        if (reload) bulk_g2s(code_cache + (size_t)lane * args.cache_stride, sd.code, my_bytes, code_bar);
-                        mbar_wait(code_bar, code_phase);
-                        code_phase ^= 1u;
-                    }
-                    if (sat_ok) cached_code = sd.code;
-                    if (!F64 && sat_ok) {
-                        const int64_t u0 = (int64_t)args.aligned_start + (int64_t)t_first * tile_len - args.start_sample + args.shifts[0];
-                        nco_tile_base(sd, u0, frac, bmod);
-                    }
+                    if (lane == 0) mbar_arrive_expect_tx(code_bar, all_bytes);
+                    __syncwarp();
+                    if (reload) bulk_g2s(code_cache + (size_t)lane * args.cache_stride, code, my_bytes, code_bar);
+                    if (sat_ok) cached_code = code;
                     if (q == 0) GAT_STAMP(10);
                 }
-                // chip windows for every satellite of this CTA, out of the smem table cache
-                if (F64 && sat_ok) {
-                    const int32_t u0 = args.aligned_start + ts_rel - args.start_sample + args.shifts[0];
-                    const int32_t b = f64_chip_floor(sd.code_ratio, sd.code_phase, u0);
-                    bmod = (uint32_t)floormod64(b, sd.code_len);
-                    meta[stage * S + lane] = (unsigned long long)(long long)b;
-                } else if (sat_ok) {
-                    meta[stage * S + lane] = frac;
-                }
-                if (lane < S) p_bmod[lane] = bmod;
-                __syncwarp();
-                {
-                    float *win = windows + (size_t)stage * S * args.win_stride;
-                    const int total = S * args.win_stride;
-#pragma unroll 2
-                    for (int e = lane; e < total; e += 32) {
-                        const int s = e / args.win_stride, j = e - s * args.win_stride;
-                        const uint32_t lc = p_lc[s];
-                        if (lc != 0u) {
-                            uint32_t idx = p_bmod[s] + (uint32_t)j;
-                            if (idx >= lc) idx %= lc;
-                            win[e] = (float)code_cache[(size_t)s * args.cache_stride + idx];
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
                 if (q == 0) GAT_STAMP(11);
-                if (!F64 && sat_ok) nco_tile_advance(sd, tile_len, frac, bmod);
             }
             g += t_last - t_first;
         }
@@ -373,8 +386,15 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
     const int sl = warp / NR;
     const int consumer_threads = 32 * W;
     const int roles_rp = NR * RP;
+    const int span = args.shifts[L - 1] - args.shifts[0];
+    // warps that work on the same satellite and the same tile share one code replica
+    const int gw = split ? AG * SL : AG;                    // warps per group
+    const int gid = split ? s_idx : sl * S + s_idx;         // group id (< W)
+    const int gr = split ? sl * AG + ag : ag;               // this warp's rank in its group
+    float *rep = rep_all + (size_t)gid * args.rep_stride;
+    const int8_t *tab = code_cache + (size_t)s_idx * args.cache_stride;
 
-    for (int64_t g = r0; g < r1;) {
+    for (int64_t g = r0; g < r1; ++seg) {
         const int job = (int)(g / TJ);
         const int t_first = (int)(g - (int64_t)job * TJ);
         const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
@@ -384,23 +404,38 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
 
         // per-satellite constants
         uint64_t delta = 0, car_phase = 0, car_delta = 0;
-        int sh = 0;
+        int64_t nco_start = 0;
+        int fp = 32;
+        uint32_t lc = 1;
         double ratio = 0.0, cphase = 0.0;
         if (active) {
             const SatDev *sd = &args.sats[(size_t)p * K + k];
             delta = (uint64_t)sd->nco_delta;
-            sh = sd->nco_fp - 32;
+            nco_start = sd->nco_start;
+            fp = sd->nco_fp;
+            lc = (uint32_t)sd->code_len;
             car_phase = sd->car_phase;
             car_delta = sd->car_delta;
             ratio = sd->code_ratio;
             cphase = sd->code_phase;
         }
-        uint64_t tapoff[L];
-#pragma unroll
-        for (int l = 0; l < L; ++l) tapoff[l] = (uint64_t)(int64_t)(args.shifts[l] - args.shifts[0]) * delta;
-        const int tt_stride = split ? 32 * SL : 32;
-        const uint64_t v_step = (uint64_t)tt_stride * delta;
-        const uint64_t ph_step = (uint64_t)tt_stride * car_delta;
+        const int sh = fp - 32;
+        const int tt_stride = args.tt_stride;
+        // inside a tile the carrier phase advances in 32 bits (2^-32 cycle per step, <= 8 steps, restarted
+        // exactly from the 64-bit accumulator at every tile): error < 2e-9 cycle
+        const uint32_t ph_step32 = (uint32_t)(((uint64_t)tt_stride * car_delta + 0x80000000ull) >> 32);
+        uint64_t frac = 0;   // NCO state of the tile this warp works on (phase under its first sample, latest tap)
+        uint32_t bmod = 0;
+        bool have_base = false;
+        // consecutive tiles of this warp are a fixed number of samples apart: split that advance into
+        // whole chips and a 2^fp fraction ONCE per segment (128-bit), so the per-tile update is a few adds
+        uint64_t adv_frac = 0;
+        uint32_t adv_chips = 0;
+        if (!F64 && active) {
+            const unsigned __int128 adv = (unsigned __int128)(uint32_t)((split ? 1 : SL) * tile_len) * (unsigned __int128)delta;
+            adv_frac = (uint64_t)adv & ((1ull << fp) - 1ull);
+            adv_chips = (uint32_t)((uint64_t)(adv >> fp) % lc);
+        }
 
         f32x2 accRe[AP][L], accIm[AP][L];
         float sRe[L], sIm[L];  // A == 1 path
@@ -411,72 +446,122 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
             for (int a = 0; a < AP; ++a) accRe[a][l] = accIm[a][l] = 0ull;
         }
 
+        mbar_wait(code_bar, seg & 1u);   // this segment's chip tables are in shared memory
+
         for (int t = t_first; t < t_last; ++t, ++q) {
             if (!split && (int)(q % (uint32_t)SL) != sl) continue;  // whole tiles go round-robin over the sample slices
             const int stage = q % stages;
             const uint32_t par = (q / stages) & 1u;
+            const int ts_rel = t * tile_len;
+            const int len = min(tile_len, args.aligned_len - ts_rel);
+            const int n0 = args.aligned_start + ts_rel - args.start_sample;  // relative index of tile sample 0
+            if (active) {
+                // ---- code replica of this tile, generated while the signal tile is still in flight ----
+                // rep[u] = chip under (tile sample 0 + latest tap + u); tap l of sample tt reads rep[tt + koff[l]]
+                // (the reference writes the same array to global memory, src/algorithms.jl:100-119, :1513-1525)
+                const int rep_len = len + span;
+                const int rows = (rep_len + 31) >> 5;                 // 32 entries per row
+                const int rows_per = (rows + gw - 1) / gw;
+                const int row0 = gr * rows_per, row1 = min(rows, row0 + rows_per);
+                if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();   // previous tile's readers are done
+                if constexpr (F64) {
+                    const int32_t u0 = n0 + args.shifts[0];
+                    const int32_t b = f64_chip_floor(ratio, cphase, u0);
+                    bmod = (uint32_t)floormod64(b, lc);
+                    int r = row0;
+                    for (; r + 1 < row1; r += 2) {
+                        const int c0 = tab[rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc)];
+                        const int c1 = tab[rep_index_f64(ratio, cphase, u0 + r * 32 + 32 + lane, b, bmod, lc)];
+                        rep[r * 32 + lane] = chip_to_float(c0);
+                        rep[r * 32 + 32 + lane] = chip_to_float(c1);
+                    }
+                    if (r < row1) rep[r * 32 + lane] = chip_to_float(tab[rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc)]);
+                } else {
+                    if (!have_base) {
+                        SatDev tmp;
+                        tmp.nco_delta = (int64_t)delta; tmp.nco_start = nco_start; tmp.nco_fp = fp; tmp.code_len = (int32_t)lc;
+                        nco_tile_base(tmp, (int64_t)n0 + args.shifts[0], frac, bmod);
+                        have_base = true;
+                    } else {
+                        frac += adv_frac;
+                        bmod += adv_chips + (uint32_t)(frac >> fp);
+                        frac &= (1ull << fp) - 1ull;
+                        if (bmod >= lc) bmod -= lc;
+                        if (bmod >= lc) bmod -= lc;
+                    }
+                    uint64_t v = frac + (uint64_t)(uint32_t)(row0 * 32 + lane) * delta;
+                    const uint64_t v32 = 32ull * delta;
+                    int r = row0;
+                    for (; r + 3 < row1; r += 4) {   // 4 independent table lookups in flight per lane
+                        int c[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            c[j] = tab[rep_index_nco(v, sh, bmod, lc)];
+                            v += v32;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rep[(r + j) * 32 + lane] = chip_to_float(c[j]);
+                    }
+                    for (; r < row1; ++r, v += v32) rep[r * 32 + lane] = chip_to_float(tab[rep_index_nco(v, sh, bmod, lc)]);
+                }
+                if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
+            }
             mbar_wait(&full_bar[stage], par);
             if (q == 0) GAT_STAMP(2);
             if (active) {
-                const int ts_rel = t * tile_len;
-                const int len = min(tile_len, args.aligned_len - ts_rel);
-                const int n0 = args.aligned_start + ts_rel - args.start_sample;  // relative index of tile sample 0
-                const float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
-                const float *tim = tre + (size_t)MP * kTileCap;
-                const float *win = windows + (size_t)(stage * S + s_idx) * args.win_stride;
-                const unsigned long long m0 = meta[stage * S + s_idx];
+                float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
+                float *tim = tre + (size_t)MP * kTileCap;
+                if (n0 < 0) {
+                    // tiles start on a 16-byte boundary: the <= 3 samples staged before start_sample are
+                    // zeroed in place (every warp clears the rows it reads), which keeps the loop branch-free.
+                    // Samples past the end never reach the loop (tt < len) and are zero-filled by TMA anyway.
+                    for (int i = lane; i < 2 * A * (-n0); i += 32) {
+                        const int col = i % (-n0), row = i / (-n0);
+                        (row < A ? tre + (size_t)row * kTileCap : tim + (size_t)(row - A) * kTileCap)[col] = 0.f;
+                    }
+                    __syncwarp();
+                }
                 const int tt0 = split ? sl * 32 + lane : lane;
-                uint64_t v = m0 + (uint64_t)tt0 * delta;                       // NCO mode: frac0 + tt*delta
-                const int32_t b64 = (int32_t)(long long)m0;                    // F64 mode: base chip
-                uint64_t ph = car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta;
+                uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
+                const uint32_t rep_s = smem_u32(rep);
+#pragma unroll 1
                 for (int tt = tt0; tt < len; tt += tt_stride) {
-                    const int n = n0 + tt;
-                    if (n >= 0 && n < args.n_samples) {
-                        // ---- carrier replica: exp(j 2 pi phase) ----
-                        float cr, ci;
-                        const float x = (float)(int32_t)(ph >> 32) * 1.4629180792671596e-9f;  // 2 pi / 2^32
-                        __sincosf(x, &ci, &cr);
-                        // ---- code replica chips for every tap ----
-                        float chip[L];
+                    // ---- carrier replica: exp(j 2 pi phase) ----
+                    float cr, ci;
+                    const float x = (float)(int32_t)ph * 1.4629180792671596e-9f;  // 2 pi / 2^32
+                    __sincosf(x, &ci, &cr);
+                    ph += ph_step32;
+                    // ---- code replica chips for every tap: one shared-memory load each ----
+                    float chip[L];
+                    const uint32_t ra = rep_s + 4u * (uint32_t)tt;
 #pragma unroll
-                        for (int l = 0; l < L; ++l) {
-                            uint32_t slot;
-                            if constexpr (F64) {
-                                slot = (uint32_t)(f64_chip_floor(ratio, cphase, n + args.shifts[l]) - b64);
-                            } else {
-                                slot = nco_slot(v + tapoff[l], sh);
-                            }
-                            chip[l] = win[slot];
-                        }
-                        if constexpr (A >= 2) {
-                            const f32x2 CR = pack2(cr, cr), CI = pack2(ci, ci), NCI = pack2(-ci, -ci);
+                    for (int l = 0; l < L; ++l) chip[l] = lds_f32_at(ra + (uint32_t)args.koff4[l]);
+                    if constexpr (A >= 2) {
+                        const f32x2 CR = pack2(cr, cr), CI = pack2(ci, ci), NCI = pack2(-ci, -ci);
 #pragma unroll
-                            for (int a = 0; a < AP; ++a) {
-                                const f32x2 X = pack2(tre[(2 * a) * kTileCap + tt], tre[(2 * a + 1) * kTileCap + tt]);
-                                const f32x2 Y = pack2(tim[(2 * a) * kTileCap + tt], tim[(2 * a + 1) * kTileCap + tt]);
-                                // d = s * conj(c):  d_re = s_re c_re + s_im c_im ; d_im = s_im c_re - s_re c_im
-                                const f32x2 Dre = fma2(Y, CI, mul2(X, CR));
-                                const f32x2 Dim = fma2(X, NCI, mul2(Y, CR));
-#pragma unroll
-                                for (int l = 0; l < L; ++l) {
-                                    const f32x2 CH = pack2(chip[l], chip[l]);
-                                    accRe[a][l] = fma2(Dre, CH, accRe[a][l]);
-                                    accIm[a][l] = fma2(Dim, CH, accIm[a][l]);
-                                }
-                            }
-                        } else {
-                            const float xr = tre[tt], xi = tim[tt];
-                            const float dre = fmaf(xi, ci, xr * cr);
-                            const float dim = fmaf(-xr, ci, xi * cr);
+                        for (int a = 0; a < AP; ++a) {
+                            const f32x2 X = pack2(lds_f32(tre + (2 * a) * kTileCap + tt), lds_f32(tre + (2 * a + 1) * kTileCap + tt));
+                            const f32x2 Y = pack2(lds_f32(tim + (2 * a) * kTileCap + tt), lds_f32(tim + (2 * a + 1) * kTileCap + tt));
+                            // d = s * conj(c):  d_re = s_re c_re + s_im c_im ; d_im = s_im c_re - s_re c_im
+                            const f32x2 Dre = fma2(Y, CI, mul2(X, CR));
+                            const f32x2 Dim = fma2(X, NCI, mul2(Y, CR));
 #pragma unroll
                             for (int l = 0; l < L; ++l) {
-                                sRe[l] = fmaf(dre, chip[l], sRe[l]);
-                                sIm[l] = fmaf(dim, chip[l], sIm[l]);
+                                const f32x2 CH = pack2(chip[l], chip[l]);
+                                accRe[a][l] = fma2(Dre, CH, accRe[a][l]);
+                                accIm[a][l] = fma2(Dim, CH, accIm[a][l]);
                             }
                         }
+                    } else {
+                        const float xr = tre[tt], xi = tim[tt];
+                        const float dre = fmaf(xi, ci, xr * cr);
+                        const float dim = fmaf(-xr, ci, xi * cr);
+#pragma unroll
+                        for (int l = 0; l < L; ++l) {
+                            sRe[l] = fmaf(dre, chip[l], sRe[l]);
+                            sIm[l] = fmaf(dim, chip[l], sIm[l]);
+                        }
                     }
-                    v += v_step;
-                    ph += ph_step;
                 }
             }
             __syncwarp();
@@ -644,37 +729,29 @@ cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaS
 __global__ void chip_index_kernel(const SatDev sd, int shift_first, int shift, int n_samples, int tile_len,
                                   bool f64, int32_t *out)
 {
-    __shared__ unsigned long long s_meta;
-    __shared__ uint32_t s_bmod;
+    // walks the tiles exactly like a consumer warp of the hot kernel: base from scratch for the first
+    // tile, nco_advance afterwards, rep_index_* per entry
     uint64_t frac = 0;
     uint32_t bmod = 0;
+    const uint32_t lc = (uint32_t)sd.code_len;
     const int tiles = (n_samples + tile_len - 1) / tile_len;
-    const uint64_t tapoff = (uint64_t)(int64_t)(shift - shift_first) * (uint64_t)sd.nco_delta;
+    const int koff = shift - shift_first;
     for (int t = 0; t < tiles; ++t) {
-        if (threadIdx.x == 0) {
-            const int64_t u0 = (int64_t)t * tile_len + shift_first;
-            if (f64) {
-                const int32_t b = f64_chip_floor(sd.code_ratio, sd.code_phase, (int32_t)u0);
-                bmod = (uint32_t)floormod64(b, sd.code_len);
-                s_meta = (unsigned long long)(long long)b;
-            } else {
-                if (t == 0) nco_tile_base(sd, u0, frac, bmod);
-                s_meta = frac;
-            }
-            s_bmod = bmod;
+        const int32_t u0 = t * tile_len + shift_first;
+        int32_t b = 0;
+        if (f64) {
+            b = f64_chip_floor(sd.code_ratio, sd.code_phase, u0);
+            bmod = (uint32_t)floormod64(b, lc);
+        } else if (t == 0) {
+            nco_tile_base(sd, u0, frac, bmod);
+        } else {
+            nco_advance((uint64_t)sd.nco_delta, sd.nco_fp, lc, (uint32_t)tile_len, frac, bmod);
         }
-        __syncthreads();
         for (int tt = threadIdx.x; tt < tile_len && t * tile_len + tt < n_samples; tt += blockDim.x) {
-            const int n = t * tile_len + tt;
-            uint32_t slot;
-            if (f64)
-                slot = (uint32_t)(f64_chip_floor(sd.code_ratio, sd.code_phase, n + shift) - (int32_t)(long long)s_meta);
-            else
-                slot = nco_slot(s_meta + (uint64_t)tt * (uint64_t)sd.nco_delta + tapoff, sd.nco_fp - 32);
-            out[n] = (int32_t)((s_bmod + slot) % (uint32_t)sd.code_len);
+            const int u = tt + koff;
+            out[t * tile_len + tt] = f64 ? (int32_t)rep_index_f64(sd.code_ratio, sd.code_phase, u0 + u, b, bmod, lc)
+                                         : (int32_t)rep_index_nco(frac + (uint64_t)u * (uint64_t)sd.nco_delta, sd.nco_fp - 32, bmod, lc);
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && !f64) nco_tile_advance(sd, tile_len, frac, bmod);
     }
 }
 

@@ -15,7 +15,7 @@ constexpr int kMaxConsumerWarps = 11;  // + 1 producer = 12 warps = 384 threads 
 constexpr int kBlockThreadsMax = 32 * (kMaxConsumerWarps + 1);
 constexpr int kMaxStages = 16;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
-constexpr int kSmemHeaderBytes = 2304;  // barriers (0..255), per-stage metadata (512..2047), producer scratch (2048..)
+constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256)
 
 // One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
 struct SatDev {
@@ -46,6 +46,8 @@ struct CorrArgs {
     unsigned int *grid_barrier; // monotonically increasing arrival counter (never reset)
     unsigned int barrier_target;// value the counter reaches when every CTA of THIS launch arrived
     int32_t shifts[kMaxTaps];
+    int32_t koff4[kMaxTaps];           // 4 * (shifts[l] - shifts[0]): byte offset of tap l in the code replica
+    int32_t tt_stride;                 // samples between two iterations of a lane: 32, or 32 * SL when tiles are split
     int32_t n_periods, n_sats, n_ants, n_taps;
     int32_t start_sample, n_samples;   // integrated range [start, start + n)
     int32_t aligned_start;             // first staged sample (== start_sample with tensor-map TMA)
@@ -54,7 +56,7 @@ struct CorrArgs {
     int32_t tiles_per_job;
     int32_t S, AG, SL, W, G;           // sats/CTA, antenna groups, sample slices, consumer warps, sat groups
     int32_t stages;
-    int32_t win_stride;                // floats per (stage, sat) chip window
+    int32_t rep_stride;                // floats per consumer warp for its code replica (>= tile_len + span)
     int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
     int32_t fin_group;                 // lanes cooperating on one output element in the finalize (pow2 <= 32)

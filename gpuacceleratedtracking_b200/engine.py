@@ -38,6 +38,13 @@ class Channel:
                           float(self.carrier_phase), float(self.carrier_frequency))
 
 
+@dataclass
+class ChannelArray:
+    arr: object   # ctypes array of gat_channel, [P * K]
+    P: int
+    K: int
+
+
 def _is_torch(x) -> bool:
     return torch is not None and isinstance(x, torch.Tensor)
 
@@ -81,7 +88,12 @@ class Engine:
         self._check(self._lib.gat_sync(self._h))
 
     def set_stream(self, cuda_stream: int | None):
-        self._check(self._lib.gat_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Queue work on a caller-owned cudaStream_t handle (0 = the legacy default stream);
+        None goes back to the engine's private stream."""
+        if cuda_stream is None:
+            self._check(self._lib.gat_use_own_stream(self._h))
+        else:
+            self._check(self._lib.gat_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def set_timing(self, on: bool):
         self._check(self._lib.gat_set_timing(self._h, int(on)))
@@ -172,15 +184,16 @@ class Engine:
         """channels[p][k]; returns complex64 [P, K, L, M] (host) or fills `out=(re, im)` torch
         CUDA tensors of that shape (asynchronous)."""
         P = len(slots)
-        K = len(channels[0])
-        assert len(channels) == P and all(len(c) == K for c in channels)
-        for row in channels:
-            for ch in row:
-                self.set_codes(ch.system)
-        arr = (GatChannel * (P * K))(*[ch.to_c() for row in channels for ch in row])
+        if isinstance(channels, ChannelArray):      # pre-marshalled: no per-call Python work
+            arr, K = channels.arr, channels.K
+            assert channels.P == P
+        else:
+            K = len(channels[0])
+            assert len(channels) == P and all(len(c) == K for c in channels)
+            arr = self.marshal(channels).arr
         sh = np.ascontiguousarray(shifts, np.int32)
         L = sh.size
-        sl = np.ascontiguousarray(slots, np.int32)
+        sl = slots if isinstance(slots, np.ndarray) and slots.dtype == np.int32 else np.ascontiguousarray(slots, np.int32)
         if n_samples is None:
             raise ValueError("n_samples is required")
         flags = (_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0)
@@ -199,6 +212,15 @@ class Engine:
                                                   sh.ctypes.data_as(i32p), L, start_sample, n_samples,
                                                   C.c_void_p(o_re.ctypes.data), C.c_void_p(o_im.ctypes.data), 0, flags))
         return (o_re + 1j * o_im).astype(np.complex64)
+
+    def marshal(self, channels: Sequence[Sequence[Channel]]) -> "ChannelArray":
+        """Turn channels[p][k] into the C array once (and upload any chip table they need), so a
+        steady-state loop can call correlate_batch without rebuilding it."""
+        for row in channels:
+            for ch in row:
+                self.set_codes(ch.system)
+        P, K = len(channels), len(channels[0])
+        return ChannelArray((GatChannel * (P * K))(*[ch.to_c() for row in channels for ch in row]), P, K)
 
     def correlate(self, slot: int, channels: Sequence[Channel], fs: float, shifts: Sequence[int], n_ants: int,
                   start_sample: int = 0, n_samples: int | None = None, out=None, accumulate: bool = False,

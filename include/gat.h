@@ -92,8 +92,10 @@ const char *gat_last_error(gat_ctx *ctx);         /* valid until the next call o
 int gat_sync(gat_ctx *ctx);                       /* cudaStreamSynchronize; CUDA.@sync of src/benchmarks.jl:872 */
 void *gat_stream(gat_ctx *ctx);                   /* the ctx's cudaStream_t, for interop */
 /* Run on a caller-owned cudaStream_t (e.g. CUDA.jl's task stream, torch's current stream) so
- * work is ordered with the caller's own kernels; NULL restores the ctx's private stream. */
+ * work is ordered with the caller's own kernels.  The handle is used as given: NULL means the
+ * legacy default stream (stream 0).  gat_use_own_stream goes back to the ctx's private stream. */
 int gat_set_stream(gat_ctx *ctx, void *cuda_stream);
+int gat_use_own_stream(gat_ctx *ctx);
 
 /* ---- chip tables (replaces the CuTexture / gmem `codes` argument, src/benchmarks.jl:829-837) */
 /* Host helper: generate the +-1 chips of one PRN of a built-in system.  Returns code length
