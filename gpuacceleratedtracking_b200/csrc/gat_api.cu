@@ -218,16 +218,20 @@ struct Shape {
 int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
 {
     const int L = sh.L, M = sh.M, K = sh.K;
-    // antennas per thread: keep 2*A*L accumulators per thread around <= 96 registers
+    // antennas per thread: as many as ~96 accumulator registers allow -- the carrier and the tap loads
+    // are per THREAD, so fewer antennas per thread means more redundant work.  Measured on B200 (batch of
+    // 64 periods, 16 antennas): 11 taps A=4 130 us vs A=2 (19 warps) 150 us; 3 taps x 32 sats A=16
+    // 143 us vs A=8 168 us vs A=4 247 us.  These shapes are issue-bound, not latency-bound.
     int A = (L <= 3) ? 16 : (L <= 5 ? 8 : 4);
     A = std::min(A, pow2_ceil(M));
     A = std::max(1, std::min(A, env_int("GAT_TUNE_A", A)));
     if (!kernel_available(A, L)) return fail(ctx, GAT_ERR_UNSUPPORTED, "no kernel for this (antennas, taps) shape");
     const int AG = (M + A - 1) / A;
-    if (AG > kMaxConsumerWarps) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
+    const int w_cap = max_consumer_warps(A, L);
+    if (AG > w_cap) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
 
-    const int w_target_multi = std::min(kMaxConsumerWarps, env_int("GAT_TUNE_WMAX", 11));
-    const int w_target_single = std::min(kMaxConsumerWarps, env_int("GAT_TUNE_W", 8));
+    const int w_target_multi = std::min(w_cap, env_int("GAT_TUNE_WMAX", w_cap));
+    const int w_target_single = std::min(w_cap, env_int("GAT_TUNE_W", w_cap == 11 ? 8 : 16));
     const int cache_stride = (sh.max_code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign;
     const size_t smem_budget = 227 * 1024;
     int S = std::max(1, std::min(K, w_target_multi / AG));
@@ -289,7 +293,8 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     int SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
     SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
     const int W = S * AG * SL;
-    if (W > kMaxConsumerWarps || S > 12) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
+    if (W > w_cap || S > 32) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
+
 
     const int ctas_per_sm = 1;
     int grid = static_cast<int>(std::min<int64_t>(total_tiles, static_cast<int64_t>(ctx->n_sm) * ctas_per_sm));
@@ -334,6 +339,8 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         // few tiles per CTA: let every slice work on every tile instead of taking turns
         a.split_tiles = (SL > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid) ? 1 : 0;
         a.split_tiles = env_int("GAT_TUNE_SPLIT", a.split_tiles);
+        // warps sharing a code replica meet at named barriers 2..15: at most 14 such groups
+        if (a.split_tiles && AG * SL > 1 && S > 14) a.split_tiles = 0;
         a.tt_stride = a.split_tiles ? 32 * SL : 32;
     }
 

@@ -266,7 +266,7 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
 // the kernel
 // --------------------------------------------------------------------------------------
 template <int A, int L, bool F64>
-__global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __grid_constant__ CorrArgs args)
+__global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int AP = (A >= 2) ? A / 2 : 1;
@@ -524,6 +524,8 @@ __global__ void __launch_bounds__(kBlockThreadsMax, 1) correlate_kernel(const __
                 const int tt0 = split ? sl * 32 + lane : lane;
                 uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
                 const uint32_t rep_s = smem_u32(rep);
+                // (unrolling by two was measured slower on the 11-tap shape: occupancy, not per-warp ILP, is
+                // what hides the MUFU / shared-memory latencies here)
 #pragma unroll 1
                 for (int tt = tt0; tt < len; tt += tt_stride) {
                     // ---- carrier replica: exp(j 2 pi phase) ----

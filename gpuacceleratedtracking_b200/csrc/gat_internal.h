@@ -11,8 +11,11 @@ namespace gat {
 constexpr int kTileCap = 256;      // samples per staged smem row (row pitch, floats)
 constexpr int kMaxTaps = 11;       // GAT_MAX_TAPS
 constexpr int kMaxAnts = 32;       // rows per plane that fit the staging ring
-constexpr int kMaxConsumerWarps = 11;  // + 1 producer = 12 warps = 384 threads -> 168 registers/thread
-constexpr int kBlockThreadsMax = 32 * (kMaxConsumerWarps + 1);
+// Two CTA classes: shapes whose accumulators need <= 48 registers run up to 19 consumer warps
+// (+ 1 producer = 640 threads, <= 102 registers/thread); the others 11 (+ 1 = 384 threads, 168 registers).
+constexpr int kMaxConsumerWarps = 19;
+__host__ __device__ constexpr int block_threads_max(int A, int L) { return 2 * A * L <= 48 ? 640 : 384; }
+__host__ __device__ constexpr int max_consumer_warps(int A, int L) { return block_threads_max(A, L) / 32 - 1; }
 constexpr int kMaxStages = 16;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
 constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256)
