@@ -239,13 +239,19 @@ def run_gpu(args):
     slots = np.arange(P, dtype=np.int32)
     o_re = torch.zeros(P, 1, N_TAPS, N_ANTS, device=dev)
     o_im = torch.zeros_like(o_re)
+    elems = P * 1 * N_TAPS * N_ANTS
     if world > 1:
-        g_buf = torch.empty(world, 2, P, 1, N_TAPS, N_ANTS, device=dev)
+        # the path's one exchange step -- gathering the (tiny) accumulators -- is fused into the kernel
+        # epilogue: every rank's CTAs store their block into all ranks' buffers over NVLink peer mappings
+        from gpuacceleratedtracking_b200.multigpu import gather_setup
+        gather_setup(eng, elems)
 
     def step():
-        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
-        if world > 1:   # the path's real exchange step: gather the (tiny) accumulators
-            dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))
+        if world > 1:
+            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+            eng.gather_wait()          # stream-ordered: every rank's block of this step has landed here
+        else:
+            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
 
     def barrier():
         if world > 1:
@@ -255,8 +261,12 @@ def run_gpu(args):
     for _ in range(max(warmup, 3)):
         step()
     barrier()
-    # sanity: the prompt found this rank's satellite in every block
-    prompt = o_re[:, 0, 1, :].mean().item()
+    # sanity: the prompt found the satellite in every block (on every rank's slice when gathered)
+    if world > 1:
+        g = eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS)
+        prompt = float(g[:, :, 0, 1, :].real.mean())
+    else:
+        prompt = o_re[:, 0, 1, :].mean().item()
     assert prompt > 0.9 * N_SAMPLES, f"prompt {prompt}"
 
     sampler = ClockSampler(local)
@@ -278,10 +288,13 @@ def run_gpu(args):
     t0.record()
     for a, b in ev:
         a.record()
-        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
-        b.record()
         if world > 1:
-            dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))
+            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+            b.record()
+            eng.gather_wait()
+        else:
+            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
+            b.record()
     t1.record()
     barrier()
     gpu_launches = eng.kernel_launches - launches0
@@ -306,7 +319,8 @@ def run_gpu(args):
         h_im = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
         h_re.copy_(re)
         h_im.copy_(im)
-    h_out = torch.empty(2, world, P, 1, N_TAPS, N_ANTS, pin_memory=True) if rank == 0 else None
+    h_out = torch.empty(2, P, 1, N_TAPS, N_ANTS, pin_memory=True) if rank == 0 else None
+    h_gather = torch.empty(world, 2, P, 1, N_TAPS, N_ANTS, pin_memory=True) if (rank == 0 and world > 1) else None
     copy_stream = torch.cuda.Stream()
     main = torch.cuda.current_stream()
     chunk_chans = {c0: eng.marshal(chan_list[c0:min(P, c0 + CH)]) for c0 in range(0, P, CH)}
@@ -329,13 +343,16 @@ def run_gpu(args):
             main.wait_event(e)
             eng.correlate_batch(slots[c0:c1], chunk_chans[c0], FS, shifts, N_ANTS, 0, N_SAMPLES,
                                 out=(o_re[c0:c1], o_im[c0:c1]))
-        if world > 1:
-            dist.all_gather_into_tensor(g_buf, torch.stack([o_re, o_im]))
-            if rank == 0:
-                h_out.copy_(g_buf.transpose(0, 1), non_blocking=True)
-        elif rank == 0:
-            h_out[:, 0].copy_(torch.stack([o_re, o_im]), non_blocking=True)
         copy_stream.wait_stream(main)                            # next step's H2D must not overtake this compute
+        if world > 1:
+            # results of all ranks reach rank 0: one more fused-gather launch over the finished batch would
+            # repeat the compute, so the e2e leg gathers the per-rank outputs with one NCCL call
+            gl = [torch.empty(2, P, 1, N_TAPS, N_ANTS, device=dev) for _ in range(world)] if rank == 0 else None
+            dist.gather(torch.stack([o_re, o_im]), gl, dst=0)
+            if rank == 0:
+                h_gather.copy_(torch.stack(gl), non_blocking=True)
+        elif rank == 0:
+            h_out.copy_(torch.stack([o_re, o_im]), non_blocking=True)
         torch.cuda.current_stream().synchronize()                # the user sees the result (D2H read)
 
     for _ in range(2):

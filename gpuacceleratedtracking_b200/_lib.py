@@ -13,6 +13,8 @@ GAT_ERR_INVALID, GAT_ERR_CUDA, GAT_ERR_UNSUPPORTED, GAT_ERR_ALIGNMENT = -1, -2, 
 GAT_ERR_NO_CODES, GAT_ERR_NO_SIGNAL, GAT_ERR_NO_DEVICE = -5, -6, -7
 GAT_ACCUMULATE = 1
 GAT_CODE_PHASE_F64 = 2
+GAT_GATHER = 4
+GAT_IPC_HANDLE_BYTES = 64
 GAT_GPSL1, GAT_GPSL5 = 0, 1
 GAT_MAX_TAPS = 11
 GAT_MAX_ANTS = 32
@@ -64,6 +66,11 @@ SYMBOLS = {
     "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
     "gat_set_timing": (_i, [_vp, _i]),
     "gat_kernel_launch_count": (C.c_uint64, [_vp]),
+    "gat_gather_create": (_i, [_vp, _i, _i, C.c_uint64, C.POINTER(C.c_ubyte)]),
+    "gat_gather_connect": (_i, [_vp, C.POINTER(C.c_ubyte)]),
+    "gat_gather_wait": (_i, [_vp]),
+    "gat_gather_read": (_i, [_vp, _vp, _vp]),
+    "gat_gather_destroy": (_i, [_vp]),
     "gat_set_timeline": (_i, [_vp, _i]),
     "gat_get_timeline": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "gat_debug_chip_indices": (_i, [_vp, _chp, _d, _i, _i, _u, _i32p]),

@@ -65,6 +65,16 @@ struct gat_ctx {
     size_t h_out_cap = 0;
     int32_t *d_dbg = nullptr;
     size_t d_dbg_cap = 0;
+    // fused multi-GPU gather
+    unsigned char *g_local = nullptr;          // this rank's allocation: re | im | flags
+    void *g_opened[kMaxPeers] = {};            // peer base pointers from cudaIpcOpenMemHandle
+    float *g_re[kMaxPeers] = {}, *g_im[kMaxPeers] = {};
+    unsigned int *g_flag[kMaxPeers] = {};
+    uint64_t g_elems = 0;
+    int g_world = 0, g_rank = 0;
+    bool g_connected = false;
+    unsigned int g_seq = 0;
+    unsigned int *d_done = nullptr;
     unsigned long long *d_timeline = nullptr;
     size_t timeline_cap = 0;
     bool timeline_on = false;
@@ -417,7 +427,8 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (!slots || !channels || !shifts || !out_re || !out_im) return fail(ctx, GAT_ERR_INVALID, "null pointer argument");
+    if (!slots || !channels || !shifts || ((!out_re || !out_im) && !(flags & GAT_GATHER)))
+        return fail(ctx, GAT_ERR_INVALID, "null pointer argument");
     if (n_periods < 1 || n_sats < 1) return fail(ctx, GAT_ERR_INVALID, "n_periods and n_sats must be >= 1");
     if (n_taps < 1 || n_taps > GAT_MAX_TAPS) return fail(ctx, GAT_ERR_UNSUPPORTED, "n_taps must be 1..11");
     if (!(fs_hz > 0.0) || !std::isfinite(fs_hz)) return fail(ctx, GAT_ERR_INVALID, "sampling frequency must be positive");
@@ -498,10 +509,30 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     args.grid_barrier = ctx->d_barrier;
     args.barrier_target = ctx->barrier_count;
 
+    const bool gather = (flags & GAT_GATHER) != 0;
+    if (gather) {
+        if (!ctx->g_connected) return fail(ctx, GAT_ERR_INVALID, "GAT_GATHER needs gat_gather_create + gat_gather_connect");
+        if (L != n_taps || (flags & GAT_ACCUMULATE)) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_GATHER needs an odd tap count and no GAT_ACCUMULATE");
+        if (n_ch * static_cast<size_t>(n_taps) * M > ctx->g_elems) return fail(ctx, GAT_ERR_INVALID, "gather buffer too small for this call");
+    }
     const size_t out_elems = n_ch * n_taps * M;          // caller-visible
     const size_t out_elems_k = n_ch * static_cast<size_t>(L) * M;  // kernel layout (padded taps)
-    const bool direct = out_is_device && L == n_taps;
-    if (direct) {
+    const bool direct = gather || (out_is_device && L == n_taps);
+    args.n_peers = 0;
+    if (gather) {
+        args.out_re = ctx->g_re[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems;
+        args.out_im = ctx->g_im[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems;
+        for (int d = 0; d < ctx->g_world; ++d) {
+            args.peer_re[d] = ctx->g_re[d];
+            args.peer_im[d] = ctx->g_im[d];
+            args.peer_flag[d] = ctx->g_flag[d];
+        }
+        args.n_peers = ctx->g_world;
+        args.my_rank = ctx->g_rank;
+        args.gather_seq = ++ctx->g_seq;
+        args.gather_elems = ctx->g_elems;
+        args.done_counter = ctx->d_done;
+    } else if (direct) {
         args.out_re = out_re;
         args.out_im = out_im;
     } else {
@@ -697,6 +728,7 @@ int gat_destroy(gat_ctx *ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+    gat_gather_destroy(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -887,6 +919,105 @@ int gat_set_timing(gat_ctx *ctx, int enable)
 }
 
 uint64_t gat_kernel_launch_count(gat_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gat_gather_destroy(gat_ctx *ctx)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    cudaStreamSynchronize(ctx->stream);
+    for (int d = 0; d < kMaxPeers; ++d) {
+        if (ctx->g_opened[d]) cudaIpcCloseMemHandle(ctx->g_opened[d]);
+        ctx->g_opened[d] = nullptr;
+        ctx->g_re[d] = ctx->g_im[d] = nullptr;
+        ctx->g_flag[d] = nullptr;
+    }
+    if (ctx->g_local) cudaFree(ctx->g_local);
+    if (ctx->d_done) cudaFree(ctx->d_done);
+    ctx->g_local = nullptr;
+    ctx->d_done = nullptr;
+    ctx->g_connected = false;
+    ctx->g_world = 0;
+    ctx->g_seq = 0;
+    return GAT_OK;
+}
+
+namespace {
+void gather_views(unsigned char *base, int world, uint64_t elems, float **re, float **im, unsigned int **flag)
+{
+    const size_t plane = static_cast<size_t>(world) * elems * sizeof(float);
+    *re = reinterpret_cast<float *>(base);
+    *im = reinterpret_cast<float *>(base + plane);
+    *flag = reinterpret_cast<unsigned int *>(base + 2 * plane);
+}
+}  // namespace
+
+int gat_gather_create(gat_ctx *ctx, int world, int rank, uint64_t elems_per_rank, unsigned char *handle_out)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || elems_per_rank < 1 || !handle_out)
+        return fail(ctx, GAT_ERR_INVALID, "bad gather arguments (1 <= world <= 8)");
+    rc = gat_gather_destroy(ctx);
+    if (rc) return rc;
+    const uint64_t elems = (elems_per_rank + 63) & ~static_cast<uint64_t>(63);   // 256-byte slices
+    const size_t bytes = 2 * static_cast<size_t>(world) * elems * sizeof(float) + 256;
+    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->g_local), bytes));
+    GAT_CUDA(ctx, cudaMemset(ctx->g_local, 0, bytes));
+    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_done), sizeof(unsigned int)));
+    GAT_CUDA(ctx, cudaMemset(ctx->d_done, 0, sizeof(unsigned int)));
+    cudaIpcMemHandle_t h;
+    GAT_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->g_local));
+    static_assert(sizeof(h) == GAT_IPC_HANDLE_BYTES, "IPC handle size");
+    std::memcpy(handle_out, &h, sizeof(h));
+    ctx->g_world = world;
+    ctx->g_rank = rank;
+    ctx->g_elems = elems;
+    return GAT_OK;
+}
+
+int gat_gather_connect(gat_ctx *ctx, const unsigned char *handles)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!handles || !ctx->g_local) return fail(ctx, GAT_ERR_INVALID, "gat_gather_create first");
+    for (int d = 0; d < ctx->g_world; ++d) {
+        unsigned char *base = ctx->g_local;
+        if (d != ctx->g_rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + static_cast<size_t>(d) * GAT_IPC_HANDLE_BYTES, sizeof(h));
+            void *p = nullptr;
+            GAT_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->g_opened[d] = p;
+            base = static_cast<unsigned char *>(p);
+        }
+        gather_views(base, ctx->g_world, ctx->g_elems, &ctx->g_re[d], &ctx->g_im[d], &ctx->g_flag[d]);
+    }
+    ctx->g_connected = true;
+    return GAT_OK;
+}
+
+int gat_gather_wait(gat_ctx *ctx)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->g_connected) return fail(ctx, GAT_ERR_INVALID, "gather not connected");
+    cudaError_t e = launch_gather_wait(nullptr, ctx->g_flag[ctx->g_rank], ctx->g_world, ctx->g_seq, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "gather wait launch");
+    ctx->launches += 1;
+    return GAT_OK;
+}
+
+int gat_gather_read(gat_ctx *ctx, float *h_re, float *h_im)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->g_connected || !h_re || !h_im) return fail(ctx, GAT_ERR_INVALID, "gather not connected");
+    const size_t bytes = static_cast<size_t>(ctx->g_world) * ctx->g_elems * sizeof(float);
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GAT_CUDA(ctx, cudaMemcpy(h_re, ctx->g_re[ctx->g_rank], bytes, cudaMemcpyDeviceToHost));
+    GAT_CUDA(ctx, cudaMemcpy(h_im, ctx->g_im[ctx->g_rank], bytes, cudaMemcpyDeviceToHost));
+    return GAT_OK;
+}
 
 int gat_set_timeline(gat_ctx *ctx, int enable)
 {

@@ -257,9 +257,17 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
     }
     const int kk = grp * S + s2, m = ag2 * A + ml;
     if (kk >= K || m >= M) return;
-    float *dst = (c ? args.out_im : args.out_re) + (((size_t)p * K + kk) * L + l) * M + m;
+    const size_t idx = (((size_t)p * K + kk) * L + l) * M + m;
+    float *dst = (c ? args.out_im : args.out_re) + idx;
     if (args.flags & 1u) val += *dst;  // GAT_ACCUMULATE
     *dst = val;
+    if (args.n_peers > 1) {
+        // fused gather: the same value goes into slice `my_rank` of every other rank's buffer
+        // (posted stores over NVLink to CUDA-IPC peer mappings; no collective launch)
+        const size_t off = (size_t)args.my_rank * args.gather_elems + idx;
+        for (int d = 0; d < args.n_peers; ++d)
+            if (d != args.my_rank) (c ? args.peer_im[d] : args.peer_re[d])[off] = val;
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -672,6 +680,20 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             if (emit && gl == 0) emit_output<A, L>(args, job, x, acc);
         }
     }
+    if (args.n_peers >= 1) {
+        // every CTA fences its (peer) stores system-wide and checks in; the last one releases the flags
+        __threadfence_system();
+        consumer_bar_sync(consumer_threads);
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(args.done_counter, 1u);
+            if (prev == (unsigned int)grid - 1u) {
+                *args.done_counter = 0u;   // self-cleaning for the next launch
+                __threadfence_system();
+                for (int d = 0; d < args.n_peers; ++d)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(args.peer_flag[d] + args.my_rank), "r"(args.gather_seq) : "memory");
+            }
+        }
+    }
     GAT_STAMP(6);
 }
 
@@ -722,6 +744,25 @@ cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaS
     KernelFn fn = pick_kernel(plan.A, plan.L, plan.f64);
     if (!fn) return cudaErrorInvalidValue;
     fn<<<plan.grid, plan.block, plan.smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
+// stream-ordered wait for the fused gather: lane r spins until rank r's flag reached `seq`
+// --------------------------------------------------------------------------------------
+__global__ void gather_wait_kernel(unsigned int *flags, int world, unsigned int seq)
+{
+    if ((int)threadIdx.x < world) {
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        } while ((int)(v - seq) < 0);
+    }
+}
+
+cudaError_t launch_gather_wait(unsigned int *const *, unsigned int *local_flags, int world, unsigned int seq, cudaStream_t stream)
+{
+    gather_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, seq);
     return cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@ constexpr int kMaxConsumerWarps = 19;
 __host__ __device__ constexpr int block_threads_max(int A, int L) { return 2 * A * L <= 48 ? 640 : 384; }
 __host__ __device__ constexpr int max_consumer_warps(int A, int L) { return block_threads_max(A, L) / 32 - 1; }
 constexpr int kMaxStages = 16;
+constexpr int kMaxPeers = 8;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
 constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256)
 
@@ -65,6 +66,14 @@ struct CorrArgs {
     int32_t fin_group;                 // lanes cooperating on one output element in the finalize (pow2 <= 32)
     int32_t split_tiles;               // 1: every slice works on every tile (small problems); 0: whole tiles round-robin
     uint32_t flags;
+    // fused multi-GPU gather (GAT_GATHER): peer mappings of every rank's buffer, this rank's slice offset
+    float *peer_re[kMaxPeers];
+    float *peer_im[kMaxPeers];
+    unsigned int *peer_flag[kMaxPeers];
+    int32_t n_peers, my_rank;
+    uint32_t gather_seq;               // value released into flags[my_rank] when this launch is complete
+    unsigned long long gather_elems;   // elements per rank slice
+    unsigned int *done_counter;        // CTAs that finished their stores (self-cleaning)
     unsigned long long *timeline;      // debug: [grid][16] globaltimer stamps, or nullptr
 };
 
@@ -85,6 +94,9 @@ __host__ __device__ inline int padded_acc(int A, int L) { return ((2 * A * L) + 
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream);
 cudaError_t configure_kernels();   // opt-in to > 48 KB dynamic smem for every instantiation
 bool kernel_available(int A, int L);
+
+cudaError_t launch_gather_wait(unsigned int *const *flags_unused, unsigned int *local_flags, int world, unsigned int seq,
+                               cudaStream_t stream);
 
 cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples,
                                 int tile_len, bool f64, int32_t *d_out, cudaStream_t stream);

@@ -180,9 +180,10 @@ class Engine:
     # -- the hot path -----------------------------------------------------------------------
     def correlate_batch(self, slots: Sequence[int], channels: Sequence[Sequence[Channel]], fs: float,
                         shifts: Sequence[int], n_ants: int, start_sample: int = 0, n_samples: int | None = None,
-                        out=None, accumulate: bool = False, code_phase_f64: bool = False):
+                        out=None, accumulate: bool = False, code_phase_f64: bool = False, gather: bool = False):
         """channels[p][k]; returns complex64 [P, K, L, M] (host) or fills `out=(re, im)` torch
-        CUDA tensors of that shape (asynchronous)."""
+        CUDA tensors of that shape (asynchronous).  gather=True (after gather_setup) makes the kernel
+        store the block into every rank's gather buffer instead (multi-GPU)."""
         P = len(slots)
         if isinstance(channels, ChannelArray):      # pre-marshalled: no per-call Python work
             arr, K = channels.arr, channels.K
@@ -198,6 +199,11 @@ class Engine:
             raise ValueError("n_samples is required")
         flags = (_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0)
         i32p = C.POINTER(C.c_int32)
+        if gather:      # outputs go straight into every rank's gather buffer (fused epilogue, no host copy)
+            self._check(self._lib.gat_correlate_batch(self._h, P, sl.ctypes.data_as(i32p), K, arr, fs,
+                                                      sh.ctypes.data_as(i32p), L, start_sample, n_samples,
+                                                      None, None, 1, flags | _lib.GAT_GATHER))
+            return None
         if out is not None:
             o_re, o_im = out
             assert _is_torch(o_re) and o_re.is_cuda and o_re.is_contiguous() and o_im.is_contiguous()
@@ -249,6 +255,29 @@ class Engine:
             sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size, start_sample, n_samples,
             C.c_void_p(o_re.ctypes.data), C.c_void_p(o_im.ctypes.data), flags))
         return (o_re + 1j * o_im).astype(np.complex64)
+
+    # -- fused multi-GPU gather -------------------------------------------------------------------
+    def gather_create(self, world: int, rank: int, elems_per_rank: int) -> bytes:
+        h = (C.c_ubyte * _lib.GAT_IPC_HANDLE_BYTES)()
+        self._check(self._lib.gat_gather_create(self._h, world, rank, elems_per_rank, h))
+        self._gather_shape = (world, (elems_per_rank + 63) & ~63)
+        return bytes(h)
+
+    def gather_connect(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.gat_gather_connect(self._h, arr))
+
+    def gather_wait(self):
+        self._check(self._lib.gat_gather_wait(self._h))
+
+    def gather_read(self) -> np.ndarray:
+        """complex64 [world, elems_per_rank(padded)] of the local gather buffer (synchronises)."""
+        world, elems = self._gather_shape
+        re = np.empty((world, elems), np.float32)
+        im = np.empty_like(re)
+        self._check(self._lib.gat_gather_read(self._h, C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data)))
+        return (re + 1j * im).astype(np.complex64)
 
     def chip_indices(self, channel: Channel, fs: float, shift: int, n_samples: int, code_phase_f64: bool = False):
         self.set_codes(channel.system)

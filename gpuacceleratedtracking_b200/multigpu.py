@@ -77,3 +77,17 @@ def sharded_correlate(channels: Sequence, correlate_fn: Callable[[Sequence], tup
     perm = np.concatenate([np.asarray(i, dtype=np.int64) for i in all_idx])
     inv = torch.as_tensor(np.argsort(perm), device=g_re.device)
     return g_re.index_select(0, inv), g_im.index_select(0, inv)
+
+
+def gather_setup(engine, elems_per_rank: int, group=None):
+    """Create this rank's gather buffer, exchange the CUDA IPC handles over torch.distributed and map
+    every peer's buffer.  After this, engine.correlate_batch(..., gather=True) stores its accumulators
+    into all ranks' buffers from the kernel epilogue (NVLink peer stores) and engine.gather_wait()
+    orders the stream behind every rank's arrival flag -- no collective launch per step."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    handle = engine.gather_create(world, rank, elems_per_rank)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    engine.gather_connect(handles)
+    dist.barrier(group=group)

@@ -56,6 +56,9 @@ typedef enum gat_status {
 /* flags for gat_correlate* */
 #define GAT_ACCUMULATE 1u     /* out += result (device outputs only): the `+=` of src/algorithms.jl:207
                                  and the atomic accumulate of :625-632.  Default overwrites.          */
+#define GAT_GATHER 4u         /* multi-GPU: the kernel epilogue stores this rank's accumulators into the gather
+                                 buffer of EVERY rank (peer memory over NVLink) instead of out_re/out_im, which
+                                 are ignored.  Needs gat_gather_create/connect.                             */
 #define GAT_CODE_PHASE_F64 2u /* chip index = mod(floor(fc/fs*(n+shift)+phase), Lc) in IEEE double,
                                  bit-exact with the reference's GPU kernels (src/algorithms.jl:179-182).
                                  Default is the Int64 Q-format NCO of Tracking.jl's CPU path, bit-exact
@@ -145,6 +148,21 @@ int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *
                                   int n_ants, int n_sats, const gat_channel *channels, double fs_hz,
                                   const int32_t *sample_shifts, int n_taps, int start_sample,
                                   int n_samples, float *h_out_re, float *h_out_im, unsigned flags);
+
+/* ---- multi-GPU gather fused into the kernel epilogue (one process per GPU, same node) ------ */
+/* Every rank allocates [world x elems_per_rank] FP32 re + im planes plus one arrival flag per rank and
+ * exports a CUDA IPC handle (64 bytes) that the host exchanges by any means (torch.distributed,
+ * MPI, a file).  After gat_gather_connect a correlate call with GAT_GATHER writes its
+ * [n_ants x n_taps x n_sats x n_periods] block into slice `rank` of all `world` buffers with plain
+ * stores to the peer mappings, then its last CTA release-stores the call's sequence number into
+ * flags[rank] of every buffer.  gat_gather_wait queues (on the ctx stream) a wait until every rank's
+ * flag reached this rank's own sequence number; all ranks must issue the same sequence of calls. */
+#define GAT_IPC_HANDLE_BYTES 64
+int gat_gather_create(gat_ctx *ctx, int world, int rank, uint64_t elems_per_rank, unsigned char *handle_out);
+int gat_gather_connect(gat_ctx *ctx, const unsigned char *handles /* [world][GAT_IPC_HANDLE_BYTES] */);
+int gat_gather_wait(gat_ctx *ctx);
+int gat_gather_read(gat_ctx *ctx, float *h_re, float *h_im); /* sync + D2H of [world x elems_per_rank] */
+int gat_gather_destroy(gat_ctx *ctx);
 
 /* ---- introspection (bench / tests) ----------------------------------------------------- */
 typedef struct gat_launch_info {
