@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json configs[1], "C2"): GPS L1 C/A, 1 satellite per GPU, 16 antennas,
 3 correlators (E/P/L), 50 000 samples per 1 ms period at 50 MHz.  A STEP is one pass of the hot
-path over a batch of P distinct 1 ms signal blocks (default P = 128 -> 819 MB per GPU, far larger
+path over a batch of P distinct 1 ms signal blocks (default P = 256 -> 1.6 GB per GPU, far larger
 than the 126 MB L2, so every step streams from HBM) = ONE fused kernel launch per GPU.
 
   value   correlations/s = finished complex accumulators (periods x sats x taps x antennas) per
@@ -263,8 +263,8 @@ def run_gpu(args):
     barrier()
     # sanity: the prompt found the satellite in every block (on every rank's slice when gathered)
     if world > 1:
-        g = eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS)
-        prompt = float(g[:, :, 0, 1, :].real.mean())
+        gathered = eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS)
+        prompt = float(gathered[:, :, 0, 1, :].real.mean())
     else:
         prompt = o_re[:, 0, 1, :].mean().item()
     assert prompt > 0.9 * N_SAMPLES, f"prompt {prompt}"
@@ -310,15 +310,40 @@ def run_gpu(args):
     value = corr_per_step / (ms_per_step * 1e-3)
     info = eng.launch_info()
 
+    # ---- side measurement for the metric's second half: real-time (1 ms) satellite channels per GPU ----
+    # K_RT channels share ONE 1 ms signal block (the receiver case: every visible satellite of every
+    # constellation over the same antenna array); channels/ms = K_RT / launch time.
+    K_RT = 264
+    rt_chans = eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, DOPPLER + 3.0 * k, 0.001 * k) for k in range(K_RT)]])
+    rt_re = torch.zeros(1, K_RT, N_TAPS, N_ANTS, device=dev)
+    rt_im = torch.zeros_like(rt_re)
+    rt_slot = np.zeros(1, np.int32)
+    for _ in range(5):
+        eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im))
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    r0.record()
+    for _ in range(20):
+        eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im))
+    r1.record()
+    barrier()
+    rt_ms = r0.elapsed_time(r1) / 20
+    rt_info = eng.launch_info()
+
     # ---- e2e: host buffers -> H2D (-> NCCL broadcast) -> correlate -> gather -> D2H ----
     e2e_steps = max(2, min(steps, args.e2e_steps))
     CH = 16                                                       # periods per pipelined chunk
-    h_re = h_im = None
-    if rank == 0:
-        h_re = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
-        h_im = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
-        h_re.copy_(re)
-        h_im.copy_(im)
+    # Host side of the ingest: with N ranks every rank owns 1/N of each chunk in pinned host memory
+    # (N PCIe links in parallel) and the chunk is completed on every GPU by an NCCL all-gather over
+    # NVLink; at N = 1 this is a plain H2D copy.
+    assert P % CH == 0 and CH % world == 0, "periods per step must be a multiple of 16 (and 16 of the GPU count)"
+    SUB = CH // world
+    h_re = torch.empty(P // CH, SUB, N_ANTS, N_SAMPLES, pin_memory=True)
+    h_im = torch.empty(P // CH, SUB, N_ANTS, N_SAMPLES, pin_memory=True)
+    for ci in range(P // CH):
+        lo = ci * CH + rank * SUB
+        h_re[ci].copy_(re[lo:lo + SUB])
+        h_im[ci].copy_(im[lo:lo + SUB])
     h_out = torch.empty(2, P, 1, N_TAPS, N_ANTS, pin_memory=True) if rank == 0 else None
     h_gather = torch.empty(world, 2, P, 1, N_TAPS, N_ANTS, pin_memory=True) if (rank == 0 and world > 1) else None
     copy_stream = torch.cuda.Stream()
@@ -327,15 +352,15 @@ def run_gpu(args):
 
     def e2e_step():
         done = []
-        for c0 in range(0, P, CH):
-            c1 = min(P, c0 + CH)
+        for ci, c0 in enumerate(range(0, P, CH)):
+            c1 = c0 + CH
             with torch.cuda.stream(copy_stream):
-                if rank == 0:
-                    re[c0:c1].copy_(h_re[c0:c1], non_blocking=True)
-                    im[c0:c1].copy_(h_im[c0:c1], non_blocking=True)
+                lo = c0 + rank * SUB
+                re[lo:lo + SUB].copy_(h_re[ci], non_blocking=True)
+                im[lo:lo + SUB].copy_(h_im[ci], non_blocking=True)
                 if world > 1:
-                    dist.broadcast(re[c0:c1], src=0)
-                    dist.broadcast(im[c0:c1], src=0)
+                    dist.all_gather_into_tensor(re[c0:c1], re[lo:lo + SUB])
+                    dist.all_gather_into_tensor(im[c0:c1], im[lo:lo + SUB])
                 e = torch.cuda.Event()
                 e.record()
             done.append((c0, c1, e))
@@ -345,8 +370,7 @@ def run_gpu(args):
                                 out=(o_re[c0:c1], o_im[c0:c1]))
         copy_stream.wait_stream(main)                            # next step's H2D must not overtake this compute
         if world > 1:
-            # results of all ranks reach rank 0: one more fused-gather launch over the finished batch would
-            # repeat the compute, so the e2e leg gathers the per-rank outputs with one NCCL call
+            # the per-rank accumulators reach rank 0 with one NCCL gather, then D2H
             gl = [torch.empty(2, P, 1, N_TAPS, N_ANTS, device=dev) for _ in range(world)] if rank == 0 else None
             dist.gather(torch.stack([o_re, o_im]), gl, dst=0)
             if rank == 0:
@@ -409,11 +433,16 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "correlations/s", "h2d_bytes_per_step": P * 8 * N_SAMPLES * N_ANTS,
                     "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "path": "pinned host -> H2D" + (" -> NCCL broadcast" if world > 1 else "") + " -> gat_correlate_batch -> D2H"},
+                    "path": "pinned host -> H2D" + (f" (1/{world} per rank) -> NCCL all-gather over NVLink" if world > 1 else "")
+                            + " -> gat_correlate_batch -> " + ("NCCL gather -> " if world > 1 else "") + "D2H"},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "cmacs_per_s": value * N_SAMPLES,
-            "realtime_channels": world * P / ms_per_step,      # 1 ms periods finished per ms of wall clock
+            "realtime_channels": world * P / ms_per_step,      # 1 ms periods finished per ms of wall clock (K = 1 per block)
+            "realtime_shared_block": {                        # K_RT channels over one shared 1 ms block, one launch
+                "channels_per_launch": K_RT, "ms_per_launch": rt_ms, "realtime_channels_per_gpu": K_RT / rt_ms,
+                "fp32_tflops": K_RT * N_SAMPLES * N_ANTS * (6 + 4 * N_TAPS) / (rt_ms * 1e-3) / 1e12,
+                "sats_per_cta": rt_info["sats_per_cta"], "sat_groups": rt_info["sat_groups"]},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -426,7 +455,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--periods", type=int, default=128, help="1 ms signal blocks per step (batch)")
+    ap.add_argument("--periods", type=int, default=256, help="1 ms signal blocks per step (batch)")
     ap.add_argument("--ref-periods", type=int, default=0, help="periods per CPU step (default 2 x cores)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
