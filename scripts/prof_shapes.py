@@ -12,7 +12,7 @@ l1, l5 = g.GPSL1(), g.GPSL5()
 N, M = 50000, 16
 fs = N / 1e-3
 torch.cuda.set_device(0)
-P = 64
+P = 256 if which == "batch256" else 64
 re = torch.randn(P, M, N, device="cuda"); im = torch.randn(P, M, N, device="cuda")
 torch.cuda.synchronize()
 for p in range(P):
@@ -30,6 +30,8 @@ def run(name, P_, K, L, pref, system=l1):
     print(name, eng.launch_info())
 
 
+if which == "batch256":
+    run("batch P=256 K=1 L=3 (bench.py step)", 256, 1, 3, 0.5)
 if which in ("batch", "all"):
     run("batch P=64 K=1 L=3", 64, 1, 3, 0.5)
 if which in ("single1", "all"):
