@@ -57,6 +57,8 @@ SYMBOLS = {
     "gat_gen_code": (_i, [_i, _i, _i8p, _i]),
     "gat_set_codes": (_i, [_vp, _i, _i8p, _i, _i]),
     "gat_upload_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i]),
+    "gat_upload_signal_sc16": (_i, [_vp, _i, _vp, _i, _i, _i, C.c_float, _i]),
+    "gat_upload_signal_sc8": (_i, [_vp, _i, _vp, _i, _i, _i, C.c_float, _i]),
     "gat_bind_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
     "gat_gen_signal": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _i, _i, _d, _d, C.c_uint64, _i]),
     "gat_download_signal": (_i, [_vp, _i, _vp, _vp]),

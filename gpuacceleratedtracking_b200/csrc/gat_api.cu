@@ -65,6 +65,8 @@ struct gat_ctx {
     size_t h_out_cap = 0;
     int32_t *d_dbg = nullptr;
     size_t d_dbg_cap = 0;
+    unsigned char *d_raw = nullptr;      // raw integer samples awaiting expansion
+    size_t d_raw_cap = 0;
     // fused multi-GPU gather
     unsigned char *g_local = nullptr;          // this rank's allocation: re | im | flags
     void *g_opened[kMaxPeers] = {};            // peer base pointers from cudaIpcOpenMemHandle
@@ -727,6 +729,7 @@ int gat_destroy(gat_ctx *ctx)
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_timeline) cudaFree(ctx->d_timeline);
     gat_gather_destroy(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -803,6 +806,44 @@ int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, 
                                         static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, ctx->stream));
     }
     return GAT_OK;
+}
+
+namespace {
+int upload_sc(gat_ctx *ctx, int slot, const void *iq, int bytes_per_component, int n_samples, int n_ants, int ld, float scale,
+              int src_is_device)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!iq || n_samples < 1 || n_ants < 1 || n_ants > kMaxAnts || ld < n_samples || !std::isfinite(scale))
+        return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
+    SignalSlot *s = slot_for(ctx, slot);
+    if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
+    if (!s->owned && s->re) *s = SignalSlot{};  // drop a zero-copy binding
+    rc = own_slot(ctx, *s, n_samples, n_ants, (static_cast<int64_t>(n_samples) + 3) & ~3LL);
+    if (rc) return rc;
+    const void *d_src = iq;
+    if (!src_is_device) {
+        const size_t bytes = (static_cast<size_t>(ld) * (n_ants - 1) + n_samples) * 2 * bytes_per_component;
+        rc = ensure_device(ctx, ctx->d_raw, ctx->d_raw_cap, bytes, false);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw, iq, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_src = ctx->d_raw;
+    }
+    cudaError_t e = launch_expand_sc(d_src, bytes_per_component, ld, s->re, s->im, s->ld, n_samples, n_ants, scale, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "expand_sc launch");
+    ctx->launches += 1;
+    return GAT_OK;
+}
+}  // namespace
+
+int gat_upload_signal_sc16(gat_ctx *ctx, int slot, const int16_t *iq, int n_samples, int n_ants, int ld, float scale, int src_is_device)
+{
+    return upload_sc(ctx, slot, iq, 2, n_samples, n_ants, ld, scale, src_is_device);
+}
+
+int gat_upload_signal_sc8(gat_ctx *ctx, int slot, const int8_t *iq, int n_samples, int n_ants, int ld, float scale, int src_is_device)
+{
+    return upload_sc(ctx, slot, iq, 1, n_samples, n_ants, ld, scale, src_is_device);
 }
 
 int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im, int n_samples, int n_ants, int ld)

@@ -806,6 +806,55 @@ cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, i
 }
 
 // --------------------------------------------------------------------------------------
+// integer ingest: interleaved complex int16 / int8 -> FP32 planes (memory-bound streaming kernel)
+// --------------------------------------------------------------------------------------
+template <typename T>
+__global__ void expand_sc_kernel(const T *__restrict__ iq, int64_t ld_in, float *__restrict__ re, float *__restrict__ im,
+                                 int64_t ld_out, int n_samples, float scale)
+{
+    const int m = blockIdx.y;
+    const T *src = iq + (int64_t)m * ld_in * 2;
+    float *dre = re + (int64_t)m * ld_out, *dim = im + (int64_t)m * ld_out;
+    // 4 complex samples per thread and trip when the row is suitably aligned, scalar otherwise
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & (8 * sizeof(T) - 1)) == 0) && ((ld_out & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dre) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dim) & 15) == 0);
+    const int stride = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int quads = n_samples >> 2;
+        for (int q = tid; q < quads; q += stride) {
+            T v[8];
+            if constexpr (sizeof(T) == 2) *reinterpret_cast<int4 *>(v) = __ldg(reinterpret_cast<const int4 *>(src) + q);
+            else *reinterpret_cast<int2 *>(v) = __ldg(reinterpret_cast<const int2 *>(src) + q);
+            *reinterpret_cast<float4 *>(dre + 4 * q) = make_float4(v[0] * scale, v[2] * scale, v[4] * scale, v[6] * scale);
+            *reinterpret_cast<float4 *>(dim + 4 * q) = make_float4(v[1] * scale, v[3] * scale, v[5] * scale, v[7] * scale);
+        }
+        for (int n = (quads << 2) + tid; n < n_samples; n += stride) {
+            dre[n] = (float)src[2 * n] * scale;
+            dim[n] = (float)src[2 * n + 1] * scale;
+        }
+    } else {
+        for (int n = tid; n < n_samples; n += stride) {
+            dre[n] = (float)src[2 * n] * scale;
+            dim[n] = (float)src[2 * n + 1] * scale;
+        }
+    }
+}
+
+cudaError_t launch_expand_sc(const void *iq, int bytes_per_component, int64_t ld_in, float *re, float *im, int64_t ld_out,
+                             int n_samples, int n_ants, float scale, cudaStream_t stream)
+{
+    const int threads = 256;
+    const int bx = max(1, min(64, (n_samples / 4 + threads - 1) / threads));
+    dim3 grid(bx, n_ants);
+    if (bytes_per_component == 2)
+        expand_sc_kernel<int16_t><<<grid, threads, 0, stream>>>(static_cast<const int16_t *>(iq), ld_in, re, im, ld_out, n_samples, scale);
+    else
+        expand_sc_kernel<int8_t><<<grid, threads, 0, stream>>>(static_cast<const int8_t *>(iq), ld_in, re, im, ld_out, n_samples, scale);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------
 // synthetic signal generator, gen_signal semantics (src/gen_signal.jl:135-152)
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)

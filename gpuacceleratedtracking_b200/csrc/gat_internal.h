@@ -101,6 +101,10 @@ cudaError_t launch_gather_wait(unsigned int *const *flags_unused, unsigned int *
 cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples,
                                 int tile_len, bool f64, int32_t *d_out, cudaStream_t stream);
 
+// expand interleaved complex integer samples [n_ants][ld_in][2] into FP32 planes [n_ants][ld_out]
+cudaError_t launch_expand_sc(const void *iq, int bytes_per_component, int64_t ld_in, float *re, float *im, int64_t ld_out,
+                             int n_samples, int n_ants, float scale, cudaStream_t stream);
+
 cudaError_t launch_gen_signal(float *re, float *im, int64_t ld, const int8_t *code, int code_len,
                               double code_ratio, double carrier_freq_hz, double fs_hz, double code_phase,
                               double carrier_phase_rad, int n_samples, int n_ants,

@@ -153,6 +153,26 @@ class Engine:
                                                 n, m, ld, int(on_dev)))
         self._keep.pop(slot, None)
 
+    def upload_signal_int(self, slot: int, iq, scale: float = 1.0):
+        """Integer front-end samples: `iq` is int16 or int8 of shape [n_ants, n_samples, 2] (I, Q interleaved,
+        numpy host array or torch device tensor).  Moves 2-4x fewer bytes than FP32; expanded on the device."""
+        if iq.ndim == 2:
+            iq = iq[None]
+        m, n, two = iq.shape
+        assert two == 2
+        on_dev = _is_torch(iq) and iq.is_cuda
+        if _is_torch(iq):
+            assert iq.is_contiguous()
+            size = iq.element_size()
+        else:
+            iq = np.ascontiguousarray(iq)
+            size = iq.dtype.itemsize
+        fn = {2: self._lib.gat_upload_signal_sc16, 1: self._lib.gat_upload_signal_sc8}[size]
+        self._check(fn(self._h, slot, C.c_void_p(_ptr(iq)), n, m, n, scale, int(on_dev)))
+        self._keep.pop(slot, None)
+        if not on_dev:
+            self._raw_keep = iq        # the H2D copy is asynchronous: keep the host array alive
+
     def bind_signal(self, slot: int, re, im, n_samples: int | None = None):
         """Zero-copy: register torch CUDA planes [n_ants, ld] as the signal of `slot`."""
         if not (_is_torch(re) and re.is_cuda):

@@ -115,6 +115,14 @@ int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im,
                       int n_samples, int n_ants, int ld, int src_is_device);
 int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im,
                     int n_samples, int n_ants, int ld);
+/* Integer front-end samples: interleaved complex (I, Q) int16 / int8 per antenna, antenna-major
+ * [n_ants][ld][2] with `ld` in complex samples -- the usual SDR wire format.  The raw block (2-4x fewer
+ * bytes than FP32) is copied to the device and a kernel expands it into the slot's FP32 planes as
+ * (float)x * scale, so everything downstream is unchanged.  scale = 1 keeps the integers exact. */
+int gat_upload_signal_sc16(gat_ctx *ctx, int slot, const int16_t *iq, int n_samples, int n_ants, int ld,
+                           float scale, int src_is_device);
+int gat_upload_signal_sc8(gat_ctx *ctx, int slot, const int8_t *iq, int n_samples, int n_ants, int ld,
+                          float scale, int src_is_device);
 /* Device-side synthetic generator with gen_signal semantics (src/gen_signal.jl:135-152):
  * code phase Float64 -> floor/mod, carrier phase Float64 -> Float32 -> cos/sin, every antenna
  * identical.  Extensions (off when zero): per-antenna phase step [rad], AWGN sigma (seeded),

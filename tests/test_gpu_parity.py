@@ -485,3 +485,37 @@ def test_caller_supplied_code_table(gat, orc, engine):
     ref = np.stack([orc.correlate_direct(re, im, table[1], 0.511e6, 77.0, 300.0, 0.0, fs, shifts)])
     assert_close(got, ref)
     assert abs(got[0, 1, 0].real - n) < 1.0
+
+
+@pytest.mark.parametrize("dtype,scale", [(np.int16, 1.0), (np.int16, 1.0 / 2048), (np.int8, 1.0), (np.int8, 0.125)])
+def test_integer_ingest(gat, orc, engine, dtype, scale):
+    """interleaved complex int16 / int8 front-end samples expanded on the device."""
+    import torch
+    rng = np.random.default_rng(7)
+    l1 = gat.GPSL1()
+    n, m, fs = 10003, 5, 1.0e7
+    lim = 2000 if dtype == np.int16 else 100
+    chans = [gat.Channel(l1, 6, 123.4, 1500.0, 0.1), gat.Channel(l1, 19, 900.0, -3300.0, -0.2)]
+    sig = np.zeros((m, n, 2))
+    for c in chans:
+        r, i = orc.gen_signal(l1.codes[c.prn - 1], 1.023e6, c.carrier_frequency, fs, n, m, c.code_phase, 2 * np.pi * c.carrier_phase)
+        sig[..., 0] += 0.3 * lim * r
+        sig[..., 1] += 0.3 * lim * i
+    sig += rng.normal(0, 0.1 * lim, sig.shape)
+    iq = np.clip(np.rint(sig), -lim * 4, lim * 4).astype(dtype)
+    re = (iq[..., 0].astype(np.float32) * np.float32(scale)).copy()
+    im = (iq[..., 1].astype(np.float32) * np.float32(scale)).copy()
+    shifts = np.array([-4, 0, 4], np.int32)
+    engine.upload_signal(0, re, im)
+    want = engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    engine.upload_signal_int(1, iq, scale)
+    got = engine.correlate(1, chans, fs, shifts, m, n_samples=n)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))         # same FP32 samples -> same bits
+    r2, i2 = engine.download_signal(1, n, m)
+    assert np.array_equal(r2, re) and np.array_equal(i2, im)
+    engine.upload_signal_int(2, torch.from_numpy(iq).cuda(), scale)         # device-resident source
+    got2 = engine.correlate(2, chans, fs, shifts, m, n_samples=n)
+    assert np.array_equal(got2.view(np.uint64), want.view(np.uint64))
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
+                                         c.carrier_phase, fs, shifts) for c in chans])
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref[:, 1]).max()
