@@ -397,6 +397,38 @@ def run_gpu(args):
     e2e_ms = te.item()
     e2e_value = corr_per_step / (e2e_ms * 1e-3)
 
+    # ---- side figure (N = 1): the same e2e step fed with interleaved complex int16 samples (SDR wire format,
+    # SURVEY 8f-2): half the PCIe bytes, expanded to FP32 on the device, same kernel, same results ----
+    e2e_sc16 = None
+    if world == 1:
+        eng_i = g.Engine(local)
+        eng_i.set_stream(work_stream.cuda_stream)
+        h_iq = torch.empty(P, N_ANTS, N_SAMPLES, 2, dtype=torch.int16, pin_memory=True)
+        for c0 in range(0, P, 32):
+            blk = torch.stack([re[c0:c0 + 32], im[c0:c0 + 32]], dim=-1)
+            h_iq[c0:c0 + 32].copy_((blk * 1024.0).round().clamp_(-32768, 32767).to(torch.int16))
+        blocks_np = [h_iq[p].numpy() for p in range(P)]
+        oi_re, oi_im = torch.zeros_like(o_re), torch.zeros_like(o_im)
+        chans_i = eng_i.marshal(chan_list)
+
+        def sc16_step():
+            for p in range(P):
+                eng_i.upload_signal_int(p, blocks_np[p], 1.0 / 1024.0)
+            eng_i.correlate_batch(slots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
+            h_out.copy_(torch.stack([oi_re, oi_im]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        sc16_step()
+        assert oi_re[:, 0, 1, :].mean().item() > 0.9 * N_SAMPLES
+        w0 = time.perf_counter()
+        for _ in range(3):
+            sc16_step()
+        sc16_ms = (time.perf_counter() - w0) * 1e3 / 3
+        e2e_sc16 = {"value": corr_per_step / (sc16_ms * 1e-3), "unit": "correlations/s", "ms_per_step": sc16_ms,
+                    "h2d_bytes_per_step": P * 4 * N_SAMPLES * N_ANTS,
+                    "path": "pinned host int16 I/Q -> H2D -> expand kernel -> gat_correlate_batch -> D2H"}
+        eng_i.close()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -435,6 +467,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "path": "pinned host -> H2D" + (f" (1/{world} per rank) -> NCCL all-gather over NVLink" if world > 1 else "")
                             + " -> gat_correlate_batch -> " + ("NCCL gather -> " if world > 1 else "") + "D2H"},
+            "e2e_sc16": e2e_sc16,
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "cmacs_per_s": value * N_SAMPLES,
