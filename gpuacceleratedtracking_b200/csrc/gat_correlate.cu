@@ -743,8 +743,12 @@ cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaS
 {
     KernelFn fn = pick_kernel(plan.A, plan.L, plan.f64);
     if (!fn) return cudaErrorInvalidValue;
-    fn<<<plan.grid, plan.block, plan.smem, stream>>>(args);
-    return cudaGetLastError();
+    // Cooperative launch: the kernel ends with a grid-wide counting barrier, so all CTAs must be
+    // co-resident.  grid <= #SMs with one CTA per SM satisfies that on an idle device; the cooperative
+    // attribute makes the driver GUARANTEE it (two such kernels from different streams are then
+    // serialised instead of dead-locking each other half-resident).
+    void *kargs[] = {const_cast<CorrArgs *>(&args)};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(fn), dim3(plan.grid), dim3(plan.block), kargs, plan.smem, stream);
 }
 
 // --------------------------------------------------------------------------------------
