@@ -548,13 +548,19 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                     for (int l = 0; l < L; ++l) chip[l] = lds_f32_at(ra + (uint32_t)args.koff4[l]);
                     if constexpr (A >= 2) {
                         const f32x2 CR = pack2(cr, cr), CI = pack2(ci, ci), NCI = pack2(-ci, -ci);
+                        // all of this sample's loads first (volatile: kept in this order, ahead of the math),
+                        // so the packed-FMA stream below never waits on shared-memory latency
+                        f32x2 X[AP], Y[AP];
 #pragma unroll
                         for (int a = 0; a < AP; ++a) {
-                            const f32x2 X = pack2(lds_f32(tre + (2 * a) * kTileCap + tt), lds_f32(tre + (2 * a + 1) * kTileCap + tt));
-                            const f32x2 Y = pack2(lds_f32(tim + (2 * a) * kTileCap + tt), lds_f32(tim + (2 * a + 1) * kTileCap + tt));
+                            X[a] = pack2(lds_f32(tre + (2 * a) * kTileCap + tt), lds_f32(tre + (2 * a + 1) * kTileCap + tt));
+                            Y[a] = pack2(lds_f32(tim + (2 * a) * kTileCap + tt), lds_f32(tim + (2 * a + 1) * kTileCap + tt));
+                        }
+#pragma unroll
+                        for (int a = 0; a < AP; ++a) {
                             // d = s * conj(c):  d_re = s_re c_re + s_im c_im ; d_im = s_im c_re - s_re c_im
-                            const f32x2 Dre = fma2(Y, CI, mul2(X, CR));
-                            const f32x2 Dim = fma2(X, NCI, mul2(Y, CR));
+                            const f32x2 Dre = fma2(Y[a], CI, mul2(X[a], CR));
+                            const f32x2 Dim = fma2(X[a], NCI, mul2(Y[a], CR));
 #pragma unroll
                             for (int l = 0; l < L; ++l) {
                                 const f32x2 CH = pack2(chip[l], chip[l]);

@@ -11,10 +11,10 @@ namespace gat {
 constexpr int kTileCap = 256;      // samples per staged smem row (row pitch, floats)
 constexpr int kMaxTaps = 11;       // GAT_MAX_TAPS
 constexpr int kMaxAnts = 32;       // rows per plane that fit the staging ring
-// Two CTA classes: shapes whose accumulators need <= 48 registers run up to 19 consumer warps
+// Two CTA classes: shapes whose accumulators need <= 32 registers run up to 19 consumer warps
 // (+ 1 producer = 640 threads, <= 102 registers/thread); the others 11 (+ 1 = 384 threads, 168 registers).
 constexpr int kMaxConsumerWarps = 19;
-__host__ __device__ constexpr int block_threads_max(int A, int L) { return 2 * A * L <= 48 ? 640 : 384; }
+__host__ __device__ constexpr int block_threads_max(int A, int L) { return 2 * A * L <= 32 ? 640 : 384; }
 __host__ __device__ constexpr int max_consumer_warps(int A, int L) { return block_threads_max(A, L) / 32 - 1; }
 constexpr int kMaxStages = 16;
 constexpr int kMaxPeers = 8;
