@@ -490,12 +490,22 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     std::vector<unsigned char> blk(blk_bytes);
     std::memcpy(blk.data(), periods.data(), per_bytes);
     std::memcpy(blk.data() + sat_off, sats.data(), sizeof(SatDev) * n_ch);
-    unsigned char *d_blk = nullptr;
     Staging *stg = nullptr;
-    rc = stage_params(ctx, blk.data(), blk_bytes, &d_blk, &stg);
-    if (rc) return rc;
-    args.periods = reinterpret_cast<const PeriodDev *>(d_blk);
-    args.sats = reinterpret_cast<const SatDev *>(d_blk + sat_off);
+    if (blk_bytes <= static_cast<size_t>(kInlineBytes)) {
+        // small call (one period, up to ~40 channels): the block rides in the kernel arguments
+        std::memcpy(args.inline_blk, blk.data(), blk_bytes);
+        args.use_inline = 1;
+        args.inline_sat_off = static_cast<int32_t>(sat_off);
+        args.periods = nullptr;
+        args.sats = nullptr;
+    } else {
+        unsigned char *d_blk = nullptr;
+        rc = stage_params(ctx, blk.data(), blk_bytes, &d_blk, &stg);
+        if (rc) return rc;
+        args.use_inline = 0;
+        args.periods = reinterpret_cast<const PeriodDev *>(d_blk);
+        args.sats = reinterpret_cast<const SatDev *>(d_blk + sat_off);
+    }
 
     // scratch
     const size_t roles_rp = static_cast<size_t>(args.S) * args.AG * plan.RP;
@@ -556,7 +566,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = launch_correlate(plan, args, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "correlate kernel launch");
-    GAT_CUDA(ctx, cudaEventRecord(stg->consumed, ctx->stream));
+    if (stg) GAT_CUDA(ctx, cudaEventRecord(stg->consumed, ctx->stream));
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     ctx->info.kernels_launched = 1;

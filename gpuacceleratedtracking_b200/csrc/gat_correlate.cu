@@ -323,6 +323,9 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     }
     __syncthreads();
 
+    // small calls carry their TMA descriptors and channel records in the kernel arguments
+    const PeriodDev *periods = args.use_inline ? reinterpret_cast<const PeriodDev *>(args.inline_blk) : args.periods;
+    const SatDev *sats = args.use_inline ? reinterpret_cast<const SatDev *>(args.inline_blk + args.inline_sat_off) : args.sats;
     const int64_t TT = args.total_tiles;
     const int grid = gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * TT / grid;
@@ -341,12 +344,12 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             const int t_first = (int)(g - (int64_t)job * TJ);
             const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
             const int p = job / G, grp = job % G;
-            const PeriodDev *per = &args.periods[p];
+            const PeriodDev *per = &periods[p];
             const bool sat_ok = (lane < S) && (grp * S + lane < K);
             const int8_t *code = nullptr;
             int code_len = 0;
             if (sat_ok) {
-                const SatDev *sd = &args.sats[(size_t)p * K + grp * S + lane];
+                const SatDev *sd = &sats[(size_t)p * K + grp * S + lane];
                 code = sd->code;
                 code_len = sd->code_len;
             }
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
         uint32_t lc = 1;
         double ratio = 0.0, cphase = 0.0;
         if (active) {
-            const SatDev *sd = &args.sats[(size_t)p * K + k];
+            const SatDev *sd = &sats[(size_t)p * K + k];
             delta = (uint64_t)sd->nco_delta;
             nco_start = sd->nco_start;
             fp = sd->nco_fp;

@@ -42,7 +42,12 @@ struct alignas(64) PeriodDev {
     CUtensorMap im;
 };
 
-struct CorrArgs {
+constexpr int kInlineBytes = 3328;   // small parameter blocks ride in the kernel arguments (no H2D copy, no events)
+
+struct alignas(64) CorrArgs {
+    // [PeriodDev x P][pad to 64][SatDev x P*K] when the whole block fits; else `periods` / `sats` point to it in global memory
+    unsigned char inline_blk[kInlineBytes];
+    int32_t use_inline, inline_sat_off;
     const PeriodDev *periods;   // [n_periods]
     const SatDev *sats;         // [n_periods * n_sats]
     float *out_re, *out_im;     // [n_periods][n_sats][n_taps][n_ants]
@@ -76,6 +81,8 @@ struct CorrArgs {
     unsigned int *done_counter;        // CTAs that finished their stores (self-cleaning)
     unsigned long long *timeline;      // debug: [grid][16] globaltimer stamps, or nullptr
 };
+
+static_assert(sizeof(CorrArgs) <= 4096, "kernel parameter space");
 
 struct LaunchPlan {
     int A;            // antennas per thread (template)
