@@ -520,19 +520,13 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             mbar_wait(&full_bar[stage], par);
             if (q == 0) GAT_STAMP(2);
             if (active) {
-                float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
-                float *tim = tre + (size_t)MP * kTileCap;
-                if (n0 < 0) {
-                    // tiles start on a 16-byte boundary: the <= 3 samples staged before start_sample are
-                    // zeroed in place (every warp clears the rows it reads), which keeps the loop branch-free.
-                    // Samples past the end never reach the loop (tt < len) and are zero-filled by TMA anyway.
-                    for (int i = lane; i < 2 * A * (-n0); i += 32) {
-                        const int col = i % (-n0), row = i / (-n0);
-                        (row < A ? tre + (size_t)row * kTileCap : tim + (size_t)(row - A) * kTileCap)[col] = 0.f;
-                    }
-                    __syncwarp();
-                }
-                const int tt0 = split ? sl * 32 + lane : lane;
+                const float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
+                const float *tim = tre + (size_t)MP * kTileCap;
+                // tiles start on a 16-byte boundary, so the first tile of a job may stage <= 3 samples that lie
+                // before start_sample (n0 < 0): the lanes that own them skip their first iteration.  Samples
+                // past the end never reach the loop (tt < len).  The loop itself stays branch-free.
+                int tt0 = split ? sl * 32 + lane : lane;
+                if (n0 + tt0 < 0) tt0 += tt_stride;
                 uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
                 const uint32_t rep_s = smem_u32(rep);
                 // (unrolling by two was measured slower on the 11-tap shape: occupancy, not per-warp ILP, is
