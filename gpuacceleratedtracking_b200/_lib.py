@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgat.so")
+# GAT_LIB_PATH: development override (A/B runs of two builds of the same library); never a fallback
+LIB_PATH = os.environ.get("GAT_LIB_PATH") or os.path.join(_HERE, "libgat.so")
 
 GAT_OK = 0
 GAT_ERR_INVALID, GAT_ERR_CUDA, GAT_ERR_UNSUPPORTED, GAT_ERR_ALIGNMENT = -1, -2, -3, -4
@@ -30,7 +31,7 @@ class GatLaunchInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "grid", "block", "smem_bytes", "ants_per_thread", "ant_groups", "sats_per_cta", "sample_slices",
         "consumer_warps", "sat_groups", "chunks_per_job", "chunk_len", "tile_len", "stages", "items",
-        "kernels_launched")] + [("last_kernel_ms", C.c_float)]
+        "kernels_launched", "sc16")] + [("last_kernel_ms", C.c_float)]
 
 
 class GatError(RuntimeError):

@@ -24,6 +24,14 @@ struct SignalSlot {
     size_t cap_floats = 0;  // per plane, when owned
     PeriodDev maps{};       // TMA descriptors of the two planes
     bool maps_valid = false;
+    bool planes_valid = false;   // re / im hold the block (false while only the raw integer copy exists)
+    // raw interleaved complex int16 copy of the block (gat_upload_signal_sc16): [n_ants][raw_ld] words of I | Q << 16
+    int16_t *raw = nullptr;
+    size_t raw_cap = 0;          // complex samples
+    int64_t raw_ld = 0;
+    float raw_scale = 1.f;
+    bool raw_valid = false;
+    PeriodDev raw_map{};         // .re = 2-D descriptor over the 32-bit I/Q words
 };
 
 struct CodeTable {
@@ -224,6 +232,7 @@ struct Shape {
     int64_t max_delta;
     bool f64;
     int max_code_len;
+    bool sc16;
 };
 
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
@@ -252,7 +261,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // every satellite batched on a CTA keeps its chip table in smem: leave room for >= 2 stages,
     // the per-warp code replicas and the flush buffer
     {
-        const size_t two_stages = kSmemHeaderBytes + 2 * smem_tile_floats(AG, A) * sizeof(float) +
+        const size_t two_stages = kSmemHeaderBytes + 2 * smem_tile_floats(AG, A, sh.sc16) * sizeof(float) +
                                   static_cast<size_t>(kMaxConsumerWarps) * (padded_acc(A, L) + kTileCap + span + 128) * sizeof(float);
         if (two_stages + cache_stride > smem_budget)
             return fail(ctx, GAT_ERR_UNSUPPORTED, "chip table too long for the shared-memory cache");
@@ -261,7 +270,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     const int G = (K + S - 1) / S;
     S = (K + G - 1) / G;  // balance the groups
     const int RP = padded_acc(A, L);
-    const size_t tile_bytes = smem_tile_floats(AG, A) * sizeof(float);
+    const size_t tile_bytes = smem_tile_floats(AG, A, sh.sc16) * sizeof(float);
     // tile coordinates stay multiples of 4 samples (16 B); the TMA unit zero-fills past the block end,
     // and the kernel masks the <= 3 samples staged before start_sample
     const int aligned_start = env_int("GAT_TUNE_NOALIGN", 0) ? sh.start : (sh.start & ~3);
@@ -299,7 +308,9 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     if (fixed_bytes + tile_bytes > smem_budget)
         return fail(ctx, GAT_ERR_UNSUPPORTED, "shape does not fit shared memory (antennas x tap span)");
     int stages = static_cast<int>((smem_budget - fixed_bytes) / tile_bytes);
-    stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 6)));
+    // (up to 12 stages where the tiles are small -- few antennas, raw int16 words -- so that one channel
+    // reading a block alone can still spread over 8..12 sample slices; 32 KB FP32 tiles fit 6)
+    stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 12)));
     stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
     // sample slices take whole tiles round-robin, so more slices than stages cannot all be fed
     int SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
@@ -315,6 +326,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     plan.A = A;
     plan.L = L;
     plan.f64 = sh.f64;
+    plan.sc16 = sh.sc16;
     plan.grid = grid;
     plan.block = 32 * (W + 1);
     plan.smem = kSmemHeaderBytes + stages * tile_bytes + static_cast<size_t>(W) * (RP + rep_stride) * sizeof(float) +
@@ -371,6 +383,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     li.tile_len = tile_len;
     li.stages = stages;
     li.items = static_cast<int32_t>(total_tiles);
+    li.sc16 = sh.sc16 ? 1 : 0;
     return GAT_OK;
 }
 
@@ -415,6 +428,92 @@ int encode_slot_maps(gat_ctx *ctx, SignalSlot &s)
     return GAT_OK;
 }
 
+SignalSlot *slot_for(gat_ctx *ctx, int slot)
+{
+    if (slot < 0 || slot >= 65536) return nullptr;
+    if (slot >= static_cast<int>(ctx->slots.size())) ctx->slots.resize(slot + 1);
+    return &ctx->slots[slot];
+}
+
+// drop the FP32 planes of a slot (owned storage is freed, a zero-copy binding is forgotten); the raw copy stays
+int free_planes(gat_ctx *ctx, SignalSlot &s)
+{
+    if (s.owned && s.re) {
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GAT_CUDA(ctx, cudaFree(s.re));
+    }
+    s.re = s.im = nullptr;
+    s.ld = 0;
+    s.owned = false;
+    s.cap_floats = 0;
+    s.maps_valid = false;
+    s.planes_valid = false;
+    return GAT_OK;
+}
+
+int release_slot(gat_ctx *ctx, SignalSlot &s)
+{
+    int rc = free_planes(ctx, s);
+    if (rc) return rc;
+    if (s.raw) {
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GAT_CUDA(ctx, cudaFree(s.raw));
+    }
+    s = SignalSlot{};
+    return GAT_OK;
+}
+
+// make `s` hold owned FP32 planes of n_ants x ld floats each (one allocation: re then im).  The caller fills
+// them in stream order; unless keep_raw, a raw integer copy of an older block is invalidated.
+int own_slot(gat_ctx *ctx, SignalSlot &s, int n_samples, int n_ants, int64_t ld, bool keep_raw = false)
+{
+    const size_t need = static_cast<size_t>(ld) * n_ants;
+    if (!s.owned || s.cap_floats < need) {
+        int rc = free_planes(ctx, s);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&s.re), 2 * need * sizeof(float)));
+        s.cap_floats = need;
+        s.owned = true;
+    }
+    s.im = s.re + s.cap_floats;
+    const bool same = s.maps_valid && s.ld == ld && s.n_samples == n_samples && s.n_ants == n_ants;
+    s.ld = ld;
+    s.n_samples = n_samples;
+    s.n_ants = n_ants;
+    s.planes_valid = true;
+    if (!keep_raw) s.raw_valid = false;
+    return same ? GAT_OK : encode_slot_maps(ctx, s);
+}
+
+// descriptor over the raw I/Q words: dims {n_samples, n_ants} of 32-bit elements, box {kTileCap, n_ants}
+int encode_raw_map(gat_ctx *ctx, SignalSlot &s)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(ctx, GAT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(s.n_samples), static_cast<cuuint64_t>(s.n_ants)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(s.raw_ld) * 4};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileCap), static_cast<cuuint32_t>(s.n_ants)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&s.raw_map.re, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, s.raw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, GAT_ERR_ALIGNMENT, "cuTensorMapEncodeTiled rejected the raw layout (CUresult " + std::to_string(r) + ")");
+    s.raw_map.im = s.raw_map.re;
+    return GAT_OK;
+}
+
+// expand the raw integer copy into FP32 planes if that has not happened yet
+int ensure_planes(gat_ctx *ctx, SignalSlot &s)
+{
+    if (s.planes_valid) return GAT_OK;
+    if (!s.raw_valid) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    int rc = own_slot(ctx, s, s.n_samples, s.n_ants, (static_cast<int64_t>(s.n_samples) + 3) & ~3LL, true);
+    if (rc) return rc;
+    cudaError_t e = launch_expand_sc(s.raw, 2, s.raw_ld, s.re, s.im, s.ld, s.n_samples, s.n_ants, s.raw_scale, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "expand_sc launch");
+    ctx->launches += 1;
+    return GAT_OK;
+}
+
 int check_ctx(gat_ctx *ctx)
 {
     if (!ctx) return GAT_ERR_INVALID;
@@ -450,24 +549,52 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     // signal slots
     std::vector<PeriodDev> periods(n_periods);
     int M = -1;
+    bool all_raw = true, all_planes = true;
+    float raw_scale = 1.f;
     for (int p = 0; p < n_periods; ++p) {
         const int s = slots[p];
-        if (s < 0 || s >= static_cast<int>(ctx->slots.size()) || !ctx->slots[s].re)
+        if (s < 0 || s >= static_cast<int>(ctx->slots.size()) || !(ctx->slots[s].planes_valid || ctx->slots[s].raw_valid))
             return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(s) + " has no signal");
         const SignalSlot &sl = ctx->slots[s];
         if (M < 0) M = sl.n_ants;
         if (sl.n_ants != M) return fail(ctx, GAT_ERR_INVALID, "all periods of a batch must have the same antenna count");
         if (static_cast<int64_t>(start_sample) + n_samples > sl.n_samples)
             return fail(ctx, GAT_ERR_INVALID, "sample range exceeds the signal in slot " + std::to_string(s));
-        if (!sl.maps_valid) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(s) + " has no TMA descriptor");
-        periods[p] = sl.maps;
+        if (p == 0) raw_scale = sl.raw_scale;
+        all_raw = all_raw && sl.raw_valid && sl.raw_scale == raw_scale;
+        all_planes = all_planes && sl.planes_valid;
     }
     if (M < 1 || M > kMaxAnts) return fail(ctx, GAT_ERR_UNSUPPORTED, "antenna count must be 1..32");
+    // Raw int16 tiles are read directly by the kernel: half the HBM bytes, and no expansion pass (4 B read +
+    // 8 B written per sample and antenna, ~1.5 us per 50000 x 16 block).  Every channel converts the words it
+    // reads, ~0.06 us per channel and block on the issue-bound loop, so: one channel per block always reads the
+    // raw words (219 us vs 250 us per 256 blocks); more channels do so only while nobody has paid for the FP32
+    // planes yet, up to 16 channels per block (break-even ~24).  The scale must be a power of two so that
+    // applying it to the accumulators is bit-identical to scaling every sample.
+    bool use_raw = false;
+    {
+        int mant_exp = 0;
+        const bool pow2 = raw_scale > 0.f && std::frexp(raw_scale, &mant_exp) == 0.5f;
+        const int pref = env_int("GAT_TUNE_RAW", -1);
+        const bool worth = n_sats <= 1 || (!all_planes && n_sats <= 16);
+        use_raw = all_raw && pow2 && !(flags & GAT_CODE_PHASE_F64) && (pref < 0 ? worth : pref != 0);
+    }
+    for (int p = 0; p < n_periods; ++p) {
+        SignalSlot &sl = ctx->slots[slots[p]];
+        if (use_raw) {
+            periods[p] = sl.raw_map;
+        } else {
+            rc = ensure_planes(ctx, sl);
+            if (rc) return rc;
+            if (!sl.maps_valid) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(slots[p]) + " has no TMA descriptor");
+            periods[p] = sl.maps;
+        }
+    }
 
     // channels
     const size_t n_ch = static_cast<size_t>(n_periods) * n_sats;
     std::vector<SatDev> sats(n_ch);
-    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1};
+    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1, use_raw};
     for (size_t i = 0; i < n_ch; ++i) {
         rc = fill_sat(ctx, channels[i], fs_hz, sats[i]);
         if (rc) return rc;
@@ -482,6 +609,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     rc = make_plan(ctx, shape, plan, args);
     if (rc) return rc;
     args.flags = flags;
+    args.out_scale = use_raw ? raw_scale : 1.f;
 
     // parameter block: [PeriodDev x P][SatDev x P*K]
     const size_t per_bytes = sizeof(PeriodDev) * n_periods;
@@ -601,42 +729,6 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     return GAT_OK;
 }
 
-SignalSlot *slot_for(gat_ctx *ctx, int slot)
-{
-    if (slot < 0 || slot >= 65536) return nullptr;
-    if (slot >= static_cast<int>(ctx->slots.size())) ctx->slots.resize(slot + 1);
-    return &ctx->slots[slot];
-}
-
-int release_slot(gat_ctx *ctx, SignalSlot &s)
-{
-    if (s.owned && s.re) {
-        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        GAT_CUDA(ctx, cudaFree(s.re));
-    }
-    s = SignalSlot{};
-    return GAT_OK;
-}
-
-// make `s` an owned slot able to hold n_ants x ld floats per plane (one allocation: re then im)
-int own_slot(gat_ctx *ctx, SignalSlot &s, int n_samples, int n_ants, int64_t ld)
-{
-    const size_t need = static_cast<size_t>(ld) * n_ants;
-    if (!s.owned || s.cap_floats < need) {
-        int rc = release_slot(ctx, s);
-        if (rc) return rc;
-        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&s.re), 2 * need * sizeof(float)));
-        s.cap_floats = need;
-        s.owned = true;
-    }
-    s.im = s.re + s.cap_floats;
-    const bool same = s.maps_valid && s.ld == ld && s.n_samples == n_samples && s.n_ants == n_ants;
-    s.ld = ld;
-    s.n_samples = n_samples;
-    s.n_ants = n_ants;
-    return same ? GAT_OK : encode_slot_maps(ctx, s);
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -724,8 +816,10 @@ int gat_destroy(gat_ctx *ctx)
     if (!ctx) return GAT_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &s : ctx->slots)
+    for (auto &s : ctx->slots) {
         if (s.owned && s.re) cudaFree(s.re);
+        if (s.raw) cudaFree(s.raw);
+    }
     for (auto &c : ctx->codes)
         if (c.d_chips) cudaFree(c.d_chips);
     for (auto &s : ctx->stg) {
@@ -797,7 +891,10 @@ int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, 
         return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
     SignalSlot *s = slot_for(ctx, slot);
     if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
-    if (!s->owned && s->re) *s = SignalSlot{};  // drop a zero-copy binding
+    if (!s->owned && s->re) {   // drop a zero-copy binding
+        rc = free_planes(ctx, *s);
+        if (rc) return rc;
+    }
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (ld % 4 == 0) {
         // same layout on both sides: one flat copy per plane
@@ -828,7 +925,37 @@ int upload_sc(gat_ctx *ctx, int slot, const void *iq, int bytes_per_component, i
         return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
     SignalSlot *s = slot_for(ctx, slot);
     if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
-    if (!s->owned && s->re) *s = SignalSlot{};  // drop a zero-copy binding
+    if (!s->owned && s->re) {   // drop a zero-copy binding
+        rc = free_planes(ctx, *s);
+        if (rc) return rc;
+    }
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (bytes_per_component == 2) {
+        // keep the raw words in the slot (rows padded to 4 samples); FP32 planes are produced only if a later
+        // call needs them (gat_correlate with many channels per block, gat_download_signal, ...)
+        const int64_t rld = (static_cast<int64_t>(n_samples) + 3) & ~3LL;
+        const size_t need = static_cast<size_t>(rld) * n_ants;
+        if (s->raw_cap < need) {
+            GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (s->raw) GAT_CUDA(ctx, cudaFree(s->raw));
+            s->raw = nullptr;
+            s->raw_cap = 0;
+            GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&s->raw), need * 4));
+            s->raw_cap = need;
+        }
+        GAT_CUDA(ctx, cudaMemcpy2DAsync(s->raw, static_cast<size_t>(rld) * 4, iq, static_cast<size_t>(ld) * 4,
+                                        static_cast<size_t>(n_samples) * 4, n_ants, kind, ctx->stream));
+        const bool same = s->raw_valid && s->raw_ld == rld && s->n_samples == n_samples && s->n_ants == n_ants;
+        // the FP32-plane descriptors describe the OLD shape: a later ensure_planes must not reuse them
+        if (s->n_samples != n_samples || s->n_ants != n_ants) s->maps_valid = false;
+        s->raw_ld = rld;
+        s->n_samples = n_samples;
+        s->n_ants = n_ants;
+        s->raw_scale = scale;
+        s->raw_valid = true;
+        s->planes_valid = false;
+        return same ? GAT_OK : encode_raw_map(ctx, *s);
+    }
     rc = own_slot(ctx, *s, n_samples, n_ants, (static_cast<int64_t>(n_samples) + 3) & ~3LL);
     if (rc) return rc;
     const void *d_src = iq;
@@ -836,7 +963,7 @@ int upload_sc(gat_ctx *ctx, int slot, const void *iq, int bytes_per_component, i
         const size_t bytes = (static_cast<size_t>(ld) * (n_ants - 1) + n_samples) * 2 * bytes_per_component;
         rc = ensure_device(ctx, ctx->d_raw, ctx->d_raw_cap, bytes, false);
         if (rc) return rc;
-        GAT_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw, iq, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        GAT_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw, iq, bytes, kind, ctx->stream));
         d_src = ctx->d_raw;
     }
     cudaError_t e = launch_expand_sc(d_src, bytes_per_component, ld, s->re, s->im, s->ld, n_samples, n_ants, scale, ctx->stream);
@@ -877,6 +1004,7 @@ int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im
     s->n_samples = n_samples;
     s->n_ants = n_ants;
     s->owned = false;
+    s->planes_valid = true;
     return encode_slot_maps(ctx, *s);
 }
 
@@ -894,14 +1022,20 @@ int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrie
     SignalSlot *s = slot_for(ctx, slot);
     if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
     if (superpose) {
-        if (!s->re || s->n_samples != n_samples || s->n_ants != n_ants)
+        if (!(s->planes_valid || s->raw_valid) || s->n_samples != n_samples || s->n_ants != n_ants)
             return fail(ctx, GAT_ERR_NO_SIGNAL, "superpose needs an existing slot of the same shape");
-    } else if (!(s->re && s->n_samples == n_samples && s->n_ants == n_ants)) {
+        rc = ensure_planes(ctx, *s);
+        if (rc) return rc;
+    } else if (!(s->planes_valid && s->re && s->n_samples == n_samples && s->n_ants == n_ants)) {
         // (a bound or owned slot of the right shape is generated into in place)
-        if (!s->owned && s->re) *s = SignalSlot{};
+        if (!s->owned && s->re) {
+            rc = free_planes(ctx, *s);
+            if (rc) return rc;
+        }
         rc = own_slot(ctx, *s, n_samples, n_ants, (static_cast<int64_t>(n_samples) + 3) & ~3LL);
         if (rc) return rc;
     }
+    s->raw_valid = false;   // the planes are about to change
     // code frequency of the system: the built-ins carry theirs; caller tables pass it via prn-independent ratio
     const double code_freq = (system_id == GAT_GPSL5) ? 10.23e6 : 1.023e6;
     cudaError_t e = launch_gen_signal(s->re, s->im, s->ld, t.d_chips + static_cast<size_t>(prn - 1) * t.col_stride, t.code_len,
@@ -916,8 +1050,11 @@ int gat_download_signal(gat_ctx *ctx, int slot, float *re, float *im)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (!re || !im || slot < 0 || slot >= static_cast<int>(ctx->slots.size()) || !ctx->slots[slot].re)
+    if (!re || !im || slot < 0 || slot >= static_cast<int>(ctx->slots.size()) ||
+        !(ctx->slots[slot].planes_valid || ctx->slots[slot].raw_valid))
         return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    rc = ensure_planes(ctx, ctx->slots[slot]);
+    if (rc) return rc;
     const SignalSlot &s = ctx->slots[slot];
     const size_t w = static_cast<size_t>(s.n_samples) * sizeof(float);
     GAT_CUDA(ctx, cudaMemcpy2DAsync(re, w, s.re, s.ld * sizeof(float), w, s.n_ants, cudaMemcpyDeviceToHost, ctx->stream));

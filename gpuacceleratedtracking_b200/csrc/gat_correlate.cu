@@ -52,11 +52,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Watchdog: a wait that lasts seconds means a broken launch (a descriptor whose box does not match the
+// expected byte count, a lost arrival).  Trap -> the host sees a CUDA error instead of a hung device.
+// Only the retry path pays for it.
+constexpr uint64_t kWaitLimitNs = 4000000000ull;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    while (!done) {
+    uint64_t t0 = 0;
+    while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -64,6 +75,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (done) break;
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kWaitLimitNs) __trap();
     }
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit).
@@ -119,6 +134,31 @@ __device__ __forceinline__ float lds_f32(const float *p)
     asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(const float *p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+    return v;
+}
+// int16 -> float.  GAT_S16_MODE 0 (default): sign-extending byte permute / arithmetic shift, then I2FP (ALU pipe).
+// GAT_S16_MODE 1: offset-binary magic-number conversion (LOP3 + PRMT under the exponent of 2^23, then one packed
+// FADD removes the bias for two antennas).  Measured on B200, 256 periods x 16 antennas x 3 taps: mode 0 265 us,
+// mode 1 277 us, (float)(short) -> I2F.S16 265 us: the loop is issue-bound, so the variant with the fewest
+// FMA-pipe instructions wins; kept for the record.
+#ifndef GAT_S16_MODE
+#define GAT_S16_MODE 0
+#endif
+[[maybe_unused]] constexpr float kS16Bias = 8388608.f + 32768.f;
+__device__ __forceinline__ uint32_t s16_flip(uint32_t w) { return w ^ 0x80008000u; }
+__device__ __forceinline__ float s16_lo_biased(uint32_t wf) { return __uint_as_float(__byte_perm(wf, 0x4B000000u, 0x7410)); }   // I
+__device__ __forceinline__ float s16_hi_biased(uint32_t wf) { return __uint_as_float(__byte_perm(wf, 0x4B000000u, 0x7432)); }   // Q
+__device__ __forceinline__ float s16_lo(uint32_t w)   // sign-extending permute (selector msb = replicate the byte's sign) + I2FP
+{
+    int v;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(v) : "r"(w));
+    return (float)v;
+}
+__device__ __forceinline__ float s16_hi(uint32_t w) { return (float)((int)w >> 16); }
 __device__ __forceinline__ float lds_f32_at(uint32_t smem_addr)
 {
     float v;
@@ -141,6 +181,12 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 {
     f32x2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
@@ -259,6 +305,7 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
     if (kk >= K || m >= M) return;
     const size_t idx = (((size_t)p * K + kk) * L + l) * M + m;
     float *dst = (c ? args.out_im : args.out_re) + idx;
+    val *= args.out_scale;             // raw integer tiles: the (power-of-two) sample scale is applied once, here
     if (args.flags & 1u) val += *dst;  // GAT_ACCUMULATE
     *dst = val;
     if (args.n_peers > 1) {
@@ -273,7 +320,9 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
 // --------------------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------------------
-template <int A, int L, bool F64>
+// SC16: the staged tile holds raw interleaved complex int16 samples (one 32-bit word = I | Q << 16 per
+// sample and antenna, a single plane) instead of two FP32 planes; they are converted in registers.
+template <int A, int L, bool F64, bool SC16>
 __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -296,7 +345,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     uint64_t *code_bar = reinterpret_cast<uint64_t *>(smem + 256);   // chip-table bulk copies, one phase per segment
     const bool split = args.split_tiles != 0;
     float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
-    const int tile_floats = 2 * MP * kTileCap;
+    const int tile_floats = (SC16 ? 1 : 2) * MP * kTileCap;   // 32-bit words per stage
     float *part = tiles + (size_t)stages * tile_floats;                               // [W][RP]
     float *rep_all = part + (size_t)W * RP;                                           // [W][rep_stride]
     int8_t *code_cache = reinterpret_cast<int8_t *>(rep_all + (size_t)W * args.rep_stride);  // [S][cache_stride]
@@ -313,11 +362,12 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     // antenna rows that pad M up to AG*A are never written by the copies: keep them zero
     if (MP > M) {
         const int pad_rows = MP - M;
-        for (int i = tid; i < stages * 2 * pad_rows * kTileCap; i += blockDim.x) {
+        constexpr int kPlanes = SC16 ? 1 : 2;
+        for (int i = tid; i < stages * kPlanes * pad_rows * kTileCap; i += blockDim.x) {
             const int col = i % kTileCap;
             const int row = (i / kTileCap) % pad_rows;
-            const int plane = (i / (kTileCap * pad_rows)) % 2;
-            const int st = i / (kTileCap * pad_rows * 2);
+            const int plane = (i / (kTileCap * pad_rows)) % kPlanes;
+            const int st = i / (kTileCap * pad_rows * kPlanes);
             tiles[(size_t)st * tile_floats + (size_t)(plane * MP + M + row) * kTileCap + col] = 0.f;
         }
     }
@@ -367,10 +417,11 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 const int ts_rel = t * tile_len;  // relative to aligned_start
                 if (lane == 0) {
                     // full boxes always: samples past the block end arrive as zeros and still count
-                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * M * kTileCap * 4));
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)((SC16 ? 1 : 2) * M * kTileCap * 4));
                     float *stage_tile = tiles + (size_t)stage * tile_floats;
-                    tma_load_2d(stage_tile, &per->re, args.aligned_start + ts_rel, 0, &full_bar[stage]);
-                    tma_load_2d(stage_tile + (size_t)MP * kTileCap, &per->im, args.aligned_start + ts_rel, 0, &full_bar[stage]);
+                    tma_load_2d(stage_tile, &per->re, args.aligned_start + ts_rel, 0, &full_bar[stage]);   // SC16: the I/Q words
+                    if constexpr (!SC16)
+                        tma_load_2d(stage_tile + (size_t)MP * kTileCap, &per->im, args.aligned_start + ts_rel, 0, &full_bar[stage]);
                 }
                 if (t == t_first) {
                     // chip tables AFTER the first tile is in flight; code_bar completes one phase per
@@ -550,8 +601,21 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                         f32x2 X[AP], Y[AP];
 #pragma unroll
                         for (int a = 0; a < AP; ++a) {
-                            X[a] = pack2(lds_f32(tre + (2 * a) * kTileCap + tt), lds_f32(tre + (2 * a + 1) * kTileCap + tt));
-                            Y[a] = pack2(lds_f32(tim + (2 * a) * kTileCap + tt), lds_f32(tim + (2 * a + 1) * kTileCap + tt));
+                            if constexpr (SC16) {
+                                const uint32_t w0 = lds_u32(tre + (2 * a) * kTileCap + tt), w1 = lds_u32(tre + (2 * a + 1) * kTileCap + tt);
+#if GAT_S16_MODE == 1
+                                const uint32_t f0 = s16_flip(w0), f1 = s16_flip(w1);
+                                const f32x2 NB = pack2(-kS16Bias, -kS16Bias);
+                                X[a] = add2(pack2(s16_lo_biased(f0), s16_lo_biased(f1)), NB);
+                                Y[a] = add2(pack2(s16_hi_biased(f0), s16_hi_biased(f1)), NB);
+#else
+                                X[a] = pack2(s16_lo(w0), s16_lo(w1));
+                                Y[a] = pack2(s16_hi(w0), s16_hi(w1));
+#endif
+                            } else {
+                                X[a] = pack2(lds_f32(tre + (2 * a) * kTileCap + tt), lds_f32(tre + (2 * a + 1) * kTileCap + tt));
+                                Y[a] = pack2(lds_f32(tim + (2 * a) * kTileCap + tt), lds_f32(tim + (2 * a + 1) * kTileCap + tt));
+                            }
                         }
 #pragma unroll
                         for (int a = 0; a < AP; ++a) {
@@ -566,7 +630,15 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                             }
                         }
                     } else {
-                        const float xr = tre[tt], xi = tim[tt];
+                        float xr, xi;
+                        if constexpr (SC16) {
+                            const uint32_t w = lds_u32(tre + tt);
+                            xr = s16_lo(w);
+                            xi = s16_hi(w);
+                        } else {
+                            xr = tre[tt];
+                            xi = tim[tt];
+                        }
                         const float dre = fmaf(xi, ci, xr * cr);
                         const float dim = fmaf(-xr, ci, xi * cr);
 #pragma unroll
@@ -637,8 +709,10 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     if (tid == 0) {
         atomicAdd(args.grid_barrier, 1u);
         unsigned int seen;
+        const uint64_t t0 = global_timer_ns();
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(args.grid_barrier) : "memory");
+            if ((int)(seen - args.barrier_target) < 0 && global_timer_ns() - t0 > 5 * kWaitLimitNs) __trap();
         } while ((int)(seen - args.barrier_target) < 0);
     }
     consumer_bar_sync(consumer_threads);
@@ -706,15 +780,16 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
 typedef void (*KernelFn)(const CorrArgs);
 
 template <int A, int L>
-static KernelFn pick_mode(bool f64)
+static KernelFn pick_mode(bool f64, bool sc16)
 {
-    return f64 ? (KernelFn)correlate_kernel<A, L, true> : (KernelFn)correlate_kernel<A, L, false>;
+    if (sc16) return f64 ? nullptr : (KernelFn)correlate_kernel<A, L, false, true>;   // raw tiles: NCO convention only
+    return f64 ? (KernelFn)correlate_kernel<A, L, true, false> : (KernelFn)correlate_kernel<A, L, false, false>;
 }
 
-static KernelFn pick_kernel(int A, int L, bool f64)
+static KernelFn pick_kernel(int A, int L, bool f64, bool sc16)
 {
 #define GAT_CASE(a, l) \
-    if (A == a && L == l) return pick_mode<a, l>(f64);
+    if (A == a && L == l) return pick_mode<a, l>(f64, sc16);
     GAT_CASE(1, 1) GAT_CASE(2, 1) GAT_CASE(4, 1) GAT_CASE(8, 1) GAT_CASE(16, 1)
     GAT_CASE(1, 3) GAT_CASE(2, 3) GAT_CASE(4, 3) GAT_CASE(8, 3) GAT_CASE(16, 3)
     GAT_CASE(1, 5) GAT_CASE(2, 5) GAT_CASE(4, 5) GAT_CASE(8, 5)
@@ -725,7 +800,7 @@ static KernelFn pick_kernel(int A, int L, bool f64)
     return nullptr;
 }
 
-bool kernel_available(int A, int L) { return pick_kernel(A, L, false) != nullptr; }
+bool kernel_available(int A, int L) { return pick_kernel(A, L, false, false) != nullptr; }
 
 cudaError_t configure_kernels()
 {
@@ -733,8 +808,8 @@ cudaError_t configure_kernels()
     static const int Ls[] = {1, 3, 5, 7, 9, 11};
     for (int A : As)
         for (int L : Ls)
-            for (int f = 0; f < 2; ++f) {
-                KernelFn fn = pick_kernel(A, L, f != 0);
+            for (int f = 0; f < 3; ++f) {
+                KernelFn fn = pick_kernel(A, L, f == 1, f == 2);
                 if (!fn) continue;
                 cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 if (e != cudaSuccess) return e;
@@ -744,7 +819,7 @@ cudaError_t configure_kernels()
 
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream)
 {
-    KernelFn fn = pick_kernel(plan.A, plan.L, plan.f64);
+    KernelFn fn = pick_kernel(plan.A, plan.L, plan.f64, plan.sc16);
     if (!fn) return cudaErrorInvalidValue;
     // Cooperative launch: the kernel ends with a grid-wide counting barrier, so all CTAs must be
     // co-resident.  grid <= #SMs with one CTA per SM satisfies that on an idle device; the cooperative

@@ -68,6 +68,7 @@ struct alignas(64) CorrArgs {
     int32_t rep_stride;                // floats per consumer warp for its code replica (>= tile_len + span)
     int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
+    float out_scale;                   // multiplies every accumulator at emit (1 unless raw integer tiles carry a scale)
     int32_t fin_group;                 // lanes cooperating on one output element in the finalize (pow2 <= 32)
     int32_t split_tiles;               // 1: every slice works on every tile (small problems); 0: whole tiles round-robin
     uint32_t flags;
@@ -88,6 +89,7 @@ struct LaunchPlan {
     int A;            // antennas per thread (template)
     int L;            // taps (template)
     bool f64;
+    bool sc16;        // raw int16 I/Q tiles
     int grid, block;
     size_t smem;
     int RP;           // padded accumulators per role
@@ -95,7 +97,7 @@ struct LaunchPlan {
 };
 
 // smem carve-up, shared by host sizing and device addressing
-__host__ __device__ inline size_t smem_tile_floats(int AG, int A) { return (size_t)2 * AG * A * kTileCap; }
+__host__ __device__ inline size_t smem_tile_floats(int AG, int A, bool sc16 = false) { return (size_t)(sc16 ? 1 : 2) * AG * A * kTileCap; }
 __host__ __device__ inline int padded_acc(int A, int L) { return ((2 * A * L) + 31) / 32 * 32; }
 
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream);

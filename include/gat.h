@@ -116,9 +116,13 @@ int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im,
 int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im,
                     int n_samples, int n_ants, int ld);
 /* Integer front-end samples: interleaved complex (I, Q) int16 / int8 per antenna, antenna-major
- * [n_ants][ld][2] with `ld` in complex samples -- the usual SDR wire format.  The raw block (2-4x fewer
- * bytes than FP32) is copied to the device and a kernel expands it into the slot's FP32 planes as
- * (float)x * scale, so everything downstream is unchanged.  scale = 1 keeps the integers exact. */
+ * [n_ants][ld][2] with `ld` in complex samples -- the usual SDR wire format (2-4x fewer bytes than FP32).
+ * Results are those of FP32 planes holding (float)x * scale; scale = 1 keeps the integers exact.
+ *  - int16: the slot keeps the raw words in HBM.  gat_correlate* reads them directly (conversion in
+ *    registers, `scale` applied to the accumulators) when scale is a power of two, the NCO code-phase
+ *    convention is used and at most 16 channels share the block; otherwise, and for gat_download_signal /
+ *    gat_gen_signal(superpose), the FP32 planes are expanded once on first need.
+ *  - int8: expanded to FP32 planes by a streaming kernel at upload. */
 int gat_upload_signal_sc16(gat_ctx *ctx, int slot, const int16_t *iq, int n_samples, int n_ants, int ld,
                            float scale, int src_is_device);
 int gat_upload_signal_sc8(gat_ctx *ctx, int slot, const int8_t *iq, int n_samples, int n_ants, int ld,
@@ -178,6 +182,7 @@ typedef struct gat_launch_info {
     int32_t ants_per_thread, ant_groups, sats_per_cta, sample_slices, consumer_warps;
     int32_t sat_groups, chunks_per_job, chunk_len, tile_len, stages, items;
     int32_t kernels_launched;   /* kernels of OURS enqueued by the last correlate call */
+    int32_t sc16;               /* 1 if the kernel read raw int16 I/Q words (gat_upload_signal_sc16 slots) */
     float last_kernel_ms;       /* device time of the last correlate kernel if timing enabled */
 } gat_launch_info;
 int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out);

@@ -488,9 +488,10 @@ def test_caller_supplied_code_table(gat, orc, engine):
 
 
 @pytest.mark.parametrize("dtype,scale", [(np.int16, 1.0), (np.int16, 1.0 / 2048), (np.int8, 1.0), (np.int8, 0.125)])
-def test_integer_ingest(gat, orc, engine, dtype, scale):
+def test_integer_ingest(gat, orc, engine, dtype, scale, monkeypatch):
     """interleaved complex int16 / int8 front-end samples expanded on the device."""
     import torch
+    monkeypatch.setenv("GAT_TUNE_STAGES", "6")      # one launch plan for the FP32 and the raw-int16 kernels
     rng = np.random.default_rng(7)
     l1 = gat.GPSL1()
     n, m, fs = 10003, 5, 1.0e7
@@ -519,3 +520,84 @@ def test_integer_ingest(gat, orc, engine, dtype, scale):
     ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
                                          c.carrier_phase, fs, shifts) for c in chans])
     assert np.abs(got - ref).max() <= TOL * np.abs(ref[:, 1]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_ch,m,taps", [(1, 4, 3), (2, 1, 3), (1, 16, 3), (6, 4, 3), (2, 3, 5), (1, 2, 11)])
+def test_int16_fused_vs_expanded(gat, orc, engine, monkeypatch, n_ch, m, taps):
+    """the kernel reading raw int16 I/Q words gives the bits of the expand-then-correlate path,
+    for an offset / ragged sample range and a multi-period batch."""
+    rng = np.random.default_rng(100 + n_ch * 7 + m)
+    l1 = gat.GPSL1()
+    n, fs, start = 5011, 5.0e6, 37
+    P = 3
+    iq = rng.integers(-2047, 2048, size=(P, m, n + start + 9, 2)).astype(np.int16)
+    scale = 1.0 / 2048
+    chans = [[gat.Channel(l1, 1 + (3 * p + k) % 32, rng.uniform(0, 1023), rng.uniform(-5e3, 5e3), rng.uniform(-0.5, 0.5))
+              for k in range(n_ch)] for p in range(P)]
+    shifts = np.arange(-(taps // 2), taps // 2 + 1, dtype=np.int32) * 2
+    for p in range(P):
+        engine.upload_signal_int(10 + p, iq[p], scale)
+    slots = [10 + p for p in range(P)]
+    out = {}
+    monkeypatch.setenv("GAT_TUNE_STAGES", "6")      # same launch plan for both -> same summation order -> same bits
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GAT_TUNE_RAW", mode)
+        out[mode] = engine.correlate_batch(slots, chans, fs, shifts, m, start_sample=start, n_samples=n).copy()
+        info = engine.launch_info()
+        assert info["sc16"] == int(mode)
+    monkeypatch.delenv("GAT_TUNE_RAW")
+    monkeypatch.delenv("GAT_TUNE_STAGES")
+    assert np.array_equal(out["0"].view(np.uint64), out["1"].view(np.uint64))
+    out["1"] = engine.correlate_batch(slots, chans, fs, shifts, m, start_sample=start, n_samples=n).copy()   # default plan
+    re = iq[..., 0].astype(np.float32) * np.float32(scale)
+    im = iq[..., 1].astype(np.float32) * np.float32(scale)
+    for p in range(P):
+        for k, c in enumerate(chans[p]):
+            ref = orc.correlate_direct(re[p][:, start:start + n].copy(), im[p][:, start:start + n].copy(), l1.codes[c.prn - 1],
+                                       1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase, fs, shifts)
+            assert np.abs(out["1"][p, k] - ref).max() <= TOL * np.abs(ref[taps // 2]).max() + 1e-3
+
+
+@pytest.mark.gpu
+def test_int16_non_pow2_scale_and_f64_fall_back(gat, orc, engine):
+    """A scale that is not a power of two, or the Float64 chip-index mode, takes the expanded FP32 planes."""
+    rng = np.random.default_rng(5)
+    l1 = gat.GPSL1()
+    n, m, fs = 4000, 2, 4.0e6
+    iq = rng.integers(-500, 500, size=(m, n, 2)).astype(np.int16)
+    chans = [gat.Channel(l1, 3, 10.5, 800.0, 0.2)]
+    shifts = np.array([-1, 0, 1], np.int32)
+    engine.upload_signal_int(0, iq, 0.3)
+    engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    assert engine.launch_info()["sc16"] == 0
+    engine.upload_signal_int(0, iq, 0.25)
+    engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    assert engine.launch_info()["sc16"] == 1
+    engine.correlate(0, chans, fs, shifts, m, n_samples=n, code_phase_f64=True)
+    assert engine.launch_info()["sc16"] == 0
+    # generating on top of a raw block expands it first and invalidates the raw copy
+    engine.upload_signal_int(0, iq, 0.25)
+    engine.gen_signal(0, l1, 3, 800.0, fs, n, m, start_code_phase=10.5, superpose=True)
+    engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    assert engine.launch_info()["sc16"] == 0
+
+
+@pytest.mark.gpu
+def test_int16_slot_reshape(gat, orc, engine, monkeypatch):
+    """Re-uploading a raw block with another antenna count into a slot whose FP32 planes were already
+    materialised must re-encode the plane descriptors (regression: stale box -> byte-count mismatch)."""
+    rng = np.random.default_rng(9)
+    l1 = gat.GPSL1()
+    n, fs = 3001, 3.0e6
+    shifts = np.array([-1, 0, 1], np.int32)
+    chans = [gat.Channel(l1, 8, 77.7, -1200.0, 0.3)]
+    monkeypatch.setenv("GAT_TUNE_RAW", "0")
+    for m in (4, 1, 3, 4):
+        iq = rng.integers(-1000, 1000, size=(m, n, 2)).astype(np.int16)
+        engine.upload_signal_int(20, iq, 0.5)
+        got = engine.correlate(20, chans, fs, shifts, m, n_samples=n)
+        re = iq[..., 0].astype(np.float32) * np.float32(0.5)
+        im = iq[..., 1].astype(np.float32) * np.float32(0.5)
+        ref = orc.correlate_direct(re, im, l1.codes[7], 1.023e6, 77.7, -1200.0, 0.3, fs, shifts)
+        assert np.abs(got[0] - ref).max() <= TOL * np.abs(ref[1]).max() + 1e-3
