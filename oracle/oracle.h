@@ -93,6 +93,13 @@ int orc_correlate_tracking_batch(const float *re, const float *im, int64_t perio
                                  double fs_hz, const int32_t *shifts, int n_taps,
                                  int n_threads, float *out_re, float *out_im);
 
+/* minimum wall time [ns] over `reps` single-thread orc_correlate_tracking calls (timed CPU baseline of the
+ * reference's per-call sweep, src/benchmarks.jl:63-79 + BenchmarkTools minimum, paper/paper.tex:150) */
+double orc_time_tracking(const float *re, const float *im, int ld, int n_ants, int n_samples,
+                         const int8_t *code, int code_len, double code_freq_hz, double code_phase,
+                         double carrier_freq_hz, double carrier_phase_cycles, double fs_hz,
+                         const int32_t *shifts, int n_taps, int reps, float *out_re, float *out_im);
+
 /* ---- tracking loop pieces [upstream Tracking.jl / TrackingLoopFilters.jl, SURVEY A.3]
  *      PARITY UNPINNED.  State layout documented in oracle.c. ---------------------- */
 typedef struct {

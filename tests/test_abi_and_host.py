@@ -167,3 +167,33 @@ def test_sharded_correlate_world_size_2_gloo():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _build_c_example():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "examples"), "abi_latency"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return os.path.join(root, "examples", "abi_latency")
+
+
+def test_c_caller_links_and_fails_loudly_without_a_device(gat):
+    """A plain-C program (no CUDA headers, no Python) links against include/gat.h + libgat.so; on a machine
+    without an sm_100 GPU gat_create reports GAT_ERR_NO_DEVICE instead of falling back to anything."""
+    import subprocess
+    exe = _build_c_example()
+    if gat.load().gat_device_count() > 0:
+        pytest.skip("a GPU is visible: covered by the gpu tier")
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_caller_runs_the_sweep():
+    import json
+    import subprocess
+    exe = _build_c_example()
+    r = subprocess.run([exe, "20"], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [json.loads(line) for line in r.stdout.splitlines()]
+    assert len(rows) == 48 and all(0 < row["resident_call_ns"] < 1e6 for row in rows)   # every shape in real time

@@ -465,6 +465,11 @@ def test_error_statuses(gat, orc):
     bad = np.ones((1, 100), np.int8) * 3
     lib = gat.load()
     assert lib.gat_set_codes(eng._h, 3, bad.ctypes.data_as(C.POINTER(C.c_int8)), 100, 1) == _lib.GAT_ERR_INVALID
+    # failures detected late in the call (after the launch plan exists) must not desynchronise the grid
+    # barrier bookkeeping: the next launch would otherwise wait forever
+    assert status(lambda: eng.correlate_batch([0], [ch], 2.5e6, shifts, 2, n_samples=2500, gather=True)) == _lib.GAT_ERR_INVALID
+    dev_out = (torch.zeros(1, 1, 2, 2, device="cuda"), torch.zeros(1, 1, 2, 2, device="cuda"))
+    assert status(lambda: eng.correlate(0, ch, 2.5e6, [-1, 1], 2, n_samples=2500, out=dev_out, accumulate=True)) == _lib.GAT_ERR_UNSUPPORTED
     # the context is still usable after every failure
     got = eng.correlate(0, ch, 2.5e6, shifts, 2, n_samples=2500)
     assert np.allclose(got[0].real, np.array([1476, 2500, 1476])[:, None], rtol=3.5e-4)
