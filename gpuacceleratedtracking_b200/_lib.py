@@ -16,6 +16,7 @@ GAT_ACCUMULATE = 1
 GAT_CODE_PHASE_F64 = 2
 GAT_GATHER = 4
 GAT_IPC_HANDLE_BYTES = 64
+GAT_SLOT_DESC_BYTES = 96
 GAT_GPSL1, GAT_GPSL5 = 0, 1
 GAT_MAX_TAPS = 11
 GAT_MAX_ANTS = 32
@@ -63,10 +64,13 @@ SYMBOLS = {
     "gat_bind_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
     "gat_gen_signal": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _i, _i, _d, _d, C.c_uint64, _i]),
     "gat_download_signal": (_i, [_vp, _i, _vp, _vp]),
+    "gat_slot_export": (_i, [_vp, _i, C.POINTER(C.c_ubyte)]),
+    "gat_slot_import": (_i, [_vp, _i, C.POINTER(C.c_ubyte)]),
     "gat_correlate": (_i, [_vp, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _i, _u]),
     "gat_correlate_batch": (_i, [_vp, _i, _i32p, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _i, _u]),
     "gat_downconvert_and_correlate": (_i, [_vp, _vp, _vp, _i, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _u]),
     "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
+    "gat_set_max_ctas": (_i, [_vp, _i]),
     "gat_set_timing": (_i, [_vp, _i]),
     "gat_kernel_launch_count": (C.c_uint64, [_vp]),
     "gat_gather_create": (_i, [_vp, _i, _i, C.c_uint64, C.POINTER(C.c_ubyte)]),

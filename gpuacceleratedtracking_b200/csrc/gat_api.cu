@@ -32,6 +32,7 @@ struct SignalSlot {
     float raw_scale = 1.f;
     bool raw_valid = false;
     PeriodDev raw_map{};         // .re = 2-D descriptor over the 32-bit I/Q words
+    void *peer_base = nullptr;   // gat_slot_import: another process's planes mapped through CUDA IPC (closed on release)
 };
 
 struct CodeTable {
@@ -55,6 +56,7 @@ constexpr int kStagingRing = 8;
 struct gat_ctx {
     int device = 0;
     int n_sm = 0;
+    int max_ctas = 0;   // gat_set_max_ctas: 0 = one CTA on every SM
     cudaStream_t stream = nullptr;      // the stream work is queued on
     cudaStream_t own_stream = nullptr;  // created by gat_create
     cudaStream_t param_stream = nullptr;  // parameter-block uploads, overlapping the previous kernel
@@ -321,6 +323,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
 
     const int ctas_per_sm = 1;
     int grid = static_cast<int>(std::min<int64_t>(total_tiles, static_cast<int64_t>(ctx->n_sm) * ctas_per_sm));
+    if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
     grid = std::max(1, std::min(grid, env_int("GAT_TUNE_GRID", grid)));
 
     plan.A = A;
@@ -441,6 +444,11 @@ int free_planes(gat_ctx *ctx, SignalSlot &s)
     if (s.owned && s.re) {
         GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         GAT_CUDA(ctx, cudaFree(s.re));
+    }
+    if (s.peer_base) {
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GAT_CUDA(ctx, cudaIpcCloseMemHandle(s.peer_base));
+        s.peer_base = nullptr;
     }
     s.re = s.im = nullptr;
     s.ld = 0;
@@ -843,6 +851,7 @@ int gat_destroy(gat_ctx *ctx)
     for (auto &s : ctx->slots) {
         if (s.owned && s.re) cudaFree(s.re);
         if (s.raw) cudaFree(s.raw);
+        if (s.peer_base) cudaIpcCloseMemHandle(s.peer_base);
     }
     for (auto &c : ctx->codes)
         if (c.d_chips) cudaFree(c.d_chips);
@@ -1032,6 +1041,66 @@ int gat_bind_signal(gat_ctx *ctx, int slot, const float *d_re, const float *d_im
     return encode_slot_maps(ctx, *s);
 }
 
+namespace {
+struct SlotDesc {                    // the opaque GAT_SLOT_DESC_BYTES blob of gat_slot_export / gat_slot_import
+    cudaIpcMemHandle_t handle;       // of the allocation holding both planes
+    uint64_t im_offset_bytes;
+    int64_t ld;
+    int32_t n_samples, n_ants;
+    uint32_t magic, reserved;
+};
+static_assert(sizeof(SlotDesc) == GAT_SLOT_DESC_BYTES, "slot descriptor layout");
+constexpr uint32_t kSlotMagic = 0x47415453u;
+}  // namespace
+
+int gat_slot_export(gat_ctx *ctx, int slot, unsigned char *desc_out)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!desc_out || slot < 0 || slot >= static_cast<int>(ctx->slots.size()) ||
+        !(ctx->slots[slot].planes_valid || ctx->slots[slot].raw_valid))
+        return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    SignalSlot &s = ctx->slots[slot];
+    rc = ensure_planes(ctx, s);
+    if (rc) return rc;
+    if (!s.owned) return fail(ctx, GAT_ERR_INVALID, "only ctx-owned slots (gat_upload_signal*, gat_gen_signal) can be exported");
+    SlotDesc d{};
+    GAT_CUDA(ctx, cudaIpcGetMemHandle(&d.handle, s.re));
+    d.im_offset_bytes = static_cast<uint64_t>(s.cap_floats) * sizeof(float);
+    d.ld = s.ld;
+    d.n_samples = s.n_samples;
+    d.n_ants = s.n_ants;
+    d.magic = kSlotMagic;
+    std::memcpy(desc_out, &d, sizeof(d));
+    return GAT_OK;
+}
+
+int gat_slot_import(gat_ctx *ctx, int slot, const unsigned char *desc)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!desc) return fail(ctx, GAT_ERR_INVALID, "null descriptor");
+    SlotDesc d;
+    std::memcpy(&d, desc, sizeof(d));
+    if (d.magic != kSlotMagic || d.n_samples < 1 || d.n_ants < 1 || d.n_ants > kMaxAnts || d.ld < d.n_samples || d.ld % 4 != 0)
+        return fail(ctx, GAT_ERR_INVALID, "not a slot descriptor");
+    SignalSlot *s = slot_for(ctx, slot);
+    if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
+    rc = release_slot(ctx, *s);
+    if (rc) return rc;
+    void *base = nullptr;
+    GAT_CUDA(ctx, cudaIpcOpenMemHandle(&base, d.handle, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_base = base;
+    s->re = static_cast<float *>(base);
+    s->im = reinterpret_cast<float *>(static_cast<unsigned char *>(base) + d.im_offset_bytes);
+    s->ld = d.ld;
+    s->n_samples = d.n_samples;
+    s->n_ants = d.n_ants;
+    s->owned = false;
+    s->planes_valid = true;
+    return encode_slot_maps(ctx, *s);
+}
+
 int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrier_freq_hz, double fs_hz,
                    double start_code_phase, double start_carrier_phase_rad, int n_samples, int n_ants,
                    double ant_phase_step_rad, double noise_sigma, uint64_t seed, int superpose)
@@ -1127,6 +1196,13 @@ int gat_set_timing(gat_ctx *ctx, int enable)
 {
     if (!ctx) return GAT_ERR_INVALID;
     ctx->timing = enable != 0;
+    return GAT_OK;
+}
+
+int gat_set_max_ctas(gat_ctx *ctx, int max_ctas)
+{
+    if (!ctx || max_ctas < 0) return GAT_ERR_INVALID;
+    ctx->max_ctas = max_ctas;
     return GAT_OK;
 }
 

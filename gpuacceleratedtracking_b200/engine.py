@@ -95,6 +95,10 @@ class Engine:
         else:
             self._check(self._lib.gat_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
+    def set_max_ctas(self, n: int):
+        """Cap the persistent kernel's grid so that concurrent communication kernels find free SMs (0 = all)."""
+        self._check(self._lib.gat_set_max_ctas(self._h, int(n)))
+
     def set_timing(self, on: bool):
         self._check(self._lib.gat_set_timing(self._h, int(on)))
 
@@ -190,6 +194,17 @@ class Engine:
         self._check(self._lib.gat_gen_signal(self._h, slot, system.system_id, prn, carrier_frequency, fs,
                                              start_code_phase, start_carrier_phase, n_samples, n_ants,
                                              ant_phase_step, noise_sigma, seed, int(superpose)))
+
+    def export_slot(self, slot: int) -> bytes:
+        """Opaque descriptor of a ctx-owned slot for gat_slot_import in ANOTHER process (multi-GPU ingest
+        without a broadcast: the importer's kernel reads the tiles over NVLink)."""
+        d = (C.c_ubyte * _lib.GAT_SLOT_DESC_BYTES)()
+        self._check(self._lib.gat_slot_export(self._h, slot, d))
+        return bytes(d)
+
+    def import_slot(self, slot: int, desc: bytes):
+        arr = (C.c_ubyte * _lib.GAT_SLOT_DESC_BYTES).from_buffer_copy(desc)
+        self._check(self._lib.gat_slot_import(self._h, slot, arr))
 
     def download_signal(self, slot: int, n_samples: int, n_ants: int):
         re = np.empty((n_ants, n_samples), np.float32)

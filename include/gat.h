@@ -138,6 +138,17 @@ int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrie
 /* Copy a slot's planes back (tests): host column-major [n_samples x n_ants], ld = n_samples. */
 int gat_download_signal(gat_ctx *ctx, int slot, float *re, float *im);
 
+/* Multi-GPU ingest without a broadcast (one process per GPU, same node): the ingest process exports a
+ * ctx-owned slot as an opaque descriptor (CUDA IPC handle + layout) that the host passes to the other
+ * processes by any means; gat_slot_import maps it and binds it like gat_bind_signal, so a correlate call
+ * on that rank TMA-loads its signal tiles straight out of the ingest GPU's HBM over NVLink -- the transfer
+ * is fused into the kernel's own tile pipeline, no receive buffer, no extra HBM write + read.  The exporter
+ * keeps ownership and must not rewrite the slot while importers still read it (host-level ordering, e.g. a
+ * barrier or an event); the importer releases the mapping by re-using or destroying the slot. */
+#define GAT_SLOT_DESC_BYTES 96
+int gat_slot_export(gat_ctx *ctx, int slot, unsigned char *desc_out /* [GAT_SLOT_DESC_BYTES] */);
+int gat_slot_import(gat_ctx *ctx, int slot, const unsigned char *desc /* [GAT_SLOT_DESC_BYTES] */);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* One integration period: n_sats channels over the same signal block.
  *   out_re/out_im: [n_ants x n_taps x n_sats].  out_is_device = 0: host pointers, the call
@@ -186,6 +197,11 @@ typedef struct gat_launch_info {
     float last_kernel_ms;       /* device time of the last correlate kernel if timing enabled */
 } gat_launch_info;
 int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out);
+/* The correlate kernel is persistent: one CTA per SM, all SMs.  A communication kernel that should run
+ * CONCURRENTLY (an NCCL broadcast of the next signal blocks, ...) then finds no free SM and the two serialise.
+ * max_ctas > 0 caps the grid so that the remaining SMs stay free (measured, 2 GPUs, NCCL broadcast of the next
+ * blocks under the kernel: 53 -> 34 us per period with 116 of 148 SMs); 0 restores the default. */
+int gat_set_max_ctas(gat_ctx *ctx, int max_ctas);
 int gat_set_timing(gat_ctx *ctx, int enable);  /* record cudaEvents around the correlate kernel */
 uint64_t gat_kernel_launch_count(gat_ctx *ctx); /* total kernels of ours launched on this ctx */
 /* Debug timeline: when enabled, every CTA of the next correlate launches stamps %globaltimer (ns) into

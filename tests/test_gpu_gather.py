@@ -87,3 +87,48 @@ def test_gather_two_gpus(gat, orc):
         p.join(60)
     assert [r for r, _ in res] == [0, 1]
     assert all(e < 1e-4 for _, e in res), res
+
+
+# ------------------------------------------------------------------------------------------------
+# ingest without a broadcast: a slot exported by one process, imported and correlated by another
+# ------------------------------------------------------------------------------------------------
+def _importer(device, desc, q_out):
+    import gpuacceleratedtracking_b200 as gat
+    import oracle as orc
+    eng = gat.Engine(device)
+    l1, n, m, fs, re, im, chans, shifts = _scenario(gat, orc)
+    eng.import_slot(3, desc)
+    got = eng.correlate(3, chans, fs, shifts, m, n_samples=n)
+    r2, i2 = eng.download_signal(3, n, m)
+    q_out.put((got, bool(np.array_equal(r2, re) and np.array_equal(i2, im))))
+    eng.close()
+
+
+def test_slot_export_import_across_processes(gat, orc):
+    """gat_slot_export / gat_slot_import: the importing process (another GPU when there is one, else the same
+    device) reads the exporter's planes through the CUDA IPC mapping and gets the exporter's own bits."""
+    import torch
+    import torch.multiprocessing as mp
+    eng = gat.Engine(0)
+    l1, n, m, fs, re, im, chans, shifts = _scenario(gat, orc)
+    eng.upload_signal(0, re, im)
+    want = eng.correlate(0, chans, fs, shifts, m, n_samples=n)
+    desc = eng.export_slot(0)
+    assert len(desc) == 96
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_importer, args=(1 if torch.cuda.device_count() > 1 else 0, desc, q))
+    p.start()
+    got, same_planes = q.get(timeout=120)
+    p.join(60)
+    assert p.exitcode == 0
+    assert same_planes
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # a zero-copy binding is not exportable; a bad descriptor is rejected
+    t = torch.zeros(2, 1024, device="cuda")
+    eng.bind_signal(1, t, t.clone())
+    with pytest.raises(gat.GatError):
+        eng.export_slot(1)
+    with pytest.raises(gat.GatError):
+        eng.import_slot(2, bytes(96))
+    eng.close()
