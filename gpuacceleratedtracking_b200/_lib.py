@@ -71,6 +71,8 @@ SYMBOLS = {
     "gat_downconvert_and_correlate": (_i, [_vp, _vp, _vp, _i, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _u]),
     "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
     "gat_set_max_ctas": (_i, [_vp, _i]),
+    "gat_beamform": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gat_eigen_weights": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, C.c_float, _i, _vp, _vp, _vp, _vp]),
     "gat_set_timing": (_i, [_vp, _i]),
     "gat_kernel_launch_count": (C.c_uint64, [_vp]),
     "gat_gather_create": (_i, [_vp, _i, _i, C.c_uint64, C.POINTER(C.c_ubyte)]),

@@ -1325,6 +1325,36 @@ int gat_get_timeline(gat_ctx *ctx, uint64_t *out, int cap_ctas)
     return n;
 }
 
+int gat_beamform(gat_ctx *ctx, int n_ch, int n_taps, int n_ants, const float *d_acc_re, const float *d_acc_im, const float *d_w_re,
+                 const float *d_w_im, float *d_y_re, float *d_y_im)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_acc_re || !d_acc_im || !d_w_re || !d_w_im || !d_y_re || !d_y_im) return fail(ctx, GAT_ERR_INVALID, "null pointer argument");
+    if (n_ch < 1 || n_taps < 1 || n_taps > GAT_MAX_TAPS || n_ants < 1 || n_ants > kMaxAnts)
+        return fail(ctx, GAT_ERR_INVALID, "bad post-correlation shape");
+    cudaError_t e = launch_beamform(d_acc_re, d_acc_im, d_w_re, d_w_im, d_y_re, d_y_im, n_ch, n_taps, n_ants, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "beamform launch");
+    ctx->launches += 1;
+    return GAT_OK;
+}
+
+int gat_eigen_weights(gat_ctx *ctx, int n_ch, int n_taps, int n_ants, const float *d_acc_re, const float *d_acc_im, int tap, float forget,
+                      int iters, float *d_cov_re, float *d_cov_im, float *d_w_re, float *d_w_im)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!d_acc_re || !d_acc_im || !d_cov_re || !d_cov_im || !d_w_re || !d_w_im) return fail(ctx, GAT_ERR_INVALID, "null pointer argument");
+    if (n_ch < 1 || n_taps < 1 || n_taps > GAT_MAX_TAPS || n_ants < 1 || n_ants > kMaxAnts || tap < 0 || tap >= n_taps || iters < 1 ||
+        iters > 1024 || !(forget >= 0.f) || !(forget <= 1.f))
+        return fail(ctx, GAT_ERR_INVALID, "bad eigen-filter arguments");
+    cudaError_t e = launch_eigen_weights(d_acc_re, d_acc_im, n_ch, n_taps, n_ants, tap, forget, iters, d_cov_re, d_cov_im, d_w_re, d_w_im,
+                                         ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "eigen-filter launch");
+    ctx->launches += 1;
+    return GAT_OK;
+}
+
 int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift, int n_samples, unsigned flags,
                            int32_t *out)
 {

@@ -111,6 +111,10 @@ cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, i
                                 int tile_len, bool f64, int32_t *d_out, cudaStream_t stream);
 
 // expand interleaved complex integer samples [n_ants][ld_in][2] into FP32 planes [n_ants][ld_out]
+cudaError_t launch_beamform(const float *acc_re, const float *acc_im, const float *w_re, const float *w_im, float *y_re, float *y_im,
+                            int n_ch, int n_taps, int n_ants, cudaStream_t stream);
+cudaError_t launch_eigen_weights(const float *acc_re, const float *acc_im, int n_ch, int n_taps, int n_ants, int tap, float forget, int iters,
+                                 float *cov_re, float *cov_im, float *w_re, float *w_im, cudaStream_t stream);
 cudaError_t launch_expand_sc(const void *iq, int bytes_per_component, int64_t ld_in, float *re, float *im, int64_t ld_out,
                              int n_samples, int n_ants, float scale, cudaStream_t stream);
 

@@ -292,6 +292,35 @@ class Engine:
         return (o_re + 1j * o_im).astype(np.complex64)
 
     # -- fused multi-GPU gather -------------------------------------------------------------------
+    # ---- post-correlation array processing (include/gat.h gat_beamform / gat_eigen_weights) ----
+    def beamform(self, acc, weights, out=None):
+        """acc = (re, im) CUDA tensors [..., L, M] (what correlate_batch(out=...) filled), weights = (re, im)
+        [..., M] with the same leading dims -> (re, im) [..., L]: y[l] = sum_m conj(w[m]) acc[l, m]."""
+        a_re, a_im = acc
+        w_re, w_im = weights
+        L, M = a_re.shape[-2], a_re.shape[-1]
+        n_ch = a_re.numel() // (L * M)
+        assert w_re.numel() == n_ch * M and all(t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+                                                for t in (a_re, a_im, w_re, w_im))
+        if out is None:
+            out = (torch.empty(a_re.shape[:-1], device=a_re.device), torch.empty(a_re.shape[:-1], device=a_re.device))
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self._lib.gat_beamform(self._h, n_ch, L, M, p(a_re), p(a_im), p(w_re), p(w_im), p(out[0]), p(out[1])))
+        return out
+
+    def eigen_weights(self, acc, cov, weights, tap: int, forget: float = 0.95, iters: int = 4):
+        """Update the per-channel covariance state `cov` = (re, im) [..., M, M] with the accumulators of tap
+        `tap` and refresh `weights` = (re, im) [..., M] in place (dominant eigenvector, power iteration)."""
+        a_re, a_im = acc
+        L, M = a_re.shape[-2], a_re.shape[-1]
+        n_ch = a_re.numel() // (L * M)
+        assert cov[0].numel() == n_ch * M * M and weights[0].numel() == n_ch * M
+        assert all(t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 for t in (*acc, *cov, *weights))
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self._lib.gat_eigen_weights(self._h, n_ch, L, M, p(a_re), p(a_im), tap, forget, iters,
+                                                p(cov[0]), p(cov[1]), p(weights[0]), p(weights[1])))
+        return weights
+
     def gather_create(self, world: int, rank: int, elems_per_rank: int) -> bytes:
         h = (C.c_ubyte * _lib.GAT_IPC_HANDLE_BYTES)()
         self._check(self._lib.gat_gather_create(self._h, world, rank, elems_per_rank, h))

@@ -172,6 +172,20 @@ int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *
                                   const int32_t *sample_shifts, int n_taps, int start_sample,
                                   int n_samples, float *h_out_re, float *h_out_im, unsigned flags);
 
+/* ---- post-correlation array processing (Tracking.jl `track(...; post_corr_filter)` [upstream]) ----
+ * For accumulators that stay on the device: all pointers are DEVICE pointers, both calls are asynchronous on the
+ * ctx stream (ordered behind the correlate call that produced `acc`).  n_ch = n_sats x n_periods of that call.
+ *   gat_beamform:      y[l, k] = sum_m conj(w[m, k]) * acc[m, l, k];  acc [n_ants x n_taps x n_ch],
+ *                      w [n_ants x n_ch], y [n_taps x n_ch].
+ *   gat_eigen_weights: eigen-beamformer.  R_k <- forget * R_k + p p^H with p = acc[:, tap, k] (cov: caller-owned
+ *                      state [n_ants x n_ants x n_ch], row-major R[i][j] per channel, zero it to start), then
+ *                      `iters` power iterations from the previous w (all-zero w = cold start from p); w comes
+ *                      back with unit norm and antenna 0 real, non-negative. */
+int gat_beamform(gat_ctx *ctx, int n_ch, int n_taps, int n_ants, const float *d_acc_re, const float *d_acc_im,
+                 const float *d_w_re, const float *d_w_im, float *d_y_re, float *d_y_im);
+int gat_eigen_weights(gat_ctx *ctx, int n_ch, int n_taps, int n_ants, const float *d_acc_re, const float *d_acc_im,
+                      int tap, float forget, int iters, float *d_cov_re, float *d_cov_im, float *d_w_re, float *d_w_im);
+
 /* ---- multi-GPU gather fused into the kernel epilogue (one process per GPU, same node) ------ */
 /* Every rank allocates [world x elems_per_rank] FP32 re + im planes plus one arrival flag per rank and
  * exports a CUDA IPC handle (64 bytes) that the host exchanges by any means (torch.distributed,
