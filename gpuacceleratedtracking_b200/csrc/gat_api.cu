@@ -575,16 +575,17 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (M < 1 || M > kMaxAnts) return fail(ctx, GAT_ERR_UNSUPPORTED, "antenna count must be 1..32");
     // Raw int16 tiles are read directly by the kernel: half the HBM bytes, and no expansion pass (4 B read +
     // 8 B written per sample and antenna, ~1.5 us per 50000 x 16 block).  Every channel converts the words it
-    // reads, ~0.06 us per channel and block on the issue-bound loop, so: one channel per block always reads the
-    // raw words (219 us vs 250 us per 256 blocks); more channels do so only while nobody has paid for the FP32
-    // planes yet, up to 16 channels per block (break-even ~24).  The scale must be a power of two so that
-    // applying it to the accumulators is bit-identical to scaling every sample.
+    // reads on the issue-bound loop, so with many channels per block the FP32 planes win again.  Measured per
+    // 256 channel-blocks of 50000 x 16: one channel per block 171 us raw vs 250 us FP32 (HBM-bound), two 163 vs
+    // 174, four 160 vs 162.  So: up to two channels per block always read the raw words; more do so only while
+    // nobody has paid for the FP32 planes yet, up to 16 channels per block.  The scale must be a power of two so
+    // that applying it to the accumulators is bit-identical to scaling every sample.
     bool use_raw = false;
     {
         int mant_exp = 0;
         const bool pow2 = raw_scale > 0.f && std::frexp(raw_scale, &mant_exp) == 0.5f;
         const int pref = env_int("GAT_TUNE_RAW", -1);
-        const bool worth = n_sats <= 1 || (!all_planes && n_sats <= 16);
+        const bool worth = n_sats <= 2 || (!all_planes && n_sats <= 16);
         use_raw = all_raw && pow2 && !(flags & GAT_CODE_PHASE_F64) && (pref < 0 ? worth : pref != 0);
     }
     for (int p = 0; p < n_periods; ++p) {

@@ -82,6 +82,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         else if (now - t0 > kWaitLimitNs) __trap();
     }
 }
+// The producer warp waits for whole tiles to be consumed (microseconds): back off between tries so that its
+// retry loop does not take issue slots from the consumer warps of its scheduler (measured: 7 % of all executed
+// instructions were this loop spinning).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(2000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kWaitLimitNs) __trap();
+    }
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit).
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
@@ -160,6 +183,12 @@ __device__ __forceinline__ float s16_lo(uint32_t w)   // sign-extending permute 
     return (float)v;
 }
 __device__ __forceinline__ float s16_hi(uint32_t w) { return (float)((int)w >> 16); }
+__device__ __forceinline__ uint32_t lds_u32_at(uint32_t smem_addr)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+    return v;
+}
 __device__ __forceinline__ float lds_f32_at(uint32_t smem_addr)
 {
     float v;
@@ -409,12 +438,12 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 // the consumers still read the cached tables while they work on the previous
                 // segment: wait until every tile issued so far has been released
                 const int live = (int)min(q, (uint32_t)stages);
-                for (int st = 0; st < live; ++st) mbar_wait(&empty_bar[st], ((q - 1u - (uint32_t)st) / (uint32_t)stages) & 1u);
+                for (int st = 0; st < live; ++st) mbar_wait_relaxed(&empty_bar[st], ((q - 1u - (uint32_t)st) / (uint32_t)stages) & 1u);
             }
             for (int t = t_first; t < t_last; ++t, ++q) {
                 const int stage = q % stages;
                 const uint32_t par = (q / stages) & 1u;
-                mbar_wait(&empty_bar[stage], par ^ 1u);
+                mbar_wait_relaxed(&empty_bar[stage], par ^ 1u);
                 const int ts_rel = t * tile_len;  // relative to aligned_start
                 if (lane == 0) {
                     // full boxes always: samples past the block end arrive as zeros and still count
@@ -456,6 +485,13 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     const int gr = split ? sl * AG + ag : ag;               // this warp's rank in its group
     float *rep = rep_all + (size_t)gid * args.rep_stride;
     const int8_t *tab = code_cache + (size_t)s_idx * args.cache_stride;
+
+    // replica rows (32 entries each) of a full tile and this warp's share of them: fixed for the whole launch;
+    // only a job's last, shorter tile recomputes them.  Likewise the tile step of this warp, and the ring stage /
+    // parity, advance by additions -- no integer division in the per-tile path.
+    // (few values stay live across the FMA loop -- it runs within 7 registers of the 168 cap)
+    const int rows_per_full = (((tile_len + span + 31) >> 5) + gw - 1) / gw;
+    const int step = split ? 1 : SL;               // this warp works on every step-th tile of the CTA's sequence
 
     for (int64_t g = r0; g < r1; ++seg) {
         const int job = (int)(g / TJ);
@@ -511,10 +547,20 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
 
         mbar_wait(code_bar, seg & 1u);   // this segment's chip tables are in shared memory
 
-        for (int t = t_first; t < t_last; ++t, ++q) {
-            if (!split && (int)(q % (uint32_t)SL) != sl) continue;  // whole tiles go round-robin over the sample slices
-            const int stage = q % stages;
-            const uint32_t par = (q / stages) & 1u;
+        // whole tiles go round-robin over the sample slices (tile q of the CTA belongs to slice q % SL); the first
+        // one of this segment that is ours, its ring stage and parity: once per segment
+        int t = t_first;
+        if (step > 1) t += (sl + step - (int)(q % (uint32_t)step)) % step;
+        int sp;                                            // 2 * ring stage + phase parity of tile t
+        {
+            const uint32_t qq = q + (uint32_t)(t - t_first);
+            sp = 2 * (int)(qq % (uint32_t)stages) + (int)((qq / (uint32_t)stages) & 1u);
+        }
+        const bool stamp_first = (q == 0);
+        q += (uint32_t)(t_last - t_first);                 // every tile of the segment counts, ours or not
+        for (; t < t_last; t += step) {
+            const int stage = sp >> 1;
+            const uint32_t par = (uint32_t)sp & 1u;
             const int ts_rel = t * tile_len;
             const int len = min(tile_len, args.aligned_len - ts_rel);
             const int n0 = args.aligned_start + ts_rel - args.start_sample;  // relative index of tile sample 0
@@ -522,9 +568,9 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 // ---- code replica of this tile, generated while the signal tile is still in flight ----
                 // rep[u] = chip under (tile sample 0 + latest tap + u); tap l of sample tt reads rep[tt + koff[l]]
                 // (the reference writes the same array to global memory, src/algorithms.jl:100-119, :1513-1525)
-                const int rep_len = len + span;
-                const int rows = (rep_len + 31) >> 5;                 // 32 entries per row
-                const int rows_per = (rows + gw - 1) / gw;
+                const int rows = (len + span + 31) >> 5;              // 32 entries per row
+                int rows_per = rows_per_full;
+                if (len != tile_len) rows_per = (rows + gw - 1) / gw;
                 const int row0 = gr * rows_per, row1 = min(rows, row0 + rows_per);
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();   // previous tile's readers are done
                 if constexpr (F64) {
@@ -570,7 +616,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
             }
             mbar_wait(&full_bar[stage], par);
-            if (q == 0) GAT_STAMP(2);
+            if (stamp_first && t == t_first) GAT_STAMP(2);
             if (active) {
                 const float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
                 const float *tim = tre + (size_t)MP * kTileCap;
@@ -580,19 +626,26 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 int tt0 = split ? sl * 32 + lane : lane;
                 if (n0 + tt0 < 0) tt0 += tt_stride;
                 uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
-                const uint32_t rep_s = smem_u32(rep);
+                // running shared-memory addresses of this lane's sample in the re / im planes and in the replica;
+                // the loop carries nothing else (no sample counter): ptxas otherwise re-derives the tile base and
+                // the phase step from the kernel arguments in every iteration
+                uint32_t ta_re = smem_u32(tre) + 4u * (uint32_t)tt0;
+                uint32_t ta_im = smem_u32(tim) + 4u * (uint32_t)tt0;
+                uint32_t ra = smem_u32(rep) + 4u * (uint32_t)tt0;
+                const uint32_t ta_end = smem_u32(tre) + 4u * (uint32_t)len;
+                uint32_t astep = 4u * (uint32_t)tt_stride, pstep = ph_step32;
+                asm volatile("" : "+r"(astep), "+r"(pstep));        // opaque: keep them in registers
                 // (unrolling by two was measured slower on the 11-tap shape: occupancy, not per-warp ILP, is
                 // what hides the MUFU / shared-memory latencies here)
 #pragma unroll 1
-                for (int tt = tt0; tt < len; tt += tt_stride) {
+                for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) {
                     // ---- carrier replica: exp(j 2 pi phase) ----
                     float cr, ci;
                     const float x = (float)(int32_t)ph * 1.4629180792671596e-9f;  // 2 pi / 2^32
                     __sincosf(x, &ci, &cr);
-                    ph += ph_step32;
+                    ph += pstep;
                     // ---- code replica chips for every tap: one shared-memory load each ----
                     float chip[L];
-                    const uint32_t ra = rep_s + 4u * (uint32_t)tt;
 #pragma unroll
                     for (int l = 0; l < L; ++l) chip[l] = lds_f32_at(ra + (uint32_t)args.koff4[l]);
                     if constexpr (A >= 2) {
@@ -603,7 +656,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
 #pragma unroll
                         for (int a = 0; a < AP; ++a) {
                             if constexpr (SC16) {
-                                const uint32_t w0 = lds_u32(tre + (2 * a) * kTileCap + tt), w1 = lds_u32(tre + (2 * a + 1) * kTileCap + tt);
+                                const uint32_t w0 = lds_u32_at(ta_re + 4u * (2 * a) * kTileCap), w1 = lds_u32_at(ta_re + 4u * (2 * a + 1) * kTileCap);
 #if GAT_S16_MODE == 1
                                 const uint32_t f0 = s16_flip(w0), f1 = s16_flip(w1);
                                 const f32x2 NB = pack2(-kS16Bias, -kS16Bias);
@@ -614,8 +667,8 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                                 Y[a] = pack2(s16_hi(w0), s16_hi(w1));
 #endif
                             } else {
-                                X[a] = pack2(lds_f32(tre + (2 * a) * kTileCap + tt), lds_f32(tre + (2 * a + 1) * kTileCap + tt));
-                                Y[a] = pack2(lds_f32(tim + (2 * a) * kTileCap + tt), lds_f32(tim + (2 * a + 1) * kTileCap + tt));
+                                X[a] = pack2(lds_f32_at(ta_re + 4u * (2 * a) * kTileCap), lds_f32_at(ta_re + 4u * (2 * a + 1) * kTileCap));
+                                Y[a] = pack2(lds_f32_at(ta_im + 4u * (2 * a) * kTileCap), lds_f32_at(ta_im + 4u * (2 * a + 1) * kTileCap));
                             }
                         }
 #pragma unroll
@@ -633,12 +686,12 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                     } else {
                         float xr, xi;
                         if constexpr (SC16) {
-                            const uint32_t w = lds_u32(tre + tt);
+                            const uint32_t w = lds_u32_at(ta_re);
                             xr = s16_lo(w);
                             xi = s16_hi(w);
                         } else {
-                            xr = tre[tt];
-                            xi = tim[tt];
+                            xr = lds_f32_at(ta_re);
+                            xi = lds_f32_at(ta_im);
                         }
                         const float dre = fmaf(xi, ci, xr * cr);
                         const float dim = fmaf(-xr, ci, xi * cr);
@@ -652,6 +705,8 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            sp += 2 * step;                                  // step <= stages: at most one wrap, which flips the parity
+            if (sp >= 2 * stages) sp = (sp - 2 * stages) ^ 1;
         }
         g += t_last - t_first;
 

@@ -12,7 +12,7 @@ l1, l5 = g.GPSL1(), g.GPSL5()
 N, M = 50000, 16
 fs = N / 1e-3
 torch.cuda.set_device(0)
-P = 256 if which == "batch256" else 64
+P = 256 if which in ("batch256", "int16") else 64
 re = torch.randn(P, M, N, device="cuda"); im = torch.randn(P, M, N, device="cuda")
 torch.cuda.synchronize()
 for p in range(P):
@@ -44,3 +44,11 @@ if which in ("c3", "all"):
     run("batch P=64 K=1 L=3 L5", 64, 1, 3, 0.5, l5)
 if which in ("k32batch", "all"):
     run("batch P=8 K=32 L=3", 8, 32, 3, 0.5)
+if which == "rt264":
+    run("single K=264 L=3 (realtime_shared_block)", 1, 264, 3, 0.5)
+if which == "int16":
+    # bench.py's int16_resident figure: 256 blocks kept as raw int16 I/Q, one channel each
+    iq = torch.randint(-2047, 2048, (P, M, N, 2), device="cuda", dtype=torch.int16)
+    for p in range(P):
+        eng.upload_signal_int(10 + p, iq[p], 1.0 / 2048)
+    run("batch P=256 K=1 L=3 raw int16", P, 1, 3, 0.5)
