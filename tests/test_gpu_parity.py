@@ -606,3 +606,28 @@ def test_int16_slot_reshape(gat, orc, engine, monkeypatch):
         im = iq[..., 1].astype(np.float32) * np.float32(0.5)
         ref = orc.correlate_direct(re, im, l1.codes[7], 1.023e6, 77.7, -1200.0, 0.3, fs, shifts)
         assert np.abs(got[0] - ref).max() <= TOL * np.abs(ref[1]).max() + 1e-3
+
+
+@pytest.mark.gpu
+def test_max_ctas_leaves_results_unchanged(gat, orc):
+    """gat_set_max_ctas (SMs left free for a concurrent communication kernel) only changes the work split."""
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(21)
+    n, m, fs = 30000, 4, 3.0e7
+    re = rng.normal(size=(m, n)).astype(np.float32)
+    im = rng.normal(size=(m, n)).astype(np.float32)
+    chans = [gat.Channel(l1, p, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)), 0.1) for p in (1, 9, 17, 25, 31)]
+    shifts = np.array([-14, 0, 14], np.int32)
+    eng.upload_signal(0, re, im)
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                         fs, shifts) for c in chans])
+    scale = np.abs(ref).max()
+    for cap in (0, 100, 7, 1):
+        eng.set_max_ctas(cap)
+        got = eng.correlate(0, chans, fs, shifts, m, n_samples=n)
+        assert eng.launch_info()["grid"] <= (cap or 148)
+        assert np.abs(got - ref).max() <= 2e-5 * scale + 1e-2
+    with pytest.raises(gat.GatError):
+        eng.set_max_ctas(-1)
+    eng.close()
