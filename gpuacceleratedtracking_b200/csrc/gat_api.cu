@@ -235,6 +235,7 @@ struct Shape {
     bool f64;
     int max_code_len;
     bool sc16;
+    int min_code_len = 1 << 30;
 };
 
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
@@ -356,6 +357,9 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.G = G;
     a.stages = stages;
     a.rep_stride = rep_stride;
+    // chips advanced across one replica (tile + tap span, + the 32-entry row granularity) < shortest code
+    a.rep_single_wrap = (static_cast<double>(tile_len + span + 64) * sh.max_ratio + 2.0 < static_cast<double>(sh.min_code_len)) ? 1 : 0;
+    a.rep_single_wrap = env_int("GAT_TUNE_REPWRAP", a.rep_single_wrap) ? a.rep_single_wrap : 0;
     a.cache_stride = cache_stride;
     a.total_tiles = static_cast<int32_t>(total_tiles);
     {
@@ -611,6 +615,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         shape.min_fp = std::min(shape.min_fp, sats[i].nco_fp);
         shape.max_delta = std::max(shape.max_delta, sats[i].nco_delta);
         shape.max_code_len = std::max(shape.max_code_len, sats[i].code_len);
+        shape.min_code_len = std::min(shape.min_code_len, sats[i].code_len);
     }
 
     LaunchPlan plan{};

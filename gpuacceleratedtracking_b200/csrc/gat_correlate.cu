@@ -189,6 +189,16 @@ __device__ __forceinline__ uint32_t lds_u32_at(uint32_t smem_addr)
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
     return v;
 }
+__device__ __forceinline__ int lds_s8_at(uint32_t smem_addr)      // chip table entry, sign-extended
+{
+    int v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+    return v;
+}
+__device__ __forceinline__ void sts_b32_at(uint32_t smem_addr, uint32_t v)
+{
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ float lds_f32_at(uint32_t smem_addr)
 {
     float v;
@@ -601,17 +611,39 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                     uint64_t v = frac + (uint64_t)(uint32_t)(row0 * 32 + lane) * delta;
                     const uint64_t v32 = 32ull * delta;
                     int r = row0;
-                    for (; r + 3 < row1; r += 4) {   // 4 independent table lookups in flight per lane
-                        int c[4];
+                    if (args.rep_single_wrap) {
+                        // the tile advances the code by less than one period (host-checked): one branch-free wrap per
+                        // entry, table and replica addressed through 32-bit shared-memory addresses
+                        const uint32_t tab_s = smem_u32(tab);
+                        uint32_t wa = smem_u32(rep) + 4u * (uint32_t)(row0 * 32 + lane);
+                        for (; r + 3 < row1; r += 4, wa += 512u) {   // 4 independent table lookups in flight per lane
+                            int c[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            c[j] = tab[rep_index_nco(v, sh, bmod, lc)];
-                            v += v32;
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
+                                c[j] = lds_s8_at(tab_s + min(idx, idx - lc));   // unsigned: idx - lc wraps high when idx < lc
+                                v += v32;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sts_b32_at(wa + 128u * j, 0x3f800000u | ((uint32_t)c[j] & 0x80000000u));
                         }
+                        for (; r < row1; ++r, v += v32, wa += 128u) {
+                            const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
+                            sts_b32_at(wa, 0x3f800000u | ((uint32_t)lds_s8_at(tab_s + min(idx, idx - lc)) & 0x80000000u));
+                        }
+                    } else {
+                        for (; r + 3 < row1; r += 4) {
+                            int c[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) rep[(r + j) * 32 + lane] = chip_to_float(c[j]);
+                            for (int j = 0; j < 4; ++j) {
+                                c[j] = tab[rep_index_nco(v, sh, bmod, lc)];
+                                v += v32;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rep[(r + j) * 32 + lane] = chip_to_float(c[j]);
+                        }
+                        for (; r < row1; ++r, v += v32) rep[r * 32 + lane] = chip_to_float(tab[rep_index_nco(v, sh, bmod, lc)]);
                     }
-                    for (; r < row1; ++r, v += v32) rep[r * 32 + lane] = chip_to_float(tab[rep_index_nco(v, sh, bmod, lc)]);
                 }
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
             }

@@ -68,7 +68,8 @@ struct alignas(64) CorrArgs {
     int32_t rep_stride;                // floats per consumer warp for its code replica (>= tile_len + span)
     int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
-    float out_scale;                   // multiplies every accumulator at emit (1 unless raw integer tiles carry a scale)
+    float out_scale;
+    int32_t rep_single_wrap;   // a tile (+ tap span) advances every code by less than one period: branch-free index wrap                   // multiplies every accumulator at emit (1 unless raw integer tiles carry a scale)
     int32_t fin_group;                 // lanes cooperating on one output element in the finalize (pow2 <= 32)
     int32_t split_tiles;               // 1: every slice works on every tile (small problems); 0: whole tiles round-robin
     uint32_t flags;
