@@ -294,7 +294,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     }
     // per-tile relative NCO phase must fit 64 bits: (tile + span + 1) * delta + 2^fp < 2^64
     if (!sh.f64) {
-        const long double need = static_cast<long double>(tile_len + span + 32) * static_cast<long double>(sh.max_delta) +
+        const long double need = static_cast<long double>(tile_len + span + 160) * static_cast<long double>(sh.max_delta) +
                                  std::ldexp(1.0L, sh.min_fp);
         if (need >= std::ldexp(1.0L, 64))
             return fail(ctx, GAT_ERR_UNSUPPORTED, "code rate too high for the fixed-point window (code_freq/fs * tile too large)");
@@ -302,7 +302,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         const double worst = sh.max_ratio * (static_cast<double>(sh.n) + std::abs(sh.shifts[0]) + std::abs(sh.shifts[L - 1]));
         if (!(worst < 1.0e9)) return fail(ctx, GAT_ERR_UNSUPPORTED, "code phase range exceeds the f64 window arithmetic");
     }
-    const int rep_stride = (tile_len + span + 31) & ~31;   // generated in rows of 32 entries
+    const int rep_stride = (tile_len + span + 127) & ~127;   // generated in rows of 32 entries, four rows at a time
     const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(kMaxConsumerWarps) * (RP + rep_stride) * sizeof(float) +
                                static_cast<size_t>(S) * cache_stride;
 
@@ -358,7 +358,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.stages = stages;
     a.rep_stride = rep_stride;
     // chips advanced across one replica (tile + tap span, + the 32-entry row granularity) < shortest code
-    a.rep_single_wrap = (static_cast<double>(tile_len + span + 64) * sh.max_ratio + 2.0 < static_cast<double>(sh.min_code_len)) ? 1 : 0;
+    a.rep_single_wrap = (static_cast<double>(tile_len + span + 160) * sh.max_ratio + 2.0 < static_cast<double>(sh.min_code_len)) ? 1 : 0;
     a.rep_single_wrap = env_int("GAT_TUNE_REPWRAP", a.rep_single_wrap) ? a.rep_single_wrap : 0;
     a.cache_stride = cache_stride;
     a.total_tiles = static_cast<int32_t>(total_tiles);

@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     // only a job's last, shorter tile recomputes them.  Likewise the tile step of this warp, and the ring stage /
     // parity, advance by additions -- no integer division in the per-tile path.
     // (few values stay live across the FMA loop -- it runs within 7 registers of the 168 cap)
-    const int rows_per_full = (((tile_len + span + 31) >> 5) + gw - 1) / gw;
+    const int rows_per_full = gw == 1 ? ((((tile_len + span + 31) >> 5) + 3) & ~3) : (((tile_len + span + 31) >> 5) + gw - 1) / gw;
     const int step = split ? 1 : SL;               // this warp works on every step-th tile of the CTA's sequence
 
     for (int64_t g = r0; g < r1; ++seg) {
@@ -578,8 +578,9 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 // ---- code replica of this tile, generated while the signal tile is still in flight ----
                 // rep[u] = chip under (tile sample 0 + latest tap + u); tap l of sample tt reads rep[tt + koff[l]]
                 // (the reference writes the same array to global memory, src/algorithms.jl:100-119, :1513-1525)
-                const int rows = (len + span + 31) >> 5;              // 32 entries per row
-                int rows_per = rows_per_full;
+                int rows = (len + span + 31) >> 5;                    // 32 entries per row
+                if (gw == 1) rows = (rows + 3) & ~3;                  // a warp on its own writes whole groups of four rows
+                int rows_per = rows_per_full;                         // (the buffer is padded to 128 entries)
                 if (len != tile_len) rows_per = (rows + gw - 1) / gw;
                 const int row0 = gr * rows_per, row1 = min(rows, row0 + rows_per);
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();   // previous tile's readers are done
