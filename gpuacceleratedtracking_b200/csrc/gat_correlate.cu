@@ -48,6 +48,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar_s)       // 32-bit shared address
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -63,9 +67,8 @@ __device__ __forceinline__ uint64_t global_timer_ns()
 // expected byte count, a lost arrival).  Trap -> the host sees a CUDA error instead of a hung device.
 // Only the retry path pays for it.
 constexpr uint64_t kWaitLimitNs = 4000000000ull;
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_s(uint32_t addr, uint32_t parity)
 {
-    const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     uint64_t t0 = 0;
     while (true) {
@@ -82,6 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         else if (now - t0 > kWaitLimitNs) __trap();
     }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { mbar_wait_s(smem_u32(bar), parity); }
 // The producer warp waits for whole tiles to be consumed (microseconds): back off between tries so that its
 // retry loop does not take issue slots from the consumer warps of its scheduler (measured: 7 % of all executed
 // instructions were this loop spinning).
@@ -495,6 +499,17 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     const int gr = split ? sl * AG + ag : ag;               // this warp's rank in its group
     float *rep = rep_all + (size_t)gid * args.rep_stride;
     const int8_t *tab = code_cache + (size_t)s_idx * args.cache_stride;
+    // 32-bit shared-memory addresses of everything the per-tile path touches, derived once (generic pointers make
+    // ptxas re-derive the shared window base -- S2R CgaCtaId, LDC ... -- at every use) and pinned in registers
+    uint32_t rep_s = smem_u32(rep), tab_s = smem_u32(tab);
+    uint32_t bars_s = smem_u32(full_bar);                                         // full[i] at +8i, empty[i] at +8(kMaxStages + i)
+    uint32_t tile0_s = smem_u32(tiles) + 4u * (uint32_t)(ag * A) * kTileCap;      // this warp's antenna rows in stage 0
+    // (pinning pays where 16 / 8 antennas per thread amortise the four registers: same-box A/B, 264-channel block
+    // 128.6 -> 124.3 us, int16 batch 169.5 -> 161.2 us; with 4 antennas per thread -- 11 taps, or the 96-register
+    // class -- it costs 2-4 %, so those instantiations leave the choice to ptxas)
+    if constexpr (A >= 8) asm volatile("" : "+r"(rep_s), "+r"(tab_s), "+r"(bars_s), "+r"(tile0_s));
+    const uint32_t tile_bytes = 4u * (uint32_t)tile_floats;
+    const uint32_t im_off = 4u * (uint32_t)MP * kTileCap;
 
     // replica rows (32 entries each) of a full tile and this warp's share of them: fixed for the whole launch;
     // only a job's last, shorter tile recomputes them.  Likewise the tile step of this warp, and the ring stage /
@@ -615,8 +630,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                     if (args.rep_single_wrap) {
                         // the tile advances the code by less than one period (host-checked): one branch-free wrap per
                         // entry, table and replica addressed through 32-bit shared-memory addresses
-                        const uint32_t tab_s = smem_u32(tab);
-                        uint32_t wa = smem_u32(rep) + 4u * (uint32_t)(row0 * 32 + lane);
+                        uint32_t wa = rep_s + 4u * (uint32_t)(row0 * 32 + lane);
                         for (; r + 3 < row1; r += 4, wa += 512u) {   // 4 independent table lookups in flight per lane
                             int c[4];
 #pragma unroll
@@ -648,11 +662,10 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 }
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
             }
-            mbar_wait(&full_bar[stage], par);
+            mbar_wait_s(bars_s + 8u * (uint32_t)stage, par);
             if (stamp_first && t == t_first) GAT_STAMP(2);
             if (active) {
-                const float *tre = tiles + (size_t)stage * tile_floats + (size_t)(ag * A) * kTileCap;
-                const float *tim = tre + (size_t)MP * kTileCap;
+                const uint32_t tre_s = tile0_s + (uint32_t)stage * tile_bytes;
                 // tiles start on a 16-byte boundary, so the first tile of a job may stage <= 3 samples that lie
                 // before start_sample (n0 < 0): the lanes that own them skip their first iteration.  Samples
                 // past the end never reach the loop (tt < len).  The loop itself stays branch-free.
@@ -662,10 +675,10 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 // running shared-memory addresses of this lane's sample in the re / im planes and in the replica;
                 // the loop carries nothing else (no sample counter): ptxas otherwise re-derives the tile base and
                 // the phase step from the kernel arguments in every iteration
-                uint32_t ta_re = smem_u32(tre) + 4u * (uint32_t)tt0;
-                uint32_t ta_im = smem_u32(tim) + 4u * (uint32_t)tt0;
-                uint32_t ra = smem_u32(rep) + 4u * (uint32_t)tt0;
-                const uint32_t ta_end = smem_u32(tre) + 4u * (uint32_t)len;
+                uint32_t ta_re = tre_s + 4u * (uint32_t)tt0;
+                uint32_t ta_im = ta_re + im_off;
+                uint32_t ra = rep_s + 4u * (uint32_t)tt0;
+                const uint32_t ta_end = tre_s + 4u * (uint32_t)len;
                 uint32_t astep = 4u * (uint32_t)tt_stride, pstep = ph_step32;
                 asm volatile("" : "+r"(astep), "+r"(pstep));        // opaque: keep them in registers
                 // (unrolling by two was measured slower on the 11-tap shape: occupancy, not per-warp ILP, is
@@ -737,7 +750,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (lane == 0) mbar_arrive_s(bars_s + 8u * (uint32_t)(kMaxStages + stage));
             sp += 2 * step;                                  // step <= stages: at most one wrap, which flips the parity
             if (sp >= 2 * stages) sp = (sp - 2 * stages) ^ 1;
         }
