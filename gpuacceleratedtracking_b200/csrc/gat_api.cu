@@ -265,7 +265,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // the per-warp code replicas and the flush buffer
     {
         const size_t two_stages = kSmemHeaderBytes + 2 * smem_tile_floats(AG, A, sh.sc16) * sizeof(float) +
-                                  static_cast<size_t>(kMaxConsumerWarps) * (padded_acc(A, L) + kTileCap + span + 128) * sizeof(float);
+                                  static_cast<size_t>(w_cap) * (padded_acc(A, L) + kTileCap + span + 128) * sizeof(float);
         if (two_stages + cache_stride > smem_budget)
             return fail(ctx, GAT_ERR_UNSUPPORTED, "chip table too long for the shared-memory cache");
         S = std::max(1, std::min<int>(S, static_cast<int>((smem_budget - two_stages) / cache_stride)));
@@ -303,7 +303,8 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         if (!(worst < 1.0e9)) return fail(ctx, GAT_ERR_UNSUPPORTED, "code phase range exceeds the f64 window arithmetic");
     }
     const int rep_stride = (tile_len + span + 127) & ~127;   // generated in rows of 32 entries, four rows at a time
-    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(kMaxConsumerWarps) * (RP + rep_stride) * sizeof(float) +
+    // (per-warp buffers sized for the most consumer warps this instantiation's CTA can hold)
+    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(w_cap) * (RP + rep_stride) * sizeof(float) +
                                static_cast<size_t>(S) * cache_stride;
 
     const int tiles_per_job = (aligned_len + tile_len - 1) / tile_len;
