@@ -631,3 +631,24 @@ def test_max_ctas_leaves_results_unchanged(gat, orc):
     with pytest.raises(gat.GatError):
         eng.set_max_ctas(-1)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_headline_shape_keeps_its_launch_plan(gat):
+    """The C2 batch (bench.py's step) must keep 6 pipeline stages and 6 sample slices: a shared-memory estimate that
+    is a few KB too generous silently drops it to 5 / 5 and costs 10 % (regression seen in round 1)."""
+    import torch
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    n, m, P = 50000, 16, 8
+    re = torch.zeros(P, m, n, device="cuda")
+    im = torch.zeros_like(re)
+    for p in range(P):
+        eng.bind_signal(p, re[p], im[p])
+    shifts = np.array([-24, 0, 24], np.int32)
+    out = (torch.zeros(P, 1, 3, m, device="cuda"), torch.zeros(P, 1, 3, m, device="cuda"))
+    eng.correlate_batch(list(range(P)), [[gat.Channel(l1, 1)]] * P, 5.0e7, shifts, m, 0, n, out=out)
+    eng.sync()
+    info = eng.launch_info()
+    assert info["stages"] >= 6 and info["consumer_warps"] >= 6 and info["tile_len"] == 256 and info["ants_per_thread"] == 16
+    eng.close()
