@@ -64,3 +64,32 @@ def get_center_frequency(system: GNSSSystem) -> float:
 
 
 GNSSDICT = {"GPSL1": GPSL1, "GPSL5": GPSL5}  # src/GPUAcceleratedTracking.jl:39-42
+
+
+# ---- derived systems: the engine takes any +-1 table, so secondary codes and binary-offset-carrier
+# ---- signals are expressed as longer tables at a higher "chip" rate; nothing in the kernel changes.
+NH10 = np.array([1, 1, 1, 1, -1, -1, 1, -1, 1, -1], np.int8)      # Neuman-Hofman 0000110101 (logic 0 -> +1), L5 I5, 1 kHz
+
+
+def with_secondary_code(system: GNSSSystem, secondary: np.ndarray, system_id: int, name: str | None = None,
+                        n_prn: int | None = None) -> GNSSSystem:
+    """Tiered code: every period of the primary code multiplied by one chip of `secondary` (length Ls) ->
+    tables of code_length * Ls chips (GNSSSignals' L5 table with NH10 applied)."""
+    sec = np.asarray(secondary, np.int8)
+    codes = system.codes if n_prn is None else system.codes[:n_prn]
+    table = (codes[:, None, :] * sec[None, :, None]).reshape(codes.shape[0], -1).astype(np.int8)
+    return GNSSSystem(name or f"{system.name}xS{sec.size}", system_id, system.code_length * sec.size, system.code_frequency,
+                      system.center_frequency, 1, system.use_gpu, table)
+
+
+def boc(system: GNSSSystem, system_id: int, sub_carrier_ratio: int = 1, name: str | None = None,
+        n_prn: int | None = None) -> GNSSSystem:
+    """Sine-phased BOC(m, n) with m / n = sub_carrier_ratio on top of `system`'s code (Galileo E1-B/C style
+    BOC(1,1) for ratio 1): each chip becomes 2 * ratio half-cycles +1, -1, ... of the square sub-carrier, i.e. a
+    table of 2 * ratio * code_length entries clocked at 2 * ratio * code_frequency."""
+    k = 2 * int(sub_carrier_ratio)
+    codes = system.codes if n_prn is None else system.codes[:n_prn]
+    sub = np.where(np.arange(k) % 2 == 0, 1, -1).astype(np.int8)
+    table = (codes[:, :, None] * sub[None, None, :]).reshape(codes.shape[0], -1).astype(np.int8)
+    return GNSSSystem(name or f"BOC({sub_carrier_ratio},1)/{system.name}", system_id, system.code_length * k,
+                      system.code_frequency * k, system.center_frequency, 1, system.use_gpu, table)

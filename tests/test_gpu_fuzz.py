@@ -87,3 +87,30 @@ def test_l5_with_secondary_code_table(gat, orc, engine):
                                              c.carrier_phase, fs, shifts, code_mode=mode) for c in chans])
         assert np.abs(got - ref).max() <= TOL * n
     assert abs(abs(got[0, 1, 0]) - n) < 0.01 * n                            # full correlation peak through the NH flip
+
+
+def test_boc_and_secondary_code_helpers(gat, orc, engine):
+    """derived systems are just longer tables.  BOC(1,1) on the C/A code: the prompt collects the
+    whole block and the +-1/4-chip taps sit on the BOC(1,1) autocorrelation 1 - 3|tau| = 0.25; the NH10 tiered L5
+    table equals the hand-built one of the test above."""
+    l1, l5 = gat.GPSL1(), gat.GPSL5()
+    e1 = gat.boc(l1, system_id=6, n_prn=4)
+    assert e1.code_length == 2046 and e1.code_frequency == 2.046e6 and e1.codes.shape == (4, 2046)
+    assert np.array_equal(e1.codes[:, 0::2], l1.codes[:4]) and np.array_equal(e1.codes[:, 1::2], -l1.codes[:4])
+    n, m = 38000, 2
+    fs = 38.0e6                                          # not commensurate with the chip rate (18.57 samples per sub-chip)
+    re, im = orc.gen_signal(e1.codes[1], e1.code_frequency, 2200.0, fs, n, m, 123.0, 0.0)
+    chans = [gat.Channel(e1, 2, 123.0, 2200.0, 0.0)]
+    shifts = np.array([-9, 0, 9], np.int32)              # +-0.2423 C/A chip
+    engine.upload_signal(0, re, im)
+    got = engine.correlate(0, chans, fs, shifts, m, n_samples=n)
+    ref = orc.correlate_direct(re, im, e1.codes[1], e1.code_frequency, 123.0, 2200.0, 0.0, fs, shifts)
+    assert np.abs(got[0] - ref).max() <= TOL * n
+    tau = 9 / fs * 1.023e6
+    # (1 - 3 tau up to the code's own adjacent-chip correlation, |sum c_i c_i+1| <= 65 of 1023 chips)
+    assert abs(got[0, 1, 0].real - n) < 2e-3 * n and abs(got[0, 0, 0].real - (1 - 3 * tau) * n) < 0.03 * n
+
+    l5nh = gat.with_secondary_code(l5, gat.NH10, system_id=7, n_prn=2)
+    nh = np.array([0, 0, 0, 0, 1, 1, 0, 1, 0, 1])
+    want = np.concatenate([l5.codes[:2].astype(np.int8) * (1 - 2 * b) for b in nh], axis=1)
+    assert l5nh.code_length == 102300 and np.array_equal(l5nh.codes, want)
