@@ -280,18 +280,12 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     const int aligned_len = sh.start + sh.n - aligned_start;
 
     const int jobs = sh.P * G;
-    int tile_len = kTileCap;
-    {
-        // small problems: shrink tiles so every SM gets one
-        const int64_t total = static_cast<int64_t>(jobs) * aligned_len;
-        // aim at >= 8 tiles per CTA so the +-1 tile quantisation of the even split stays small
-        const int64_t per_tile = (total + 8LL * ctx->n_sm - 1) / (8LL * ctx->n_sm);
-        const int quantum = 32;
-        int want = static_cast<int>(std::min<int64_t>(kTileCap, (per_tile + quantum - 1) / quantum * quantum));
-        tile_len = std::min(kTileCap, std::max(total >= 64LL * ctx->n_sm ? 64 : quantum, want));
-        tile_len = env_int("GAT_TUNE_TILE", tile_len);
-        if (tile_len < 32 || tile_len > kTileCap || tile_len % 32) return fail(ctx, GAT_ERR_INVALID, "bad GAT_TUNE_TILE");
-    }
+    // Tiles are always the full 256-sample TMA box.  Shrinking them to spread a small problem over more SMs was
+    // measured slower on every single-block shape (same box, back-to-back / synchronous call: 2048 x 1 antenna
+    // 17.7 -> 11.3 / 27.6 -> 22.4 us, 50000 x 16 14.4 -> 12.3 / 28.8 -> 26.6 us, 32 satellites 32.8 -> 28.8 us):
+    // the per-tile work (replica generation, barriers) and the number of partials to finalise outweigh the idle SMs.
+    int tile_len = env_int("GAT_TUNE_TILE", kTileCap);
+    if (tile_len < 32 || tile_len > kTileCap || tile_len % 32) return fail(ctx, GAT_ERR_INVALID, "bad GAT_TUNE_TILE");
     // per-tile relative NCO phase must fit 64 bits: (tile + span + 1) * delta + 2^fp < 2^64
     if (!sh.f64) {
         const long double need = static_cast<long double>(tile_len + span + 160) * static_cast<long double>(sh.max_delta) +
@@ -317,7 +311,22 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 12)));
     stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
     // sample slices take whole tiles round-robin, so more slices than stages cannot all be fed
-    int SL = std::max(1, std::min(env_int("GAT_TUNE_SPLIT", 0) == 1 ? w_cap : stages, w_target_single / (S * AG)));
+    int SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
+    // few tiles per CTA: let every slice work on every tile instead of taking turns ("split").  Then the slices
+    // stride through the tile together, 32 * SL samples per step, so SL is a power of two <= 8 (it divides the
+    // 256-sample tile: every warp gets the same number of samples) and is no longer bounded by the stage count.
+    const int grid_est = static_cast<int>(std::min<int64_t>(total_tiles, ctx->max_ctas > 0 ? std::min(ctx->n_sm, ctx->max_ctas) : ctx->n_sm));
+    int split_tiles = (w_target_single / (S * AG) > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid_est) ? 1 : 0;
+    split_tiles = env_int("GAT_TUNE_SPLIT", split_tiles);
+    // warps sharing a code replica meet at named barriers 2..15: at most 14 such groups
+    if (split_tiles && S > 14) split_tiles = 0;
+    if (split_tiles) {
+        int cap = std::min(8, std::min(w_cap, w_target_single) / (S * AG));
+        SL = 1;
+        while (2 * SL <= cap && (tile_len % (64 * SL)) == 0) SL *= 2;
+        if (SL == 1) split_tiles = 0;
+    }
+    if (!split_tiles) SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
     SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
     const int W = S * AG * SL;
     if (W > w_cap || S > 32) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
@@ -368,11 +377,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         const int64_t per_cta = std::max<int64_t>(1, total_tiles / grid);
         const int64_t max_contrib = std::min<int64_t>(grid, (tiles_per_job + per_cta - 1) / per_cta + 1);
         a.fin_group = max_contrib <= 8 ? 1 : 32;
-        // few tiles per CTA: let every slice work on every tile instead of taking turns
-        a.split_tiles = (SL > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid) ? 1 : 0;
-        a.split_tiles = env_int("GAT_TUNE_SPLIT", a.split_tiles);
-        // warps sharing a code replica meet at named barriers 2..15: at most 14 such groups
-        if (a.split_tiles && AG * SL > 1 && S > 14) a.split_tiles = 0;
+        a.split_tiles = (split_tiles && SL > 1) ? 1 : 0;
         a.tt_stride = a.split_tiles ? 32 * SL : 32;
     }
 
