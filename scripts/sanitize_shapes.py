@@ -31,6 +31,25 @@ for (system, K, M, L, N, P, start, f64) in [(l1, 1, 1, 3, 2500, 1, 0, False), (l
                                           c.carrier_frequency, c.carrier_phase, fs, shifts, start_sample=start, n_samples=N,
                                           code_mode="f64" if f64 else "nco")
             worst = max(worst, np.abs(got[p, k] - ref).max() / (3 * np.sqrt(N)))
+# raw int16 tiles (SC16 kernel) and the post-correlation kernels
+import torch
+iq = rng.integers(-2000, 2000, size=(5, 3000, 2)).astype(np.int16)
+eng.upload_signal_int(7, iq, 1.0 / 1024)
+ch = [g.Channel(l1, 4, 100.5, 1200.0, 0.1)]
+sh3 = np.array([-2, 0, 2], np.int32)
+got = eng.correlate(7, ch, 3.0e6, sh3, 5, start_sample=2, n_samples=2990)
+assert eng.launch_info()["sc16"] == 1
+q_re, q_im = iq[..., 0].astype(np.float32) / 1024, iq[..., 1].astype(np.float32) / 1024
+ref = oracle.correlate_direct(q_re, q_im, l1.codes[3], 1.023e6, 100.5, 1200.0, 0.1, 3.0e6, sh3, start_sample=2, n_samples=2990)
+worst = max(worst, np.abs(got[0] - ref).max() / (3 * np.sqrt(2990)))
+out = (torch.zeros(1, 1, 3, 5, device="cuda"), torch.zeros(1, 1, 3, 5, device="cuda"))
+eng.correlate_batch([7], [ch], 3.0e6, sh3, 5, 2, 2990, out=out)
+cov = (torch.zeros(1, 5, 5, device="cuda"), torch.zeros(1, 5, 5, device="cuda"))
+w = (torch.zeros(1, 5, device="cuda"), torch.zeros(1, 5, device="cuda"))
+eng.eigen_weights(out, cov, w, tap=1, forget=0.9, iters=3)
+y = eng.beamform(out, w)
+eng.sync()
+assert torch.isfinite(y[0]).all()
 print("worst normalised error", worst)
 assert worst < 1e-4
 eng.close()
