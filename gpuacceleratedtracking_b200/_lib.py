@@ -15,6 +15,7 @@ GAT_ERR_NO_CODES, GAT_ERR_NO_SIGNAL, GAT_ERR_NO_DEVICE = -5, -6, -7
 GAT_ACCUMULATE = 1
 GAT_CODE_PHASE_F64 = 2
 GAT_GATHER = 4
+GAT_TENSOR_TF32 = 8
 GAT_IPC_HANDLE_BYTES = 64
 GAT_SLOT_DESC_BYTES = 96
 GAT_GPSL1, GAT_GPSL5 = 0, 1
@@ -32,7 +33,7 @@ class GatLaunchInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "grid", "block", "smem_bytes", "ants_per_thread", "ant_groups", "sats_per_cta", "sample_slices",
         "consumer_warps", "sat_groups", "chunks_per_job", "chunk_len", "tile_len", "stages", "items",
-        "kernels_launched", "sc16")] + [("last_kernel_ms", C.c_float)]
+        "kernels_launched", "sc16", "tensor")] + [("last_kernel_ms", C.c_float)]
 
 
 class GatError(RuntimeError):

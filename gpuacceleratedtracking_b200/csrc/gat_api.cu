@@ -33,6 +33,8 @@ struct SignalSlot {
     bool raw_valid = false;
     PeriodDev raw_map{};         // .re = 2-D descriptor over the 32-bit I/Q words
     void *peer_base = nullptr;   // gat_slot_import: another process's planes mapped through CUDA IPC (closed on release)
+    TcPeriod tc_map{};           // 4-D descriptor of both planes for the tensor-core path (encoded on first use)
+    int tc_state = 0;            // 0 = not tried, 1 = valid, -1 = the layout cannot be expressed (im <= re, ...)
 };
 
 struct CodeTable {
@@ -420,6 +422,7 @@ EncodeTiledFn encode_tiled_fn()
 // (re)build the two plane descriptors of a slot: dims {n_samples, n_ants}, box {kTileCap, n_ants}
 int encode_slot_maps(gat_ctx *ctx, SignalSlot &s)
 {
+    s.tc_state = 0;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(ctx, GAT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(s.n_samples), static_cast<cuuint64_t>(s.n_ants)};
@@ -532,6 +535,29 @@ int ensure_planes(gat_ctx *ctx, SignalSlot &s)
     return GAT_OK;
 }
 
+// 4-D view {4 samples, antennas, planes, sample groups} of a slot's two FP32 planes: one TMA box {4, 16, 2, 64} is the
+// [sample/4][plane][antenna][sample%4] tile the tensor-core kernel uses as its K-major B operand
+bool encode_tc_map(SignalSlot &s)
+{
+    if (s.tc_state) return s.tc_state > 0;
+    s.tc_state = -1;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || !s.re || !s.im || s.im <= s.re || s.n_ants > 16) return false;
+    const uint64_t plane_bytes = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(s.im) - reinterpret_cast<uintptr_t>(s.re));
+    uint64_t row_bytes = static_cast<uint64_t>(s.ld) * sizeof(float);
+    if (s.n_ants == 1) row_bytes = (static_cast<uint64_t>(s.n_samples) * sizeof(float) + 15) / 16 * 16;
+    if (plane_bytes % 16 || plane_bytes >= (1ull << 40) || row_bytes % 16 || (reinterpret_cast<uintptr_t>(s.re) & 15u)) return false;
+    const cuuint64_t dims[4] = {4, static_cast<cuuint64_t>(s.n_ants), 2, static_cast<cuuint64_t>((s.n_samples + 3) / 4)};
+    const cuuint64_t strides[3] = {row_bytes, plane_bytes, 16};
+    const cuuint32_t box[4] = {4, 16, 2, 64};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&s.tc_map.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s.re, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    s.tc_state = 1;
+    return true;
+}
+
 int check_ctx(gat_ctx *ctx)
 {
     if (!ctx) return GAT_ERR_INVALID;
@@ -597,6 +623,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         const int pref = env_int("GAT_TUNE_RAW", -1);
         const bool worth = n_sats <= 2 || (!all_planes && n_sats <= 16);
         use_raw = all_raw && pow2 && !(flags & GAT_CODE_PHASE_F64) && (pref < 0 ? worth : pref != 0);
+        if (flags & GAT_TENSOR_TF32) use_raw = false;       // the tensor-core path works on the FP32 planes
     }
     for (int p = 0; p < n_periods; ++p) {
         SignalSlot &sl = ctx->slots[slots[p]];
@@ -622,6 +649,102 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         shape.max_delta = std::max(shape.max_delta, sats[i].nco_delta);
         shape.max_code_len = std::max(shape.max_code_len, sats[i].code_len);
         shape.min_code_len = std::min(shape.min_code_len, sats[i].code_len);
+    }
+
+    // ---- tensor-core path (opt-in): many channels over the same block(s), see gat_correlate_tc.cu ----
+    ctx->info.tensor = 0;
+    if (flags & GAT_TENSOR_TF32) {
+        const int span = sh_pad[n_taps - 1] - sh_pad[0];
+        bool ok = !(flags & (GAT_CODE_PHASE_F64 | GAT_ACCUMULATE | GAT_GATHER)) && n_taps <= 4 && M <= 16 && span <= 224 &&
+                  shape.max_code_len <= 1024 &&
+                  static_cast<double>(kTileCap + span + 64) * shape.max_ratio + 2.0 < static_cast<double>(shape.min_code_len);
+        {
+            const long double need = static_cast<long double>(kTileCap + span + 64) * static_cast<long double>(shape.max_delta) +
+                                     std::ldexp(1.0L, shape.min_fp);
+            ok = ok && need < std::ldexp(1.0L, 64);
+        }
+        for (int p = 0; ok && p < n_periods; ++p) ok = encode_tc_map(ctx->slots[slots[p]]);
+        if (ok) {
+            const int aligned_start = start_sample & ~3;
+            const int aligned_len = start_sample + n_samples - aligned_start;
+            const int G = (n_sats + 31) / 32;
+            const int jobs = n_periods * G;
+            const int tiles_per_job = (aligned_len + kTileCap - 1) / kTileCap;
+            const int64_t total_units = static_cast<int64_t>(jobs) * tiles_per_job;
+            int grid = static_cast<int>(std::min<int64_t>(total_units, ctx->n_sm));
+            if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
+            // parameter block: [TcPeriod x P][SatDev x P*K]
+            const size_t per_bytes = sizeof(TcPeriod) * n_periods;
+            std::vector<unsigned char> blk(per_bytes + sizeof(SatDev) * n_ch);
+            for (int p = 0; p < n_periods; ++p) std::memcpy(blk.data() + sizeof(TcPeriod) * p, &ctx->slots[slots[p]].tc_map, sizeof(TcPeriod));
+            std::memcpy(blk.data() + per_bytes, sats.data(), sizeof(SatDev) * n_ch);
+            unsigned char *d_blk = nullptr;
+            Staging *stg = nullptr;
+            rc = stage_params(ctx, blk.data(), blk.size(), &d_blk, &stg);
+            if (rc) return rc;
+            rc = ensure_device(ctx, ctx->d_partials, ctx->partials_cap, (static_cast<size_t>(jobs) + grid) * 2 * 128 * 16, false);
+            if (rc) return rc;
+            const size_t out_elems = n_ch * static_cast<size_t>(n_taps) * M;
+            if (!out_is_device && 2 * out_elems > ctx->h_out_cap) {
+                if (ctx->h_out) {
+                    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    GAT_CUDA(ctx, cudaFreeHost(ctx->h_out));
+                }
+                ctx->h_out = nullptr;
+                ctx->h_out_cap = 0;
+                GAT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), 4 * out_elems * sizeof(float), cudaHostAllocMapped));
+                ctx->h_out_cap = 4 * out_elems;
+            }
+            TcArgs ta{};
+            ta.periods = reinterpret_cast<const TcPeriod *>(d_blk);
+            ta.sats = reinterpret_cast<const SatDev *>(d_blk + per_bytes);
+            ta.partials = ctx->d_partials;
+            ta.out_re = out_is_device ? out_re : ctx->h_out;
+            ta.out_im = out_is_device ? out_im : ctx->h_out + out_elems;
+            ta.n_periods = n_periods;
+            ta.n_sats = n_sats;
+            ta.n_ants = M;
+            ta.n_taps = n_taps;
+            ta.shift0 = sh_pad[0];
+            ta.span = span;
+            for (int l = 0; l < 4; ++l) ta.koff[l] = l < n_taps ? sh_pad[l] - sh_pad[0] : 0;
+            ta.start_sample = start_sample;
+            ta.n_samples = n_samples;
+            ta.aligned_start = aligned_start;
+            ta.tiles_per_job = tiles_per_job;
+            ta.G = G;
+            ta.total_units = total_units;
+            if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+            cudaError_t e = launch_correlate_tc(ta, grid, jobs, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "tensor-core correlate launch");
+            GAT_CUDA(ctx, cudaEventRecord(stg->consumed, ctx->stream));
+            if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+            ctx->launches += 2;
+            gat_launch_info &li = ctx->info;
+            li = gat_launch_info{};
+            li.grid = grid;
+            li.block = 32 * 17;
+            li.sats_per_cta = 32;
+            li.sat_groups = G;
+            li.tile_len = kTileCap;
+            li.stages = 2;
+            li.items = static_cast<int32_t>(total_units);
+            li.kernels_launched = 2;
+            li.tensor = 1;
+            if (!out_is_device) {
+                GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                std::memcpy(out_re, ctx->h_out, out_elems * sizeof(float));
+                std::memcpy(out_im, ctx->h_out + out_elems, out_elems * sizeof(float));
+            }
+            if (ctx->timing) {
+                GAT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+                float ms = 0.f;
+                GAT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+                ctx->info.last_kernel_ms = ms;
+            }
+            return GAT_OK;
+        }
+        // otherwise: the shape is outside the tensor-core path's envelope -> the FP32 kernel below
     }
 
     LaunchPlan plan{};
@@ -827,7 +950,7 @@ int gat_create(gat_ctx **out, int device_id)
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->param_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-        configure_kernels() != cudaSuccess) {
+        configure_kernels() != cudaSuccess || configure_tc_kernel() != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return GAT_ERR_CUDA;

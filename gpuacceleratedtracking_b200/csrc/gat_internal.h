@@ -101,6 +101,25 @@ struct LaunchPlan {
 __host__ __device__ inline size_t smem_tile_floats(int AG, int A, bool sc16 = false) { return (size_t)(sc16 ? 1 : 2) * AG * A * kTileCap; }
 __host__ __device__ inline int padded_acc(int A, int L) { return ((2 * A * L) + 31) / 32 * 32; }
 
+// ---- tensor-core path (gat_correlate_tc.cu) ----
+struct alignas(64) TcPeriod {
+    CUtensorMap map;   // 4-D view of the two planes: {4 samples, antennas, planes, sample groups}, box {4, 16, 2, 64}
+};
+struct alignas(64) TcArgs {
+    const TcPeriod *periods;
+    const SatDev *sats;          // [n_periods][n_sats]
+    float *partials;             // [(jobs + grid)][re, im][128 rows][16 antennas]
+    float *out_re, *out_im;      // [n_ants x n_taps x n_sats x n_periods]
+    int32_t n_periods, n_sats, n_ants, n_taps;
+    int32_t shift0, span;        // first tap's sample shift, last - first
+    int32_t koff[4];             // tap offsets relative to the first tap
+    int32_t start_sample, n_samples, aligned_start;
+    int32_t tiles_per_job, G;
+    int64_t total_units;
+};
+cudaError_t configure_tc_kernel();
+cudaError_t launch_correlate_tc(const TcArgs &args, int grid, int jobs, cudaStream_t stream);
+
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream);
 cudaError_t configure_kernels();   // opt-in to > 48 KB dynamic smem for every instantiation
 bool kernel_available(int A, int L);

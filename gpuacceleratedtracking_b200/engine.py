@@ -215,7 +215,8 @@ class Engine:
     # -- the hot path -----------------------------------------------------------------------
     def correlate_batch(self, slots: Sequence[int], channels: Sequence[Sequence[Channel]], fs: float,
                         shifts: Sequence[int], n_ants: int, start_sample: int = 0, n_samples: int | None = None,
-                        out=None, accumulate: bool = False, code_phase_f64: bool = False, gather: bool = False):
+                        out=None, accumulate: bool = False, code_phase_f64: bool = False, gather: bool = False,
+                        tensor: bool = False):
         """channels[p][k]; returns complex64 [P, K, L, M] (host) or fills `out=(re, im)` torch
         CUDA tensors of that shape (asynchronous).  gather=True (after gather_setup) makes the kernel
         store the block into every rank's gather buffer instead (multi-GPU)."""
@@ -232,7 +233,8 @@ class Engine:
         sl = slots if isinstance(slots, np.ndarray) and slots.dtype == np.int32 else np.ascontiguousarray(slots, np.int32)
         if n_samples is None:
             raise ValueError("n_samples is required")
-        flags = (_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0)
+        flags = ((_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0) |
+                 (_lib.GAT_TENSOR_TF32 if tensor else 0))
         i32p = C.POINTER(C.c_int32)
         if gather:      # outputs go straight into every rank's gather buffer (fused epilogue, no host copy)
             self._check(self._lib.gat_correlate_batch(self._h, P, sl.ctypes.data_as(i32p), K, arr, fs,
@@ -265,10 +267,10 @@ class Engine:
 
     def correlate(self, slot: int, channels: Sequence[Channel], fs: float, shifts: Sequence[int], n_ants: int,
                   start_sample: int = 0, n_samples: int | None = None, out=None, accumulate: bool = False,
-                  code_phase_f64: bool = False):
+                  code_phase_f64: bool = False, tensor: bool = False):
         """One period: returns complex64 [K, L, M]."""
         res = self.correlate_batch([slot], [list(channels)], fs, shifts, n_ants, start_sample, n_samples,
-                                   out=out, accumulate=accumulate, code_phase_f64=code_phase_f64)
+                                   out=out, accumulate=accumulate, code_phase_f64=code_phase_f64, tensor=tensor)
         return res if out is not None else res[0]
 
     def downconvert_and_correlate_host(self, re: np.ndarray, im: np.ndarray, channels: Sequence[Channel], fs: float,

@@ -59,6 +59,12 @@ typedef enum gat_status {
 #define GAT_GATHER 4u         /* multi-GPU: the kernel epilogue stores this rank's accumulators into the gather
                                  buffer of EVERY rank (peer memory over NVLink) instead of out_re/out_im, which
                                  are ignored.  Needs gat_gather_create/connect.                             */
+#define GAT_TENSOR_TF32 8u    /* allow the tensor-core path (tcgen05.mma kind::tf32) for blocks shared by many channels:
+                                 <= 4 taps, <= 16 antennas, NCO convention, chip tables <= 1023 chips.  W and the
+                                 samples are rounded to TF32 (10-bit mantissa), sums are FP32: <= 12-bit integer
+                                 samples stay exact, the accumulators carry ~3e-4 * sqrt(N) * rms(sample) of rounding
+                                 noise instead of the FP32 kernel's ~1e-7 relative.  Shapes outside the envelope run
+                                 on the FP32 kernel as usual (gat_launch_info.tensor tells which one ran).          */
 #define GAT_CODE_PHASE_F64 2u /* chip index = mod(floor(fc/fs*(n+shift)+phase), Lc) in IEEE double,
                                  bit-exact with the reference's GPU kernels (src/algorithms.jl:179-182).
                                  Default is the Int64 Q-format NCO of Tracking.jl's CPU path, bit-exact
@@ -208,6 +214,7 @@ typedef struct gat_launch_info {
     int32_t sat_groups, chunks_per_job, chunk_len, tile_len, stages, items;
     int32_t kernels_launched;   /* kernels of OURS enqueued by the last correlate call */
     int32_t sc16;               /* 1 if the kernel read raw int16 I/Q words (gat_upload_signal_sc16 slots) */
+    int32_t tensor;             /* 1 if the call ran on the tensor-core path (GAT_TENSOR_TF32) */
     float last_kernel_ms;       /* device time of the last correlate kernel if timing enabled */
 } gat_launch_info;
 int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out);

@@ -1,0 +1,96 @@
+"""GPU tier: the opt-in tensor-core path (GAT_TENSOR_TF32, csrc/gat_correlate_tc.cu) against the double-precision
+oracle and against the FP32 kernel.  Tolerance: W and the samples are rounded to TF32, so the accumulators carry
+~3e-4 * sqrt(N) * rms(sample) of rounding noise; the bar here is 2e-5 of N * rms(sample) (the FP32 kernel's bar is 1e-4
+of the prompt magnitude, which a full-strength signal satisfies with two orders of margin on this path too)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(gat, orc, rng, n_ch, m, n, fs, noise=1.0, extra=0):
+    l1 = gat.GPSL1()
+    chans = [gat.Channel(l1, 1 + k % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)), float(rng.uniform(-.5, .5)))
+             for k in range(n_ch)]
+    re = rng.normal(0, noise, size=(m, n + extra)).astype(np.float32)
+    im = rng.normal(0, noise, size=(m, n + extra)).astype(np.float32)
+    for c in chans[:3]:                                    # three channels actually present in the block
+        r, i = orc.gen_signal(l1.codes[c.prn - 1], 1.023e6, c.carrier_frequency, fs, n + extra, m, c.code_phase, 2 * np.pi * c.carrier_phase)
+        re += 0.5 * r
+        im += 0.5 * i
+    return l1, chans, re, im
+
+
+@pytest.mark.parametrize("n_ch,m,taps,n", [(32, 16, 3, 20000), (40, 16, 3, 12000), (33, 5, 4, 6000), (70, 16, 1, 9000), (3, 2, 2, 5000)])
+def test_tensor_path_matches_oracle(gat, orc, engine, n_ch, m, taps, n):
+    rng = np.random.default_rng(n_ch * 31 + m)
+    fs = 2.0e7
+    l1, chans, re, im = _scene(gat, orc, rng, n_ch, m, n, fs)
+    shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 9
+    engine.upload_signal(40, re, im)
+    got = engine.correlate(40, chans, fs, shifts, m, n_samples=n, tensor=True)
+    assert engine.launch_info()["tensor"] == 1
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                         fs, shifts) for c in chans])
+    rms = float(np.sqrt(np.mean(re.astype(np.float64) ** 2 + im.astype(np.float64) ** 2)))
+    assert np.abs(got - ref).max() <= 2e-5 * n * rms
+    # the present channels are found at full strength, and within the FP32 kernel's own bar of their prompt
+    p = taps // 2
+    assert abs(abs(got[0, p, 0]) - 0.5 * n) < 0.05 * n
+    assert np.abs(got[0] - ref[0]).max() <= 1e-4 * np.abs(ref[0, p]).max()
+    fp32 = engine.correlate(40, chans, fs, shifts, m, n_samples=n)
+    assert engine.launch_info()["tensor"] == 0
+    assert np.abs(got - fp32).max() <= 2e-5 * n * rms
+
+
+def test_tensor_path_ragged_batch_and_device_outputs(gat, orc, engine):
+    import torch
+    rng = np.random.default_rng(77)
+    fs, n, start, m, n_ch, P = 1.6e7, 5011, 37, 7, 35, 3
+    shifts = np.array([-7, 0, 7], np.int32)
+    blocks, chans = [], []
+    for p in range(P):
+        l1, ch, re, im = _scene(gat, orc, rng, n_ch, m, n, fs, extra=start + 11)
+        engine.upload_signal(50 + p, re, im)
+        blocks.append((re, im))
+        chans.append(ch)
+    out = (torch.zeros(P, n_ch, 3, m, device="cuda"), torch.zeros(P, n_ch, 3, m, device="cuda"))
+    engine.correlate_batch([50, 51, 52], chans, fs, shifts, m, start_sample=start, n_samples=n, out=out, tensor=True)
+    engine.sync()
+    assert engine.launch_info()["tensor"] == 1
+    got = (out[0] + 1j * out[1]).cpu().numpy()
+    for p in range(P):
+        re, im = blocks[p]
+        for k in (0, 1, 17, 34):
+            c = chans[p][k]
+            ref = orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase, fs,
+                                       shifts, start_sample=start, n_samples=n)
+            assert np.abs(got[p, k] - ref).max() <= 3e-5 * n * 1.6
+    again = (torch.zeros_like(out[0]), torch.zeros_like(out[1]))
+    engine.correlate_batch([50, 51, 52], chans, fs, shifts, m, start_sample=start, n_samples=n, out=again, tensor=True)
+    engine.sync()
+    assert torch.equal(out[0], again[0]) and torch.equal(out[1], again[1])            # deterministic
+
+
+def test_tensor_path_integer_samples_and_fallbacks(gat, orc, engine):
+    rng = np.random.default_rng(5)
+    l1 = gat.GPSL1()
+    fs, n, m, n_ch = 2.5e7, 16000, 16, 48
+    chans = [gat.Channel(l1, 1 + k % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)), 0.0) for k in range(n_ch)]
+    iq = rng.integers(-2047, 2048, size=(m, n, 2)).astype(np.int16)                   # 12-bit samples: exact in TF32
+    shifts = np.array([-12, 0, 12], np.int32)
+    engine.upload_signal_int(60, iq, 1.0)
+    got = engine.correlate(60, chans, fs, shifts, m, n_samples=n, tensor=True)
+    assert engine.launch_info()["tensor"] == 1 and engine.launch_info()["sc16"] == 0
+    re, im = iq[..., 0].astype(np.float32), iq[..., 1].astype(np.float32)
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                         fs, shifts) for c in chans[:6]])
+    assert np.abs(got[:6] - ref).max() <= 1e-5 * n * 1675.0                            # only W is rounded
+    # outside the envelope (5 taps; Float64 chip index mode) the FP32 kernel runs and the flag is harmless
+    five = (np.arange(5, dtype=np.int32) - 2) * 6
+    a = engine.correlate(60, chans[:4], fs, five, m, n_samples=n, tensor=True)
+    assert engine.launch_info()["tensor"] == 0
+    b = engine.correlate(60, chans[:4], fs, five, m, n_samples=n)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    engine.correlate(60, chans[:4], fs, shifts, m, n_samples=n, tensor=True, code_phase_f64=True)
+    assert engine.launch_info()["tensor"] == 0
