@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         const uint32_t a_re = s32(sA + (buf * 2 + 0) * kTcAChunk), a_im = s32(sA + (buf * 2 + 1) * kTcAChunk);
                         const uint32_t b0 = bt + (uint32_t)c * (kTcChunk / 4) * kTcBGroup;
 #pragma unroll
-                        for (int j = 0; j < kTcSteps; ++j) {
+                        for (int j = 0; j < kTcSteps && !(args.debug & 2); ++j) {
                             const uint64_t db = umma_desc(b0 + j * 2 * kTcBGroup, kTcBGroup, 128);
                             const uint32_t acc = (t > t_first || c > 0 || j > 0) ? 1u : 0u;
                             umma_tf32(tmem, umma_desc(a_re + j * kTcAStep, kTcRows * 16, 128), db, acc);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             bar_wait(B_FULL + 8 * st, (qb >> 1) & 1u);
             {
                 unsigned char *bp = sB + st * kTcBTile;
-                for (int i = tid; i < kTcBTile / 16; i += 32 * kTcGenWarps) {        // 16 B = 4 samples of one column
+                for (int i = tid; i < kTcBTile / 16 && !(args.debug & 8); i += 32 * kTcGenWarps) {        // 16 B = 4 samples of one column
                     const int g = i >> 5;                                             // sample group in the tile
                     uint4 w = reinterpret_cast<uint4 *>(bp)[i];
                     const int n = n0 + 4 * g;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     const int sl = warp + 16 * h;
                     float cr = 0.f, ci = 0.f;
                     const int n = n0 + c * kTcChunk + lane;
-                    if (live[h] && n >= 0 && n < args.n_samples) {
+                    if (live[h] && n >= 0 && n < args.n_samples && !(args.debug & 4)) {
                         const uint64_t ph = cph[h] + (uint64_t)(c * kTcChunk + lane) * cdel[h];
                         __sincosf((float)(int32_t)(uint32_t)(ph >> 32) * 1.4629180792671596e-9f, &ci, &cr);   // 2 pi / 2^32
                     }
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 gen_bar_sync();                               // carrier rows (and, for c == 0, replica bits and the rounded tile) ready
                 if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
                 // ---- tap rows: rows 8 w .. 8 w + 7, four samples per step; one 128-byte core matrix per store ----
-                if (tap < L) {
+                if (tap < L && !(args.debug & 1)) {
                     const uint32_t a_re = s32(sA + (buf * 2 + 0) * kTcAChunk) + (uint32_t)warp * 128u + (uint32_t)lane * 4u;
                     const uint32_t a_im = a_re + kTcAChunk;
                     const uint32_t car_s = s32(sCar + (buf * kTcSats + my_sat) * kTcChunk + k4);
@@ -358,20 +358,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     if (warp == kTcGenWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
 }
 
-// sum the partials of every job in CTA order (fixed -> deterministic) and write the caller's [M x L x K x P] planes
+// sum the partials of every job in CTA order (fixed -> deterministic) and write the caller's [M x L x K x P] planes.
+// 8 lanes per output element: lane j adds contributors b_first + j, + 8, ...; a fixed xor tree combines the eight sums.
 __global__ void __launch_bounds__(256) tc_finalize_kernel(const TcArgs args, int grid)
 {
-    const int job = blockIdx.x;
+    const int job = blockIdx.x / 128;
     const int G = args.G, TJ = args.tiles_per_job, K = args.n_sats, L = args.n_taps, M = args.n_ants;
     const int p = job / G, grp = job % G;
     const int b_first = tc_owner((int64_t)job * TJ, grid, args.total_units);
     const int b_last = tc_owner((int64_t)(job + 1) * TJ - 1, grid, args.total_units);
-    for (int x = threadIdx.x; x < 2 * kTcRows * kTcAnts; x += blockDim.x) {
-        const int c = x / (kTcRows * kTcAnts), row = (x / kTcAnts) % kTcRows, m = x % kTcAnts;
-        const int k = grp * kTcSats + (row >> 2), tap = row & 3;
-        if (k >= K || tap >= L || m >= M) continue;
-        float acc = 0.f;
-        for (int b = b_first; b <= b_last; ++b) acc += __ldcg(args.partials + (size_t)(job + b) * 2 * kTcRows * kTcAnts + x);
+    const int x = (blockIdx.x % 128) * 32 + (threadIdx.x >> 3), j = threadIdx.x & 7;      // element of [re, im][128 rows][16 antennas]
+    const size_t stride = (size_t)2 * kTcRows * kTcAnts;
+    const float *src = args.partials + (size_t)(job + b_first + j) * stride + x;
+    float a0 = 0.f, a1 = 0.f;
+    int b = b_first + j;
+    for (; b + 8 <= b_last; b += 16, src += 16 * stride) {
+        a0 += __ldcg(src);
+        a1 += __ldcg(src + 8 * stride);
+    }
+    if (b <= b_last) a0 += __ldcg(src);
+    float acc = a0 + a1;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    const int c = x / (kTcRows * kTcAnts), row = (x / kTcAnts) % kTcRows, m = x % kTcAnts;
+    const int k = grp * kTcSats + (row >> 2), tap = row & 3;
+    if (j == 0 && k < K && tap < L && m < M) {
         float *out = c ? args.out_im : args.out_re;
         out[(((size_t)p * K + k) * L + tap) * M + m] = acc;
     }
@@ -387,7 +399,7 @@ cudaError_t launch_correlate_tc(const TcArgs &args, int grid, int jobs, cudaStre
     correlate_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    tc_finalize_kernel<<<jobs, 256, 0, stream>>>(args, grid);
+    tc_finalize_kernel<<<jobs * 128, 256, 0, stream>>>(args, grid);
     return cudaGetLastError();
 }
 
