@@ -657,9 +657,9 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         const int span = sh_pad[n_taps - 1] - sh_pad[0];
         bool ok = !(flags & (GAT_CODE_PHASE_F64 | GAT_ACCUMULATE | GAT_GATHER)) && n_taps <= 4 && M <= 16 && span <= 224 &&
                   shape.max_code_len <= 1024 &&
-                  static_cast<double>(kTileCap + span + 64) * shape.max_ratio + 2.0 < static_cast<double>(shape.min_code_len);
+                  static_cast<double>(kTileCap + span + 192) * shape.max_ratio + 2.0 < static_cast<double>(shape.min_code_len);
         {
-            const long double need = static_cast<long double>(kTileCap + span + 64) * static_cast<long double>(shape.max_delta) +
+            const long double need = static_cast<long double>(kTileCap + span + 192) * static_cast<long double>(shape.max_delta) +
                                      std::ldexp(1.0L, shape.min_fp);
             ok = ok && need < std::ldexp(1.0L, 64);
         }

@@ -39,8 +39,8 @@ constexpr int kTcBTile = (kTcTile / 4) * kTcBGroup;        // 32 KB
 constexpr int kTcGenWarps = 16;
 constexpr int kTcThreads = 32 * (kTcGenWarps + 1);
 constexpr int kTcTabStride = 1024;                         // chip table bytes per channel in shared memory
-constexpr int kTcRepWords = 16;                            // replica sign bits per channel and tile: 512 entries
-constexpr int kTcSmemBytes = 2 * kTcBTile + 4 * kTcAChunk + kTcSats * kTcTabStride + kTcSats * kTcRepWords * 4 + 2 * kTcSats * kTcChunk * 8;
+constexpr int kTcRepWords = 20;                            // replica sign bits per channel and tile: <= 512 entries (+ one spare word)
+constexpr int kTcSmemBytes = 2 * kTcBTile + 4 * kTcAChunk + kTcSats * kTcTabStride + kTcSats * kTcRepWords * 4 + kTcSats * kTcChunk * 8;
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint32_t a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(n)); }
@@ -101,7 +101,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[31])
         : "r"(taddr));
 }
-__device__ __forceinline__ void gen_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kTcGenWarps) : "memory"); }
 __device__ __forceinline__ int tc_owner(int64_t x, int grid, int64_t total) { return (int)(((x + 1) * grid - 1) / total); }
 
 }  // namespace
@@ -113,7 +112,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     unsigned char *sA = sB + 2 * kTcBTile;                               // [2 buffers][re, im][kTcAChunk]
     int8_t *sTab = reinterpret_cast<int8_t *>(sA + 4 * kTcAChunk);       // [32][1024]
     uint32_t *sRep = reinterpret_cast<uint32_t *>(sTab + kTcSats * kTcTabStride);   // [32][16] sign bits of the tile's replica
-    float2 *sCar = reinterpret_cast<float2 *>(sRep + kTcSats * kTcRepWords);        // [2][32][32] (cos, -sin) as TF32
+    float2 *sCar = reinterpret_cast<float2 *>(sRep + kTcSats * kTcRepWords);        // [32][32] (cos, -sin) as TF32, private to the owning warp
     __shared__ uint32_t tmem_base;
     __shared__ __align__(8) uint64_t bars[9];   // 0,1 B full; 2,3 B free; 4,5 A full; 6,7 A free; 8 accumulators ready
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
 
     // lane roles of the tap-row phase: this warp owns row group `warp` = channels 2 warp, 2 warp + 1
     const int r8 = lane >> 2, k4 = lane & 3, tap = r8 & 3;
-    const int my_sat = 2 * warp + (r8 >> 2);
+    const int my_sat = 2 * warp + (r8 >> 2);    // the channel of this lane's tap row
     uint32_t qa = 0;      // running chunk counter (A buffer + parity)
     uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity)
     uint32_t seg = 0;
@@ -161,15 +160,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         const int p = job / G, grp = job % G;
         const TcPeriod *per = &args.periods[p];
 
-        // ---- segment set-up (generator warps): chip tables and the per-channel NCO / carrier state of channels w, w + 16 ----
-        uint64_t frac[2] = {0, 0}, cph[2] = {0, 0}, cdel[2] = {0, 0}, ndel[2] = {0, 0};
+        // ---- segment set-up: every generator warp owns channels 2 w and 2 w + 1 of the group -- their chip tables, replica
+        // bits, carrier rows and tap rows -- so the generator warps never wait for each other, only for the MMA thread ----
+        uint64_t frac[2] = {0, 0}, cphl[2] = {0, 0}, cdel32[2] = {0, 0}, ndel[2] = {0, 0};
         uint32_t bmod[2] = {0, 0}, lc[2] = {1, 1};
         int fp[2] = {32, 32};
         bool live[2] = {false, false};
         if (warp < kTcGenWarps) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int sl = warp + 16 * h, k = grp * kTcSats + sl;
+                const int sl = 2 * warp + h, k = grp * kTcSats + sl;
                 live[h] = k < K;
                 if (live[h]) {
                     const SatDev *sd = &args.sats[(size_t)p * K + k];
@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     ndel[h] = (uint64_t)sd->nco_delta;
                     fp[h] = sd->nco_fp;
                     lc[h] = (uint32_t)clen;
-                    cdel[h] = sd->car_delta;
                     // state at the first sample of tile t_first (relative index n0 may be < 0 for the alignment head)
                     const int64_t n0 = (int64_t)args.aligned_start + (int64_t)t_first * kTcTile - args.start_sample;
                     const __int128 tot = (__int128)(n0 + args.shift0) * (__int128)sd->nco_delta + (__int128)sd->nco_start;
@@ -188,7 +187,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     if (b < 0) b += clen;
                     bmod[h] = (uint32_t)b;
                     frac[h] = (uint64_t)tot & ((1ull << sd->nco_fp) - 1ull);
-                    cph[h] = sd->car_phase + (uint64_t)n0 * sd->car_delta;
+                    // carrier phase (Q0.64) of THIS LANE's sample in the next chunk, advanced by 32 samples per chunk
+                    cphl[h] = sd->car_phase + (uint64_t)(n0 + lane) * sd->car_delta;
+                    cdel32[h] = 32ull * sd->car_delta;
                 }
             }
         }
@@ -239,24 +240,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             }
 
             // ================================= generator warps =================================
-            gen_bar_sync();                                   // everybody is done with the previous tile's replica bits
-            // ---- replica sign bits of this tile for channels w, w + 16: entry e <-> sample n0 + e + shift0 ----
+            // ---- replica sign bits of this tile for the warp's two channels: entry e <-> sample n0 + e + shift0 ----
+            __syncwarp();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (!live[h]) continue;
-                const int sl = warp + 16 * h;
+                const int sl = 2 * warp + h;
                 const uint32_t tab_s = s32(sTab + sl * kTcTabStride);
                 const int sh = fp[h] - 32;
                 uint64_t v = frac[h] + (uint64_t)lane * ndel[h];
                 const uint64_t v32 = 32ull * ndel[h];
                 const int rows = (kTcTile + args.span + 31) >> 5;
-                for (int r = 0; r < rows; ++r, v += v32) {
-                    uint32_t idx = bmod[h] + ((uint32_t)(v >> 32) >> sh);
-                    idx = min(idx, idx - lc[h]);              // single wrap (host-checked)
-                    int chip;
-                    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(chip) : "r"(tab_s + idx));
-                    const uint32_t bits = __ballot_sync(0xffffffffu, chip < 0);
-                    if (lane == 0) sRep[sl * kTcRepWords + r] = bits;
+                for (int r = 0; r < rows; r += 4) {                 // four independent table lookups in flight
+                    int chip[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j, v += v32) {
+                        uint32_t idx = bmod[h] + ((uint32_t)(v >> 32) >> sh);
+                        idx = min(idx, idx - lc[h]);                // single wrap (host-checked)
+                        asm volatile("ld.shared.s8 %0, [%1];" : "=r"(chip[j]) : "r"(tab_s + idx));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t bits = __ballot_sync(0xffffffffu, chip[j] < 0);
+                        if (lane == j) sRep[sl * kTcRepWords + r + j] = bits;       // (rows are padded to 20 words)
+                    }
                 }
                 // advance the NCO base to the next tile
                 const unsigned __int128 nf = (unsigned __int128)frac[h] + (unsigned __int128)kTcTile * (unsigned __int128)ndel[h];
@@ -280,47 +287,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     reinterpret_cast<uint4 *>(bp)[i] = w;
                 }
             }
+            const uint32_t car_w = s32(sCar + (2 * warp) * kTcChunk);               // this warp's two carrier rows
             for (int c = 0; c < kTcChunks; ++c, ++qa) {
                 const uint32_t buf = qa & 1u, use = qa >> 1;
-                // ---- carrier rows of this chunk for channels w, w + 16: lane = sample ----
+                // ---- carrier rows of this chunk for the warp's two channels: lane = sample ----
+                __syncwarp();                                                       // previous chunk's readers are done
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int sl = warp + 16 * h;
                     float cr = 0.f, ci = 0.f;
                     const int n = n0 + c * kTcChunk + lane;
-                    if (live[h] && n >= 0 && n < args.n_samples && !(args.debug & 4)) {
-                        const uint64_t ph = cph[h] + (uint64_t)(c * kTcChunk + lane) * cdel[h];
-                        __sincosf((float)(int32_t)(uint32_t)(ph >> 32) * 1.4629180792671596e-9f, &ci, &cr);   // 2 pi / 2^32
-                    }
-                    sCar[(buf * kTcSats + sl) * kTcChunk + lane] = make_float2(__uint_as_float(tf32_rna(cr)), __uint_as_float(tf32_rna(-ci)));
+                    if (live[h] && n >= 0 && n < args.n_samples && !(args.debug & 4))
+                        __sincosf((float)(int32_t)(uint32_t)(cphl[h] >> 32) * 1.4629180792671596e-9f, &ci, &cr);   // 2 pi / 2^32
+                    cphl[h] += cdel32[h];
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(car_w + (uint32_t)(h * kTcChunk + lane) * 8u), "r"(tf32_rna(cr)),
+                                 "r"(tf32_rna(-ci)) : "memory");
                 }
-                gen_bar_sync();                               // carrier rows (and, for c == 0, replica bits and the rounded tile) ready
+                __syncwarp();
                 if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
                 // ---- tap rows: rows 8 w .. 8 w + 7, four samples per step; one 128-byte core matrix per store ----
                 if (tap < L && !(args.debug & 1)) {
                     const uint32_t a_re = s32(sA + (buf * 2 + 0) * kTcAChunk) + (uint32_t)warp * 128u + (uint32_t)lane * 4u;
                     const uint32_t a_im = a_re + kTcAChunk;
-                    const uint32_t car_s = s32(sCar + (buf * kTcSats + my_sat) * kTcChunk + k4);
-                    const uint32_t rep_s = s32(sRep + my_sat * kTcRepWords);
-                    int e = c * kTcChunk + k4 + args.koff[tap];                       // replica entry of this lane's sample
+                    const uint32_t car_s = car_w + (uint32_t)((r8 >> 2) * kTcChunk + k4) * 8u;
+                    // the lane's eight replica entries e, e + 4, ..., e + 28 sit in two consecutive words
+                    const int e = c * kTcChunk + k4 + args.koff[tap];
+                    const uint32_t rep_s = s32(sRep + my_sat * kTcRepWords + (e >> 5));
+                    uint32_t w0, w1;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rep_s));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(rep_s + 4u));
+                    const uint32_t bits = __funnelshift_r(w0, w1, e & 31);            // bit 4 i = sign of entry e + 4 i
 #pragma unroll
-                    for (int i = 0; i < 8; ++i, e += 4) {
-                        float2 cv;
-                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cv.x), "=f"(cv.y) : "r"(car_s + 32u * i));
-                        uint32_t word;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(rep_s + 4u * (uint32_t)(e >> 5)));
-                        const uint32_t sign = (word >> (e & 31)) << 31;
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t cx, cy;
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cx), "=r"(cy) : "r"(car_s + 32u * i));
+                        const uint32_t sign = (bits << (31 - 4 * i)) & 0x80000000u;
                         const uint32_t off = (uint32_t)(i >> 1) * kTcAStep + (uint32_t)(i & 1) * 2048u;
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_re + off), "r"(__float_as_uint(cv.x) ^ sign) : "memory");
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_im + off), "r"(__float_as_uint(cv.y) ^ sign) : "memory");
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_re + off), "r"(cx ^ sign) : "memory");
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_im + off), "r"(cy ^ sign) : "memory");
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) bar_arrive(A_FULL + 8 * buf);
             }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) cph[h] += (uint64_t)kTcTile * cdel[h];
         }
         u += t_last - t_first;
 
