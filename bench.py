@@ -332,6 +332,24 @@ def run_gpu(args):
     barrier()
     rt_ms = r0.elapsed_time(r1) / 20
     rt_info = eng.launch_info()
+    # the same launch on the opt-in tensor-core path (tcgen05 kind::tf32, csrc/gat_correlate_tc.cu): TF32-rounded replica
+    # and samples, FP32 sums -- a different numeric contract (include/gat.h GAT_TENSOR_TF32), hence a side figure
+    rt_tensor = None
+    try:
+        for _ in range(5):
+            eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im), tensor=True)
+        if eng.launch_info()["tensor"] == 1:
+            barrier()
+            r0.record()
+            for _ in range(20):
+                eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im), tensor=True)
+            r1.record()
+            barrier()
+            rtt_ms = r0.elapsed_time(r1) / 20
+            rt_tensor = {"channels_per_launch": K_RT, "ms_per_launch": rtt_ms, "realtime_channels_per_gpu": K_RT / rtt_ms,
+                         "path": "tcgen05.mma kind::tf32 (opt-in GAT_TENSOR_TF32)"}
+    except Exception as exc:      # the side figure must never take the contract line down
+        rt_tensor = {"error": str(exc)[:200]}
 
     # ---- e2e: host buffers -> H2D (-> NCCL broadcast) -> correlate -> gather -> D2H ----
     e2e_steps = max(2, min(steps, args.e2e_steps))
@@ -528,6 +546,7 @@ def run_gpu(args):
                 "channels_per_launch": K_RT, "ms_per_launch": rt_ms, "realtime_channels_per_gpu": K_RT / rt_ms,
                 "fp32_tflops": K_RT * N_SAMPLES * N_ANTS * (6 + 4 * N_TAPS) / (rt_ms * 1e-3) / 1e12,
                 "sats_per_cta": rt_info["sats_per_cta"], "sat_groups": rt_info["sat_groups"]},
+            "realtime_shared_block_tensor": rt_tensor,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -31,16 +31,16 @@ namespace gat {
 namespace {
 
 constexpr int kTcRows = 128, kTcRowsPerSat = 4, kTcSats = kTcRows / kTcRowsPerSat, kTcAnts = 16, kTcCols = 2 * kTcAnts;
-constexpr int kTcTile = 256, kTcChunk = 32, kTcChunks = kTcTile / kTcChunk, kTcSteps = kTcChunk / 8;
+constexpr int kTcTile = 256, kTcChunk = 64, kTcChunks = kTcTile / kTcChunk, kTcSteps = kTcChunk / 8;
 constexpr int kTcAStep = kTcRows * 8 * 4;                  // one K-step (8 samples) of A: 4096 B
-constexpr int kTcAChunk = kTcSteps * kTcAStep;             // 16 KB per part (re / im) and buffer
+constexpr int kTcAChunk = kTcSteps * kTcAStep;             // 32 KB per part (re / im) and buffer
 constexpr int kTcBGroup = kTcCols * 16;                    // 4 samples of all 32 columns: 512 B
 constexpr int kTcBTile = (kTcTile / 4) * kTcBGroup;        // 32 KB
 constexpr int kTcGenWarps = 16;
 constexpr int kTcThreads = 32 * (kTcGenWarps + 1);
-constexpr int kTcTabStride = 1024;                         // chip table bytes per channel in shared memory
+constexpr int kTcTabWords = 32;                            // chip table of a channel as sign bits: 1024 chips in 128 B
 constexpr int kTcRepWords = 20;                            // replica sign bits per channel and tile: <= 512 entries (+ one spare word)
-constexpr int kTcSmemBytes = 2 * kTcBTile + 4 * kTcAChunk + kTcSats * kTcTabStride + kTcSats * kTcRepWords * 4 + kTcSats * kTcChunk * 8;
+constexpr int kTcSmemBytes = 2 * kTcBTile + 4 * kTcAChunk + kTcSats * kTcTabWords * 4 + kTcSats * kTcRepWords * 4 + kTcSats * kTcChunk * 8;
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint32_t a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(n)); }
@@ -110,19 +110,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sB = smem;                                            // [2][kTcBTile]
     unsigned char *sA = sB + 2 * kTcBTile;                               // [2 buffers][re, im][kTcAChunk]
-    int8_t *sTab = reinterpret_cast<int8_t *>(sA + 4 * kTcAChunk);       // [32][1024]
-    uint32_t *sRep = reinterpret_cast<uint32_t *>(sTab + kTcSats * kTcTabStride);   // [32][16] sign bits of the tile's replica
-    float2 *sCar = reinterpret_cast<float2 *>(sRep + kTcSats * kTcRepWords);        // [32][32] (cos, -sin) as TF32, private to the owning warp
+    uint32_t *sTab = reinterpret_cast<uint32_t *>(sA + 4 * kTcAChunk);   // [32][32] chip tables as sign bits
+    uint32_t *sRep = sTab + kTcSats * kTcTabWords;                       // [32][20] sign bits of the tile's replica
+    float2 *sCar = reinterpret_cast<float2 *>(sRep + kTcSats * kTcRepWords);        // [32][64] (cos, -sin) as TF32, private to the owning warp
     __shared__ uint32_t tmem_base;
-    __shared__ __align__(8) uint64_t bars[9];   // 0,1 B full; 2,3 B free; 4,5 A full; 6,7 A free; 8 accumulators ready
+    __shared__ __align__(8) uint64_t bars[7];   // 0,1 B full; 2,3 A full; 4,5 A free; 6 accumulators ready
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = s32(bars);
-    const uint32_t B_FULL = bar0, B_FREE = bar0 + 16, A_FULL = bar0 + 32, A_FREE = bar0 + 48, ACC = bar0 + 64;
+    const uint32_t B_FULL = bar0, A_FULL = bar0 + 16, A_FREE = bar0 + 32, ACC = bar0 + 48;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             bar_init(B_FULL + 8 * i, 1);
-            bar_init(B_FREE + 8 * i, 1);
             bar_init(A_FULL + 8 * i, kTcGenWarps);
             bar_init(A_FREE + 8 * i, 1);
         }
@@ -175,8 +174,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     const SatDev *sd = &args.sats[(size_t)p * K + k];
                     const int8_t *code = sd->code;
                     const int clen = sd->code_len;
-                    for (int i = lane * 16; i < clen; i += 512)                       // columns are padded to 16 B
-                        *reinterpret_cast<uint4 *>(sTab + sl * kTcTabStride + i) = *reinterpret_cast<const uint4 *>(code + i);
+                    for (int i = 0; i < kTcTabWords; ++i) {                           // 32 chips per ballot: bit = (chip < 0)
+                        const int ci = i * 32 + lane;
+                        const uint32_t bits = __ballot_sync(0xffffffffu, ci < clen && code[ci] < 0);
+                        if (lane == 0) sTab[sl * kTcTabWords + i] = bits;
+                    }
                     ndel[h] = (uint64_t)sd->nco_delta;
                     fp[h] = sd->nco_fp;
                     lc[h] = (uint32_t)clen;
@@ -211,7 +213,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     const int64_t un = u + (t - t_first) + 1;
                     if (un < r1) {
                         const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
-                        if (qb >= 1) bar_wait(B_FREE + 8 * (st ^ 1u), ((qb - 1) >> 1) & 1u);   // its previous reader is done
+                        if (qb >= 1) {                                               // its previous reader, tile qb - 1, is done:
+                            const uint32_t ql = qb * kTcChunks - 1;                  // ... that tile's last chunk has been committed
+                            bar_wait(A_FREE + 8 * (ql & 1u), (ql >> 1) & 1u);
+                        }
                         bar_expect(B_FULL + 8 * (st ^ 1u), kTcBTile);
                         tma_load_4d(s32(sB + (st ^ 1u) * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4,
                                     B_FULL + 8 * (st ^ 1u));
@@ -232,7 +237,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         }
                         umma_commit(A_FREE + 8 * buf);
                     }
-                    umma_commit(B_FREE + 8 * st);
                     if (t == t_last - 1) umma_commit(ACC);
                 }
                 qa += kTcChunks;
@@ -246,22 +250,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             for (int h = 0; h < 2; ++h) {
                 if (!live[h]) continue;
                 const int sl = 2 * warp + h;
-                const uint32_t tab_s = s32(sTab + sl * kTcTabStride);
+                const uint32_t tab_s = s32(sTab + sl * kTcTabWords);
                 const int sh = fp[h] - 32;
                 uint64_t v = frac[h] + (uint64_t)lane * ndel[h];
                 const uint64_t v32 = 32ull * ndel[h];
                 const int rows = (kTcTile + args.span + 31) >> 5;
                 for (int r = 0; r < rows; r += 4) {                 // four independent table lookups in flight
-                    int chip[4];
+                    uint32_t word[4], sft[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j, v += v32) {
                         uint32_t idx = bmod[h] + ((uint32_t)(v >> 32) >> sh);
                         idx = min(idx, idx - lc[h]);                // single wrap (host-checked)
-                        asm volatile("ld.shared.s8 %0, [%1];" : "=r"(chip[j]) : "r"(tab_s + idx));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word[j]) : "r"(tab_s + 4u * (idx >> 5)));
+                        sft[j] = idx & 31u;
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t bits = __ballot_sync(0xffffffffu, chip[j] < 0);
+                        const uint32_t bits = __ballot_sync(0xffffffffu, (word[j] >> sft[j]) & 1u);
                         if (lane == j) sRep[sl * kTcRepWords + r + j] = bits;       // (rows are padded to 20 words)
                     }
                 }
@@ -294,13 +299,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 __syncwarp();                                                       // previous chunk's readers are done
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    float cr = 0.f, ci = 0.f;
-                    const int n = n0 + c * kTcChunk + lane;
-                    if (live[h] && n >= 0 && n < args.n_samples && !(args.debug & 4))
-                        __sincosf((float)(int32_t)(uint32_t)(cphl[h] >> 32) * 1.4629180792671596e-9f, &ci, &cr);   // 2 pi / 2^32
-                    cphl[h] += cdel32[h];
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(car_w + (uint32_t)(h * kTcChunk + lane) * 8u), "r"(tf32_rna(cr)),
-                                 "r"(tf32_rna(-ci)) : "memory");
+#pragma unroll
+                    for (int half = 0; half < kTcChunk / 32; ++half) {
+                        float cr = 0.f, ci = 0.f;
+                        const int n = n0 + c * kTcChunk + half * 32 + lane;
+                        if (live[h] && n >= 0 && n < args.n_samples && !(args.debug & 4))
+                            __sincosf((float)(int32_t)(uint32_t)(cphl[h] >> 32) * 1.4629180792671596e-9f, &ci, &cr);   // 2 pi / 2^32
+                        cphl[h] += cdel32[h];
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(car_w + (uint32_t)(h * kTcChunk + half * 32 + lane) * 8u),
+                                     "r"(tf32_rna(cr)), "r"(tf32_rna(-ci)) : "memory");
+                    }
                 }
                 __syncwarp();
                 if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
@@ -309,18 +317,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     const uint32_t a_re = s32(sA + (buf * 2 + 0) * kTcAChunk) + (uint32_t)warp * 128u + (uint32_t)lane * 4u;
                     const uint32_t a_im = a_re + kTcAChunk;
                     const uint32_t car_s = car_w + (uint32_t)((r8 >> 2) * kTcChunk + k4) * 8u;
-                    // the lane's eight replica entries e, e + 4, ..., e + 28 sit in two consecutive words
+                    // the lane's sixteen replica entries e, e + 4, ..., e + 60 sit in three consecutive words
                     const int e = c * kTcChunk + k4 + args.koff[tap];
                     const uint32_t rep_s = s32(sRep + my_sat * kTcRepWords + (e >> 5));
-                    uint32_t w0, w1;
+                    uint32_t w0, w1, w2;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rep_s));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(rep_s + 4u));
-                    const uint32_t bits = __funnelshift_r(w0, w1, e & 31);            // bit 4 i = sign of entry e + 4 i
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(rep_s + 8u));
+                    const uint32_t bits_lo = __funnelshift_r(w0, w1, e & 31);         // bit 4 i = sign of entry e + 4 i, i < 8
+                    const uint32_t bits_hi = __funnelshift_r(w1, w2, e & 31);         // ... of entry e + 32 + 4 (i - 8)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < kTcChunk / 4; ++i) {
                         uint32_t cx, cy;
                         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cx), "=r"(cy) : "r"(car_s + 32u * i));
-                        const uint32_t sign = (bits << (31 - 4 * i)) & 0x80000000u;
+                        const uint32_t sign = ((i < 8 ? bits_lo : bits_hi) << (31 - 4 * (i & 7))) & 0x80000000u;
                         const uint32_t off = (uint32_t)(i >> 1) * kTcAStep + (uint32_t)(i & 1) * 2048u;
                         asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_re + off), "r"(cx ^ sign) : "memory");
                         asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_im + off), "r"(cy ^ sign) : "memory");
