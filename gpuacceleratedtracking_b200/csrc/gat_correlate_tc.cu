@@ -51,16 +51,21 @@ __device__ __forceinline__ void bar_expect(uint32_t a, uint32_t bytes)
 }
 __device__ __forceinline__ void bar_wait(uint32_t a, uint32_t parity)
 {
-    uint32_t done = 0;
-    uint64_t t0 = 0;
+    // tight polling: the wake-up latency of these waits is on the critical path of the A-buffer hand-over, so the
+    // watchdog clock is looked at only once in 256 failed polls (reading %globaltimer in every poll cost ~1 us per wait)
+    uint32_t done = 0, polls = 0;
+    long long t0 = 0;
     while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        // (with a suspend-time hint the thread sleeps in hardware until the phase flips -- the 16 generator warps
+        // polling here took 28 % of all issued instructions)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");
         if (done) break;
-        uint64_t now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000ull) __trap();          // a broken launch becomes a CUDA error, not a hang
+        if ((++polls & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();       // ~4 s: a broken launch becomes a CUDA error, not a hang
+        }
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c3, uint32_t bar)
@@ -293,6 +298,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 }
             }
             const uint32_t car_w = s32(sCar + (2 * warp) * kTcChunk);               // this warp's two carrier rows
+            // carrier phase of this lane's sample inside the tile: 32 bits (2^-32 cycle), restarted exactly from the
+            // 64-bit accumulator at every tile; a step is 32 samples.  Only a job's first / last tile has samples
+            // outside [0, n_samples): there the signal tile is zeroed, so the carrier needs no range check at all.
+            uint32_t ph32[2], st32[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                ph32[h] = (uint32_t)(cphl[h] >> 32);
+                st32[h] = (uint32_t)((cdel32[h] + 0x80000000ull) >> 32);
+                cphl[h] += 8ull * cdel32[h];                                          // next tile: 256 samples on
+            }
             for (int c = 0; c < kTcChunks; ++c, ++qa) {
                 const uint32_t buf = qa & 1u, use = qa >> 1;
                 // ---- carrier rows of this chunk for the warp's two channels: lane = sample ----
@@ -301,13 +316,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
                     for (int half = 0; half < kTcChunk / 32; ++half) {
-                        float cr = 0.f, ci = 0.f;
-                        const int n = n0 + c * kTcChunk + half * 32 + lane;
-                        if (live[h] && n >= 0 && n < args.n_samples && !(args.debug & 4))
-                            __sincosf((float)(int32_t)(uint32_t)(cphl[h] >> 32) * 1.4629180792671596e-9f, &ci, &cr);   // 2 pi / 2^32
-                        cphl[h] += cdel32[h];
+                        float cr, ci;
+                        __sincosf((float)(int32_t)ph32[h] * 1.4629180792671596e-9f, &ci, &cr);        // 2 pi / 2^32
+                        ph32[h] += st32[h];
+                        const uint32_t keep = (live[h] && !(args.debug & 4)) ? 0xffffffffu : 0u;
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(car_w + (uint32_t)(h * kTcChunk + half * 32 + lane) * 8u),
-                                     "r"(tf32_rna(cr)), "r"(tf32_rna(-ci)) : "memory");
+                                     "r"(tf32_rna(cr) & keep), "r"((tf32_rna(ci) ^ 0x80000000u) & keep) : "memory");
                     }
                 }
                 __syncwarp();
