@@ -210,13 +210,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 // =========================== control warp: TMA + MMA issue, one thread ===========================
                 if (lane == 0) {
                     const int c3 = (args.aligned_start + t * kTcTile) / 4;
-                    if (qb == 0) {                                                   // the CTA's very first tile
+                    if (qb == 0 && !(args.debug & 16)) {                             // the CTA's very first tile
                         bar_expect(B_FULL + 8 * st, kTcBTile);
                         tma_load_4d(bt, &per->map, c3, B_FULL + 8 * st);
                     }
                     // prefetch the next tile of this CTA (same job or the next one) into the other stage
                     const int64_t un = u + (t - t_first) + 1;
-                    if (un < r1) {
+                    if (un < r1 && !(args.debug & 16)) {
                         const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
                         if (qb >= 1) {                                               // its previous reader, tile qb - 1, is done:
                             const uint32_t ql = qb * kTcChunks - 1;                  // ... that tile's last chunk has been committed
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 frac[h] = (uint64_t)nf & ((1ull << fp[h]) - 1ull);
             }
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----
-            bar_wait(B_FULL + 8 * st, (qb >> 1) & 1u);
+            if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 1) & 1u);
             {
                 unsigned char *bp = sB + st * kTcBTile;
                 for (int i = tid; i < kTcBTile / 16 && !(args.debug & 8); i += 32 * kTcGenWarps) {        // 16 B = 4 samples of one column
