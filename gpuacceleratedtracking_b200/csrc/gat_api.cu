@@ -542,16 +542,20 @@ bool encode_tc_map(SignalSlot &s)
     if (s.tc_state) return s.tc_state > 0;
     s.tc_state = -1;
     EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc || !s.re || !s.im || s.im <= s.re || s.n_ants > 16) return false;
-    const uint64_t plane_bytes = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(s.im) - reinterpret_cast<uintptr_t>(s.re));
+    if (!enc || !s.re || !s.im || s.im == s.re || s.n_ants > 16) return false;
+    // the view starts at the lower plane; `swapped` tells the kernel's epilogue which one that is
+    const bool swapped = s.im < s.re;
+    float *lo = swapped ? s.im : s.re, *hi = swapped ? s.re : s.im;
+    const uint64_t plane_bytes = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(hi) - reinterpret_cast<uintptr_t>(lo));
     uint64_t row_bytes = static_cast<uint64_t>(s.ld) * sizeof(float);
     if (s.n_ants == 1) row_bytes = (static_cast<uint64_t>(s.n_samples) * sizeof(float) + 15) / 16 * 16;
-    if (plane_bytes % 16 || plane_bytes >= (1ull << 40) || row_bytes % 16 || (reinterpret_cast<uintptr_t>(s.re) & 15u)) return false;
+    if (plane_bytes % 16 || plane_bytes >= (1ull << 40) || row_bytes % 16 || (reinterpret_cast<uintptr_t>(lo) & 15u)) return false;
     const cuuint64_t dims[4] = {4, static_cast<cuuint64_t>(s.n_ants), 2, static_cast<cuuint64_t>((s.n_samples + 3) / 4)};
     const cuuint64_t strides[3] = {row_bytes, plane_bytes, 16};
     const cuuint32_t box[4] = {4, 16, 2, 64};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&s.tc_map.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s.re, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    s.tc_map.swapped = swapped ? 1 : 0;
+    CUresult r = enc(&s.tc_map.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     s.tc_state = 1;

@@ -369,19 +369,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             const int row = warp * 32 + lane;
             float *pr = args.partials + ((size_t)(job + (int)blockIdx.x) * 2 * kTcRows + row) * kTcAnts;
             float *pi = pr + (size_t)kTcRows * kTcAnts;
+            // columns 0..15 of both accumulators belong to plane 0 of the view, 16..31 to plane 1; plane 0 is the re plane
+            // unless the slot's im plane lies lower in memory
+            const bool sw = per->swapped != 0;
 #pragma unroll
             for (int m = 0; m < kTcAnts; m += 4) {
-                float4 a, b;
-                a.x = __uint_as_float(vr[m + 0]) - __uint_as_float(vi[16 + m + 0]);
-                a.y = __uint_as_float(vr[m + 1]) - __uint_as_float(vi[16 + m + 1]);
-                a.z = __uint_as_float(vr[m + 2]) - __uint_as_float(vi[16 + m + 2]);
-                a.w = __uint_as_float(vr[m + 3]) - __uint_as_float(vi[16 + m + 3]);
-                b.x = __uint_as_float(vi[m + 0]) + __uint_as_float(vr[16 + m + 0]);
-                b.y = __uint_as_float(vi[m + 1]) + __uint_as_float(vr[16 + m + 1]);
-                b.z = __uint_as_float(vi[m + 2]) + __uint_as_float(vr[16 + m + 2]);
-                b.w = __uint_as_float(vi[m + 3]) + __uint_as_float(vr[16 + m + 3]);
-                *reinterpret_cast<float4 *>(pr + m) = a;
-                *reinterpret_cast<float4 *>(pi + m) = b;
+                float o_re[4], o_im[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float cr_re = __uint_as_float(sw ? vr[16 + m + j] : vr[m + j]);      // W_re x S_re
+                    const float cr_im = __uint_as_float(sw ? vr[m + j] : vr[16 + m + j]);      // W_re x S_im
+                    const float ci_re = __uint_as_float(sw ? vi[16 + m + j] : vi[m + j]);      // W_im x S_re
+                    const float ci_im = __uint_as_float(sw ? vi[m + j] : vi[16 + m + j]);      // W_im x S_im
+                    o_re[j] = cr_re - ci_im;
+                    o_im[j] = ci_re + cr_im;
+                }
+                *reinterpret_cast<float4 *>(pr + m) = make_float4(o_re[0], o_re[1], o_re[2], o_re[3]);
+                *reinterpret_cast<float4 *>(pi + m) = make_float4(o_im[0], o_im[1], o_im[2], o_im[3]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }

@@ -104,6 +104,7 @@ __host__ __device__ inline int padded_acc(int A, int L) { return ((2 * A * L) + 
 // ---- tensor-core path (gat_correlate_tc.cu) ----
 struct alignas(64) TcPeriod {
     CUtensorMap map;   // 4-D view of the two planes: {4 samples, antennas, planes, sample groups}, box {4, 16, 2, 64}
+    int32_t swapped;   // the im plane lies BELOW the re plane in memory: plane 0 of the view is im
 };
 struct alignas(64) TcArgs {
     const TcPeriod *periods;

@@ -94,3 +94,22 @@ def test_tensor_path_integer_samples_and_fallbacks(gat, orc, engine):
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
     engine.correlate(60, chans[:4], fs, shifts, m, n_samples=n, tensor=True, code_phase_f64=True)
     assert engine.launch_info()["tensor"] == 0
+
+
+def test_tensor_path_on_bound_planes_in_either_order(gat, orc, engine):
+    """Zero-copy planes: the 4-D view starts at whichever plane lies lower in memory."""
+    import torch
+    rng = np.random.default_rng(11)
+    fs, n, m, n_ch = 2.0e7, 8192, 4, 34
+    l1, chans, re, im = _scene(gat, orc, rng, n_ch, m, n, fs)
+    shifts = np.array([-9, 0, 9], np.int32)
+    buf = torch.zeros(2, m, n, device="cuda")
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                         fs, shifts) for c in chans[:5]])
+    for order in ((0, 1), (1, 0)):                         # re below im, then im below re
+        buf[order[0]].copy_(torch.from_numpy(re))
+        buf[order[1]].copy_(torch.from_numpy(im))
+        engine.bind_signal(70, buf[order[0]], buf[order[1]])
+        got = engine.correlate(70, chans, fs, shifts, m, n_samples=n, tensor=True)
+        assert engine.launch_info()["tensor"] == 1
+        assert np.abs(got[:5] - ref).max() <= 2e-5 * n * 1.6
