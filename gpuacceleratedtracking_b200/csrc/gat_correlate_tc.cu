@@ -226,19 +226,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         tma_load_4d(s32(sB + (st ^ 1u) * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4,
                                     B_FULL + 8 * (st ^ 1u));
                     }
+                    // descriptors differ only in their 14-bit start-address field: one base per operand, then 64-bit adds of
+                    // small constants -- the issuing thread shares its scheduler with four generator warps, so every
+                    // instruction it needs per MMA is time the tensor pipe idles
+                    const uint64_t da0 = umma_desc(s32(sA), kTcRows * 16, 128);
+                    const uint64_t db0 = umma_desc(bt, kTcBGroup, 128);
                     uint32_t q = qa;
+                    uint32_t acc = (t > t_first) ? 1u : 0u;
                     for (int c = 0; c < kTcChunks; ++c, ++q) {
                         const uint32_t buf = q & 1u;
                         bar_wait(A_FULL + 8 * buf, (q >> 1) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_re = s32(sA + (buf * 2 + 0) * kTcAChunk), a_im = s32(sA + (buf * 2 + 1) * kTcAChunk);
-                        const uint32_t b0 = bt + (uint32_t)c * (kTcChunk / 4) * kTcBGroup;
+                        const uint64_t da_re = da0 + (uint64_t)((buf * 2 * kTcAChunk) >> 4);
+                        const uint64_t da_im = da_re + (uint64_t)(kTcAChunk >> 4);
+                        const uint64_t db = db0 + (uint64_t)(((uint32_t)c * (kTcChunk / 4) * kTcBGroup) >> 4);
 #pragma unroll
-                        for (int j = 0; j < kTcSteps && !(args.debug & 2); ++j) {
-                            const uint64_t db = umma_desc(b0 + j * 2 * kTcBGroup, kTcBGroup, 128);
-                            const uint32_t acc = (t > t_first || c > 0 || j > 0) ? 1u : 0u;
-                            umma_tf32(tmem, umma_desc(a_re + j * kTcAStep, kTcRows * 16, 128), db, acc);
-                            umma_tf32(tmem + 32, umma_desc(a_im + j * kTcAStep, kTcRows * 16, 128), db, acc);
+                        for (int j = 0; j < kTcSteps; ++j) {
+                            if (args.debug & 2) break;
+                            umma_tf32(tmem, da_re + (uint64_t)((j * kTcAStep) >> 4), db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
+                            umma_tf32(tmem + 32, da_im + (uint64_t)((j * kTcAStep) >> 4), db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
+                            acc = 1u;
                         }
                         umma_commit(A_FREE + 8 * buf);
                     }
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             __syncwarp();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (!live[h]) continue;
+                if (!live[h] || (args.debug & 64)) continue;
                 const int sl = 2 * warp + h;
                 const uint32_t tab_s = s32(sTab + sl * kTcTabWords);
                 const int sh = fp[h] - 32;
@@ -340,17 +347,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(rep_s + 8u));
                     const uint32_t bits_lo = __funnelshift_r(w0, w1, e & 31);         // bit 4 i = sign of entry e + 4 i, i < 8
                     const uint32_t bits_hi = __funnelshift_r(w1, w2, e & 31);         // ... of entry e + 32 + 4 (i - 8)
+                    // all sixteen carrier loads first, then the sign flips and stores: volatile asm statements keep their
+                    // order, so interleaving them made every store wait for its own load (ncu: 29 % of all stall samples)
+                    uint32_t cx[kTcChunk / 4], cy[kTcChunk / 4];
+#pragma unroll
+                    for (int i = 0; i < kTcChunk / 4; ++i)
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cx[i]), "=r"(cy[i]) : "r"(car_s + 32u * i));
 #pragma unroll
                     for (int i = 0; i < kTcChunk / 4; ++i) {
-                        uint32_t cx, cy;
-                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cx), "=r"(cy) : "r"(car_s + 32u * i));
                         const uint32_t sign = ((i < 8 ? bits_lo : bits_hi) << (31 - 4 * (i & 7))) & 0x80000000u;
                         const uint32_t off = (uint32_t)(i >> 1) * kTcAStep + (uint32_t)(i & 1) * 2048u;
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_re + off), "r"(cx ^ sign) : "memory");
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_im + off), "r"(cy ^ sign) : "memory");
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_re + off), "r"(cx[i] ^ sign) : "memory");
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_im + off), "r"(cy[i] ^ sign) : "memory");
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (!(args.debug & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) bar_arrive(A_FULL + 8 * buf);
             }
