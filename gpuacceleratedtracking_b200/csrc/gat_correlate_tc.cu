@@ -274,19 +274,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 uint64_t v = frac[h] + (uint64_t)lane * ndel[h];
                 const uint64_t v32 = 32ull * ndel[h];
                 const int rows = (kTcTile + args.span + 31) >> 5;
-                for (int r = 0; r < rows; r += 4) {                 // four independent table lookups in flight
-                    uint32_t word[4], sft[4];
+                for (int r = 0; r < rows; r += 2) {                 // two independent table lookups in flight (the row count is
+                    uint32_t word[2], sft[2];                       // rounded up to even: the buffer has 20 words per channel)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j, v += v32) {
+                    for (int j = 0; j < 2; ++j, v += v32) {
                         uint32_t idx = bmod[h] + ((uint32_t)(v >> 32) >> sh);
                         idx = min(idx, idx - lc[h]);                // single wrap (host-checked)
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word[j]) : "r"(tab_s + 4u * (idx >> 5)));
                         sft[j] = idx & 31u;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 2; ++j) {
                         const uint32_t bits = __ballot_sync(0xffffffffu, (word[j] >> sft[j]) & 1u);
-                        if (lane == j) sRep[sl * kTcRepWords + r + j] = bits;       // (rows are padded to 20 words)
+                        if (lane == j) sRep[sl * kTcRepWords + r + j] = bits;
                     }
                 }
                 // advance the NCO base to the next tile
@@ -300,14 +300,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 1) & 1u);
             {
                 unsigned char *bp = sB + st * kTcBTile;
+                const bool edge = n0 < 0 || n0 + kTcTile > args.n_samples;            // only a job's first / last tile
                 for (int i = tid; i < kTcBTile / 16 && !(args.debug & 8); i += 32 * kTcGenWarps) {        // 16 B = 4 samples of one column
-                    const int g = i >> 5;                                             // sample group in the tile
                     uint4 w = reinterpret_cast<uint4 *>(bp)[i];
-                    const int n = n0 + 4 * g;
-                    w.x = (n + 0 >= 0 && n + 0 < args.n_samples) ? tf32_rna(__uint_as_float(w.x)) : 0u;
-                    w.y = (n + 1 >= 0 && n + 1 < args.n_samples) ? tf32_rna(__uint_as_float(w.y)) : 0u;
-                    w.z = (n + 2 >= 0 && n + 2 < args.n_samples) ? tf32_rna(__uint_as_float(w.z)) : 0u;
-                    w.w = (n + 3 >= 0 && n + 3 < args.n_samples) ? tf32_rna(__uint_as_float(w.w)) : 0u;
+                    w.x = tf32_rna(__uint_as_float(w.x));
+                    w.y = tf32_rna(__uint_as_float(w.y));
+                    w.z = tf32_rna(__uint_as_float(w.z));
+                    w.w = tf32_rna(__uint_as_float(w.w));
+                    if (edge) {
+                        const int n = n0 + 4 * (i >> 5);                              // i >> 5 = sample group in the tile
+                        if (n + 0 < 0 || n + 0 >= args.n_samples) w.x = 0u;
+                        if (n + 1 < 0 || n + 1 >= args.n_samples) w.y = 0u;
+                        if (n + 2 < 0 || n + 2 >= args.n_samples) w.z = 0u;
+                        if (n + 3 < 0 || n + 3 >= args.n_samples) w.w = 0u;
+                    }
                     reinterpret_cast<uint4 *>(bp)[i] = w;
                 }
             }

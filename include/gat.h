@@ -66,7 +66,7 @@ typedef enum gat_status {
                                  noise instead of the FP32 kernel's ~1e-7 relative.  Shapes outside the envelope run
                                  on the FP32 kernel as usual (gat_launch_info.tensor tells which one ran).  Measured
                                  on B200 (16 antennas, 3 taps, 50000 samples): faster than the FP32 kernel from ~128
-                                 channel-blocks per call (1024 channels: 447 -> 319 us), slower below; the caller
+                                 channel-blocks per call (1024 channels: 447 -> 281 us), slower below; the caller
                                  decides.                                                                           */
 #define GAT_CODE_PHASE_F64 2u /* chip index = mod(floor(fc/fs*(n+shift)+phase), Lc) in IEEE double,
                                  bit-exact with the reference's GPU kernels (src/algorithms.jl:179-182).
