@@ -10,11 +10,14 @@
 //   * B operand  = the signal tile [256 samples x (2 planes x 16 antennas)] exactly as ONE 4-D TMA load delivers it in
 //                  the no-swizzle K-major canonical layout [sample/4][plane][antenna][sample%4]; a pass over the tile
 //                  rounds it to TF32 (truncation would bias the magnitude) and zeroes samples outside the range.
-//   * A operand  = W, 32 channels x 4 tap rows = 128 rows, generated in 32-sample chunks into double-buffered
-//                  shared memory, directly in the canonical layout: lane = (row % 8, sample % 4), so every store
-//                  instruction of a warp writes one contiguous 128-byte core matrix.  Per channel one replica row (sign
-//                  bits, ballot-packed) per tile and one carrier row (TF32 cos, -sin) per chunk are shared by the tap
-//                  rows, whose entries are then load - sign flip - store.
+//   * A operand  = W, 32 channels x 4 tap rows = 128 rows, generated in 64-sample chunks straight into TENSOR MEMORY
+//                  (tcgen05.st, double-buffered: lane = row, column = sample): with A in shared memory every MMA re-read
+//                  4 KB of it (45 cycles per MMA at N = 32) and the generator's stores and the MMA's reads shared one
+//                  128 B/clk pipe -- the kernel was shared-memory-bound.  A thread owns one (channel, tap) row and 16
+//                  consecutive samples of the chunk; the four warps of a TMEM lane quarter split the chunk's samples.
+//                  Per channel one replica row (sign bits, ballot-packed, double-buffered per tile and shared by the
+//                  quarter's four warps through a 128-thread named barrier) and one warp-private carrier row (TF32
+//                  cos, -sin) per chunk feed the tap rows, whose entries are load - sign flip - tcgen05.st.
 //   * D          = two 128 x 32 FP32 accumulators in TMEM: C_r = W_re x [S_re | S_im], C_i = W_im x [S_re | S_im];
 //                  acc_re = C_r.re - C_i.im, acc_im = C_i.re + C_r.im in the epilogue.
 // Work split: the flattened (period, channel group, tile) space is divided evenly over the CTAs (like the default
@@ -32,15 +35,18 @@ namespace {
 
 constexpr int kTcRows = 128, kTcRowsPerSat = 4, kTcSats = kTcRows / kTcRowsPerSat, kTcAnts = 16, kTcCols = 2 * kTcAnts;
 constexpr int kTcTile = 256, kTcChunk = 64, kTcChunks = kTcTile / kTcChunk, kTcSteps = kTcChunk / 8;
-constexpr int kTcAStep = kTcRows * 8 * 4;                  // one K-step (8 samples) of A: 4096 B
-constexpr int kTcAChunk = kTcSteps * kTcAStep;             // 32 KB per part (re / im) and buffer
+constexpr int kTcDCols = 2 * kTcCols;                      // TMEM columns of the two accumulators
+constexpr int kTcABufCols = 2 * kTcChunk;                  // TMEM columns of one A buffer: W_re | W_im, one column per sample
+constexpr int kTcTmemCols = 512;                           // 64 + 2 x 128 = 320, rounded up to the next power of two
+constexpr int kTcLaneSamples = kTcChunk / 4;               // samples per thread and chunk (four warps share a lane quarter)
+constexpr int kTcCarStride = kTcLaneSamples * 8 + 16;      // bytes per channel in a warp's carrier rows (+16: bank spread)
 constexpr int kTcBGroup = kTcCols * 16;                    // 4 samples of all 32 columns: 512 B
 constexpr int kTcBTile = (kTcTile / 4) * kTcBGroup;        // 32 KB
 constexpr int kTcGenWarps = 16;
 constexpr int kTcThreads = 32 * (kTcGenWarps + 1);
 constexpr int kTcTabWords = 32;                            // chip table of a channel as sign bits: 1024 chips in 128 B
 constexpr int kTcRepWords = 20;                            // replica sign bits per channel and tile: <= 512 entries (+ one spare word)
-constexpr int kTcSmemBytes = 2 * kTcBTile + 4 * kTcAChunk + kTcSats * kTcTabWords * 4 + kTcSats * kTcRepWords * 4 + kTcSats * kTcChunk * 8;
+constexpr int kTcSmemBytes = 2 * kTcBTile + kTcSats * kTcTabWords * 4 + 2 * kTcSats * kTcRepWords * 4 + kTcGenWarps * 8 * kTcCarStride;
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint32_t a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(n)); }
@@ -80,10 +86,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint3
 }
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
-__device__ __forceinline__ void umma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t accumulate)
+// D[tmem_d] (+)= A[tmem_a] x B[smem]: A = 128 lanes x 8 columns of TF32 in tensor memory (lane = row, column = k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem), "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(kTcIdesc), "r"(accumulate) : "memory");
+}
+// this thread's TMEM lane, 16 consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
@@ -114,10 +128,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sB = smem;                                            // [2][kTcBTile]
-    unsigned char *sA = sB + 2 * kTcBTile;                               // [2 buffers][re, im][kTcAChunk]
-    uint32_t *sTab = reinterpret_cast<uint32_t *>(sA + 4 * kTcAChunk);   // [32][32] chip tables as sign bits
-    uint32_t *sRep = sTab + kTcSats * kTcTabWords;                       // [32][20] sign bits of the tile's replica
-    float2 *sCar = reinterpret_cast<float2 *>(sRep + kTcSats * kTcRepWords);        // [32][64] (cos, -sin) as TF32, private to the owning warp
+    uint32_t *sTab = reinterpret_cast<uint32_t *>(sB + 2 * kTcBTile);    // [32][32] chip tables as sign bits
+    uint32_t *sRep = sTab + kTcSats * kTcTabWords;                       // [2][32][20] sign bits of a tile's replicas (tile parity)
+    unsigned char *sCar = reinterpret_cast<unsigned char *>(sRep + 2 * kTcSats * kTcRepWords);   // [16 warps][8 channels][kTcCarStride]
     __shared__ uint32_t tmem_base;
     __shared__ __align__(8) uint64_t bars[7];   // 0,1 B full; 2,3 A full; 4,5 A free; 6 accumulators ready
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,27 +147,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kTcGenWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(s32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "n"(kTcTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // rows of taps that do not exist (n_taps < 4) are never written: both A buffers start as zeros
-    for (int i = tid; i < 4 * kTcAChunk / 16; i += kTcThreads) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_base;
+    const uint32_t tmem = tmem_base;            // columns 0..63: accumulators; 64..191, 192..319: the two A buffers
+    const uint32_t tmem_a = tmem + kTcDCols;
 
-    const int K = args.n_sats, G = args.G, TJ = args.tiles_per_job, L = args.n_taps;
+    const int K = args.n_sats, G = args.G, TJ = args.tiles_per_job;
     const int64_t TT = args.total_units;
     const int grid = gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * TT / grid, r1 = (int64_t)(blockIdx.x + 1) * TT / grid;
 
-    // lane roles of the tap-row phase: this warp owns row group `warp` = channels 2 warp, 2 warp + 1
-    const int r8 = lane >> 2, k4 = lane & 3, tap = r8 & 3;
-    const int my_sat = 2 * warp + (r8 >> 2);    // the channel of this lane's tap row
+    // Roles of a generator warp.  TMEM lane quarter q = warp % 4 (hardware: a warp reaches lanes 32 q .. 32 q + 31 only) =
+    // channels 8 q .. 8 q + 7 of the group; sub = warp / 4 = which 16 samples of every 64-sample chunk.
+    //   replica bits : the warp generates the tile's sign bits of channels 8 q + 2 sub, + 1 (read by the quarter's four warps)
+    //   carrier rows : lane = (channel 8 q + lane / 4, samples 4 (lane % 4) .. + 3 of the warp's 16), warp-private
+    //   tap rows     : lane = row 32 q + lane = (channel 8 q + lane / 4, tap lane % 4), the warp's 16 samples
+    const int q4 = warp & 3, sub = warp >> 2, kq = lane >> 2, tap = lane & 3;
+    const int my_sat = 8 * q4 + kq;
     uint32_t qa = 0;      // running chunk counter (A buffer + parity)
-    uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity)
+    uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity, replica buffer)
     uint32_t seg = 0;
 
     for (int64_t u = r0; u < r1; ++seg) {
@@ -164,16 +179,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         const int p = job / G, grp = job % G;
         const TcPeriod *per = &args.periods[p];
 
-        // ---- segment set-up: every generator warp owns channels 2 w and 2 w + 1 of the group -- their chip tables, replica
-        // bits, carrier rows and tap rows -- so the generator warps never wait for each other, only for the MMA thread ----
-        uint64_t frac[2] = {0, 0}, cphl[2] = {0, 0}, cdel32[2] = {0, 0}, ndel[2] = {0, 0};
+        // ---- segment set-up ----
+        uint64_t frac[2] = {0, 0}, ndel[2] = {0, 0};
         uint32_t bmod[2] = {0, 0}, lc[2] = {1, 1};
         int fp[2] = {32, 32};
         bool live[2] = {false, false};
+        uint64_t cph = 0, cd1 = 0;       // carrier phase (Q0.64 cycles) of this lane's first sample in the next chunk; step per sample
         if (warp < kTcGenWarps) {
+            const int64_t n0 = (int64_t)args.aligned_start + (int64_t)t_first * kTcTile - args.start_sample;   // may be < 0 (alignment head)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int sl = 2 * warp + h, k = grp * kTcSats + sl;
+                const int sl = 8 * q4 + 2 * sub + h, k = grp * kTcSats + sl;
                 live[h] = k < K;
                 if (live[h]) {
                     const SatDev *sd = &args.sats[(size_t)p * K + k];
@@ -194,17 +210,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     ndel[h] = (uint64_t)sd->nco_delta;
                     fp[h] = sd->nco_fp;
                     lc[h] = (uint32_t)clen;
-                    // state at the first sample of tile t_first (relative index n0 may be < 0 for the alignment head)
-                    const int64_t n0 = (int64_t)args.aligned_start + (int64_t)t_first * kTcTile - args.start_sample;
+                    // state at the first sample of tile t_first
                     const __int128 tot = (__int128)(n0 + args.shift0) * (__int128)sd->nco_delta + (__int128)sd->nco_start;
                     int64_t b = (int64_t)(tot >> sd->nco_fp) % clen;
                     if (b < 0) b += clen;
                     bmod[h] = (uint32_t)b;
                     frac[h] = (uint64_t)tot & ((1ull << sd->nco_fp) - 1ull);
-                    // carrier phase (Q0.64) of THIS LANE's sample in the next chunk, advanced by 32 samples per chunk
-                    cphl[h] = sd->car_phase + (uint64_t)(n0 + lane) * sd->car_delta;
-                    cdel32[h] = 32ull * sd->car_delta;
                 }
+            }
+            if (grp * kTcSats + my_sat < K) {
+                const SatDev *sd = &args.sats[(size_t)p * K + grp * kTcSats + my_sat];
+                cd1 = sd->car_delta;
+                cph = sd->car_phase + (uint64_t)(n0 + sub * kTcLaneSamples + 4 * tap) * cd1;      // 64-bit wrap = whole cycles
             }
         }
         __syncthreads();   // tables in place; previous segment's epilogue done (TMEM free)
@@ -233,10 +250,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         tma_load_4d(s32(sB + (st ^ 1u) * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4,
                                     B_FULL + 8 * (st ^ 1u));
                     }
-                    // descriptors differ only in their 14-bit start-address field: one base per operand, then 64-bit adds of
-                    // small constants -- the issuing thread shares its scheduler with four generator warps, so every
-                    // instruction it needs per MMA is time the tensor pipe idles
-                    const uint64_t da0 = umma_desc(s32(sA), kTcRows * 16, 128);
+                    // B descriptors differ only in their 14-bit start-address field: one base, then 64-bit adds of constants
                     const uint64_t db0 = umma_desc(bt, kTcBGroup, 128);
                     uint32_t q = qa;
                     uint32_t acc = (t > t_first) ? 1u : 0u;
@@ -244,14 +258,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         const uint32_t buf = q & 1u;
                         bar_wait(A_FULL + 8 * buf, (q >> 1) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t da_re = da0 + (uint64_t)((buf * 2 * kTcAChunk) >> 4);
-                        const uint64_t da_im = da_re + (uint64_t)(kTcAChunk >> 4);
+                        const uint32_t ta_re = tmem_a + buf * kTcABufCols, ta_im = ta_re + kTcChunk;
                         const uint64_t db = db0 + (uint64_t)(((uint32_t)c * (kTcChunk / 4) * kTcBGroup) >> 4);
 #pragma unroll
                         for (int j = 0; j < kTcSteps; ++j) {
                             if (args.debug & 2) break;
-                            umma_tf32(tmem, da_re + (uint64_t)((j * kTcAStep) >> 4), db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
-                            umma_tf32(tmem + 32, da_im + (uint64_t)((j * kTcAStep) >> 4), db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
+                            umma_tf32_ts(tmem, ta_re + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
+                            umma_tf32_ts(tmem + kTcCols, ta_im + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
                             acc = 1u;
                         }
                         umma_commit(A_FREE + 8 * buf);
@@ -263,39 +276,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             }
 
             // ================================= generator warps =================================
-            // ---- replica sign bits of this tile for the warp's two channels: entry e <-> sample n0 + e + shift0 ----
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (!live[h] || (args.debug & 64)) continue;
-                const int sl = 2 * warp + h;
-                const uint32_t tab_s = s32(sTab + sl * kTcTabWords);
-                const int sh = fp[h] - 32;
-                uint64_t v = frac[h] + (uint64_t)lane * ndel[h];
-                const uint64_t v32 = 32ull * ndel[h];
+            // ---- replica sign bits of this tile for the warp's two channels: entry e <-> sample n0 + e + shift0.  Both
+            // channels' table lookups are in flight together (four independent load -> ballot chains per round) ----
+            uint32_t *rep_t = sRep + st * (kTcSats * kTcRepWords);
+            if (!(args.debug & 64)) {
                 const int rows = (kTcTile + args.span + 31) >> 5;
-                for (int r = 0; r < rows; r += 2) {                 // two independent table lookups in flight (the row count is
-                    uint32_t word[2], sft[2];                       // rounded up to even: the buffer has 20 words per channel)
+                uint64_t v[2], v32[2];
+                uint32_t tab_s[2];
+                int sh[2];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j, v += v32) {
-                        uint32_t idx = bmod[h] + ((uint32_t)(v >> 32) >> sh);
-                        idx = min(idx, idx - lc[h]);                // single wrap (host-checked)
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word[j]) : "r"(tab_s + 4u * (idx >> 5)));
-                        sft[j] = idx & 31u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t bits = __ballot_sync(0xffffffffu, (word[j] >> sft[j]) & 1u);
-                        if (lane == j) sRep[sl * kTcRepWords + r + j] = bits;
-                    }
+                for (int h = 0; h < 2; ++h) {
+                    v[h] = frac[h] + (uint64_t)lane * ndel[h];
+                    v32[h] = 32ull * ndel[h];
+                    tab_s[h] = s32(sTab + (8 * q4 + 2 * sub + h) * kTcTabWords);
+                    sh[h] = fp[h] - 32;
                 }
-                // advance the NCO base to the next tile
-                const unsigned __int128 nf = (unsigned __int128)frac[h] + (unsigned __int128)kTcTile * (unsigned __int128)ndel[h];
-                uint64_t x = (uint64_t)bmod[h] + (uint64_t)(nf >> fp[h]);
-                if (x >= lc[h]) x %= lc[h];
-                bmod[h] = (uint32_t)x;
-                frac[h] = (uint64_t)nf & ((1ull << fp[h]) - 1ull);
+                for (int r = 0; r < rows; r += 2) {                 // (the row count is rounded up to even: 20 words per channel)
+                    uint32_t word[2][2], sft[2][2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t idx = bmod[h] + ((uint32_t)(v[h] >> 32) >> sh[h]);
+                            idx = min(idx, idx - lc[h]);            // single wrap (host-checked)
+                            idx = min(idx, 1023u);                  // (a channel that is not live has no table: stay inside it)
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word[j][h]) : "r"(tab_s[h] + 4u * (idx >> 5)));
+                            sft[j][h] = idx & 31u;
+                            v[h] += v32[h];
+                        }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t bits = __ballot_sync(0xffffffffu, (word[j][h] >> sft[j][h]) & 1u);
+                            if (lane == 2 * j + h) rep_t[(8 * q4 + 2 * sub + h) * kTcRepWords + r + j] = bits;
+                        }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                       // advance the NCO base to the next tile
+                    const unsigned __int128 nf = (unsigned __int128)frac[h] + (unsigned __int128)kTcTile * (unsigned __int128)ndel[h];
+                    uint64_t x = (uint64_t)bmod[h] + (uint64_t)(nf >> fp[h]);
+                    if (x >= lc[h]) x %= lc[h];
+                    bmod[h] = (uint32_t)x;
+                    frac[h] = (uint64_t)nf & ((1ull << fp[h]) - 1ull);
+                }
             }
+            // the quarter's four warps exchange their replica rows.  The buffer alternates per tile: a warp that runs ahead
+            // into tile t + 1 writes the other buffer, and it cannot reach tile t + 2 before everyone has left tile t.
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
+
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----
             if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 1) & 1u);
             {
@@ -317,64 +346,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     reinterpret_cast<uint4 *>(bp)[i] = w;
                 }
             }
-            const uint32_t car_w = s32(sCar + (2 * warp) * kTcChunk);               // this warp's two carrier rows
-            // carrier phase of this lane's sample inside the tile: 32 bits (2^-32 cycle), restarted exactly from the
-            // 64-bit accumulator at every tile; a step is 32 samples.  Only a job's first / last tile has samples
-            // outside [0, n_samples): there the signal tile is zeroed, so the carrier needs no range check at all.
-            uint32_t ph32[2], st32[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                ph32[h] = (uint32_t)(cphl[h] >> 32);
-                st32[h] = (uint32_t)((cdel32[h] + 0x80000000ull) >> 32);
-                cphl[h] += 8ull * cdel32[h];                                          // next tile: 256 samples on
-            }
+            // Only a job's first / last tile has samples outside [0, n_samples): there the signal tile is zeroed, so neither
+            // the carrier nor the replica needs a range check.  Rows of taps or channels that do not exist hold finite
+            // junk: a row of A only reaches its own row of D, which the finalize kernel never reads.
+            const uint32_t car_w = s32(sCar + warp * (8 * kTcCarStride));             // this warp's carrier rows
+            const uint32_t car_st = car_w + (uint32_t)(kq * kTcCarStride + tap * 32);  // writer: 4 samples = 32 B
+            const uint32_t car_ld = car_w + (uint32_t)(kq * kTcCarStride);             // reader: the channel's 16 samples
+            const uint32_t rep_s0 = s32(rep_t + my_sat * kTcRepWords);
+            const uint32_t t_row = tmem_a + ((uint32_t)(32 * q4) << 16) + (uint32_t)(sub * kTcLaneSamples);
             for (int c = 0; c < kTcChunks; ++c, ++qa) {
                 const uint32_t buf = qa & 1u, use = qa >> 1;
-                // ---- carrier rows of this chunk for the warp's two channels: lane = sample ----
+                // ---- carrier rows of this chunk: four consecutive samples of one channel per lane ----
                 __syncwarp();                                                       // previous chunk's readers are done
+                {
+                    uint32_t cw[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int half = 0; half < kTcChunk / 32; ++half) {
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t ph = (uint32_t)((cph + (uint64_t)i * cd1) >> 32);
                         float cr, ci;
-                        __sincosf((float)(int32_t)ph32[h] * 1.4629180792671596e-9f, &ci, &cr);        // 2 pi / 2^32
-                        ph32[h] += st32[h];
-                        const uint32_t keep = (live[h] && !(args.debug & 4)) ? 0xffffffffu : 0u;
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(car_w + (uint32_t)(h * kTcChunk + half * 32 + lane) * 8u),
-                                     "r"(tf32_rna(cr) & keep), "r"((tf32_rna(ci) ^ 0x80000000u) & keep) : "memory");
+                        __sincosf((float)(int32_t)ph * 1.4629180792671596e-9f, &ci, &cr);        // 2 pi / 2^32
+                        cw[2 * i] = tf32_rna(cr);
+                        cw[2 * i + 1] = tf32_rna(ci) ^ 0x80000000u;
+                    }
+                    cph += (uint64_t)kTcChunk * cd1;
+                    if (!(args.debug & 4)) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(car_st), "r"(cw[0]), "r"(cw[1]), "r"(cw[2]), "r"(cw[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(car_st + 16u), "r"(cw[4]), "r"(cw[5]), "r"(cw[6]), "r"(cw[7]) : "memory");
                     }
                 }
                 __syncwarp();
-                if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
-                // ---- tap rows: rows 8 w .. 8 w + 7, four samples per step; one 128-byte core matrix per store ----
-                if (tap < L && !(args.debug & 1)) {
-                    const uint32_t a_re = s32(sA + (buf * 2 + 0) * kTcAChunk) + (uint32_t)warp * 128u + (uint32_t)lane * 4u;
-                    const uint32_t a_im = a_re + kTcAChunk;
-                    const uint32_t car_s = car_w + (uint32_t)((r8 >> 2) * kTcChunk + k4) * 8u;
-                    // the lane's sixteen replica entries e, e + 4, ..., e + 60 sit in three consecutive words
-                    const int e = c * kTcChunk + k4 + args.koff[tap];
-                    const uint32_t rep_s = s32(sRep + my_sat * kTcRepWords + (e >> 5));
-                    uint32_t w0, w1, w2;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rep_s));
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(rep_s + 4u));
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(rep_s + 8u));
-                    const uint32_t bits_lo = __funnelshift_r(w0, w1, e & 31);         // bit 4 i = sign of entry e + 4 i, i < 8
-                    const uint32_t bits_hi = __funnelshift_r(w1, w2, e & 31);         // ... of entry e + 32 + 4 (i - 8)
-                    // all sixteen carrier loads first, then the sign flips and stores: volatile asm statements keep their
-                    // order, so interleaving them made every store wait for its own load (ncu: 29 % of all stall samples)
-                    uint32_t cx[kTcChunk / 4], cy[kTcChunk / 4];
+                // ---- tap rows: this lane's row, the warp's 16 samples of the chunk ----
+                // the row's sixteen replica entries e .. e + 15 sit in two consecutive words
+                const int e = c * kTcChunk + sub * kTcLaneSamples + args.koff[tap];
+                uint32_t w0, w1;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rep_s0 + 4u * (uint32_t)(e >> 5)));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(rep_s0 + 4u * (uint32_t)(e >> 5) + 4u));
+                uint32_t cx[kTcLaneSamples], cy[kTcLaneSamples];
 #pragma unroll
-                    for (int i = 0; i < kTcChunk / 4; ++i)
-                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cx[i]), "=r"(cy[i]) : "r"(car_s + 32u * i));
+                for (int i = 0; i < kTcLaneSamples / 2; ++i)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(cx[2 * i]), "=r"(cy[2 * i]), "=r"(cx[2 * i + 1]), "=r"(cy[2 * i + 1])
+                                 : "r"(car_ld + 16u * i));
+                const uint32_t bits = __funnelshift_r(w0, w1, e & 31);              // bit i = sign of entry e + i
 #pragma unroll
-                    for (int i = 0; i < kTcChunk / 4; ++i) {
-                        const uint32_t sign = ((i < 8 ? bits_lo : bits_hi) << (31 - 4 * (i & 7))) & 0x80000000u;
-                        const uint32_t off = (uint32_t)(i >> 1) * kTcAStep + (uint32_t)(i & 1) * 2048u;
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_re + off), "r"(cx[i] ^ sign) : "memory");
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_im + off), "r"(cy[i] ^ sign) : "memory");
-                    }
+                for (int i = 0; i < kTcLaneSamples; ++i) {
+                    const uint32_t sign = (bits << (31 - i)) & 0x80000000u;
+                    cx[i] ^= sign;
+                    cy[i] ^= sign;
                 }
-                if (!(args.debug & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (!(args.debug & 1)) {
+                    tmem_st16(t_row + buf * kTcABufCols, cx);
+                    tmem_st16(t_row + buf * kTcABufCols + kTcChunk, cy);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the rounded signal tile -> the MMA's proxy
                 __syncwarp();
                 if (lane == 0) bar_arrive(A_FULL + 8 * buf);
             }
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == kTcGenWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+    if (warp == kTcGenWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTcTmemCols) : "memory");
 }
 
 // sum the partials of every job in CTA order (fixed -> deterministic) and write the caller's [M x L x K x P] planes.
