@@ -35,7 +35,7 @@ namespace {
 
 constexpr int kTcRows = 128, kTcRowsPerSat = 4, kTcSats = kTcRows / kTcRowsPerSat, kTcAnts = 16, kTcCols = 2 * kTcAnts;
 constexpr int kTcTile = 256, kTcChunk = 64, kTcChunks = kTcTile / kTcChunk, kTcSteps = kTcChunk / 8;
-constexpr int kTcDCols = 2 * kTcCols;                      // TMEM columns of the two accumulators
+constexpr int kTcDCols = 2 * kTcCols;                      // TMEM columns of the two accumulators C_r | C_i
 constexpr int kTcABufCols = 2 * kTcChunk;                  // TMEM columns of one A buffer: W_re | W_im, one column per sample
 constexpr int kTcTmemCols = 512;                           // 64 + 2 x 128 = 320, rounded up to the next power of two
 constexpr int kTcLaneSamples = kTcChunk / 4;               // samples per thread and chunk (four warps share a lane quarter)
@@ -74,6 +74,17 @@ __device__ __forceinline__ void bar_wait(uint32_t a, uint32_t parity)
         }
     }
 }
+// the MMA thread's wait: one thread, on the critical path of every hand-over -> plain polling, no hardware suspend
+__device__ __forceinline__ void bar_wait_spin(uint32_t a, uint32_t parity)
+{
+    uint32_t done = 0, polls = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        if (++polls > (1u << 26)) __trap();
+    }
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c3, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -87,6 +98,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint3
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcCols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 // D[tmem_d] (+)= A[tmem_a] x B[smem]: A = 128 lanes x 8 columns of TF32 in tensor memory (lane = row, column = k)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e != 0;
+}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
@@ -133,7 +150,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     unsigned char *sCar = reinterpret_cast<unsigned char *>(sRep + 2 * kTcSats * kTcRepWords);   // [16 warps][8 channels][kTcCarStride]
     __shared__ uint32_t tmem_base;
     __shared__ __align__(8) uint64_t bars[7];   // 0,1 B full; 2,3 A full; 4,5 A free; 6 accumulators ready
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (the warp index through a shuffle from lane 0: ptxas then KNOWS it is warp-uniform, and everything the MMA warp derives
+    // from it stays in uniform registers -- with operands it could not prove uniform, every tcgen05.mma was wrapped in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~10 instructions, ~45 cycles per MMA: the path's real bottleneck)
+    const int tid = threadIdx.x, warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)tid >> 5), lane = tid & 31;
     const uint32_t bar0 = s32(bars);
     const uint32_t B_FULL = bar0, A_FULL = bar0 + 16, A_FREE = bar0 + 32, ACC = bar0 + 48;
 
@@ -153,7 +173,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_base;            // columns 0..63: accumulators; 64..191, 192..319: the two A buffers
+    const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base);            // columns 0..63: accumulators; 64..191, 192..319: the two A buffers
     const uint32_t tmem_a = tmem + kTcDCols;
 
     const int K = args.n_sats, G = args.G, TJ = args.tiles_per_job;
@@ -168,11 +188,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     //   tap rows     : lane = row 32 q + lane = (channel 8 q + lane / 4, tap lane % 4), the warp's 16 samples
     const int q4 = warp & 3, sub = warp >> 2, kq = lane >> 2, tap = lane & 3;
     const int my_sat = 8 * q4 + kq;
+    if (warp == kTcGenWarps) {
+        // ================= control warp: its own copy of the segment / tile loop =================
+        // Everything here derives from kernel parameters, blockIdx and two REDUX results, so ptxas keeps it in UNIFORM
+        // registers and a tcgen05.mma costs the issuing warp ~3 instructions.  (When this code shared the generator warps'
+        // loop its operands lived in vector registers and every MMA was wrapped in ELECT / R2UR.BROADCAST / VOTEU sequences
+        // of 10+ instructions on a scheduler shared with four generator warps: ~45 cycles per MMA, the path's bottleneck.)
+        uint32_t qa = 0, qb = 0;
+        for (int64_t u = r0; u < r1;) {
+            const int job = (int)(u / TJ);
+            const int t_first = (int)(u - (int64_t)job * TJ);
+            const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - u));
+            const TcPeriod *per = &args.periods[job / G];
+            __syncthreads();   // (pairs with the generator warps' segment barrier)
+            for (int t = t_first; t < t_last; ++t, ++qb) {
+                const uint32_t st = qb & 1u;
+                const uint32_t bt = s32(sB + st * kTcBTile);
+                if (elect_one()) {
+                    const int c3 = (args.aligned_start + t * kTcTile) / 4;
+                    if (qb == 0 && !(args.debug & 16)) {                             // the CTA's very first tile
+                        bar_expect(B_FULL + 8 * st, kTcBTile);
+                        tma_load_4d(bt, &per->map, c3, B_FULL + 8 * st);
+                    }
+                    // prefetch the next tile of this CTA (same job or the next one) into the other stage
+                    const int64_t un = u + (t - t_first) + 1;
+                    if (un < r1 && !(args.debug & 16)) {
+                        const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
+                        if (qb >= 1) {                                               // its previous reader, tile qb - 1, is done:
+                            const uint32_t ql = qb * kTcChunks - 1;                  // ... that tile's last chunk has been committed
+                            bar_wait_spin(A_FREE + 8 * (ql & 1u), (ql >> 1) & 1u);
+                        }
+                        bar_expect(B_FULL + 8 * (st ^ 1u), kTcBTile);
+                        tma_load_4d(s32(sB + (st ^ 1u) * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4,
+                                    B_FULL + 8 * (st ^ 1u));
+                    }
+                }
+                __syncwarp();
+                // B descriptors differ only in their 14-bit start-address field: one base, then 64-bit adds of constants
+                const uint64_t db0 = umma_desc(bt, kTcBGroup, 128);
+                for (int c = 0; c < kTcChunks; ++c, ++qa) {
+                    const uint32_t buf = qa & 1u;
+                    bar_wait_spin(A_FULL + 8 * buf, (qa >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ta_re = tmem_a + buf * kTcABufCols, ta_im = ta_re + kTcChunk;
+                    const uint64_t db = db0 + (uint64_t)(((uint32_t)c * (kTcChunk / 4) * kTcBGroup) >> 4);
+                    const uint32_t acc0 = (t > t_first || c > 0) ? 1u : 0u;
+                    if (elect_one()) {
+                        if (!(args.debug & 2)) {
+#pragma unroll
+                            for (int j = 0; j < kTcSteps; ++j) {
+                                umma_tf32_ts(tmem, ta_re + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), j ? 1u : acc0);
+                                umma_tf32_ts(tmem + kTcCols, ta_im + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), j ? 1u : acc0);
+                            }
+                        }
+                        umma_commit(A_FREE + 8 * buf);
+                        if (c == kTcChunks - 1 && t == t_last - 1) umma_commit(ACC);
+                    }
+                    __syncwarp();
+                }
+            }
+            u += t_last - t_first;
+        }
+    }
     uint32_t qa = 0;      // running chunk counter (A buffer + parity)
     uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity, replica buffer)
     uint32_t seg = 0;
 
-    for (int64_t u = r0; u < r1; ++seg) {
+    for (int64_t u = r0; u < r1 && warp < kTcGenWarps; ++seg) {
         const int job = (int)(u / TJ);
         const int t_first = (int)(u - (int64_t)job * TJ);
         const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - u));
@@ -230,51 +312,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             const uint32_t st = qb & 1u;
             const int n0 = args.aligned_start + t * kTcTile - args.start_sample;      // relative index of tile sample 0
             const uint32_t bt = s32(sB + st * kTcBTile);
-            if (warp == kTcGenWarps) {
-                // =========================== control warp: TMA + MMA issue, one thread ===========================
-                if (lane == 0) {
-                    const int c3 = (args.aligned_start + t * kTcTile) / 4;
-                    if (qb == 0 && !(args.debug & 16)) {                             // the CTA's very first tile
-                        bar_expect(B_FULL + 8 * st, kTcBTile);
-                        tma_load_4d(bt, &per->map, c3, B_FULL + 8 * st);
-                    }
-                    // prefetch the next tile of this CTA (same job or the next one) into the other stage
-                    const int64_t un = u + (t - t_first) + 1;
-                    if (un < r1 && !(args.debug & 16)) {
-                        const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
-                        if (qb >= 1) {                                               // its previous reader, tile qb - 1, is done:
-                            const uint32_t ql = qb * kTcChunks - 1;                  // ... that tile's last chunk has been committed
-                            bar_wait(A_FREE + 8 * (ql & 1u), (ql >> 1) & 1u);
-                        }
-                        bar_expect(B_FULL + 8 * (st ^ 1u), kTcBTile);
-                        tma_load_4d(s32(sB + (st ^ 1u) * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4,
-                                    B_FULL + 8 * (st ^ 1u));
-                    }
-                    // B descriptors differ only in their 14-bit start-address field: one base, then 64-bit adds of constants
-                    const uint64_t db0 = umma_desc(bt, kTcBGroup, 128);
-                    uint32_t q = qa;
-                    uint32_t acc = (t > t_first) ? 1u : 0u;
-                    for (int c = 0; c < kTcChunks; ++c, ++q) {
-                        const uint32_t buf = q & 1u;
-                        bar_wait(A_FULL + 8 * buf, (q >> 1) & 1u);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t ta_re = tmem_a + buf * kTcABufCols, ta_im = ta_re + kTcChunk;
-                        const uint64_t db = db0 + (uint64_t)(((uint32_t)c * (kTcChunk / 4) * kTcBGroup) >> 4);
-#pragma unroll
-                        for (int j = 0; j < kTcSteps; ++j) {
-                            if (args.debug & 2) break;
-                            umma_tf32_ts(tmem, ta_re + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
-                            umma_tf32_ts(tmem + kTcCols, ta_im + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), acc);
-                            acc = 1u;
-                        }
-                        umma_commit(A_FREE + 8 * buf);
-                    }
-                    if (t == t_last - 1) umma_commit(ACC);
-                }
-                qa += kTcChunks;
-                continue;
-            }
-
             // ================================= generator warps =================================
             // ---- replica sign bits of this tile for the warp's two channels: entry e <-> sample n0 + e + shift0.  Both
             // channels' table lookups are in flight together (four independent load -> ballot chains per round) ----
@@ -356,6 +393,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             const uint32_t t_row = tmem_a + ((uint32_t)(32 * q4) << 16) + (uint32_t)(sub * kTcLaneSamples);
             for (int c = 0; c < kTcChunks; ++c, ++qa) {
                 const uint32_t buf = qa & 1u, use = qa >> 1;
+                if (args.debug & 128) {                                             // experiment: the hand-over skeleton alone
+                    if (use > 0) {
+                        if (args.debug & 2048) bar_wait_spin(A_FREE + 8 * buf, (use - 1) & 1u);
+                        else bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(A_FULL + 8 * buf);
+                    continue;
+                }
                 // ---- carrier rows of this chunk: four consecutive samples of one channel per lane ----
                 __syncwarp();                                                       // previous chunk's readers are done
                 {
@@ -393,7 +441,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     cx[i] ^= sign;
                     cy[i] ^= sign;
                 }
-                if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
+                if (use > 0) {                                                       // the MMAs that read this buffer are done
+                    if (args.debug & 2048) bar_wait_spin(A_FREE + 8 * buf, (use - 1) & 1u);
+                    else bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (!(args.debug & 1)) {
                     tmem_st16(t_row + buf * kTcABufCols, cx);
