@@ -37,7 +37,10 @@ constexpr int kTcRows = 128, kTcRowsPerSat = 4, kTcSats = kTcRows / kTcRowsPerSa
 constexpr int kTcTile = 256, kTcChunk = 64, kTcChunks = kTcTile / kTcChunk, kTcSteps = kTcChunk / 8;
 constexpr int kTcDCols = 2 * kTcCols;                      // TMEM columns of the two accumulators C_r | C_i
 constexpr int kTcABufCols = 2 * kTcChunk;                  // TMEM columns of one A buffer: W_re | W_im, one column per sample
-constexpr int kTcTmemCols = 512;                           // 64 + 2 x 128 = 320, rounded up to the next power of two
+constexpr int kTcABufs = 3;                                // A ring: a hand-over round trip (arrive -> MMA -> commit -> wake) costs
+                                                           // ~0.85 us, more than a chunk's generation: two buffers serialised them
+constexpr int kTcBStages = 4;                              // signal tiles in flight (TMA runs two tiles ahead of the MMA)
+constexpr int kTcTmemCols = 512;                           // 64 + 3 x 128 = 448, rounded up to the next power of two
 constexpr int kTcLaneSamples = kTcChunk / 4;               // samples per thread and chunk (four warps share a lane quarter)
 constexpr int kTcCarStride = kTcLaneSamples * 8 + 16;      // bytes per channel in a warp's carrier rows (+16: bank spread)
 constexpr int kTcBGroup = kTcCols * 16;                    // 4 samples of all 32 columns: 512 B
@@ -46,7 +49,7 @@ constexpr int kTcGenWarps = 16;
 constexpr int kTcThreads = 32 * (kTcGenWarps + 1);
 constexpr int kTcTabWords = 32;                            // chip table of a channel as sign bits: 1024 chips in 128 B
 constexpr int kTcRepWords = 20;                            // replica sign bits per channel and tile: <= 512 entries (+ one spare word)
-constexpr int kTcSmemBytes = 2 * kTcBTile + kTcSats * kTcTabWords * 4 + 2 * kTcSats * kTcRepWords * 4 + kTcGenWarps * 8 * kTcCarStride;
+constexpr int kTcSmemBytes = kTcBStages * kTcBTile + kTcSats * kTcTabWords * 4 + 2 * kTcSats * kTcRepWords * 4 + kTcGenWarps * 8 * kTcCarStride;
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint32_t a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(n)); }
@@ -120,10 +123,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ uint32_t tf32_rna(float x)
+// round to nearest (ties away from zero) to TF32 = add half an ulp of the 10-bit mantissa to the magnitude, drop 13 bits.
+// cvt.rna.tf32.f32 is not a native instruction on sm_100a: ptxas emits exactly this plus an |x| < inf test, which finite
+// samples and sines do not need (an infinite or NaN sample comes out as NaN either way).
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// a ^ (b & c) in one LOP3
+__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c)
 {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -144,22 +152,25 @@ __device__ __forceinline__ int tc_owner(int64_t x, int grid, int64_t total) { re
 __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __grid_constant__ TcArgs args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *sB = smem;                                            // [2][kTcBTile]
-    uint32_t *sTab = reinterpret_cast<uint32_t *>(sB + 2 * kTcBTile);    // [32][32] chip tables as sign bits
+    unsigned char *sB = smem;                                            // [kTcBStages][kTcBTile]
+    uint32_t *sTab = reinterpret_cast<uint32_t *>(sB + kTcBStages * kTcBTile);    // [32][32] chip tables as sign bits
     uint32_t *sRep = sTab + kTcSats * kTcTabWords;                       // [2][32][20] sign bits of a tile's replicas (tile parity)
     unsigned char *sCar = reinterpret_cast<unsigned char *>(sRep + 2 * kTcSats * kTcRepWords);   // [16 warps][8 channels][kTcCarStride]
     __shared__ uint32_t tmem_base;
-    __shared__ __align__(8) uint64_t bars[7];   // 0,1 B full; 2,3 A full; 4,5 A free; 6 accumulators ready
+    __shared__ __align__(8) uint64_t bars[2 * kTcBStages + 2 * kTcABufs + 1];   // B full x 4; B free x 4; A full x 3; A free x 3; accumulators ready
     // (the warp index through a shuffle from lane 0: ptxas then KNOWS it is warp-uniform, and everything the MMA warp derives
     // from it stays in uniform registers -- with operands it could not prove uniform, every tcgen05.mma was wrapped in an
     // ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~10 instructions, ~45 cycles per MMA: the path's real bottleneck)
     const int tid = threadIdx.x, warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)tid >> 5), lane = tid & 31;
     const uint32_t bar0 = s32(bars);
-    const uint32_t B_FULL = bar0, A_FULL = bar0 + 16, A_FREE = bar0 + 32, ACC = bar0 + 48;
+    const uint32_t B_FULL = bar0, B_FREE = B_FULL + 8 * kTcBStages, A_FULL = B_FREE + 8 * kTcBStages, A_FREE = A_FULL + 8 * kTcABufs, ACC = A_FREE + 8 * kTcABufs;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kTcBStages; ++i) {
             bar_init(B_FULL + 8 * i, 1);
+            bar_init(B_FREE + 8 * i, 1);
+        }
+        for (int i = 0; i < kTcABufs; ++i) {
             bar_init(A_FULL + 8 * i, kTcGenWarps);
             bar_init(A_FREE + 8 * i, 1);
         }
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base);            // columns 0..63: accumulators; 64..191, 192..319: the two A buffers
+    const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base);            // columns 0..63: accumulators; then the three A buffers of 128 columns
     const uint32_t tmem_a = tmem + kTcDCols;
 
     const int K = args.n_sats, G = args.G, TJ = args.tiles_per_job;
@@ -194,43 +205,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         // registers and a tcgen05.mma costs the issuing warp ~3 instructions.  (When this code shared the generator warps'
         // loop its operands lived in vector registers and every MMA was wrapped in ELECT / R2UR.BROADCAST / VOTEU sequences
         // of 10+ instructions on a scheduler shared with four generator warps: ~45 cycles per MMA, the path's bottleneck.)
-        uint32_t qa = 0, qb = 0;
+        uint32_t qb = 0, abuf = 0, ause = 0;       // tile counter; A ring position and the use count of its buffers
+        auto load_tile = [&](int64_t un, uint32_t qn) {       // unit un of this CTA's range = its tile number qn
+            const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
+            const uint32_t sn = qn & (kTcBStages - 1);
+            bar_expect(B_FULL + 8 * sn, kTcBTile);
+            tma_load_4d(s32(sB + sn * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4, B_FULL + 8 * sn);
+        };
+        if (elect_one() && !(args.debug & 16)) {              // the first two tiles are on their way during the segment set-up
+            if (r0 < r1) load_tile(r0, 0);
+            if (r0 + 1 < r1) load_tile(r0 + 1, 1);
+        }
+        __syncwarp();
         for (int64_t u = r0; u < r1;) {
             const int job = (int)(u / TJ);
             const int t_first = (int)(u - (int64_t)job * TJ);
             const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - u));
-            const TcPeriod *per = &args.periods[job / G];
             __syncthreads();   // (pairs with the generator warps' segment barrier)
             for (int t = t_first; t < t_last; ++t, ++qb) {
-                const uint32_t st = qb & 1u;
-                const uint32_t bt = s32(sB + st * kTcBTile);
-                if (elect_one()) {
-                    const int c3 = (args.aligned_start + t * kTcTile) / 4;
-                    if (qb == 0 && !(args.debug & 16)) {                             // the CTA's very first tile
-                        bar_expect(B_FULL + 8 * st, kTcBTile);
-                        tma_load_4d(bt, &per->map, c3, B_FULL + 8 * st);
-                    }
-                    // prefetch the next tile of this CTA (same job or the next one) into the other stage
-                    const int64_t un = u + (t - t_first) + 1;
-                    if (un < r1 && !(args.debug & 16)) {
-                        const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
-                        if (qb >= 1) {                                               // its previous reader, tile qb - 1, is done:
-                            const uint32_t ql = qb * kTcChunks - 1;                  // ... that tile's last chunk has been committed
-                            bar_wait_spin(A_FREE + 8 * (ql & 1u), (ql >> 1) & 1u);
-                        }
-                        bar_expect(B_FULL + 8 * (st ^ 1u), kTcBTile);
-                        tma_load_4d(s32(sB + (st ^ 1u) * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4,
-                                    B_FULL + 8 * (st ^ 1u));
+                const uint32_t bt = s32(sB + (qb & (kTcBStages - 1)) * kTcBTile);
+                if (elect_one() && !(args.debug & 16)) {
+                    // the TMA runs two tiles ahead: tile qb + 2 goes into the stage tile qb - 2 was read from
+                    const int64_t uc = u + (t - t_first);
+                    if (uc + 2 < r1) {
+                        // (its own barrier per stage, waited for exactly once per use: a parity wait on an A barrier of two
+                        // tiles ago could alias with that buffer's later phases)
+                        if (qb >= 2) bar_wait_spin(B_FREE + 8 * ((qb + 2) & (kTcBStages - 1)), ((qb - 2) >> 2) & 1u);
+                        load_tile(uc + 2, qb + 2);
                     }
                 }
                 __syncwarp();
                 // B descriptors differ only in their 14-bit start-address field: one base, then 64-bit adds of constants
                 const uint64_t db0 = umma_desc(bt, kTcBGroup, 128);
-                for (int c = 0; c < kTcChunks; ++c, ++qa) {
-                    const uint32_t buf = qa & 1u;
-                    bar_wait_spin(A_FULL + 8 * buf, (qa >> 1) & 1u);
+                for (int c = 0; c < kTcChunks; ++c) {
+                    bar_wait_spin(A_FULL + 8 * abuf, ause & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t ta_re = tmem_a + buf * kTcABufCols, ta_im = ta_re + kTcChunk;
+                    const uint32_t ta_re = tmem_a + abuf * kTcABufCols, ta_im = ta_re + kTcChunk;
                     const uint64_t db = db0 + (uint64_t)(((uint32_t)c * (kTcChunk / 4) * kTcBGroup) >> 4);
                     const uint32_t acc0 = (t > t_first || c > 0) ? 1u : 0u;
                     if (elect_one()) {
@@ -241,16 +251,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                                 umma_tf32_ts(tmem + kTcCols, ta_im + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), j ? 1u : acc0);
                             }
                         }
-                        umma_commit(A_FREE + 8 * buf);
-                        if (c == kTcChunks - 1 && t == t_last - 1) umma_commit(ACC);
+                        umma_commit(A_FREE + 8 * abuf);
+                        if (c == kTcChunks - 1) {
+                            umma_commit(B_FREE + 8 * (qb & (kTcBStages - 1)));
+                            if (t == t_last - 1) umma_commit(ACC);
+                        }
                     }
                     __syncwarp();
+                    if (++abuf == kTcABufs) { abuf = 0; ++ause; }
                 }
             }
             u += t_last - t_first;
         }
     }
-    uint32_t qa = 0;      // running chunk counter (A buffer + parity)
+    const int koff_tap = args.koff[tap];
+    const bool skeleton = (args.debug & 128) != 0;
+    uint32_t abuf = 0, ause = 0;      // A ring position and the use count of its buffers
     uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity, replica buffer)
     uint32_t seg = 0;
 
@@ -309,13 +325,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         __syncthreads();   // tables in place; previous segment's epilogue done (TMEM free)
 
         for (int t = t_first; t < t_last; ++t, ++qb) {
-            const uint32_t st = qb & 1u;
+            const uint32_t st = qb & (kTcBStages - 1);
             const int n0 = args.aligned_start + t * kTcTile - args.start_sample;      // relative index of tile sample 0
-            const uint32_t bt = s32(sB + st * kTcBTile);
             // ================================= generator warps =================================
             // ---- replica sign bits of this tile for the warp's two channels: entry e <-> sample n0 + e + shift0.  Both
             // channels' table lookups are in flight together (four independent load -> ballot chains per round) ----
-            uint32_t *rep_t = sRep + st * (kTcSats * kTcRepWords);
+            uint32_t *rep_t = sRep + (qb & 1u) * (kTcSats * kTcRepWords);
             if (!(args.debug & 64)) {
                 const int rows = (kTcTile + args.span + 31) >> 5;
                 uint64_t v[2], v32[2];
@@ -363,11 +378,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
 
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----
-            if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 1) & 1u);
+            if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 2) & 1u);
             {
                 unsigned char *bp = sB + st * kTcBTile;
                 const bool edge = n0 < 0 || n0 + kTcTile > args.n_samples;            // only a job's first / last tile
-                for (int i = tid; i < kTcBTile / 16 && !(args.debug & 8); i += 32 * kTcGenWarps) {        // 16 B = 4 samples of one column
+                for (int i = tid; i < kTcBTile / 16; i += 32 * kTcGenWarps) {        // 16 B = 4 samples of one column
                     uint4 w = reinterpret_cast<uint4 *>(bp)[i];
                     w.x = tf32_rna(__uint_as_float(w.x));
                     w.y = tf32_rna(__uint_as_float(w.y));
@@ -390,14 +405,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             const uint32_t car_st = car_w + (uint32_t)(kq * kTcCarStride + tap * 32);  // writer: 4 samples = 32 B
             const uint32_t car_ld = car_w + (uint32_t)(kq * kTcCarStride);             // reader: the channel's 16 samples
             const uint32_t rep_s0 = s32(rep_t + my_sat * kTcRepWords);
+            const int e_lane = sub * kTcLaneSamples + koff_tap;
             const uint32_t t_row = tmem_a + ((uint32_t)(32 * q4) << 16) + (uint32_t)(sub * kTcLaneSamples);
-            for (int c = 0; c < kTcChunks; ++c, ++qa) {
-                const uint32_t buf = qa & 1u, use = qa >> 1;
-                if (args.debug & 128) {                                             // experiment: the hand-over skeleton alone
-                    if (use > 0) {
-                        if (args.debug & 2048) bar_wait_spin(A_FREE + 8 * buf, (use - 1) & 1u);
-                        else bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
-                    }
+            for (int c = 0; c < kTcChunks; ++c) {
+                const uint32_t buf = abuf, use = ause;
+                if (++abuf == kTcABufs) { abuf = 0; ++ause; }
+                if (skeleton) {                                                     // experiment: the hand-over skeleton alone
+                    if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -417,15 +431,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         cw[2 * i + 1] = tf32_rna(ci) ^ 0x80000000u;
                     }
                     cph += (uint64_t)kTcChunk * cd1;
-                    if (!(args.debug & 4)) {
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(car_st), "r"(cw[0]), "r"(cw[1]), "r"(cw[2]), "r"(cw[3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(car_st + 16u), "r"(cw[4]), "r"(cw[5]), "r"(cw[6]), "r"(cw[7]) : "memory");
-                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(car_st), "r"(cw[0]), "r"(cw[1]), "r"(cw[2]), "r"(cw[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(car_st + 16u), "r"(cw[4]), "r"(cw[5]), "r"(cw[6]), "r"(cw[7]) : "memory");
                 }
                 __syncwarp();
                 // ---- tap rows: this lane's row, the warp's 16 samples of the chunk ----
                 // the row's sixteen replica entries e .. e + 15 sit in two consecutive words
-                const int e = c * kTcChunk + sub * kTcLaneSamples + args.koff[tap];
+                const int e = c * kTcChunk + e_lane;
                 uint32_t w0, w1;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rep_s0 + 4u * (uint32_t)(e >> 5)));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(rep_s0 + 4u * (uint32_t)(e >> 5) + 4u));
@@ -437,20 +449,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 const uint32_t bits = __funnelshift_r(w0, w1, e & 31);              // bit i = sign of entry e + i
 #pragma unroll
                 for (int i = 0; i < kTcLaneSamples; ++i) {
-                    const uint32_t sign = (bits << (31 - i)) & 0x80000000u;
-                    cx[i] ^= sign;
-                    cy[i] ^= sign;
+                    const uint32_t sh = bits << (31 - i);                           // bit 31 = sign of sample i
+                    cx[i] = xor_and(cx[i], sh, 0x80000000u);
+                    cy[i] = xor_and(cy[i], sh, 0x80000000u);
                 }
-                if (use > 0) {                                                       // the MMAs that read this buffer are done
-                    if (args.debug & 2048) bar_wait_spin(A_FREE + 8 * buf, (use - 1) & 1u);
-                    else bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
-                }
+                if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (!(args.debug & 1)) {
-                    tmem_st16(t_row + buf * kTcABufCols, cx);
-                    tmem_st16(t_row + buf * kTcABufCols + kTcChunk, cy);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                }
+                tmem_st16(t_row + buf * kTcABufCols, cx);
+                tmem_st16(t_row + buf * kTcABufCols + kTcChunk, cy);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the rounded signal tile -> the MMA's proxy
                 __syncwarp();
