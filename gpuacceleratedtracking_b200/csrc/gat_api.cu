@@ -718,6 +718,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
             ta.tiles_per_job = tiles_per_job;
             ta.G = G;
             ta.total_units = total_units;
+            ta.win_ok = (static_cast<double>(kTileCap + span + 64) * shape.max_ratio + 2.0 < 32.0 && !env_int("GAT_TC_NO_WINDOW", 0)) ? 1 : 0;
             ta.debug = env_int("GAT_TC_DEBUG", 0);
             if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
             cudaError_t e = launch_correlate_tc(ta, grid, jobs, ctx->stream);

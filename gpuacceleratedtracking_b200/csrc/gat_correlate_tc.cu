@@ -145,6 +145,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[31])
         : "r"(taddr));
 }
+// experiment (GAT_TC_DEBUG bit 4096): SM-clock timestamps of the first 64 chunk hand-overs of CTA 0, read back with gat_debug_tc_trace
+constexpr int kTcTraceChunks = 64, kTcTraceKinds = 6;
+__device__ unsigned long long g_tc_trace[kTcTraceKinds * kTcTraceChunks];
+__device__ __forceinline__ void tc_trace(bool on, int kind, uint32_t g)
+{
+    if (on && g < (uint32_t)kTcTraceChunks) g_tc_trace[kind * kTcTraceChunks + g] = clock64();
+}
 __device__ __forceinline__ int tc_owner(int64_t x, int grid, int64_t total) { return (int)(((x + 1) * grid - 1) / total); }
 
 }  // namespace
@@ -206,6 +213,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         // loop its operands lived in vector registers and every MMA was wrapped in ELECT / R2UR.BROADCAST / VOTEU sequences
         // of 10+ instructions on a scheduler shared with four generator warps: ~45 cycles per MMA, the path's bottleneck.)
         uint32_t qb = 0, abuf = 0, ause = 0;       // tile counter; A ring position and the use count of its buffers
+        const bool tr = (args.debug & 4096) && blockIdx.x == 0 && lane == 0;
+        uint32_t gch = 0;
         auto load_tile = [&](int64_t un, uint32_t qn) {       // unit un of this CTA's range = its tile number qn
             const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
             const uint32_t sn = qn & (kTcBStages - 1);
@@ -239,6 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 const uint64_t db0 = umma_desc(bt, kTcBGroup, 128);
                 for (int c = 0; c < kTcChunks; ++c) {
                     bar_wait_spin(A_FULL + 8 * abuf, ause & 1u);
+                    tc_trace(tr, 0, gch);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ta_re = tmem_a + abuf * kTcABufCols, ta_im = ta_re + kTcChunk;
                     const uint64_t db = db0 + (uint64_t)(((uint32_t)c * (kTcChunk / 4) * kTcBGroup) >> 4);
@@ -251,13 +261,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                                 umma_tf32_ts(tmem + kTcCols, ta_im + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), j ? 1u : acc0);
                             }
                         }
-                        umma_commit(A_FREE + 8 * abuf);
+                        if (args.debug & 256) bar_arrive(A_FREE + 8 * abuf);      // experiment (skeleton only): no tcgen05.commit
+                        else umma_commit(A_FREE + 8 * abuf);
                         if (c == kTcChunks - 1) {
                             umma_commit(B_FREE + 8 * (qb & (kTcBStages - 1)));
                             if (t == t_last - 1) umma_commit(ACC);
                         }
                     }
                     __syncwarp();
+                    tc_trace(tr, 1, gch++);
                     if (++abuf == kTcABufs) { abuf = 0; ++ause; }
                 }
             }
@@ -265,6 +277,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         }
     }
     const int koff_tap = args.koff[tap];
+    const bool tr = (args.debug & 4096) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15);
+    const int trk = warp == 0 ? 2 : 4;
+    uint32_t gch = 0;
     const bool skeleton = (args.debug & 128) != 0;
     uint32_t abuf = 0, ause = 0;      // A ring position and the use count of its buffers
     uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity, replica buffer)
@@ -343,6 +358,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     tab_s[h] = s32(sTab + (8 * q4 + 2 * sub + h) * kTcTabWords);
                     sh[h] = fp[h] - 32;
                 }
+                if (args.win_ok) {
+                    // Oversampled signals (the whole replica of a tile spans < 32 chips -- host-checked): one 32-chip window
+                    // per channel and tile, bit j = chip (first chip + j) mod length, fetched by one table lookup; an entry's
+                    // sign is then bit (chips advanced since the tile's first entry) of the window -- no wrap, no table
+                    // address, no load per row.  Same Int64 NCO, same bits as the general path below.
+                    uint32_t win[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t idx = bmod[h] + (uint32_t)lane, word;
+                        idx = min(idx, idx - lc[h]);
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(tab_s[h] + 4u * (idx >> 5)));
+                        win[h] = __ballot_sync(0xffffffffu, ((word >> (idx & 31u)) & 1u) != 0u);
+                    }
+                    for (int r = 0; r < rows; r += 2) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t rel = (uint32_t)(v[h] >> 32) >> sh[h];
+                                const uint32_t bits = __ballot_sync(0xffffffffu, ((win[h] >> rel) & 1u) != 0u);
+                                if (lane == 2 * j + h) rep_t[(8 * q4 + 2 * sub + h) * kTcRepWords + r + j] = bits;
+                                v[h] += v32[h];
+                            }
+                    }
+                } else
                 for (int r = 0; r < rows; r += 2) {                 // (the row count is rounded up to even: 20 words per channel)
                     uint32_t word[2][2], sft[2][2];
 #pragma unroll
@@ -351,7 +391,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                         for (int h = 0; h < 2; ++h) {
                             uint32_t idx = bmod[h] + ((uint32_t)(v[h] >> 32) >> sh[h]);
                             idx = min(idx, idx - lc[h]);            // single wrap (host-checked)
-                            idx = min(idx, 1023u);                  // (a channel that is not live has no table: stay inside it)
                             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word[j][h]) : "r"(tab_s[h] + 4u * (idx >> 5)));
                             sft[j][h] = idx & 31u;
                             v[h] += v32[h];
@@ -360,7 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const uint32_t bits = __ballot_sync(0xffffffffu, (word[j][h] >> sft[j][h]) & 1u);
+                            const uint32_t bits = __ballot_sync(0xffffffffu, ((word[j][h] >> sft[j][h]) & 1u) != 0u);
                             if (lane == 2 * j + h) rep_t[(8 * q4 + 2 * sub + h) * kTcRepWords + r + j] = bits;
                         }
                 }
@@ -375,7 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             }
             // the quarter's four warps exchange their replica rows.  The buffer alternates per tile: a warp that runs ahead
             // into tile t + 1 writes the other buffer, and it cannot reach tile t + 2 before everyone has left tile t.
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
+            if (!(args.debug & 1024)) asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
 
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----
             if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 2) & 1u);
@@ -412,9 +451,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 if (++abuf == kTcABufs) { abuf = 0; ++ause; }
                 if (skeleton) {                                                     // experiment: the hand-over skeleton alone
                     if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tc_trace(tr, trk, gch);
+                    if (!(args.debug & 512)) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
                     __syncwarp();
+                    tc_trace(tr, trk + 1, gch++);
                     if (lane == 0) bar_arrive(A_FULL + 8 * buf);
                     continue;
                 }
@@ -454,6 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     cy[i] = xor_and(cy[i], sh, 0x80000000u);
                 }
                 if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);              // the MMAs that read this buffer are done
+                tc_trace(tr, trk, gch);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 tmem_st16(t_row + buf * kTcABufCols, cx);
                 tmem_st16(t_row + buf * kTcABufCols + kTcChunk, cy);
@@ -461,6 +505,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the rounded signal tile -> the MMA's proxy
                 __syncwarp();
+                tc_trace(tr, trk + 1, gch++);
                 if (lane == 0) bar_arrive(A_FULL + 8 * buf);
             }
         }
@@ -534,6 +579,14 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const TcArgs args, int
         out[(((size_t)p * K + k) * L + tap) * M + m] = acc;
     }
 }
+
+}  // namespace gat
+extern "C" int gat_debug_tc_trace(unsigned long long *out, int n)       // experiment read-back, not part of include/gat.h
+{
+    if (n > gat::kTcTraceKinds * gat::kTcTraceChunks) n = gat::kTcTraceKinds * gat::kTcTraceChunks;
+    return (int)cudaMemcpyFromSymbol(out, gat::g_tc_trace, sizeof(unsigned long long) * n);
+}
+namespace gat {
 
 cudaError_t configure_tc_kernel()
 {

@@ -117,6 +117,7 @@ struct alignas(64) TcArgs {
     int32_t start_sample, n_samples, aligned_start;
     int32_t tiles_per_job, G;
     int64_t total_units;
+    int32_t win_ok;              // a tile's replica (tile + tap span + row padding) advances < 32 chips on every channel
     int32_t debug;               // GAT_TC_DEBUG bit mask (experiments): 1 skip tap rows, 2 skip MMAs, 4 skip carrier rows, 8 skip rounding
 };
 cudaError_t configure_tc_kernel();

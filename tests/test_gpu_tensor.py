@@ -113,3 +113,26 @@ def test_tensor_path_on_bound_planes_in_either_order(gat, orc, engine):
         got = engine.correlate(70, chans, fs, shifts, m, n_samples=n, tensor=True)
         assert engine.launch_info()["tensor"] == 1
         assert np.abs(got[:5] - ref).max() <= 2e-5 * n * 1.6
+
+
+@pytest.mark.parametrize("fs", [2.5e6, 6.0e6, 5.0e7])
+def test_tensor_path_replica_generators_agree(gat, orc, engine, fs, monkeypatch):
+    """The replica sign bits come from the general generator (one table lookup per entry) at low sampling rates and from
+    the chip-window generator (a tile's replica spans < 32 chips) at high ones; both run the same Int64 NCO, so forcing
+    the general one (GAT_TC_NO_WINDOW) must reproduce the accumulators bit for bit -- and both match the oracle."""
+    rng = np.random.default_rng(int(fs) % 1000 + 3)
+    n, m, n_ch = 9000, 6, 37
+    l1, chans, re, im = _scene(gat, orc, rng, n_ch, m, n, fs)
+    step = max(1, round(0.5 * fs / 1.023e6))
+    shifts = np.array([-step, 0, step], np.int32)
+    engine.upload_signal(45, re, im)
+    got = engine.correlate(45, chans, fs, shifts, m, n_samples=n, tensor=True)
+    assert engine.launch_info()["tensor"] == 1
+    monkeypatch.setenv("GAT_TC_NO_WINDOW", "1")
+    general = engine.correlate(45, chans, fs, shifts, m, n_samples=n, tensor=True)
+    monkeypatch.delenv("GAT_TC_NO_WINDOW")
+    assert np.array_equal(got.view(np.uint64), general.view(np.uint64))
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                         fs, shifts) for c in chans[:8]])
+    rms = float(np.sqrt(np.mean(re.astype(np.float64) ** 2 + im.astype(np.float64) ** 2)))
+    assert np.abs(got[:8] - ref).max() <= 2e-5 * n * rms
