@@ -261,8 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                                 umma_tf32_ts(tmem + kTcCols, ta_im + 8 * j, db + (uint64_t)((j * 2 * kTcBGroup) >> 4), j ? 1u : acc0);
                             }
                         }
-                        if (args.debug & 256) bar_arrive(A_FREE + 8 * abuf);      // experiment (skeleton only): no tcgen05.commit
-                        else umma_commit(A_FREE + 8 * abuf);
+                        umma_commit(A_FREE + 8 * abuf);
                         if (c == kTcChunks - 1) {
                             umma_commit(B_FREE + 8 * (qb & (kTcBStages - 1)));
                             if (t == t_last - 1) umma_commit(ACC);
@@ -414,7 +413,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             }
             // the quarter's four warps exchange their replica rows.  The buffer alternates per tile: a warp that runs ahead
             // into tile t + 1 writes the other buffer, and it cannot reach tile t + 2 before everyone has left tile t.
-            if (!(args.debug & 1024)) asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
 
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----
             if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 2) & 1u);
@@ -452,10 +451,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 if (skeleton) {                                                     // experiment: the hand-over skeleton alone
                     if (use > 0) bar_wait(A_FREE + 8 * buf, (use - 1) & 1u);
                     tc_trace(tr, trk, gch);
-                    if (!(args.debug & 512)) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (c == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     tc_trace(tr, trk + 1, gch++);
                     if (lane == 0) bar_arrive(A_FULL + 8 * buf);

@@ -118,7 +118,8 @@ struct alignas(64) TcArgs {
     int32_t tiles_per_job, G;
     int64_t total_units;
     int32_t win_ok;              // a tile's replica (tile + tap span + row padding) advances < 32 chips on every channel
-    int32_t debug;               // GAT_TC_DEBUG bit mask (experiments): 1 skip tap rows, 2 skip MMAs, 4 skip carrier rows, 8 skip rounding
+    int32_t debug;               // GAT_TC_DEBUG bit mask (experiments; results are wrong with 2..128 set): 2 skip MMAs, 16 skip TMA,
+                                 // 64 skip replica rows, 128 hand-over skeleton only, 4096 record the hand-over timeline of CTA 0
 };
 cudaError_t configure_tc_kernel();
 cudaError_t launch_correlate_tc(const TcArgs &args, int grid, int jobs, cudaStream_t stream);

@@ -13,7 +13,7 @@ shifts = np.array([-24, 0, 24], np.int32)
 re = torch.randn(M, N, device="cuda"); im = torch.randn(M, N, device="cuda")
 eng._check(eng._lib.gat_upload_signal(eng._h, 0, ctypes.c_void_p(re.data_ptr()), ctypes.c_void_p(im.data_ptr()), N, M, N, 1))
 Ks = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1024").split(",")]
-masks = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0,1,2,4,8,16,64,3,67,71,79,95").split(",")]
+masks = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0,2,64,128,192,210").split(",")]
 for K in Ks:
     ch = eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, 1500.0 + 3.0 * k, 0.001 * k) for k in range(K)]])
     out = (torch.zeros(1, K, L, M, device="cuda"), torch.zeros(1, K, L, M, device="cuda"))
