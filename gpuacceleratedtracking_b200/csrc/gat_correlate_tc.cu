@@ -146,7 +146,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr));
 }
 // experiment (GAT_TC_DEBUG bit 4096): SM-clock timestamps of the first 64 chunk hand-overs of CTA 0, read back with gat_debug_tc_trace
-constexpr int kTcTraceChunks = 64, kTcTraceKinds = 6;
+constexpr int kTcTraceChunks = 64, kTcTraceKinds = 7;      // kind 6: one-off events of CTA 0 (entry, set-up, first tile, epilogue, exit)
 __device__ unsigned long long g_tc_trace[kTcTraceKinds * kTcTraceChunks];
 __device__ __forceinline__ void tc_trace(bool on, int kind, uint32_t g)
 {
@@ -168,6 +168,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     // (the warp index through a shuffle from lane 0: ptxas then KNOWS it is warp-uniform, and everything the MMA warp derives
     // from it stays in uniform registers -- with operands it could not prove uniform, every tcgen05.mma was wrapped in an
     // ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~10 instructions, ~45 cycles per MMA: the path's real bottleneck)
+    // the finalize kernel is launched with programmatic stream serialisation: its blocks may take their places now and wait
+    // (griddepcontrol.wait) until this grid has completed -- its launch latency leaves the call's critical path
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool tr_ev = (args.debug & 4096) && blockIdx.x == 0 && threadIdx.x == 0;
+    tc_trace(tr_ev, 6, 0);
     const int tid = threadIdx.x, warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)tid >> 5), lane = tid & 31;
     const uint32_t bar0 = s32(bars);
     const uint32_t B_FULL = bar0, B_FREE = B_FULL + 8 * kTcBStages, A_FULL = B_FREE + 8 * kTcBStages, A_FREE = A_FULL + 8 * kTcABufs, ACC = A_FREE + 8 * kTcABufs;
@@ -191,6 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_trace(tr_ev, 6, 1);
     const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base);            // columns 0..63: accumulators; then the three A buffers of 128 columns
     const uint32_t tmem_a = tmem + kTcDCols;
 
@@ -295,48 +301,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
         uint64_t frac[2] = {0, 0}, ndel[2] = {0, 0};
         uint32_t bmod[2] = {0, 0}, lc[2] = {1, 1};
         int fp[2] = {32, 32};
-        bool live[2] = {false, false};
         uint64_t cph = 0, cd1 = 0;       // carrier phase (Q0.64 cycles) of this lane's first sample in the next chunk; step per sample
         if (warp < kTcGenWarps) {
             const int64_t n0 = (int64_t)args.aligned_start + (int64_t)t_first * kTcTile - args.start_sample;   // may be < 0 (alignment head)
+            // Slots past the last channel of a ragged group alias the last channel: their rows are generated like any
+            // other (no branches in the generators) and never read by the finalize kernel.  All global loads of the
+            // set-up are issued before anything consumes them (it was a chain of six dependent round trips, 3.2 us).
+            const SatDev *sdp[2];
+            const int8_t *code[2];
+            int clen[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int sl = 8 * q4 + 2 * sub + h, k = grp * kTcSats + sl;
-                live[h] = k < K;
-                if (live[h]) {
-                    const SatDev *sd = &args.sats[(size_t)p * K + k];
-                    const int8_t *code = sd->code;
-                    const int clen = sd->code_len;
-                    // 16 chips per lane and step (one 16-byte load; the columns are zero-padded to 16 B): their sign bits
-                    // are squeezed into 16 bits, two lanes make one word -- 2 steps for a 1023-chip code instead of 32
-                    // dependent byte loads + ballots
-                    for (int i0 = 0; i0 < kTcTabWords * 32; i0 += 512) {
-                        const int ci = i0 + lane * 16;
-                        uint4 w = make_uint4(0, 0, 0, 0);
-                        if (ci < clen) w = *reinterpret_cast<const uint4 *>(code + ci);
-                        auto squeeze = [](uint32_t x) { return ((x >> 7) & 1u) | ((x >> 14) & 2u) | ((x >> 21) & 4u) | ((x >> 28) & 8u); };
-                        const uint32_t half = squeeze(w.x) | (squeeze(w.y) << 4) | (squeeze(w.z) << 8) | (squeeze(w.w) << 12);
-                        const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
-                        if (!(lane & 1)) sTab[sl * kTcTabWords + (ci >> 5)] = half | (other << 16);
-                    }
-                    ndel[h] = (uint64_t)sd->nco_delta;
-                    fp[h] = sd->nco_fp;
-                    lc[h] = (uint32_t)clen;
-                    // state at the first sample of tile t_first
-                    const __int128 tot = (__int128)(n0 + args.shift0) * (__int128)sd->nco_delta + (__int128)sd->nco_start;
-                    int64_t b = (int64_t)(tot >> sd->nco_fp) % clen;
-                    if (b < 0) b += clen;
-                    bmod[h] = (uint32_t)b;
-                    frac[h] = (uint64_t)tot & ((1ull << sd->nco_fp) - 1ull);
-                }
+                const int k = min(grp * kTcSats + 8 * q4 + 2 * sub + h, K - 1);
+                sdp[h] = &args.sats[(size_t)p * K + k];
             }
-            if (grp * kTcSats + my_sat < K) {
-                const SatDev *sd = &args.sats[(size_t)p * K + grp * kTcSats + my_sat];
-                cd1 = sd->car_delta;
-                cph = sd->car_phase + (uint64_t)(n0 + sub * kTcLaneSamples + 4 * tap) * cd1;      // 64-bit wrap = whole cycles
+            const SatDev *sdc = &args.sats[(size_t)p * K + min(grp * kTcSats + my_sat, K - 1)];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                code[h] = sdp[h]->code;
+                clen[h] = sdp[h]->code_len;
+                ndel[h] = (uint64_t)sdp[h]->nco_delta;
+                fp[h] = sdp[h]->nco_fp;
+            }
+            cd1 = sdc->car_delta;
+            cph = sdc->car_phase + (uint64_t)(n0 + sub * kTcLaneSamples + 4 * tap) * cd1;      // 64-bit wrap = whole cycles
+            // 16 chips per lane and step (one 16-byte load; the columns are zero-padded to 16 B): their sign bits are
+            // squeezed into 16 bits, two lanes make one word -- 2 steps for a 1023-chip code
+            uint4 cw[2][kTcTabWords * 32 / 512];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < kTcTabWords * 32 / 512; ++i) {
+                    const int ci = i * 512 + lane * 16;
+                    cw[h][i] = make_uint4(0, 0, 0, 0);
+                    if (ci < clen[h]) cw[h][i] = *reinterpret_cast<const uint4 *>(code[h] + ci);
+                }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int sl = 8 * q4 + 2 * sub + h;
+#pragma unroll
+                for (int i = 0; i < kTcTabWords * 32 / 512; ++i) {
+                    const uint4 w = cw[h][i];
+                    auto squeeze = [](uint32_t x) { return ((x >> 7) & 1u) | ((x >> 14) & 2u) | ((x >> 21) & 4u) | ((x >> 28) & 8u); };
+                    const uint32_t half = squeeze(w.x) | (squeeze(w.y) << 4) | (squeeze(w.z) << 8) | (squeeze(w.w) << 12);
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
+                    if (!(lane & 1)) sTab[sl * kTcTabWords + ((i * 512 + lane * 16) >> 5)] = half | (other << 16);
+                }
+                lc[h] = (uint32_t)clen[h];
+                // state at the first sample of tile t_first
+                const __int128 tot = (__int128)(n0 + args.shift0) * (__int128)(int64_t)ndel[h] + (__int128)sdp[h]->nco_start;
+                int64_t b = (int64_t)(tot >> fp[h]) % clen[h];
+                if (b < 0) b += clen[h];
+                bmod[h] = (uint32_t)b;
+                frac[h] = (uint64_t)tot & ((1ull << fp[h]) - 1ull);
             }
         }
         __syncthreads();   // tables in place; previous segment's epilogue done (TMEM free)
+        tc_trace(tr_ev, 6, 2 + 8 * seg);
 
         for (int t = t_first; t < t_last; ++t, ++qb) {
             const uint32_t st = qb & (kTcBStages - 1);
@@ -414,6 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             // the quarter's four warps exchange their replica rows.  The buffer alternates per tile: a warp that runs ahead
             // into tile t + 1 writes the other buffer, and it cannot reach tile t + 2 before everyone has left tile t.
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
+            if (t == t_first) tc_trace(tr_ev, 6, 3 + 8 * seg);
 
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----
             if (!(args.debug & 16)) bar_wait(B_FULL + 8 * st, (qb >> 2) & 1u);
@@ -439,6 +461,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             // Only a job's first / last tile has samples outside [0, n_samples): there the signal tile is zeroed, so neither
             // the carrier nor the replica needs a range check.  Rows of taps or channels that do not exist hold finite
             // junk: a row of A only reaches its own row of D, which the finalize kernel never reads.
+            if (t == t_first) tc_trace(tr_ev, 6, 4 + 8 * seg);
             const uint32_t car_w = s32(sCar + warp * (8 * kTcCarStride));             // this warp's carrier rows
             const uint32_t car_st = car_w + (uint32_t)(kq * kTcCarStride + tap * 32);  // writer: 4 samples = 32 B
             const uint32_t car_ld = car_w + (uint32_t)(kq * kTcCarStride);             // reader: the channel's 16 samples
@@ -507,10 +530,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             }
         }
         u += t_last - t_first;
+        tc_trace(tr_ev, 6, 5 + 8 * seg);
 
         // ---- epilogue of the segment: warps 0..3 read the accumulators and publish this CTA's partial of the job ----
         if (warp < 4) {
             bar_wait(ACC, seg & 1u);
+            tc_trace(tr_ev, 6, 6 + 8 * seg);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t vr[32], vi[32];
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -539,10 +564,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 *reinterpret_cast<float4 *>(pi + m) = make_float4(o_im[0], o_im[1], o_im[2], o_im[3]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_trace(tr_ev, 6, 7 + 8 * seg);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    tc_trace(tr_ev, 6, 40);
     if (warp == kTcGenWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTcTmemCols) : "memory");
 }
 
@@ -550,6 +577,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
 // 8 lanes per output element: lane j adds contributors b_first + j, + 8, ...; a fixed xor tree combines the eight sums.
 __global__ void __launch_bounds__(256) tc_finalize_kernel(const TcArgs args, int grid)
 {
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // the correlate grid has completed, its partials are visible
     const int job = blockIdx.x / 128;
     const int G = args.G, TJ = args.tiles_per_job, K = args.n_sats, L = args.n_taps, M = args.n_ants;
     const int p = job / G, grp = job % G;
@@ -595,8 +623,16 @@ cudaError_t launch_correlate_tc(const TcArgs &args, int grid, int jobs, cudaStre
     correlate_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    tc_finalize_kernel<<<jobs * 128, 256, 0, stream>>>(args, grid);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(jobs * 128);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_finalize_kernel, args, grid);
 }
 
 }  // namespace gat
