@@ -65,9 +65,9 @@ typedef enum gat_status {
                                  samples stay exact, the accumulators carry ~3e-4 * sqrt(N) * rms(sample) of rounding
                                  noise instead of the FP32 kernel's ~1e-7 relative.  Shapes outside the envelope run
                                  on the FP32 kernel as usual (gat_launch_info.tensor tells which one ran).  Measured
-                                 on B200 (16 antennas, 3 taps, 50000 samples): faster than the FP32 kernel from ~64
-                                 channel-blocks per call (264 channels: 126 -> 70 us, 1024 channels: 447 -> 206 us),
-                                 slower below; the caller decides.                                                  */
+                                 on B200 (16 antennas, 3 taps, 50000 samples): 2.0-2.2x the FP32 kernel from 64
+                                 channel-blocks per call (264 channels: 126 -> 66 us, 1024 channels: 446 -> 202 us),
+                                 on par at 32; the caller decides.                                                  */
 #define GAT_CODE_PHASE_F64 2u /* chip index = mod(floor(fc/fs*(n+shift)+phase), Lc) in IEEE double,
                                  bit-exact with the reference's GPU kernels (src/algorithms.jl:179-182).
                                  Default is the Int64 Q-format NCO of Tracking.jl's CPU path, bit-exact
