@@ -548,7 +548,10 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "correlations/s", "h2d_bytes_per_step": P * 8 * N_SAMPLES * N_ANTS,
                     "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "path": "pinned host -> H2D" + (f" (1/{world} per rank) -> NCCL all-gather over NVLink" if world > 1 else "")
-                            + " -> gat_correlate_batch -> " + ("NCCL gather -> " if world > 1 else "") + "D2H"},
+                            + " -> gat_correlate_batch -> " + ("NCCL gather -> " if world > 1 else "") + "D2H",
+                    # what bounds it: one satellite per 6.4 MB block is 2.25 flop/B, the block crosses PCIe once
+                    "h2d_gb_per_s_per_gpu": P * 8 * N_SAMPLES * N_ANTS / world / (e2e_ms * 1e-3) / 1e9,
+                    "bound": "PCIe host->device copy (the kernel needs %.2f ms of the %.1f ms step)" % (ms_per_step, e2e_ms)},
             "e2e_sc16": e2e_sc16,
             "int16_resident": int16_resident,
             "e2e_shared_block": e2e_shared,
