@@ -152,6 +152,10 @@ __device__ __forceinline__ void tc_trace(bool on, int kind, uint32_t g)
 {
     if (on && g < (uint32_t)kTcTraceChunks) g_tc_trace[kind * kTcTraceChunks + g] = clock64();
 }
+// The segment barrier of all 17 warps.  The control warp and the generator warps reach it from different loops, so it is a
+// named barrier with an explicit thread count (PTX semantics) and not __syncthreads(), whose contract is one call site
+// reached convergently by the whole block (compute-sanitizer synccheck enforces that).
+__device__ __forceinline__ void seg_barrier() { asm volatile("bar.sync 5, %0;" ::"n"(kTcThreads) : "memory"); }
 __device__ __forceinline__ int tc_owner(int64_t x, int grid, int64_t total) { return (int)(((x + 1) * grid - 1) / total); }
 
 }  // namespace
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             const int job = (int)(u / TJ);
             const int t_first = (int)(u - (int64_t)job * TJ);
             const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - u));
-            __syncthreads();   // (pairs with the generator warps' segment barrier)
+            seg_barrier();     // (pairs with the generator warps' segment barrier)
             for (int t = t_first; t < t_last; ++t, ++qb) {
                 const uint32_t bt = s32(sB + (qb & (kTcBStages - 1)) * kTcBTile);
                 if (elect_one() && !(args.debug & 16)) {
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 frac[h] = (uint64_t)tot & ((1ull << fp[h]) - 1ull);
             }
         }
-        __syncthreads();   // tables in place; previous segment's epilogue done (TMEM free)
+        seg_barrier();     // tables in place; previous segment's epilogue done (TMEM free)
         tc_trace(tr_ev, 6, 2 + 8 * seg);
 
         for (int t = t_first; t < t_last; ++t, ++qb) {
