@@ -152,9 +152,7 @@ __device__ __forceinline__ void tc_trace(bool on, int kind, uint32_t g)
 {
     if (on && g < (uint32_t)kTcTraceChunks) g_tc_trace[kind * kTcTraceChunks + g] = clock64();
 }
-// The segment barrier of all 17 warps.  The control warp and the generator warps reach it from different loops, so it is a
-// named barrier with an explicit thread count (PTX semantics) and not __syncthreads(), whose contract is one call site
-// reached convergently by the whole block (compute-sanitizer synccheck enforces that).
+// The segment barrier of all 17 warps (a counted named barrier; both roles reach it at one call site of the segment loop).
 __device__ __forceinline__ void seg_barrier() { asm volatile("bar.sync 5, %0;" ::"n"(kTcThreads) : "memory"); }
 __device__ __forceinline__ int tc_owner(int64_t x, int grid, int64_t total) { return (int)(((x + 1) * grid - 1) / total); }
 
@@ -216,31 +214,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     //   tap rows     : lane = row 32 q + lane = (channel 8 q + lane / 4, tap lane % 4), the warp's 16 samples
     const int q4 = warp & 3, sub = warp >> 2, kq = lane >> 2, tap = lane & 3;
     const int my_sat = 8 * q4 + kq;
-    if (warp == kTcGenWarps) {
-        // ================= control warp: its own copy of the segment / tile loop =================
-        // Everything here derives from kernel parameters, blockIdx and two REDUX results, so ptxas keeps it in UNIFORM
-        // registers and a tcgen05.mma costs the issuing warp ~3 instructions.  (When this code shared the generator warps'
-        // loop its operands lived in vector registers and every MMA was wrapped in ELECT / R2UR.BROADCAST / VOTEU sequences
-        // of 10+ instructions on a scheduler shared with four generator warps: ~45 cycles per MMA, the path's bottleneck.)
-        uint32_t qb = 0, abuf = 0, ause = 0;       // tile counter; A ring position and the use count of its buffers
-        const bool tr = (args.debug & 4096) && blockIdx.x == 0 && lane == 0;
-        uint32_t gch = 0;
-        auto load_tile = [&](int64_t un, uint32_t qn) {       // unit un of this CTA's range = its tile number qn
+    // ================= control warp: its own tile loop and its own counters =================
+    // Everything it touches derives from kernel parameters, blockIdx and two REDUX results, so ptxas keeps it in UNIFORM
+    // registers and a tcgen05.mma costs the issuing warp ~3 instructions.  (When this code shared the generator warps'
+    // tile loop and counters its operands lived in vector registers and every MMA was wrapped in ELECT / R2UR.BROADCAST /
+    // VOTEU sequences of 10+ instructions on a scheduler shared with four generator warps: ~45 cycles per MMA.)
+    uint32_t c_qb = 0, c_abuf = 0, c_ause = 0;       // tile counter; A ring position and the use count of its buffers
+    uint32_t c_gch = 0;
+    const bool c_tr = (args.debug & 4096) && blockIdx.x == 0 && lane == 0 && warp == kTcGenWarps;
+    auto load_tile = [&](int64_t un, uint32_t qn) {       // unit un of this CTA's range = its tile number qn
             const int jn = (int)(un / TJ), tn = (int)(un - (int64_t)jn * TJ);
             const uint32_t sn = qn & (kTcBStages - 1);
             bar_expect(B_FULL + 8 * sn, kTcBTile);
             tma_load_4d(s32(sB + sn * kTcBTile), &args.periods[jn / G].map, (args.aligned_start + tn * kTcTile) / 4, B_FULL + 8 * sn);
         };
+    if (warp == kTcGenWarps) {
         if (elect_one() && !(args.debug & 16)) {              // the first two tiles are on their way during the segment set-up
             if (r0 < r1) load_tile(r0, 0);
             if (r0 + 1 < r1) load_tile(r0 + 1, 1);
         }
         __syncwarp();
-        for (int64_t u = r0; u < r1;) {
-            const int job = (int)(u / TJ);
-            const int t_first = (int)(u - (int64_t)job * TJ);
-            const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - u));
-            seg_barrier();     // (pairs with the generator warps' segment barrier)
+    }
+    auto control_segment = [&](int64_t u, int t_first, int t_last) {
+        {
+            uint32_t qb = c_qb, abuf = c_abuf, ause = c_ause, gch = c_gch;
+            const bool tr = c_tr;
             for (int t = t_first; t < t_last; ++t, ++qb) {
                 const uint32_t bt = s32(sB + (qb & (kTcBStages - 1)) * kTcBTile);
                 if (elect_one() && !(args.debug & 16)) {
@@ -282,9 +280,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                     if (++abuf == kTcABufs) { abuf = 0; ++ause; }
                 }
             }
-            u += t_last - t_first;
+            c_qb = qb; c_abuf = abuf; c_ause = ause; c_gch = gch;
         }
-    }
+    };
     const int koff_tap = args.koff[tap];
     const bool tr = (args.debug & 4096) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15);
     const int trk = warp == 0 ? 2 : 4;
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
     uint32_t qb = 0;      // running tile counter of this CTA (B stage + parity, replica buffer)
     uint32_t seg = 0;
 
-    for (int64_t u = r0; u < r1 && warp < kTcGenWarps; ++seg) {
+    for (int64_t u = r0; u < r1; ++seg) {
         const int job = (int)(u / TJ);
         const int t_first = (int)(u - (int64_t)job * TJ);
         const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - u));
@@ -360,7 +358,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
                 frac[h] = (uint64_t)tot & ((1ull << fp[h]) - 1ull);
             }
         }
-        seg_barrier();     // tables in place; previous segment's epilogue done (TMEM free)
+        seg_barrier();     // all 17 warps, one call site: tables in place; previous segment's epilogue done (TMEM free)
+        if (warp == kTcGenWarps) {
+            control_segment(u, t_first, t_last);
+            u += t_last - t_first;
+            continue;
+        }
         tc_trace(tr_ev, 6, 2 + 8 * seg);
 
         for (int t = t_first; t < t_last; ++t, ++qb) {
