@@ -660,7 +660,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (flags & GAT_TENSOR_TF32) {
         const int span = sh_pad[n_taps - 1] - sh_pad[0];
         bool ok = !(flags & (GAT_CODE_PHASE_F64 | GAT_ACCUMULATE | GAT_GATHER)) && n_taps <= 4 && M <= 16 && span <= 224 &&
-                  shape.max_code_len <= 1024 &&
+                  shape.max_code_len <= 10240 &&      // kTcTabWords * 32 chips of sign bits per channel in shared memory (GPS L5: 10 230)
                   static_cast<double>(kTileCap + span + 192) * shape.max_ratio + 2.0 < static_cast<double>(shape.min_code_len);
         {
             const long double need = static_cast<long double>(kTileCap + span + 192) * static_cast<long double>(shape.max_delta) +

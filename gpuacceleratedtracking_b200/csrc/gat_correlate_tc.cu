@@ -47,7 +47,7 @@ constexpr int kTcBGroup = kTcCols * 16;                    // 4 samples of all 3
 constexpr int kTcBTile = (kTcTile / 4) * kTcBGroup;        // 32 KB
 constexpr int kTcGenWarps = 16;
 constexpr int kTcThreads = 32 * (kTcGenWarps + 1);
-constexpr int kTcTabWords = 32;                            // chip table of a channel as sign bits: 1024 chips in 128 B
+constexpr int kTcTabWords = 320;                           // chip table of a channel as sign bits: up to 10 240 chips (GPS L5) in 1 280 B
 constexpr int kTcRepWords = 20;                            // replica sign bits per channel and tile: <= 512 entries (+ one spare word)
 constexpr int kTcSmemBytes = kTcBStages * kTcBTile + kTcSats * kTcTabWords * 4 + 2 * kTcSats * kTcRepWords * 4 + kTcGenWarps * 8 * kTcCarStride;
 
@@ -329,26 +329,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             cph = sdc->car_phase + (uint64_t)(n0 + sub * kTcLaneSamples + 4 * tap) * cd1;      // 64-bit wrap = whole cycles
             // 16 chips per lane and step (one 16-byte load; the columns are zero-padded to 16 B): their sign bits are
             // squeezed into 16 bits, two lanes make one word -- 2 steps for a 1023-chip code
-            uint4 cw[2][kTcTabWords * 32 / 512];
+            const int tab_steps = (max(clen[0], clen[1]) + 511) >> 9;       // 2 for a 1 023-chip code, 20 for GPS L5
+            for (int i0 = 0; i0 < tab_steps; i0 += 2) {                      // four loads in flight per round
+                uint4 cw[2][2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int i = 0; i < kTcTabWords * 32 / 512; ++i) {
-                    const int ci = i * 512 + lane * 16;
-                    cw[h][i] = make_uint4(0, 0, 0, 0);
-                    if (ci < clen[h]) cw[h][i] = *reinterpret_cast<const uint4 *>(code[h] + ci);
-                }
+                    for (int i = 0; i < 2; ++i) {
+                        const int ci = (i0 + i) * 512 + lane * 16;
+                        cw[h][i] = make_uint4(0, 0, 0, 0);
+                        if (ci < clen[h]) cw[h][i] = *reinterpret_cast<const uint4 *>(code[h] + ci);
+                    }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint4 w = cw[h][i];
+                        auto squeeze = [](uint32_t x) { return ((x >> 7) & 1u) | ((x >> 14) & 2u) | ((x >> 21) & 4u) | ((x >> 28) & 8u); };
+                        const uint32_t half = squeeze(w.x) | (squeeze(w.y) << 4) | (squeeze(w.z) << 8) | (squeeze(w.w) << 12);
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
+                        const int ci = (i0 + i) * 512 + lane * 16;
+                        if (!(lane & 1) && ci < kTcTabWords * 32)
+                            sTab[(8 * q4 + 2 * sub + h) * kTcTabWords + (ci >> 5)] = half | (other << 16);
+                    }
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int sl = 8 * q4 + 2 * sub + h;
-#pragma unroll
-                for (int i = 0; i < kTcTabWords * 32 / 512; ++i) {
-                    const uint4 w = cw[h][i];
-                    auto squeeze = [](uint32_t x) { return ((x >> 7) & 1u) | ((x >> 14) & 2u) | ((x >> 21) & 4u) | ((x >> 28) & 8u); };
-                    const uint32_t half = squeeze(w.x) | (squeeze(w.y) << 4) | (squeeze(w.z) << 8) | (squeeze(w.w) << 12);
-                    const uint32_t other = __shfl_xor_sync(0xffffffffu, half, 1);
-                    if (!(lane & 1)) sTab[sl * kTcTabWords + ((i * 512 + lane * 16) >> 5)] = half | (other << 16);
-                }
                 lc[h] = (uint32_t)clen[h];
                 // state at the first sample of tile t_first
                 const __int128 tot = (__int128)(n0 + args.shift0) * (__int128)(int64_t)ndel[h] + (__int128)sdp[h]->nco_start;

@@ -60,7 +60,7 @@ typedef enum gat_status {
                                  buffer of EVERY rank (peer memory over NVLink) instead of out_re/out_im, which
                                  are ignored.  Needs gat_gather_create/connect.                             */
 #define GAT_TENSOR_TF32 8u    /* allow the tensor-core path (tcgen05.mma kind::tf32) for blocks shared by many channels:
-                                 <= 4 taps, <= 16 antennas, NCO convention, chip tables <= 1023 chips.  W and the
+                                 <= 4 taps, <= 16 antennas, NCO convention, chip tables <= 10240 chips (GPS L1 C/A, L5).  W and the
                                  samples are rounded to TF32 (10-bit mantissa), sums are FP32: <= 12-bit integer
                                  samples stay exact, the accumulators carry ~3e-4 * sqrt(N) * rms(sample) of rounding
                                  noise instead of the FP32 kernel's ~1e-7 relative.  Shapes outside the envelope run

@@ -136,3 +136,32 @@ def test_tensor_path_replica_generators_agree(gat, orc, engine, fs, monkeypatch)
                                          fs, shifts) for c in chans[:8]])
     rms = float(np.sqrt(np.mean(re.astype(np.float64) ** 2 + im.astype(np.float64) ** 2)))
     assert np.abs(got[:8] - ref).max() <= 2e-5 * n * rms
+
+
+def test_tensor_path_gps_l5_codes(gat, orc, engine):
+    """10 230-chip codes (GPS L5 I5): 1 280 B of sign bits per channel in shared memory, general replica generator at 25 MHz
+    (0.41 chip per sample), chip-window generator at 400 MHz."""
+    rng = np.random.default_rng(55)
+    l5 = gat.GPSL5()
+    m, n_ch = 8, 34
+    for fs, n in ((2.5e7, 26000), (4.0e8, 9000)):
+        chans = [gat.Channel(l5, 1 + k % 32, float(rng.uniform(0, 10230)), float(rng.uniform(-5e3, 5e3)), float(rng.uniform(-.5, .5)))
+                 for k in range(n_ch)]
+        re = rng.normal(size=(m, n)).astype(np.float32)
+        im = rng.normal(size=(m, n)).astype(np.float32)
+        c0 = chans[0]
+        r, i = orc.gen_signal(l5.codes[c0.prn - 1], 10.23e6, c0.carrier_frequency, fs, n, m, c0.code_phase, 2 * np.pi * c0.carrier_phase)
+        re += 0.5 * r
+        im += 0.5 * i
+        step = max(1, round(0.5 * fs / 10.23e6))
+        shifts = np.array([-step, 0, step], np.int32)
+        engine.upload_signal(46, re, im)
+        got = engine.correlate(46, chans, fs, shifts, m, n_samples=n, tensor=True)
+        assert engine.launch_info()["tensor"] == 1
+        ref = np.stack([orc.correlate_direct(re, im, l5.codes[c.prn - 1], 10.23e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                             fs, shifts) for c in (chans[0], chans[1], chans[33])])
+        rms = float(np.sqrt(np.mean(re.astype(np.float64) ** 2 + im.astype(np.float64) ** 2)))
+        assert np.abs(got[[0, 1, 33]] - ref).max() <= 2e-5 * n * rms
+        assert abs(abs(got[0, 1, 0]) - 0.5 * n) < 0.05 * n                  # the present L5 signal is found at full strength
+        fp32 = engine.correlate(46, chans, fs, shifts, m, n_samples=n)
+        assert np.abs(got - fp32).max() <= 2e-5 * n * rms
