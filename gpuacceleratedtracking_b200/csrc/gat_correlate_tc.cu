@@ -11,15 +11,18 @@
 //                  the no-swizzle K-major canonical layout [sample/4][plane][antenna][sample%4]; a pass over the tile
 //                  rounds it to TF32 (truncation would bias the magnitude) and zeroes samples outside the range.
 //   * A operand  = W, 32 channels x 4 tap rows = 128 rows, generated in 64-sample chunks straight into TENSOR MEMORY
-//                  (tcgen05.st, double-buffered: lane = row, column = sample): with A in shared memory every MMA re-read
-//                  4 KB of it (45 cycles per MMA at N = 32) and the generator's stores and the MMA's reads shared one
-//                  128 B/clk pipe -- the kernel was shared-memory-bound.  A thread owns one (channel, tap) row and 16
+//                  (tcgen05.st into a ring of three buffers: lane = row, column = sample): with A in shared memory every
+//                  MMA re-read 4 KB of it and the generator's stores and the MMA's reads shared one 128 B/clk pipe.
+//                  A thread owns one (channel, tap) row and 16
 //                  consecutive samples of the chunk; the four warps of a TMEM lane quarter split the chunk's samples.
 //                  Per channel one replica row (sign bits, ballot-packed, double-buffered per tile and shared by the
 //                  quarter's four warps through a 128-thread named barrier) and one warp-private carrier row (TF32
 //                  cos, -sin) per chunk feed the tap rows, whose entries are load - sign flip - tcgen05.st.
 //   * D          = two 128 x 32 FP32 accumulators in TMEM: C_r = W_re x [S_re | S_im], C_i = W_im x [S_re | S_im];
 //                  acc_re = C_r.re - C_i.im, acc_im = C_i.re + C_r.im in the epilogue.
+// Warp roles: 16 generator warps + 1 control warp (TMA loads two tiles ahead into four signal stages, tcgen05.mma issue from
+// uniform registers, tcgen05.commit hand-backs).  Reference semantics followed: the multi-correlator sum of
+// /root/reference/src/algorithms.jl:482-516 (replica-buffer form) with Tracking.jl's Int64 code NCO.
 // Work split: the flattened (period, channel group, tile) space is divided evenly over the CTAs (like the default
 // kernel); every CTA writes one partial per job it touches and a second, tiny kernel sums the partials in a fixed order
 // (deterministic, no float atomics).
