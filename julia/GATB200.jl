@@ -15,6 +15,7 @@ const libgat = get(ENV, "LIBGAT", "libgat.so")
 
 const GAT_ACCUMULATE     = Cuint(1)
 const GAT_CODE_PHASE_F64 = Cuint(2)
+const GAT_TENSOR_TF32    = Cuint(8)      # opt-in tensor-core path for blocks shared by many channels (include/gat.h)
 const GAT_GPSL1 = Cint(0)
 const GAT_GPSL5 = Cint(1)
 
@@ -85,6 +86,31 @@ function kernel_algorithm(ctx::Context, system_id::Integer,
                       CuPtr{Cfloat}, CuPtr{Cfloat}, Cint, Cuint),
                      ctx.handle, 0, 1, ch, hz(sampling_frequency), shifts, NCOR, 0, num_samples,
                      pointer(accum_re), pointer(accum_im), 1, GAT_ACCUMULATE))
+    return nothing
+end
+
+"""
+The receiver case the reference's 3-D kernels index with `sat = blockIdx.z` (src/algorithms.jl:656): K satellite
+channels over ONE bound signal block in one launch.  `out_re`/`out_im` are `CuArray{Float32}` [num_ants x NCOR x K]
+(the 3d_4431 layout, src/algorithms.jl:712).  `tensor = true` allows the `tcgen05` path (TF32 operands, FP32 sums;
+<= 4 taps, <= 16 antennas) -- it pays from 32 channels per block upwards; the call is asynchronous.
+"""
+function correlate_channels!(ctx::Context, out_re::CuArray{Float32}, out_im::CuArray{Float32},
+        channels::Vector{GatChannel}, signal_re::CuArray{Float32}, signal_im::CuArray{Float32},
+        correlator_sample_shifts::SVector{NCOR, Int64}, sampling_frequency, num_samples::Integer;
+        start_sample::Integer = 0, tensor::Bool = false, accumulate::Bool = false) where {NCOR}
+    M = size(signal_re, 2)
+    ld = size(signal_re, 1)
+    check(ctx, ccall((:gat_bind_signal, libgat), Cint,
+                     (Ptr{Cvoid}, Cint, CuPtr{Cfloat}, CuPtr{Cfloat}, Cint, Cint, Cint),
+                     ctx.handle, 0, pointer(signal_re), pointer(signal_im), start_sample + num_samples, M, ld))
+    shifts = Int32.(collect(correlator_sample_shifts))
+    flags = (tensor ? GAT_TENSOR_TF32 : Cuint(0)) | (accumulate ? GAT_ACCUMULATE : Cuint(0))
+    check(ctx, ccall((:gat_correlate, libgat), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Ptr{GatChannel}, Cdouble, Ptr{Int32}, Cint, Cint, Cint,
+                      CuPtr{Cfloat}, CuPtr{Cfloat}, Cint, Cuint),
+                     ctx.handle, 0, length(channels), channels, hz(sampling_frequency), shifts, NCOR, start_sample,
+                     num_samples, pointer(out_re), pointer(out_im), 1, flags))
     return nothing
 end
 
