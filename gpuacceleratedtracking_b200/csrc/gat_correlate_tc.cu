@@ -54,6 +54,9 @@ constexpr int kTcTabWords = 320;                           // chip table of a ch
 constexpr int kTcRepWords = 20;                            // replica sign bits per channel and tile: <= 512 entries (+ one spare word)
 constexpr int kTcSmemBytes = kTcBStages * kTcBTile + kTcSats * kTcTabWords * 4 + 2 * kTcSats * kTcRepWords * 4 + kTcGenWarps * 8 * kTcCarStride;
 
+static_assert(kTcDCols + kTcABufs * kTcABufCols <= kTcTmemCols, "accumulators + A ring must fit the TMEM allocation");
+static_assert(kTcSmemBytes <= 227 * 1024, "dynamic shared memory beyond the sm_100 per-CTA limit");
+static_assert((kTcBStages & (kTcBStages - 1)) == 0 && kTcChunk == 4 * kTcLaneSamples && kTcCarStride % 16 == 0, "layout assumptions");
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint32_t a, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(n)); }
 __device__ __forceinline__ void bar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
