@@ -16,6 +16,7 @@ GAT_ACCUMULATE = 1
 GAT_CODE_PHASE_F64 = 2
 GAT_GATHER = 4
 GAT_TENSOR_TF32 = 8
+GAT_DEBUG_STALL_CONSUMERS = 0x100
 GAT_IPC_HANDLE_BYTES = 64
 GAT_SLOT_DESC_BYTES = 96
 GAT_GPSL1, GAT_GPSL5 = 0, 1

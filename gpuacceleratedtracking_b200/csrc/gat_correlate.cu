@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint64_t *code_bar = reinterpret_cast<uint64_t *>(smem + 256);   // chip-table bulk copies, one phase per segment
+    uint64_t *code_free = code_bar + 1;                              // back-pressure: every consumer warp has SEEN that phase
     const bool split = args.split_tiles != 0;
     float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
     const int tile_floats = (SC16 ? 1 : 2) * MP * kTileCap;   // 32-bit words per stage
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             mbar_init(&empty_bar[s], (uint32_t)(split ? W : NR));  // one arrival per consumer warp that reads the stage
         }
         mbar_init(code_bar, 1);
+        mbar_init(code_free, (uint32_t)W);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // antenna rows that pad M up to AG*A are never written by the copies: keep them zero
@@ -469,7 +471,13 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 }
                 if (t == t_first) {
                     // chip tables AFTER the first tile is in flight; code_bar completes one phase per
-                    // segment (with zero bytes when nothing changed) and releases the consumers
+                    // segment (with zero bytes when nothing changed) and releases the consumers.
+                    // A parity wait only tells the current phase from the previous one, so the producer must not
+                    // complete phase seg before every consumer warp has observed phase seg - 1: with a first
+                    // segment shorter than the ring it could otherwise finish two phases before a consumer looks
+                    // (the consumer then waits for a parity that is the CURRENT phase's -> dead CTA -> watchdog trap),
+                    // or arrive while the previous phase's bulk-copy bytes are still pending.
+                    if (seg > 0) mbar_wait_relaxed(code_free, (seg - 1u) & 1u);
                     const uint32_t my_bytes = reload ? (uint32_t)((code_len + 15) & ~15) : 0u;
                     const uint32_t all_bytes = __reduce_add_sync(0xffffffffu, my_bytes);
                     if (lane == 0) mbar_arrive_expect_tx(code_bar, all_bytes);
@@ -570,7 +578,10 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             for (int a = 0; a < AP; ++a) accRe[a][l] = accIm[a][l] = 0ull;
         }
 
+        if (args.flags & kFlagStallConsumers) __nanosleep(20000);   // test hook: let the producer run ahead
         mbar_wait(code_bar, seg & 1u);   // this segment's chip tables are in shared memory
+        __syncwarp();                    // every lane is past the wait before the producer may flip the phase again
+        if (lane == 0) mbar_arrive(code_free);
 
         // whole tiles go round-robin over the sample slices (tile q of the CTA belongs to slice q % SL); the first
         // one of this segment that is ours, its ring stage and parity: once per segment

@@ -19,7 +19,8 @@ __host__ __device__ constexpr int max_consumer_warps(int A, int L) { return bloc
 constexpr int kMaxStages = 16;
 constexpr int kMaxPeers = 8;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
-constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256)
+constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256) + its back-pressure barrier (264)
+constexpr uint32_t kFlagStallConsumers = 0x100u;   // == GAT_DEBUG_STALL_CONSUMERS (include/gat.h)
 
 // One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
 struct SatDev {

@@ -216,7 +216,7 @@ class Engine:
     def correlate_batch(self, slots: Sequence[int], channels: Sequence[Sequence[Channel]], fs: float,
                         shifts: Sequence[int], n_ants: int, start_sample: int = 0, n_samples: int | None = None,
                         out=None, accumulate: bool = False, code_phase_f64: bool = False, gather: bool = False,
-                        tensor: bool = False):
+                        tensor: bool = False, debug_stall: bool = False):
         """channels[p][k]; returns complex64 [P, K, L, M] (host) or fills `out=(re, im)` torch
         CUDA tensors of that shape (asynchronous).  gather=True (after gather_setup) makes the kernel
         store the block into every rank's gather buffer instead (multi-GPU)."""
@@ -234,7 +234,7 @@ class Engine:
         if n_samples is None:
             raise ValueError("n_samples is required")
         flags = ((_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0) |
-                 (_lib.GAT_TENSOR_TF32 if tensor else 0))
+                 (_lib.GAT_TENSOR_TF32 if tensor else 0) | (_lib.GAT_DEBUG_STALL_CONSUMERS if debug_stall else 0))
         i32p = C.POINTER(C.c_int32)
         if gather:      # outputs go straight into every rank's gather buffer (fused epilogue, no host copy)
             self._check(self._lib.gat_correlate_batch(self._h, P, sl.ctypes.data_as(i32p), K, arr, fs,

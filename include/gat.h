@@ -73,6 +73,10 @@ typedef enum gat_status {
                                  Default is the Int64 Q-format NCO of Tracking.jl's CPU path, bit-exact
                                  with gen_code_replica! [upstream].                                   */
 
+#define GAT_DEBUG_STALL_CONSUMERS 0x100u /* test hook: the consumer warps of the FP32 kernel sleep ~20 us at every
+                                 segment start, so the producer warp runs as far ahead as the ring lets it
+                                 (regression test of the chip-table hand-shake; results are unchanged).   */
+
 /* built-in GNSS ids for gat_gen_code / the `system_id` of a channel.  Any other non-negative
  * id may be used for caller-supplied tables (gat_set_codes). */
 #define GAT_GPSL1 0
