@@ -71,6 +71,9 @@ SYMBOLS = {
     "gat_correlate": (_i, [_vp, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _i, _u]),
     "gat_correlate_batch": (_i, [_vp, _i, _i32p, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _i, _u]),
     "gat_downconvert_and_correlate": (_i, [_vp, _vp, _vp, _i, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _u]),
+    "gat_ingest_correlate": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _u]),
+    "gat_host_register": (_i, [_vp, C.c_uint64]),
+    "gat_host_unregister": (_i, [_vp]),
     "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
     "gat_set_max_ctas": (_i, [_vp, _i]),
     "gat_beamform": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -79,9 +82,21 @@ SYMBOLS = {
     "gat_kernel_launch_count": (C.c_uint64, [_vp]),
     "gat_gather_create": (_i, [_vp, _i, _i, C.c_uint64, C.POINTER(C.c_ubyte)]),
     "gat_gather_connect": (_i, [_vp, C.POINTER(C.c_ubyte)]),
+    "gat_gather_set_offset": (_i, [_vp, C.c_uint64]),
     "gat_gather_wait": (_i, [_vp]),
     "gat_gather_read": (_i, [_vp, _vp, _vp]),
     "gat_gather_destroy": (_i, [_vp]),
+    "gat_ring_create": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_ubyte)]),
+    "gat_ring_connect": (_i, [_vp, C.POINTER(C.c_ubyte)]),
+    "gat_ring_connect_local": (_i, [_vp, C.POINTER(_vp)]),
+    "gat_ring_part": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "gat_ring_upload": (_i, [_vp, _i, _vp, _vp, _i, _i]),
+    "gat_ring_upload_part": (_i, [_vp, _i, _vp, _vp, _i, _i]),
+    "gat_ring_publish": (_i, [_vp]),
+    "gat_ring_wait": (_i, [_vp, _i]),
+    "gat_ring_release": (_i, [_vp]),
+    "gat_ring_acquire": (_i, [_vp, _i]),
+    "gat_ring_destroy": (_i, [_vp]),
     "gat_set_timeline": (_i, [_vp, _i]),
     "gat_get_timeline": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "gat_debug_chip_indices": (_i, [_vp, _chp, _d, _i, _i, _u, _i32p]),

@@ -1,151 +1,13 @@
 // gat_api.cu -- the C ABI of include/gat.h: contexts, chip tables, signal slots, launch
 // planning and the correlate entry points.  Host logic only; the kernels live in
 // gat_correlate.cu.  No CPU fallback exists: every entry point needs a live sm_100 device.
-#include <algorithm>
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
 #include <new>
-#include <string>
-#include <vector>
 
-#include "../../include/gat.h"
-#include "gat_internal.h"
+#include "gat_ctx.h"
 
 using namespace gat;
 
 namespace {
-
-struct SignalSlot {
-    float *re = nullptr, *im = nullptr;
-    int64_t ld = 0;
-    int n_samples = 0, n_ants = 0;
-    bool owned = false;
-    size_t cap_floats = 0;  // per plane, when owned
-    PeriodDev maps{};       // TMA descriptors of the two planes
-    bool maps_valid = false;
-    bool planes_valid = false;   // re / im hold the block (false while only the raw integer copy exists)
-    // raw interleaved complex int16 copy of the block (gat_upload_signal_sc16): [n_ants][raw_ld] words of I | Q << 16
-    int16_t *raw = nullptr;
-    size_t raw_cap = 0;          // complex samples
-    int64_t raw_ld = 0;
-    float raw_scale = 1.f;
-    bool raw_valid = false;
-    PeriodDev raw_map{};         // .re = 2-D descriptor over the 32-bit I/Q words
-    void *peer_base = nullptr;   // gat_slot_import: another process's planes mapped through CUDA IPC (closed on release)
-    TcPeriod tc_map{};           // 4-D descriptor of both planes for the tensor-core path (encoded on first use)
-    int tc_state = 0;            // 0 = not tried, 1 = valid, -1 = the layout cannot be expressed (im <= re, ...)
-};
-
-struct CodeTable {
-    int8_t *d_chips = nullptr;   // [n_prn][col_stride], columns zero-padded to kCodeColAlign bytes
-    int code_len = 0, n_prn = 0, col_stride = 0;
-};
-
-struct Staging {
-    unsigned char *h = nullptr;  // pinned
-    unsigned char *d = nullptr;
-    size_t cap = 0;
-    cudaEvent_t done = nullptr;      // H2D copy finished (param stream)
-    cudaEvent_t consumed = nullptr;  // the kernel reading `d` was queued behind this (main stream)
-    bool pending = false;
-};
-
-constexpr int kStagingRing = 8;
-
-}  // namespace
-
-struct gat_ctx {
-    int device = 0;
-    int n_sm = 0;
-    int max_ctas = 0;   // gat_set_max_ctas: 0 = one CTA on every SM
-    cudaStream_t stream = nullptr;      // the stream work is queued on
-    cudaStream_t own_stream = nullptr;  // created by gat_create
-    cudaStream_t param_stream = nullptr;  // parameter-block uploads, overlapping the previous kernel
-    std::string err;
-    CodeTable codes[GAT_MAX_SYSTEMS];
-    std::vector<SignalSlot> slots;
-    Staging stg[kStagingRing];
-    int stg_next = 0;
-    float *d_partials = nullptr;
-    size_t partials_cap = 0;
-    unsigned int *d_barrier = nullptr;   // grid-barrier arrival counter (monotonic)
-    unsigned int barrier_count = 0;      // host mirror: value after all launches queued so far
-    float *d_out = nullptr;
-    size_t d_out_cap = 0;
-    float *h_out = nullptr;  // pinned
-    size_t h_out_cap = 0;
-    int32_t *d_dbg = nullptr;
-    size_t d_dbg_cap = 0;
-    unsigned char *d_raw = nullptr;      // raw integer samples awaiting expansion
-    size_t d_raw_cap = 0;
-    // fused multi-GPU gather
-    unsigned char *g_local = nullptr;          // this rank's allocation: re | im | flags
-    void *g_opened[kMaxPeers] = {};            // peer base pointers from cudaIpcOpenMemHandle
-    float *g_re[kMaxPeers] = {}, *g_im[kMaxPeers] = {};
-    unsigned int *g_flag[kMaxPeers] = {};
-    uint64_t g_elems = 0;
-    int g_world = 0, g_rank = 0;
-    bool g_connected = false;
-    unsigned int g_seq = 0;
-    unsigned int *d_done = nullptr;
-    unsigned long long *d_timeline = nullptr;
-    size_t timeline_cap = 0;
-    bool timeline_on = false;
-    int timeline_ctas = 0;
-    gat_launch_info info{};
-    bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint64_t launches = 0;
-};
-
-namespace {
-
-int fail(gat_ctx *ctx, int status, const std::string &msg)
-{
-    if (ctx) ctx->err = msg;
-    return status;
-}
-
-int cuda_fail(gat_ctx *ctx, cudaError_t e, const char *what)
-{
-    return fail(ctx, GAT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-}
-
-#define GAT_CUDA(ctx, call)                                          \
-    do {                                                             \
-        cudaError_t e__ = (call);                                    \
-        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);   \
-    } while (0)
-
-int env_int(const char *name, int dflt)
-{
-    const char *v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : dflt;
-}
-
-int pow2_ceil(int x)
-{
-    int p = 1;
-    while (p < x) p <<= 1;
-    return p;
-}
-
-template <typename T>
-int ensure_device(gat_ctx *ctx, T *&ptr, size_t &cap, size_t need, bool zero)
-{
-    if (need <= cap) return GAT_OK;
-    // the old buffer may still be in use by work queued on the stream
-    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ptr) GAT_CUDA(ctx, cudaFree(ptr));
-    ptr = nullptr;
-    cap = 0;
-    const size_t grow = need + need / 2;
-    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ptr), grow * sizeof(T)));
-    if (zero) GAT_CUDA(ctx, cudaMemsetAsync(ptr, 0, grow * sizeof(T), ctx->stream));
-    cap = grow;
-    return GAT_OK;
-}
 
 // Host staging -> device for the per-call parameter block.  The upload runs on a side stream so
 // that, with calls queued back to back, block i+1 is copied while kernel i runs; a ring of pinned
@@ -238,6 +100,7 @@ struct Shape {
     int max_code_len;
     bool sc16;
     int min_code_len = 1 << 30;
+    int n_parts = 1, part_tiles = 0;   // sharded slots (signal ring)
 };
 
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
@@ -288,6 +151,8 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // the per-tile work (replica generation, barriers) and the number of partials to finalise outweigh the idle SMs.
     int tile_len = env_int("GAT_TUNE_TILE", kTileCap);
     if (tile_len < 32 || tile_len > kTileCap || tile_len % 32) return fail(ctx, GAT_ERR_INVALID, "bad GAT_TUNE_TILE");
+    if (sh.n_parts > 1 && (tile_len != kTileCap || aligned_start % kTileCap))
+        return fail(ctx, GAT_ERR_UNSUPPORTED, "sharded (ring) slots need start_sample to be a multiple of 256");
     // per-tile relative NCO phase must fit 64 bits: (tile + span + 1) * delta + 2^fp < 2^64
     if (!sh.f64) {
         const long double need = static_cast<long double>(tile_len + span + 160) * static_cast<long double>(sh.max_delta) +
@@ -368,6 +233,8 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.W = W;
     a.G = G;
     a.stages = stages;
+    a.n_parts = sh.n_parts;
+    a.part_tiles = sh.part_tiles;
     a.rep_stride = rep_stride;
     // chips advanced across one replica (tile + tap span, + the 32-entry row granularity) < shortest code
     a.rep_single_wrap = (static_cast<double>(tile_len + span + 160) * sh.max_ratio + 2.0 < static_cast<double>(sh.min_code_len)) ? 1 : 0;
@@ -447,7 +314,6 @@ int encode_slot_maps(gat_ctx *ctx, SignalSlot &s)
 SignalSlot *slot_for(gat_ctx *ctx, int slot)
 {
     if (slot < 0 || slot >= 65536) return nullptr;
-    if (slot >= static_cast<int>(ctx->slots.size())) ctx->slots.resize(slot + 1);
     return &ctx->slots[slot];
 }
 
@@ -595,15 +461,22 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     for (int l = 0; l < L; ++l) sh_pad[l] = shifts[std::min(l, n_taps - 1)];
 
     // signal slots
-    std::vector<PeriodDev> periods(n_periods);
     int M = -1;
     bool all_raw = true, all_planes = true;
     float raw_scale = 1.f;
+    int n_parts = -1, part_tiles = 0;
     for (int p = 0; p < n_periods; ++p) {
         const int s = slots[p];
-        if (s < 0 || s >= static_cast<int>(ctx->slots.size()) || !(ctx->slots[s].planes_valid || ctx->slots[s].raw_valid))
-            return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(s) + " has no signal");
-        const SignalSlot &sl = ctx->slots[s];
+        const SignalSlot *slp = find_slot(ctx, s);
+        if (!slot_has_signal(slp)) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(s) + " has no signal");
+        const SignalSlot &sl = *slp;
+        const int np = sl.parts.empty() ? 1 : static_cast<int>(sl.parts.size());
+        if (n_parts < 0) {
+            n_parts = np;
+            part_tiles = sl.part_tiles;
+        }
+        if (np != n_parts || sl.part_tiles != part_tiles)
+            return fail(ctx, GAT_ERR_INVALID, "a batch must not mix ring slots and plain slots (or rings of different geometry)");
         if (M < 0) M = sl.n_ants;
         if (sl.n_ants != M) return fail(ctx, GAT_ERR_INVALID, "all periods of a batch must have the same antenna count");
         if (static_cast<int64_t>(start_sample) + n_samples > sl.n_samples)
@@ -629,9 +502,17 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         use_raw = all_raw && pow2 && !(flags & GAT_CODE_PHASE_F64) && (pref < 0 ? worth : pref != 0);
         if (flags & GAT_TENSOR_TF32) use_raw = false;       // the tensor-core path works on the FP32 planes
     }
+    const bool sharded = part_tiles > 0;
+    if (sharded) {
+        use_raw = false;
+        flags &= ~static_cast<unsigned>(GAT_TENSOR_TF32);     // ring slots run on the FP32 kernel
+    }
+    std::vector<PeriodDev> periods(static_cast<size_t>(n_periods) * n_parts);
     for (int p = 0; p < n_periods; ++p) {
         SignalSlot &sl = ctx->slots[slots[p]];
-        if (use_raw) {
+        if (sharded) {
+            for (int j = 0; j < n_parts; ++j) periods[static_cast<size_t>(p) * n_parts + j] = sl.parts[j].maps;
+        } else if (use_raw) {
             periods[p] = sl.raw_map;
         } else {
             rc = ensure_planes(ctx, sl);
@@ -645,6 +526,8 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     const size_t n_ch = static_cast<size_t>(n_periods) * n_sats;
     std::vector<SatDev> sats(n_ch);
     Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1, use_raw};
+    shape.n_parts = n_parts;
+    shape.part_tiles = part_tiles;
     for (size_t i = 0; i < n_ch; ++i) {
         rc = fill_sat(ctx, channels[i], fs_hz, sats[i]);
         if (rc) return rc;
@@ -761,7 +644,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     args.out_scale = use_raw ? raw_scale : 1.f;
 
     // parameter block: [PeriodDev x P][SatDev x P*K]
-    const size_t per_bytes = sizeof(PeriodDev) * n_periods;
+    const size_t per_bytes = sizeof(PeriodDev) * periods.size();
     const size_t sat_off = (per_bytes + 63) & ~static_cast<size_t>(63);
     const size_t blk_bytes = sat_off + sizeof(SatDev) * n_ch;
     std::vector<unsigned char> blk(blk_bytes);
@@ -804,7 +687,8 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (gather) {
         if (!ctx->g_connected) return fail(ctx, GAT_ERR_INVALID, "GAT_GATHER needs gat_gather_create + gat_gather_connect");
         if (L != n_taps || (flags & GAT_ACCUMULATE)) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_GATHER needs an odd tap count and no GAT_ACCUMULATE");
-        if (n_ch * static_cast<size_t>(n_taps) * M > ctx->g_elems) return fail(ctx, GAT_ERR_INVALID, "gather buffer too small for this call");
+        if (ctx->g_off + n_ch * static_cast<size_t>(n_taps) * M > ctx->g_elems)
+            return fail(ctx, GAT_ERR_INVALID, "gather buffer too small for this call (elements + gat_gather_set_offset)");
     }
     const size_t out_elems = n_ch * n_taps * M;          // caller-visible
     const size_t out_elems_k = n_ch * static_cast<size_t>(L) * M;  // kernel layout (padded taps)
@@ -824,8 +708,9 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     }
     args.n_peers = 0;
     if (gather) {
-        args.out_re = ctx->g_re[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems;
-        args.out_im = ctx->g_im[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems;
+        args.out_re = ctx->g_re[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems + ctx->g_off;
+        args.out_im = ctx->g_im[ctx->g_rank] + static_cast<size_t>(ctx->g_rank) * ctx->g_elems + ctx->g_off;
+        args.gather_off = ctx->g_off;
         for (int d = 0; d < ctx->g_world; ++d) {
             args.peer_re[d] = ctx->g_re[d];
             args.peer_im[d] = ctx->g_im[d];
@@ -955,6 +840,7 @@ int gat_create(gat_ctx **out, int device_id)
     ctx->n_sm = prop.multiProcessorCount;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->param_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         configure_kernels() != cudaSuccess || configure_tc_kernel() != cudaSuccess) {
         cudaGetLastError();
@@ -989,7 +875,8 @@ int gat_destroy(gat_ctx *ctx)
     if (!ctx) return GAT_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &s : ctx->slots) {
+    for (auto &kv : ctx->slots) {
+        SignalSlot &s = kv.second;
         if (s.owned && s.re) cudaFree(s.re);
         if (s.raw) cudaFree(s.raw);
         if (s.peer_base) cudaIpcCloseMemHandle(s.peer_base);
@@ -1009,7 +896,14 @@ int gat_destroy(gat_ctx *ctx)
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_timeline) cudaFree(ctx->d_timeline);
+    if (ctx->d_ing_out) cudaFree(ctx->d_ing_out);
+    for (int b = 0; b < kIngestDepth; ++b) {
+        if (ctx->ing_ready[b]) cudaEventDestroy(ctx->ing_ready[b]);
+        if (ctx->ing_free[b]) cudaEventDestroy(ctx->ing_free[b]);
+    }
     gat_gather_destroy(ctx);
+    gat_ring_destroy(ctx);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1025,6 +919,7 @@ int gat_sync(gat_ctx *ctx)
     int rc = check_ctx(ctx);
     if (rc) return rc;
     GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->ring.local) GAT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));   // ingest queued by gat_ring_upload*
     return GAT_OK;
 }
 
@@ -1056,15 +951,17 @@ int gat_set_codes(gat_ctx *ctx, int system_id, const int8_t *chips, int code_len
     return GAT_OK;
 }
 
-int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, int n_samples, int n_ants, int ld,
-                      int src_is_device)
+namespace {
+// copy [n_ants x ld] planes into ctx-owned, padded storage of `slot` on `stream` (the ctx stream, or the ingest stream)
+int upload_planes(gat_ctx *ctx, int slot, const float *re, const float *im, int n_samples, int n_ants, int ld, int src_is_device,
+                  cudaStream_t stream)
 {
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
     if (!re || !im || n_samples < 1 || n_ants < 1 || n_ants > kMaxAnts || ld < n_samples)
         return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
     SignalSlot *s = slot_for(ctx, slot);
     if (!s) return fail(ctx, GAT_ERR_INVALID, "slot out of range");
+    if (!s->parts.empty()) return fail(ctx, GAT_ERR_INVALID, "slot belongs to the signal ring (use gat_ring_upload)");
+    int rc = GAT_OK;
     if (!s->owned && s->re) {   // drop a zero-copy binding
         rc = free_planes(ctx, *s);
         if (rc) return rc;
@@ -1075,18 +972,27 @@ int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, 
         rc = own_slot(ctx, *s, n_samples, n_ants, ld);
         if (rc) return rc;
         const size_t bytes = (static_cast<size_t>(ld) * (n_ants - 1) + n_samples) * sizeof(float);
-        GAT_CUDA(ctx, cudaMemcpyAsync(s->re, re, bytes, kind, ctx->stream));
-        GAT_CUDA(ctx, cudaMemcpyAsync(s->im, im, bytes, kind, ctx->stream));
+        GAT_CUDA(ctx, cudaMemcpyAsync(s->re, re, bytes, kind, stream));
+        GAT_CUDA(ctx, cudaMemcpyAsync(s->im, im, bytes, kind, stream));
     } else {
         const int64_t dld = (static_cast<int64_t>(n_samples) + 3) & ~3LL;
         rc = own_slot(ctx, *s, n_samples, n_ants, dld);
         if (rc) return rc;
         GAT_CUDA(ctx, cudaMemcpy2DAsync(s->re, dld * sizeof(float), re, static_cast<size_t>(ld) * sizeof(float),
-                                        static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, ctx->stream));
+                                        static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, stream));
         GAT_CUDA(ctx, cudaMemcpy2DAsync(s->im, dld * sizeof(float), im, static_cast<size_t>(ld) * sizeof(float),
-                                        static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, ctx->stream));
+                                        static_cast<size_t>(n_samples) * sizeof(float), n_ants, kind, stream));
     }
     return GAT_OK;
+}
+}  // namespace
+
+int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, int n_samples, int n_ants, int ld,
+                      int src_is_device)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    return upload_planes(ctx, slot, re, im, n_samples, n_ants, ld, src_is_device, ctx->stream);
 }
 
 namespace {
@@ -1198,10 +1104,9 @@ int gat_slot_export(gat_ctx *ctx, int slot, unsigned char *desc_out)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (!desc_out || slot < 0 || slot >= static_cast<int>(ctx->slots.size()) ||
-        !(ctx->slots[slot].planes_valid || ctx->slots[slot].raw_valid))
-        return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
-    SignalSlot &s = ctx->slots[slot];
+    SignalSlot *sp = find_slot(ctx, slot);
+    if (!desc_out || !sp || !(sp->planes_valid || sp->raw_valid)) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    SignalSlot &s = *sp;
     rc = ensure_planes(ctx, s);
     if (rc) return rc;
     if (!s.owned) return fail(ctx, GAT_ERR_INVALID, "only ctx-owned slots (gat_upload_signal*, gat_gen_signal) can be exported");
@@ -1284,12 +1189,11 @@ int gat_download_signal(gat_ctx *ctx, int slot, float *re, float *im)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (!re || !im || slot < 0 || slot >= static_cast<int>(ctx->slots.size()) ||
-        !(ctx->slots[slot].planes_valid || ctx->slots[slot].raw_valid))
-        return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
-    rc = ensure_planes(ctx, ctx->slots[slot]);
+    SignalSlot *sp = find_slot(ctx, slot);
+    if (!re || !im || !sp || !(sp->planes_valid || sp->raw_valid)) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    rc = ensure_planes(ctx, *sp);
     if (rc) return rc;
-    const SignalSlot &s = ctx->slots[slot];
+    const SignalSlot &s = *sp;
     const size_t w = static_cast<size_t>(s.n_samples) * sizeof(float);
     GAT_CUDA(ctx, cudaMemcpy2DAsync(re, w, s.re, s.ld * sizeof(float), w, s.n_ants, cudaMemcpyDeviceToHost, ctx->stream));
     GAT_CUDA(ctx, cudaMemcpy2DAsync(im, w, s.im, s.ld * sizeof(float), w, s.n_ants, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1319,11 +1223,95 @@ int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *
                                   int start_sample, int n_samples, float *h_out_re, float *h_out_im, unsigned flags)
 {
     if (!ctx) return GAT_ERR_INVALID;
-    const int scratch_slot = 65535;
+    const int scratch_slot = 65535;   // (slots are a sparse map: a high id costs nothing)
+    if (start_sample < 0 || n_samples < 1 || static_cast<int64_t>(start_sample) + n_samples > INT32_MAX)
+        return fail(ctx, GAT_ERR_INVALID, "empty, negative or overflowing sample range");
     int rc = gat_upload_signal(ctx, scratch_slot, h_re, h_im, start_sample + n_samples, n_ants, ld, 0);
     if (rc) return rc;
     return gat_correlate(ctx, scratch_slot, n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples,
                          h_out_re, h_out_im, 0, flags);
+}
+
+// The CPU-style call over MANY periods with the host<->device traffic pipelined inside the library: the drop-in for a
+// host loop of Tracking.downconvert_and_correlate! calls (src/benchmarks.jl:63-79) over consecutive 1 ms blocks whose
+// channel parameters are known up front.  Chunks of kIngestChunk periods go H2D on the ingest stream into a ring of
+// kIngestDepth staging buffers while the kernel of the previous chunk runs; two events per buffer order the streams.
+int gat_ingest_correlate(gat_ctx *ctx, int n_periods, const float *const *h_re, const float *const *h_im, int ld, int n_ants,
+                         int n_sats, const gat_channel *channels, double fs_hz, const int32_t *sample_shifts, int n_taps,
+                         int start_sample, int n_samples, float *h_out_re, float *h_out_im, unsigned flags)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!h_re || !h_im || !channels || !sample_shifts || !h_out_re || !h_out_im || n_periods < 1 || n_sats < 1)
+        return fail(ctx, GAT_ERR_INVALID, "null pointer or empty batch");
+    if (flags & (GAT_ACCUMULATE | GAT_GATHER)) return fail(ctx, GAT_ERR_INVALID, "gat_ingest_correlate returns host results: no ACCUMULATE / GATHER");
+    if (n_taps < 1 || n_taps > GAT_MAX_TAPS) return fail(ctx, GAT_ERR_UNSUPPORTED, "n_taps must be 1..11");
+    if (start_sample < 0 || n_samples < 1 || static_cast<int64_t>(start_sample) + n_samples > INT32_MAX)
+        return fail(ctx, GAT_ERR_INVALID, "empty, negative or overflowing sample range");
+    for (int b = 0; b < kIngestDepth; ++b)
+        if (!ctx->ing_ready[b]) {
+            GAT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ing_ready[b], cudaEventDisableTiming));
+            GAT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ing_free[b], cudaEventDisableTiming));
+        }
+    const size_t per_period = static_cast<size_t>(n_sats) * n_taps * n_ants;
+    const size_t out_elems = per_period * n_periods;
+    rc = ensure_device(ctx, ctx->d_ing_out, ctx->ing_out_cap, 2 * out_elems, false);
+    if (rc) return rc;
+    float *d_re = ctx->d_ing_out, *d_im = ctx->d_ing_out + out_elems;
+    const int n_up = start_sample + n_samples;
+    int32_t slot_ids[kIngestChunk];
+    // nothing queued earlier on the ctx stream may still be reading the staging slots
+    GAT_CUDA(ctx, cudaEventRecord(ctx->ing_free[0], ctx->stream));
+    for (int b = 1; b < kIngestDepth; ++b) GAT_CUDA(ctx, cudaEventRecord(ctx->ing_free[b], ctx->stream));
+    int chunk = 0;
+    for (int p0 = 0; p0 < n_periods; p0 += kIngestChunk, ++chunk) {
+        const int b = chunk % kIngestDepth;
+        const int cnt = std::min(kIngestChunk, n_periods - p0);
+        GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ing_free[b], 0));      // the kernel that read buffer b is done
+        for (int i = 0; i < cnt; ++i) {
+            slot_ids[i] = kIngestSlotBase + b * kIngestChunk + i;
+            if (!h_re[p0 + i] || !h_im[p0 + i]) return fail(ctx, GAT_ERR_INVALID, "null signal pointer");
+            rc = upload_planes(ctx, slot_ids[i], h_re[p0 + i], h_im[p0 + i], n_up, n_ants, ld, 0, ctx->copy_stream);
+            if (rc) return rc;
+        }
+        GAT_CUDA(ctx, cudaEventRecord(ctx->ing_ready[b], ctx->copy_stream));
+        GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ing_ready[b], 0));
+        rc = correlate_impl(ctx, cnt, slot_ids, n_sats, channels + static_cast<size_t>(p0) * n_sats, fs_hz, sample_shifts, n_taps,
+                            start_sample, n_samples, d_re + per_period * p0, d_im + per_period * p0, 1, flags);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaEventRecord(ctx->ing_free[b], ctx->stream));
+    }
+    GAT_CUDA(ctx, cudaMemcpyAsync(h_out_re, d_re, out_elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GAT_CUDA(ctx, cudaMemcpyAsync(h_out_im, d_im, out_elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GAT_OK;
+}
+
+// Page-lock caller memory (a Julia Array, a numpy buffer) so that the H2D copies of gat_upload_signal* /
+// gat_ingest_correlate / gat_ring_upload* run asynchronously at full PCIe rate instead of through the driver's bounce buffers.
+int gat_host_register(void *ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return GAT_ERR_INVALID;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return GAT_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return GAT_ERR_CUDA;
+    }
+    return GAT_OK;
+}
+
+int gat_host_unregister(void *ptr)
+{
+    if (!ptr) return GAT_ERR_INVALID;
+    if (cudaHostUnregister(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return GAT_ERR_CUDA;
+    }
+    return GAT_OK;
 }
 
 int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out)
@@ -1367,6 +1355,7 @@ int gat_gather_destroy(gat_ctx *ctx)
     ctx->g_connected = false;
     ctx->g_world = 0;
     ctx->g_seq = 0;
+    ctx->g_off = 0;
     return GAT_OK;
 }
 
@@ -1422,6 +1411,14 @@ int gat_gather_connect(gat_ctx *ctx, const unsigned char *handles)
         gather_views(base, ctx->g_world, ctx->g_elems, &ctx->g_re[d], &ctx->g_im[d], &ctx->g_flag[d]);
     }
     ctx->g_connected = true;
+    return GAT_OK;
+}
+
+int gat_gather_set_offset(gat_ctx *ctx, uint64_t elem_offset)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    if (elem_offset >= ctx->g_elems && ctx->g_elems) return fail(ctx, GAT_ERR_INVALID, "gather offset beyond the slice");
+    ctx->g_off = elem_offset;
     return GAT_OK;
 }
 

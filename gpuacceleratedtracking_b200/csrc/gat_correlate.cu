@@ -355,7 +355,7 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
     if (args.n_peers > 1) {
         // fused gather: the same value goes into slice `my_rank` of every other rank's buffer
         // (posted stores over NVLink to CUDA-IPC peer mappings; no collective launch)
-        const size_t off = (size_t)args.my_rank * args.gather_elems + idx;
+        const size_t off = (size_t)args.my_rank * args.gather_elems + args.gather_off + idx;
         for (int d = 0; d < args.n_peers; ++d)
             if (d != args.my_rank) (c ? args.peer_im[d] : args.peer_re[d])[off] = val;
     }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             const int t_first = (int)(g - (int64_t)job * TJ);
             const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
             const int p = job / G, grp = job % G;
-            const PeriodDev *per = &periods[p];
+            const PeriodDev *per = &periods[(size_t)p * args.n_parts];
             const bool sat_ok = (lane < S) && (grp * S + lane < K);
             const int8_t *code = nullptr;
             int code_len = 0;
@@ -465,9 +465,18 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                     // full boxes always: samples past the block end arrive as zeros and still count
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)((SC16 ? 1 : 2) * M * kTileCap * 4));
                     float *stage_tile = tiles + (size_t)stage * tile_floats;
-                    tma_load_2d(stage_tile, &per->re, args.aligned_start + ts_rel, 0, &full_bar[stage]);   // SC16: the I/Q words
+                    int c0 = args.aligned_start + ts_rel;
+                    const PeriodDev *src = per;
+                    if (args.n_parts > 1) {
+                        // sharded slot: this tile lives in ONE owner's HBM (local or a peer over NVLink); the all-gather of
+                        // the block is this kernel's own tile pipeline -- no receive buffer, no second pass over HBM
+                        const int part = min(c0 / (args.part_tiles * kTileCap), args.n_parts - 1);
+                        src = per + part;
+                        c0 -= part * args.part_tiles * kTileCap;
+                    }
+                    tma_load_2d(stage_tile, &src->re, c0, 0, &full_bar[stage]);   // SC16: the I/Q words
                     if constexpr (!SC16)
-                        tma_load_2d(stage_tile + (size_t)MP * kTileCap, &per->im, args.aligned_start + ts_rel, 0, &full_bar[stage]);
+                        tma_load_2d(stage_tile + (size_t)MP * kTileCap, &src->im, c0, 0, &full_bar[stage]);
                 }
                 if (t == t_first) {
                     // chip tables AFTER the first tile is in flight; code_bar completes one phase per
@@ -946,14 +955,45 @@ cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaS
 // --------------------------------------------------------------------------------------
 // stream-ordered wait for the fused gather: lane r spins until rank r's flag reached `seq`
 // --------------------------------------------------------------------------------------
+// A peer that died or diverged never raises its flag: after 20 s the wait traps (-> a CUDA error on this rank's
+// stream) instead of hanging the device for good.
 __global__ void gather_wait_kernel(unsigned int *flags, int world, unsigned int seq)
 {
     if ((int)threadIdx.x < world) {
         unsigned int v;
+        uint64_t t0 = 0;
+        unsigned int polls = 0;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if ((int)(v - seq) < 0 && (++polls & 1023u) == 0) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 5 * kWaitLimitNs) __trap();
+            }
         } while ((int)(v - seq) < 0);
     }
+}
+
+__global__ void flag_signal_kernel(const FlagPtrs dst, int world, int my_rank, unsigned int seq)
+{
+    // stream order put everything this flag announces (H2D copies, the kernel that read the blocks) before this
+    // kernel; the fence + release store make it visible system-wide before the flag
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst.p[threadIdx.x] + my_rank), "r"(seq) : "memory");
+    }
+}
+
+cudaError_t launch_flag_signal(const FlagPtrs &dst, int world, int my_rank, unsigned int seq, cudaStream_t stream)
+{
+    flag_signal_kernel<<<1, 32, 0, stream>>>(dst, world, my_rank, seq);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flag_wait(unsigned int *local_flags, int world, unsigned int seq, cudaStream_t stream)
+{
+    gather_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, seq);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gather_wait(unsigned int *const *, unsigned int *local_flags, int world, unsigned int seq, cudaStream_t stream)

@@ -66,6 +66,8 @@ struct alignas(64) CorrArgs {
     int32_t tiles_per_job;
     int32_t S, AG, SL, W, G;           // sats/CTA, antenna groups, sample slices, consumer warps, sat groups
     int32_t stages;
+    int32_t n_parts;                   // sharded slots: `periods` holds n_parts descriptors pairs per period, part j covers tiles
+    int32_t part_tiles;                //   [j * part_tiles, (j + 1) * part_tiles) of the block (absolute, kTileCap samples each)
     int32_t rep_stride;                // floats per consumer warp for its code replica (>= tile_len + span)
     int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
@@ -81,6 +83,7 @@ struct alignas(64) CorrArgs {
     int32_t n_peers, my_rank;
     uint32_t gather_seq;               // value released into flags[my_rank] when this launch is complete
     unsigned long long gather_elems;   // elements per rank slice
+    unsigned long long gather_off;     // this call's first element inside the slice (gat_gather_set_offset)
     unsigned int *done_counter;        // CTAs that finished their stores (self-cleaning)
     unsigned long long *timeline;      // debug: [grid][16] globaltimer stamps, or nullptr
 };
@@ -131,6 +134,10 @@ bool kernel_available(int A, int L);
 
 cudaError_t launch_gather_wait(unsigned int *const *flags_unused, unsigned int *local_flags, int world, unsigned int seq,
                                cudaStream_t stream);
+// cross-rank flags of the signal ring: lane d release-stores `seq` into dst[d][my_rank]; the wait spins on local flags
+struct FlagPtrs { unsigned int *p[kMaxPeers]; };
+cudaError_t launch_flag_signal(const FlagPtrs &dst, int world, int my_rank, unsigned int seq, cudaStream_t stream);
+cudaError_t launch_flag_wait(unsigned int *local_flags, int world, unsigned int seq, cudaStream_t stream);
 
 cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples,
                                 int tile_len, bool f64, int32_t *d_out, cudaStream_t stream);

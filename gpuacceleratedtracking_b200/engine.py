@@ -293,6 +293,44 @@ class Engine:
             C.c_void_p(o_re.ctypes.data), C.c_void_p(o_im.ctypes.data), flags))
         return (o_re + 1j * o_im).astype(np.complex64)
 
+    def ingest_correlate(self, re, im, channels, fs: float, shifts: Sequence[int], start_sample: int = 0,
+                         n_samples: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """Host blocks in, host accumulators out, ONE C call for a whole batch of periods (gat_ingest_correlate): the
+        library pipelines the H2D copies of chunk i + 1 under the kernel of chunk i.  re / im: host arrays
+        [P, n_ants, ld] (numpy, or CPU torch tensors -- pinned ones copy asynchronously at full PCIe rate);
+        channels[p][k] or a ChannelArray.  Returns complex64 [P, K, L, M]."""
+        if _is_torch(re):
+            assert not re.is_cuda and re.dtype == torch.float32 and re.is_contiguous() and im.is_contiguous()
+            base_re, base_im, shape = re.data_ptr(), im.data_ptr(), tuple(re.shape)
+        else:
+            assert re.dtype == np.float32 and re.flags.c_contiguous and im.flags.c_contiguous
+            base_re, base_im, shape = re.ctypes.data, im.ctypes.data, re.shape
+        P, m, ld = shape
+        n_samples = ld - start_sample if n_samples is None else n_samples
+        if isinstance(channels, ChannelArray):
+            arr, K = channels.arr, channels.K
+            assert channels.P == P
+        else:
+            K = len(channels[0])
+            arr = self.marshal(channels).arr
+        key = (base_re, base_im, shape)
+        if getattr(self, "_ingest_key", None) != key:             # pointer tables are rebuilt only when the buffers change
+            stride = m * ld * 4
+            self._ingest_ptrs = ((C.c_void_p * P)(*[base_re + p * stride for p in range(P)]),
+                                 (C.c_void_p * P)(*[base_im + p * stride for p in range(P)]))
+            self._ingest_key = key
+        sh = np.ascontiguousarray(shifts, np.int32)
+        if out is None:
+            out = np.empty((2, P, K, sh.size, m), np.float32)
+        assert out.shape == (2, P, K, sh.size, m) and out.dtype == np.float32
+        self._check(self._lib.gat_ingest_correlate(self._h, P, self._ingest_ptrs[0], self._ingest_ptrs[1], ld, m, K, arr, fs,
+                                                   sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size, start_sample, n_samples,
+                                                   C.c_void_p(out[0].ctypes.data), C.c_void_p(out[1].ctypes.data), 0))
+        return out
+
+    def gather_set_offset(self, elems: int):
+        self._check(self._lib.gat_gather_set_offset(self._h, int(elems)))
+
     # -- fused multi-GPU gather -------------------------------------------------------------------
     # ---- post-correlation array processing (include/gat.h gat_beamform / gat_eigen_weights) ----
     def beamform(self, acc, weights, out=None):
@@ -344,6 +382,56 @@ class Engine:
         im = np.empty_like(re)
         self._check(self._lib.gat_gather_read(self._h, C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data)))
         return (re + 1j * im).astype(np.complex64)
+
+    # -- signal ring: all-gather fused into the kernel's tile pipeline (include/gat.h gat_ring_*) -------------
+    def ring_create(self, world: int, rank: int, n_slots: int, n_samples: int, n_ants: int) -> bytes:
+        h = (C.c_ubyte * _lib.GAT_IPC_HANDLE_BYTES)()
+        self._check(self._lib.gat_ring_create(self._h, world, rank, n_slots, n_samples, n_ants, h))
+        self._ring = (world, rank, n_slots, n_samples, n_ants)
+        return bytes(h)
+
+    def ring_connect(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.gat_ring_connect(self._h, arr))
+
+    def ring_connect_local(self, engines: Sequence["Engine"]):
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        self._check(self._lib.gat_ring_connect_local(self._h, arr))
+
+    def ring_part(self, rank: int | None = None) -> tuple[int, int]:
+        a, b = C.c_int(), C.c_int()
+        self._check(self._lib.gat_ring_part(self._h, self._ring[1] if rank is None else rank, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ring_upload(self, slot: int, re, im, part: bool = False):
+        """Copy this rank's sample range of a block into ring slot `slot` (asynchronous, ingest stream).  re / im are
+        [n_ants, ld] planes of the WHOLE block, or with part=True planes that start at this rank's first sample.
+        Host arrays must stay alive (and should be pinned) until the copy has run."""
+        re, im, m, n, ld = self._planes(re, im)
+        on_dev = _is_torch(re) and re.is_cuda
+        fn = self._lib.gat_ring_upload_part if part else self._lib.gat_ring_upload
+        self._check(fn(self._h, slot, C.c_void_p(_ptr(re)), C.c_void_p(_ptr(im)), ld, int(on_dev)))
+
+    def _count(self, rc: int) -> int:
+        if rc < 0:
+            self._check(rc)
+        return rc
+
+    def ring_publish(self) -> int:
+        return self._count(self._lib.gat_ring_publish(self._h))
+
+    def ring_wait(self, generation: int):
+        self._check(self._lib.gat_ring_wait(self._h, int(generation)))
+
+    def ring_release(self) -> int:
+        return self._count(self._lib.gat_ring_release(self._h))
+
+    def ring_acquire(self, releases: int):
+        self._check(self._lib.gat_ring_acquire(self._h, int(releases)))
+
+    def ring_destroy(self):
+        self._check(self._lib.gat_ring_destroy(self._h))
 
     def chip_indices(self, channel: Channel, fs: float, shift: int, n_samples: int, code_phase_f64: bool = False):
         self.set_codes(channel.system)

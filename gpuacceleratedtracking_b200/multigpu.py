@@ -91,3 +91,16 @@ def gather_setup(engine, elems_per_rank: int, group=None):
     dist.all_gather_object(handles, handle, group=group)
     engine.gather_connect(handles)
     dist.barrier(group=group)
+
+
+def ring_setup(engine, n_slots: int, n_samples: int, n_ants: int, group=None):
+    """Create this rank's share of the signal ring (include/gat.h gat_ring_*), exchange the CUDA IPC handles over
+    torch.distributed and map every owner's memory.  Afterwards the engine's slots 0 .. n_slots-1 are blocks whose
+    samples live on all ranks; a correlate call on any rank gathers its tiles over NVLink inside the kernel."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    handle = engine.ring_create(world, rank, n_slots, n_samples, n_ants)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    engine.ring_connect(handles)
+    dist.barrier(group=group)

@@ -185,6 +185,19 @@ int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *
                                   const int32_t *sample_shifts, int n_taps, int start_sample,
                                   int n_samples, float *h_out_re, float *h_out_im, unsigned flags);
 
+/* The same over a BATCH of periods with the host<->device traffic pipelined inside the library (a host loop of
+ * downconvert_and_correlate! calls over consecutive 1 ms blocks, src/benchmarks.jl:63-79): h_re[p] / h_im[p] are the
+ * host planes of period p ([n_ants x ld]); chunks of 16 periods are copied on an internal ingest stream into a ring of
+ * staging buffers while the kernel of the previous chunk runs; channels[p * n_sats + k]; results
+ * [n_ants x n_taps x n_sats x n_periods] in host memory, one synchronisation at the end.  Pinned host memory
+ * (cudaMallocHost, or gat_host_register on caller memory) makes the copies asynchronous at full PCIe rate. */
+int gat_ingest_correlate(gat_ctx *ctx, int n_periods, const float *const *h_re, const float *const *h_im, int ld,
+                         int n_ants, int n_sats, const gat_channel *channels, double fs_hz,
+                         const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples,
+                         float *h_out_re, float *h_out_im, unsigned flags);
+int gat_host_register(void *ptr, uint64_t bytes);   /* cudaHostRegister (portable); already registered = GAT_OK */
+int gat_host_unregister(void *ptr);
+
 /* ---- post-correlation array processing (Tracking.jl `track(...; post_corr_filter)` [upstream]) ----
  * For accumulators that stay on the device: all pointers are DEVICE pointers, both calls are asynchronous on the
  * ctx stream (ordered behind the correlate call that produced `acc`).  n_ch = n_sats x n_periods of that call.
@@ -210,9 +223,47 @@ int gat_eigen_weights(gat_ctx *ctx, int n_ch, int n_taps, int n_ants, const floa
 #define GAT_IPC_HANDLE_BYTES 64
 int gat_gather_create(gat_ctx *ctx, int world, int rank, uint64_t elems_per_rank, unsigned char *handle_out);
 int gat_gather_connect(gat_ctx *ctx, const unsigned char *handles /* [world][GAT_IPC_HANDLE_BYTES] */);
+/* Where inside its slice the NEXT GAT_GATHER calls put their first element (default 0; sticky): lets a step made of
+ * several launches (chunks of periods) fill one gather buffer.  gat_gather_wait after the last launch covers them all. */
+int gat_gather_set_offset(gat_ctx *ctx, uint64_t elem_offset);
 int gat_gather_wait(gat_ctx *ctx);
 int gat_gather_read(gat_ctx *ctx, float *h_re, float *h_im); /* sync + D2H of [world x elems_per_rank] */
 int gat_gather_destroy(gat_ctx *ctx);
+
+/* ---- signal ring: the all-gather of the signal blocks fused into the correlate kernel ----------
+ * Satellite channels shard across the GPUs of a box, so every GPU needs every signal block (north_star: "each
+ * integration period's signal block is NCCL-broadcast over NVLink").  The ring replaces the broadcast + receive
+ * buffer by peer reads inside the kernel: a block is cut into `world` contiguous sample ranges of whole 256-sample
+ * tiles, rank r keeps range r of each of the ring's `n_slots` blocks in its own HBM (fed through its own PCIe link),
+ * every rank maps all owners' memory once, and the correlate kernel's producer warp TMA-loads each tile from the
+ * owner it lives on -- the exchange overlaps the math tile by tile, each byte crosses NVLink once per reader and
+ * never lands in the reader's HBM.  After gat_ring_connect* the ctx's slots 0 .. n_slots-1 ARE the ring's blocks
+ * (use them in gat_correlate* like any slot; start_sample must be a multiple of 256; FP32 kernel only).
+ *   one process per GPU : gat_ring_create on every rank, exchange the 64-byte handles, gat_ring_connect.
+ *   one process, n GPUs : gat_ring_create on every ctx, gat_ring_connect_local with the array of all ctxs
+ *                         (several ctxs may share one device: "logical ranks", used by the single-GPU tests).
+ * Cross-rank ordering is by sequence flags in the ring memory, all stream-ordered (no host blocking):
+ *   ingest stream (internal) : gat_ring_acquire(releases) -> gat_ring_upload*(slot ...) -> g = gat_ring_publish()
+ *   ctx stream               : gat_ring_wait(g) -> gat_correlate*(...) -> r = gat_ring_release()
+ * gat_ring_wait(g) holds the ctx stream until EVERY rank has published its g-th generation; gat_ring_acquire(r)
+ * holds the ingest stream until every rank has released r generations (pass the count that frees the slots about
+ * to be overwritten; <= 0 waits for nothing).  All ranks must issue the same sequence.  A peer that never
+ * arrives trips a 20 s watchdog (CUDA error on the waiting rank) instead of hanging the device. */
+int gat_ring_create(gat_ctx *ctx, int world, int rank, int n_slots, int n_samples, int n_ants,
+                    unsigned char *handle_out /* [GAT_IPC_HANDLE_BYTES] */);
+int gat_ring_connect(gat_ctx *ctx, const unsigned char *handles /* [world][GAT_IPC_HANDLE_BYTES] */);
+int gat_ring_connect_local(gat_ctx *ctx, gat_ctx *const *peers /* [world], peers[rank] may be NULL */);
+int gat_ring_part(gat_ctx *ctx, int rank, int *start_out, int *len_out);   /* sample range owned by `rank` */
+/* Copy THIS rank's sample range of a block into ring slot `slot` (asynchronous, ingest stream).  gat_ring_upload takes
+ * the planes of the whole block ([n_ants x ld], like gat_upload_signal) and reads only its own range of each row;
+ * gat_ring_upload_part takes planes that START at the rank's first sample (a host that holds only its share). */
+int gat_ring_upload(gat_ctx *ctx, int slot, const float *re, const float *im, int ld, int src_is_device);
+int gat_ring_upload_part(gat_ctx *ctx, int slot, const float *re_part, const float *im_part, int ld, int src_is_device);
+int gat_ring_publish(gat_ctx *ctx);                 /* returns this rank's generation count (>= 1), or < 0 */
+int gat_ring_wait(gat_ctx *ctx, int generation);
+int gat_ring_release(gat_ctx *ctx);                 /* returns this rank's release count (>= 1), or < 0 */
+int gat_ring_acquire(gat_ctx *ctx, int releases);
+int gat_ring_destroy(gat_ctx *ctx);
 
 /* ---- introspection (bench / tests) ----------------------------------------------------- */
 typedef struct gat_launch_info {
