@@ -10,14 +10,22 @@ than the 126 MB L2, so every step streams from HBM) = ONE fused kernel launch pe
 
   value   correlations/s = finished complex accumulators (periods x sats x taps x antennas) per
           second, whole job, signal blocks already resident in HBM.
-  e2e     same metric through the C ABI with HOST buffers: every step copies its signal blocks
-          from pinned host memory (H2D, chunked and overlapped with compute on two streams) and
-          reads the accumulators back (D2H).
-  N > 1   one process per GPU (torchrun).  Satellite channels are independent given the signal
-          block, so they shard across ranks: rank r correlates its own satellite over the same
-          blocks (weak scaling, per-GPU work fixed), and the small accumulators are all-gathered
-          over NCCL every step.  In the e2e leg rank 0 owns the host buffers and the blocks reach
-          the other GPUs by NCCL broadcast over NVLink.
+  e2e     same metric through the C ABI with HOST buffers.  N = 1: one gat_ingest_correlate call per step (the
+          library copies 16-period chunks from pinned host memory on its ingest stream under the kernel of the
+          previous chunk and returns host accumulators).
+  N > 1   one process per GPU (torchrun).  Satellite channels are independent given the signal block, so they
+          shard across ranks (rank r correlates its own satellite: weak scaling, per-GPU work fixed) and EVERY rank
+          needs EVERY block -- north_star's per-period signal exchange.  The blocks live scattered over the ranks'
+          HBM (rank r owns one sample range of every block: what its own PCIe link delivers) and each rank's correlate
+          kernel gathers its tiles over NVLink inside its own TMA pipeline (gat_ring_*: the all-gather fused into
+          the kernel; no NCCL call, no receive buffer).  That exchange is INSIDE the timed region of `value`.  The
+          accumulators go back through the gather fused into the kernel epilogue (peer stores).  Before timing, the
+          accumulators every rank sees are checked against the oracle (`parity_max_rel`, bar 1e-4).  The e2e leg adds
+          the H2D copy of every rank's share from its pinned host memory and the D2H read on rank 0.
+  c5      BASELINE configs[4] (32 L1 + L5 satellites, sharded) at the same N: strong and weak, us per 1 ms period.
+
+  The contract line is assembled BEFORE the optional legs run and is printed no matter how they end (exception
+  handler, SIGALRM deadline, os._exit without interpreter teardown): a faulting side leg can no longer take it down.
 
   --sweep   the reference's own per-call sweep (processing time against the number of samples, M in {1, 4, 16},
           L in {3, 7}, L1 and L5): one JSON line per point with GPU and CPU-port times; see run_sweep.
@@ -114,8 +122,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU path, restated (oracle/), on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_arm(periods: int, steps: int, warmup: int, budget_s: float | None = None):
-    """Returns (correlations/s, ms_per_step, cores, kind, sample description)."""
+CPU_DISTINCT = 64        # distinct 1 ms blocks held in host memory (819 MB of signal: larger than any L3)
+
+
+def cpu_arm(periods: int, steps: int, warmup: int, threads: int = 0, budget_s: float | None = None):
+    """One step = `periods` one-ms blocks of the C2 shape through the oracle's port of Tracking.downconvert_and_correlate!
+    (OpenMP over periods).  The step walks cyclically over min(periods, 64) DISTINCT blocks, so a 256-period step is four
+    passes over 819 MB.  Returns (correlations/s, ms_per_step, threads used, kind, sample description)."""
     import ctypes as C
     import oracle
     native = True
@@ -132,32 +145,38 @@ def cpu_arm(periods: int, steps: int, warmup: int, budget_s: float | None = None
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
+    threads = threads or cores
     periods = max(periods, 1)
+    distinct = min(periods, CPU_DISTINCT)
     rng = np.random.default_rng(7)
     base_re, base_im = oracle.gen_signal(code, CODE_FREQ, DOPPLER, FS, N_SAMPLES, N_ANTS)
-    re = np.empty((periods, N_ANTS, N_SAMPLES), np.float32)
+    re = np.empty((distinct, N_ANTS, N_SAMPLES), np.float32)
     im = np.empty_like(re)
     pool = [rng.normal(0, 1, base_re.shape).astype(np.float32) for _ in range(4)]   # unit AWGN, reused cyclically
-    for p in range(periods):
+    for p in range(distinct):
         re[p] = base_re + pool[p % 4]
         im[p] = base_im + pool[(p + 1) % 4]
-    jobs = periods
-    codes = (C.POINTER(C.c_int8) * jobs)(*[code.ctypes.data_as(C.POINTER(C.c_int8))] * jobs)
-    lens = np.full(jobs, code.size, np.int32)
-    fc = np.full(jobs, CODE_FREQ)
-    cp = np.zeros(jobs)
-    fd = np.full(jobs, DOPPLER)
-    ph = np.zeros(jobs)
-    o_re = np.empty((jobs, N_TAPS, N_ANTS), np.float32)
+    codes = (C.POINTER(C.c_int8) * distinct)(*[code.ctypes.data_as(C.POINTER(C.c_int8))] * distinct)
+    lens = np.full(distinct, code.size, np.int32)
+    fc = np.full(distinct, CODE_FREQ)
+    cp = np.zeros(distinct)
+    fd = np.full(distinct, DOPPLER)
+    ph = np.zeros(distinct)
+    o_re = np.empty((distinct, N_TAPS, N_ANTS), np.float32)
     o_im = np.empty_like(o_re)
     f32p, f64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
 
     def step():
-        return lib.orc_correlate_tracking_batch(
-            re.ctypes.data_as(f32p), im.ctypes.data_as(f32p), N_ANTS * N_SAMPLES, N_SAMPLES, N_ANTS, N_SAMPLES,
-            periods, 1, codes, lens.ctypes.data_as(i32p), fc.ctypes.data_as(f64p), cp.ctypes.data_as(f64p),
-            fd.ctypes.data_as(f64p), ph.ctypes.data_as(f64p), FS, shifts.ctypes.data_as(i32p), N_TAPS, cores,
-            o_re.ctypes.data_as(f32p), o_im.ctypes.data_as(f32p))
+        used, left = 1, periods
+        while left > 0:
+            n = min(left, distinct)
+            used = lib.orc_correlate_tracking_batch(
+                re.ctypes.data_as(f32p), im.ctypes.data_as(f32p), N_ANTS * N_SAMPLES, N_SAMPLES, N_ANTS, N_SAMPLES,
+                n, 1, codes, lens.ctypes.data_as(i32p), fc.ctypes.data_as(f64p), cp.ctypes.data_as(f64p),
+                fd.ctypes.data_as(f64p), ph.ctypes.data_as(f64p), FS, shifts.ctypes.data_as(i32p), N_TAPS, threads,
+                o_re.ctypes.data_as(f32p), o_im.ctypes.data_as(f32p))
+            left -= n
+        return used
 
     used = 1
     for _ in range(warmup):
@@ -173,25 +192,36 @@ def cpu_arm(periods: int, steps: int, warmup: int, budget_s: float | None = None
     assert abs(float(o_re[0, 1, 0]) - N_SAMPLES) < 0.02 * N_SAMPLES          # it really correlated
     t = float(np.mean(times))
     value = periods * N_TAPS * N_ANTS / t
-    sample = (f"{len(times)} steps x {periods} one-ms periods of the C2 shape, OpenMP over periods, "
+    sample = (f"{len(times)} steps x {periods} one-ms periods of the C2 shape ({-(-periods // distinct)} pass(es) over {distinct} distinct "
+              f"blocks = {distinct * 8 * N_SAMPLES * N_ANTS / 1e6:.0f} MB), OpenMP over periods, {int(used)} thread(s), "
               f"{'-march=native' if native else 'x86-64-v3'} build of oracle/oracle.c")
     return value, t * 1e3, int(used), "port", sample
+
+
+def bench_config(P: int, world: int, extra: dict | None = None) -> dict:
+    """The `config` object: identical keys (and, for the same --periods, values) in both arms."""
+    cfg = {"workload": WORKLOAD, "periods_per_step": P, "n_sats_per_gpu": 1, "n_ants": N_ANTS, "n_taps": N_TAPS,
+           "n_samples": N_SAMPLES, "parallelism": f"satellite-sharded x{world}",
+           "l2_policy": f"inputs larger than L2 ({P * 8 * N_SAMPLES * N_ANTS / 1e6:.0f} MB of distinct signal blocks per step)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    periods = args.ref_periods or max(16, 2 * cores)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    periods = args.ref_periods or args.periods
     value, ms, used, kind, sample = cpu_arm(periods, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "correlations/sec", "value": value, "unit": "correlations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "periods_per_step": periods, "n_sats": 1, "n_ants": N_ANTS, "n_taps": N_TAPS,
-                   "n_samples": N_SAMPLES, "note": "CPU restatement of Tracking.downconvert_and_correlate! (Julia absent)"},
-        "cpu_baseline": {"value": value, "unit": "correlations/s", "cores": used, "kind": kind, "sample": sample},
+        "config": bench_config(periods, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "correlations/s", "cores": used, "kind": kind, "sample": sample,
+                         "note": "CPU restatement of Tracking.downconvert_and_correlate! (Julia is not installed; the reference cannot run)"},
         "e2e": {"value": value, "unit": "correlations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "realtime_channels": periods / ms,
     }
@@ -201,7 +231,32 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+_T0 = time.perf_counter()
+
+
+def log(msg: str):
+    """Progress on stderr: when a run dies, the last line names the leg (round 1's abort left none)."""
+    print(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+class Emitter:
+    """The ONE JSON line, printed exactly once and no matter what: normally at the end, from the exception handler
+    when a leg dies, or from the SIGALRM deadline when a leg hangs.  Side legs only ever ADD keys to `line`."""
+
+    def __init__(self, rank: int):
+        self.rank = rank
+        self.line: dict | None = None
+        self.done = False
+
+    def emit(self):
+        if self.done or self.line is None or self.rank != 0:
+            return
+        self.done = True
+        print(json.dumps(self.line), flush=True)
+
+
 def run_gpu(args):
+    import signal
     import torch
     import torch.distributed as dist
     import gpuacceleratedtracking_b200 as g
@@ -216,8 +271,44 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    em = Emitter(rank)
 
-    P, steps, warmup = args.periods, args.steps, args.warmup
+    def on_deadline(signum, frame):
+        log("DEADLINE reached: emitting what has been measured")
+        if em.line is not None:
+            em.line.setdefault("side_errors", []).append("deadline: a leg did not return in time")
+        em.emit()
+        os._exit(0 if em.done or rank != 0 else 3)
+
+    signal.signal(signal.SIGALRM, on_deadline)
+    signal.alarm(int(args.deadline))
+    status = 0
+    try:
+        _gpu_legs(args, em, world, rank, local, dev, torch, dist, g)
+    except BaseException as exc:      # noqa: BLE001 -- the contract line must survive any leg
+        import traceback
+        traceback.print_exc()
+        log(f"FAILED: {type(exc).__name__}: {str(exc)[:300]}")
+        if em.line is not None:
+            em.line.setdefault("side_errors", []).append(f"{type(exc).__name__}: {str(exc)[:200]}")
+        else:
+            status = 1
+    finally:
+        em.emit()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # no interpreter teardown: after a sticky CUDA error torch's destructors abort (rc 134) and would take a line
+        # that is already printed down with them
+        os._exit(status)
+
+
+def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
+    import oracle
+    from gpuacceleratedtracking_b200.multigpu import gather_setup, ring_setup, shard_channels
+
+    P, steps, warmup = args.periods, args.steps, max(args.warmup, 3)
+    CH = 16                                                        # periods per pipelined e2e chunk
+    assert P % CH == 0, "--periods must be a multiple of 16"
     eng = g.Engine(local)
     # one explicit (non-default) stream for everything: libgat's kernels, torch's events and the
     # NCCL hand-offs are all ordered on it, so torch.cuda.Event brackets exactly what libgat queued
@@ -228,26 +319,47 @@ def run_gpu(args):
     corr = g.EarlyPromptLateCorrelator(g.NumAnts(N_ANTS), g.NumAccumulators(N_TAPS))
     shifts = g.get_correlator_sample_shifts(l1, corr, FS, 0.5)
 
-    # ---- synthetic input, resident in HBM: P distinct blocks (every visible PRN + unit AWGN) ----
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic input: P distinct blocks (every rank's PRN + unit AWGN), generated on the device ----
+    log(f"generating {P} blocks, world {world}")
     re = torch.empty(P, N_ANTS, N_SAMPLES, device=dev)
     im = torch.empty(P, N_ANTS, N_SAMPLES, device=dev)
+    FULL = 20000                                                   # slot ids of the full (replicated) copies
     for p in range(P):
-        eng.bind_signal(p, re[p], im[p])
+        eng.bind_signal(FULL + p, re[p], im[p])
         for s in range(world):
-            eng.gen_signal(p, l1, s + 1, DOPPLER + 10.0 * s, FS, N_SAMPLES, N_ANTS, start_code_phase=3.0 * p,
+            eng.gen_signal(FULL + p, l1, s + 1, DOPPLER + 10.0 * s, FS, N_SAMPLES, N_ANTS, start_code_phase=3.0 * p,
                            noise_sigma=(1.0 if s == 0 else 0.0), seed=1000 + p, superpose=(s > 0))
+    eng.sync()
     my_prn = rank % 32 + 1
-    chan_list = [[g.Channel(l1, my_prn, 3.0 * p, DOPPLER + 10.0 * rank, 0.0)] for p in range(P)]
+    chan_of = lambda r, p: g.Channel(l1, r % 32 + 1, 3.0 * p, DOPPLER + 10.0 * r, 0.0)
+    chan_list = [[chan_of(rank, p)] for p in range(P)]
     chans = eng.marshal(chan_list)                 # C array built once: the timed loop is pure launches
-    slots = np.arange(P, dtype=np.int32)
     o_re = torch.zeros(P, 1, N_TAPS, N_ANTS, device=dev)
     o_im = torch.zeros_like(o_re)
     elems = P * 1 * N_TAPS * N_ANTS
+    part_lo, part_len = 0, N_SAMPLES
     if world > 1:
-        # the path's one exchange step -- gathering the (tiny) accumulators -- is fused into the kernel
-        # epilogue: every rank's CTAs store their block into all ranks' buffers over NVLink peer mappings
-        from gpuacceleratedtracking_b200.multigpu import gather_setup
+        # north_star data flow: the satellites are sharded over the ranks, so every rank needs every block.  The blocks
+        # live SCATTERED over the ranks' HBM (rank r owns one contiguous sample range of every block -- what its own PCIe
+        # link delivers) and every rank's correlate kernel gathers its tiles over NVLink inside its TMA pipeline
+        # (include/gat.h gat_ring_*).  The accumulators go back through the gather fused into the kernel epilogue.
+        ring_setup(eng, P, N_SAMPLES, N_ANTS)
+        part_lo, part_len = eng.ring_part()
+        for p in range(P):
+            eng.ring_upload(p, re[p], im[p])       # D2D: this rank's range only
+        gen = eng.ring_publish()
+        eng.ring_wait(gen)
+        eng.ring_release()
         gather_setup(eng, elems)
+        slots = np.arange(P, dtype=np.int32)
+    else:
+        slots = np.arange(FULL, FULL + P, dtype=np.int32)
+    barrier()
 
     def step():
         if world > 1:
@@ -256,29 +368,39 @@ def run_gpu(args):
         else:
             eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(warmup, 3)):
+    log("warm-up")
+    for _ in range(warmup):
         step()
     barrier()
-    # sanity: the prompt found the satellite in every block (on every rank's slice when gathered)
+
+    # ---- parity gate: the accumulators every rank sees against the oracle (double-precision direct formula) ----
     if world > 1:
-        gathered = eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS)
-        prompt = float(gathered[:, :, 0, 1, :].real.mean())
+        seen = eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS)
     else:
-        prompt = o_re[:, 0, 1, :].mean().item()
-    assert prompt > 0.9 * N_SAMPLES, f"prompt {prompt}"
+        seen = (o_re + 1j * o_im).cpu().numpy().reshape(1, P, 1, N_TAPS, N_ANTS)
+    pairs = sorted({(0, 0), (world - 1, P - 1), (world // 2, P // 2), (rank, (7 * rank + 3) % P)})
+    parity = 0.0
+    for r, p in pairs:
+        c = chan_of(r, p)
+        ref = oracle.correlate_direct(re[p].cpu().numpy(), im[p].cpu().numpy(), l1.codes[c.prn - 1], CODE_FREQ, c.code_phase,
+                                      c.carrier_frequency, c.carrier_phase, FS, shifts)
+        parity = max(parity, float(np.abs(seen[r, p, 0] - ref).max() / np.abs(ref[N_TAPS // 2]).max()))
+    pt = torch.tensor([parity], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+    parity = pt.item()
+    log(f"parity_max_rel {parity:.2e} over {len(pairs)} (rank, period) pairs per rank")
+    assert parity < 1e-4, f"parity {parity}"
+    assert float(np.abs(seen[:, :, 0, 1, :]).mean()) > 0.9 * N_SAMPLES
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # The timed region lasts only a few ms (K x ~0.15 ms), shorter than nvidia-smi's sampling period,
+    # The timed region lasts only a few ms (K x ~0.3 ms), shorter than nvidia-smi's sampling period,
     # so the same step is first run untimed for ~0.6 s under the sampler; the timed steps follow
     # immediately at the same load and the clock record covers both.
     barrier()
+    log("load phase + timed steps")
     t_load = time.perf_counter()
     while time.perf_counter() - t_load < 0.6:
         for _ in range(50):
@@ -312,262 +434,414 @@ def run_gpu(args):
     corr_per_step = world * P * 1 * N_TAPS * N_ANTS
     value = corr_per_step / (ms_per_step * 1e-3)
     info = eng.launch_info()
+    log(f"value {value / 1e6:.2f} M corr/s, {ms_per_step:.4f} ms/step, kernel {kernel_ms:.4f} ms")
 
-    # ---- side measurement for the metric's second half: real-time (1 ms) satellite channels per GPU ----
-    # K_RT channels share ONE 1 ms signal block (the receiver case: every visible satellite of every
-    # constellation over the same antenna array); channels/ms = K_RT / launch time.
-    K_RT = 264
-    rt_chans = eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, DOPPLER + 3.0 * k, 0.001 * k) for k in range(K_RT)]])
-    rt_re = torch.zeros(1, K_RT, N_TAPS, N_ANTS, device=dev)
-    rt_im = torch.zeros_like(rt_re)
-    rt_slot = np.zeros(1, np.int32)
-    for _ in range(5):
-        eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im))
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    r0.record()
-    for _ in range(20):
-        eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im))
-    r1.record()
-    barrier()
-    rt_ms = r0.elapsed_time(r1) / 20
-    rt_info = eng.launch_info()
-    # the same launch on the opt-in tensor-core path (tcgen05 kind::tf32, csrc/gat_correlate_tc.cu): TF32-rounded replica
-    # and samples, FP32 sums -- a different numeric contract (include/gat.h GAT_TENSOR_TF32), hence a side figure
-    rt_tensor = None
-    try:
-        for _ in range(5):
-            eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im), tensor=True)
-        if eng.launch_info()["tensor"] == 1:
-            barrier()
-            r0.record()
-            for _ in range(20):
-                eng.correlate_batch(rt_slot, rt_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(rt_re, rt_im), tensor=True)
-            r1.record()
-            barrier()
-            rtt_ms = r0.elapsed_time(r1) / 20
-            rt_tensor = {"channels_per_launch": K_RT, "ms_per_launch": rtt_ms, "realtime_channels_per_gpu": K_RT / rtt_ms,
-                         "path": "tcgen05.mma kind::tf32 (opt-in GAT_TENSOR_TF32)"}
-            # the same path with the launch's fixed cost amortised: 1 024 channels over the one block
-            K_BIG = 1024
-            big_chans = eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, DOPPLER + 3.0 * k, 0.001 * k) for k in range(K_BIG)]])
-            big_out = (torch.zeros(1, K_BIG, N_TAPS, N_ANTS, device=dev), torch.zeros(1, K_BIG, N_TAPS, N_ANTS, device=dev))
-            for _ in range(3):
-                eng.correlate_batch(rt_slot, big_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=big_out, tensor=True)
-            barrier()
-            r0.record()
-            for _ in range(10):
-                eng.correlate_batch(rt_slot, big_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=big_out, tensor=True)
-            r1.record()
-            barrier()
-            big_ms = r0.elapsed_time(r1) / 10
-            rt_tensor["k1024"] = {"channels_per_launch": K_BIG, "ms_per_launch": big_ms, "realtime_channels_per_gpu": K_BIG / big_ms}
-    except Exception as exc:      # the side figure must never take the contract line down
-        rt_tensor = {"error": str(exc)[:200]}
-
-    # ---- e2e: host buffers -> H2D (-> NCCL broadcast) -> correlate -> gather -> D2H ----
+    # ---- e2e: host buffers -> H2D -> correlate -> D2H, through the C ABI ----
     e2e_steps = max(2, min(steps, args.e2e_steps))
-    CH = 16                                                       # periods per pipelined chunk
-    # Host side of the ingest: with N ranks every rank owns 1/N of each chunk in pinned host memory
-    # (N PCIe links in parallel) and the chunk is completed on every GPU by an NCCL all-gather over
-    # NVLink; at N = 1 this is a plain H2D copy.
-    assert P % CH == 0 and CH % world == 0, "periods per step must be a multiple of 16 (and 16 of the GPU count)"
-    SUB = CH // world
-    h_re = torch.empty(P // CH, SUB, N_ANTS, N_SAMPLES, pin_memory=True)
-    h_im = torch.empty(P // CH, SUB, N_ANTS, N_SAMPLES, pin_memory=True)
-    for ci in range(P // CH):
-        lo = ci * CH + rank * SUB
-        h_re[ci].copy_(re[lo:lo + SUB])
-        h_im[ci].copy_(im[lo:lo + SUB])
-    h_out = torch.empty(2, P, 1, N_TAPS, N_ANTS, pin_memory=True) if rank == 0 else None
-    h_gather = torch.empty(world, 2, P, 1, N_TAPS, N_ANTS, pin_memory=True) if (rank == 0 and world > 1) else None
-    copy_stream = torch.cuda.Stream()
-    main = torch.cuda.current_stream()
-    chunk_chans = {c0: eng.marshal(chan_list[c0:min(P, c0 + CH)]) for c0 in range(0, P, CH)}
+    if world == 1:
+        # ONE C call per step (gat_ingest_correlate): the library pipelines the H2D copies of chunk i + 1 (16 periods,
+        # pinned host memory, its own ingest stream) under the kernel of chunk i and returns host accumulators
+        h_re = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
+        h_im = torch.empty(P, N_ANTS, N_SAMPLES, pin_memory=True)
+        h_re.copy_(re)
+        h_im.copy_(im)
+        h_res = np.empty((2, P, 1, N_TAPS, N_ANTS), np.float32)
+        torch.cuda.synchronize()
 
-    def e2e_step():
-        done = []
-        for ci, c0 in enumerate(range(0, P, CH)):
-            c1 = c0 + CH
-            with torch.cuda.stream(copy_stream):
-                lo = c0 + rank * SUB
-                re[lo:lo + SUB].copy_(h_re[ci], non_blocking=True)
-                im[lo:lo + SUB].copy_(h_im[ci], non_blocking=True)
-                if world > 1:
-                    dist.all_gather_into_tensor(re[c0:c1], re[lo:lo + SUB])
-                    dist.all_gather_into_tensor(im[c0:c1], im[lo:lo + SUB])
-                e = torch.cuda.Event()
-                e.record()
-            done.append((c0, c1, e))
-        for c0, c1, e in done:                                    # compute chunk i while chunk i+1 is in flight
-            main.wait_event(e)
-            eng.correlate_batch(slots[c0:c1], chunk_chans[c0], FS, shifts, N_ANTS, 0, N_SAMPLES,
-                                out=(o_re[c0:c1], o_im[c0:c1]))
-        copy_stream.wait_stream(main)                            # next step's H2D must not overtake this compute
-        if world > 1:
-            # the per-rank accumulators reach rank 0 with one NCCL gather, then D2H
-            gl = [torch.empty(2, P, 1, N_TAPS, N_ANTS, device=dev) for _ in range(world)] if rank == 0 else None
-            dist.gather(torch.stack([o_re, o_im]), gl, dst=0)
+        def e2e_step():
+            eng.ingest_correlate(h_re, h_im, chans, FS, shifts, 0, N_SAMPLES, out=h_res)
+
+        e2e_path = "pinned host -> gat_ingest_correlate (H2D in 16-period chunks on the ingest stream, overlapped with the kernels) -> host"
+    else:
+        # every rank holds ITS sample range of every block in pinned host memory (N PCIe links in parallel), uploads it into
+        # its share of the ring chunk by chunk and publishes; the kernels gather the other ranges over NVLink
+        part_ld = max(4, (part_len + 3) & ~3)
+        hp_re = torch.zeros(P, N_ANTS, part_ld, pin_memory=True)
+        hp_im = torch.zeros(P, N_ANTS, part_ld, pin_memory=True)
+        if part_len:
+            hp_re[:, :, :part_len].copy_(re[:, :, part_lo:part_lo + part_len])
+            hp_im[:, :, :part_len].copy_(im[:, :, part_lo:part_lo + part_len])
+        chunk_chans = [eng.marshal(chan_list[c0:c0 + CH]) for c0 in range(0, P, CH)]
+        n_chunks = P // CH
+        g_host = (np.empty((world, (elems + 63) & ~63), np.float32), np.empty((world, (elems + 63) & ~63), np.float32))
+        torch.cuda.synchronize()
+        state = {"pub": 1, "rel": 1, "steps": 0}                       # the set-up above published and released once
+
+        def e2e_step():
+            pub0, rel0 = state["pub"], state["rel"]
+            for ci in range(n_chunks):                               # ingest stream: runs ahead of the kernels
+                # the chunk's slots were last read by the same chunk of the previous step: wait for every rank's release of it
+                eng.ring_acquire(rel0 - n_chunks + ci + 1 if state["steps"] else 0)
+                if part_len:
+                    for p in range(ci * CH, (ci + 1) * CH):
+                        eng.ring_upload(p, hp_re[p], hp_im[p], part=True)
+                assert eng.ring_publish() == pub0 + ci + 1
+            for ci in range(n_chunks):                               # main stream
+                eng.ring_wait(pub0 + ci + 1)                         # every rank's share of the chunk is in place
+                eng.gather_set_offset(ci * CH * N_TAPS * N_ANTS)
+                eng.correlate_batch(slots[ci * CH:(ci + 1) * CH], chunk_chans[ci], FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+                eng.ring_release()
+            eng.gather_set_offset(0)
+            state.update(pub=pub0 + n_chunks, rel=rel0 + n_chunks, steps=state["steps"] + 1)
+            eng.gather_wait()
             if rank == 0:
-                h_gather.copy_(torch.stack(gl), non_blocking=True)
-        elif rank == 0:
-            h_out.copy_(torch.stack([o_re, o_im]), non_blocking=True)
-        torch.cuda.current_stream().synchronize()                # the user sees the result (D2H read)
+                eng.gather_read(out=g_host)                          # synchronises + D2H of every rank's accumulators
+            else:
+                eng.sync()
 
+        e2e_path = (f"pinned host (1/{world} of every block per rank) -> gat_ring_upload_part over {world} PCIe links -> kernels gather the "
+                    "tiles over NVLink (fused all-gather) -> gather fused into the epilogue -> D2H on rank 0")
+    log("e2e leg")
     for _ in range(2):
         e2e_step()
     barrier()
     w0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     for _ in range(e2e_steps):
         e2e_step()
-    e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    e2e_wall_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
-    te = torch.tensor([max(e2e_ms, e2e_wall_ms)], device=dev, dtype=torch.float64)
+    e2e_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
+    te = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = te.item()
     e2e_value = corr_per_step / (e2e_ms * 1e-3)
-
-    # ---- side figure (N = 1): e2e when 32 satellites share each uploaded block (the receiver case: the
-    # PCIe transfer of a block is paid once, not once per channel) ----
-    e2e_shared = None
     if world == 1:
-        PB, KB = 32, 32
-        sb_chans = eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, DOPPLER + 3.0 * k, 0.001 * k) for k in range(KB)]
-                                for _ in range(PB)])
-        sb_re = torch.zeros(PB, KB, N_TAPS, N_ANTS, device=dev)
-        sb_im = torch.zeros_like(sb_re)
-        sb_host = torch.empty(2, PB, KB, N_TAPS, N_ANTS, pin_memory=True)
+        e2e_err = float(np.abs(h_res[0].reshape(P, N_TAPS, N_ANTS) - o_re.cpu().numpy().reshape(P, N_TAPS, N_ANTS)).max())
+        # (16-period launches split the tiles differently from the 256-period launch: same sums, another order)
+        assert e2e_err <= 1e-5 * N_SAMPLES, f"e2e accumulators differ from the resident run by {e2e_err}"
+    log(f"e2e {e2e_value / 1e6:.3f} M corr/s, {e2e_ms:.2f} ms/step")
 
-        def shared_step():
-            with torch.cuda.stream(copy_stream):
-                re[:PB].copy_(h_re.view(-1, N_ANTS, N_SAMPLES)[:PB], non_blocking=True)
-                im[:PB].copy_(h_im.view(-1, N_ANTS, N_SAMPLES)[:PB], non_blocking=True)
-                ev_up = torch.cuda.Event()
-                ev_up.record()
-            main.wait_event(ev_up)
-            eng.correlate_batch(slots[:PB], sb_chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(sb_re, sb_im))
-            copy_stream.wait_stream(main)
-            sb_host.copy_(torch.stack([sb_re, sb_im]), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        shared_step()
-        w0 = time.perf_counter()
-        for _ in range(5):
-            shared_step()
-        sb_ms = (time.perf_counter() - w0) * 1e3 / 5
-        e2e_shared = {"value": PB * KB * N_TAPS * N_ANTS / (sb_ms * 1e-3), "unit": "correlations/s", "ms_per_step": sb_ms,
-                      "blocks_per_step": PB, "sats_per_block": KB, "h2d_bytes_per_step": PB * 8 * N_SAMPLES * N_ANTS,
-                      "channel_periods_per_s": PB * KB / (sb_ms * 1e-3),
-                      "path": "pinned host -> H2D -> gat_correlate_batch (32 satellites per block) -> D2H"}
-
-    # ---- side figure (N = 1): the same e2e step fed with interleaved complex int16 samples (SDR wire format,
-    # SURVEY 8f-2): half the PCIe bytes, expanded to FP32 on the device, same kernel, same results ----
-    e2e_sc16 = None
-    int16_resident = None
-    if world == 1:
-        eng_i = g.Engine(local)
-        eng_i.set_stream(work_stream.cuda_stream)
-        h_iq = torch.empty(P, N_ANTS, N_SAMPLES, 2, dtype=torch.int16, pin_memory=True)
-        for c0 in range(0, P, 32):
-            blk = torch.stack([re[c0:c0 + 32], im[c0:c0 + 32]], dim=-1)
-            h_iq[c0:c0 + 32].copy_((blk * 1024.0).round().clamp_(-32768, 32767).to(torch.int16))
-        blocks_np = [h_iq[p].numpy() for p in range(P)]
-        oi_re, oi_im = torch.zeros_like(o_re), torch.zeros_like(o_im)
-        chans_i = eng_i.marshal(chan_list)
-
-        def sc16_step():
-            for p in range(P):
-                eng_i.upload_signal_int(p, blocks_np[p], 1.0 / 1024.0)
-            eng_i.correlate_batch(slots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
-            h_out.copy_(torch.stack([oi_re, oi_im]), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        sc16_step()
-        assert oi_re[:, 0, 1, :].mean().item() > 0.9 * N_SAMPLES
-        w0 = time.perf_counter()
-        for _ in range(3):
-            sc16_step()
-        sc16_ms = (time.perf_counter() - w0) * 1e3 / 3
-        e2e_sc16 = {"value": corr_per_step / (sc16_ms * 1e-3), "unit": "correlations/s", "ms_per_step": sc16_ms,
-                    "h2d_bytes_per_step": P * 4 * N_SAMPLES * N_ANTS,
-                    "path": "pinned host int16 I/Q -> H2D -> gat_correlate_batch reading the raw words (no FP32 expansion) -> D2H"}
-        # the same blocks resident in HBM as int16: device time of the kernel that converts in registers
-        for _ in range(3):
-            eng_i.correlate_batch(slots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record()
-        for _ in range(10):
-            eng_i.correlate_batch(slots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
-        i1.record()
-        torch.cuda.current_stream().synchronize()
-        i_ms = i0.elapsed_time(i1) / 10
-        int16_resident = {"value": corr_per_step / (i_ms * 1e-3), "unit": "correlations/s", "ms_per_step": i_ms,
-                          "hbm_bytes_per_step": P * 4 * N_SAMPLES * N_ANTS, "raw_int16_kernel": eng_i.launch_info()["sc16"],
-                          "note": "device time, blocks resident as interleaved int16 I/Q (gat_upload_signal_sc16)"}
-        eng_i.close()
-
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-        algo_bytes = P * (8 * N_SAMPLES * N_ANTS) + P * (8 * N_TAPS * N_ANTS) + 1023   # signal once + outputs + chip table
-        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                if tj.get("periods_per_step") == P:
-                    traffic = tj["dram_bytes_per_launch"]
-            except Exception:
-                pass
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, ms, used, kind, sample = cpu_arm(max(16, 2 * cores), 1000, 1, budget_s=args.cpu_seconds)
-            cpu = {"value": v, "unit": "correlations/s", "cores": used, "kind": kind, "sample": sample}
-        line = {
-            "metric": "correlations/sec", "value": value, "unit": "correlations/s", "n_gpus": world, "steps": steps,
-            "warmup": max(warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "periods_per_step": P, "n_sats_per_gpu": 1, "n_ants": N_ANTS,
-                       "n_taps": N_TAPS, "n_samples": N_SAMPLES, "parallelism": f"satellite-sharded x{world}",
-                       "l2_policy": f"inputs larger than L2 ({P * 8 * N_SAMPLES * N_ANTS / 1e6:.0f} MB of distinct signal blocks per step)",
-                       "launch": {k: info[k] for k in ("grid", "block", "smem_bytes", "stages", "tile_len", "consumer_warps")}},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "correlations/s", "h2d_bytes_per_step": P * 8 * N_SAMPLES * N_ANTS,
-                    "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "path": "pinned host -> H2D" + (f" (1/{world} per rank) -> NCCL all-gather over NVLink" if world > 1 else "")
-                            + " -> gat_correlate_batch -> " + ("NCCL gather -> " if world > 1 else "") + "D2H",
-                    # what bounds it: one satellite per 6.4 MB block is 2.25 flop/B, the block crosses PCIe once
-                    "h2d_gb_per_s_per_gpu": P * 8 * N_SAMPLES * N_ANTS / world / (e2e_ms * 1e-3) / 1e9,
-                    "bound": "PCIe host->device copy (the kernel needs %.2f ms of the %.1f ms step)" % (ms_per_step, e2e_ms)},
-            "e2e_sc16": e2e_sc16,
-            "int16_resident": int16_resident,
-            "e2e_shared_block": e2e_shared,
-            "gpu_launches": int(gpu_launches),
-            "clocks": clocks,
-            "cmacs_per_s": value * N_SAMPLES,
-            "realtime_channels": world * P / ms_per_step,      # 1 ms periods finished per ms of wall clock (K = 1 per block)
-            "realtime_shared_block": {                        # K_RT channels over one shared 1 ms block, one launch
-                "channels_per_launch": K_RT, "ms_per_launch": rt_ms, "realtime_channels_per_gpu": K_RT / rt_ms,
-                "fp32_tflops": K_RT * N_SAMPLES * N_ANTS * (6 + 4 * N_TAPS) / (rt_ms * 1e-3) / 1e12,
-                "sats_per_cta": rt_info["sats_per_cta"], "sat_groups": rt_info["sat_groups"]},
-            "realtime_shared_block_tensor": rt_tensor,
-        }
-        print(json.dumps(line), flush=True)
+    if rank != 0 and world == 1:
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    algo_bytes = P * (8 * N_SAMPLES * N_ANTS) + P * (8 * N_TAPS * N_ANTS) + 1023   # signal once + outputs + chip table
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("periods_per_step") == P:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    remote_frac = (N_SAMPLES - part_len) / N_SAMPLES if world > 1 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms}
+    exchange = None
     if world > 1:
-        dist.destroy_process_group()
+        # the kernel's binding resource is now the NVLink ingress of every GPU: (world - 1) / world of every block is remote
+        nv_bytes = P * 8 * N_SAMPLES * N_ANTS * remote_frac
+        nv_gbs = nv_bytes / (kernel_ms * 1e-3) / 1e9
+        exchange = {"kind": "all-gather of the signal blocks fused into the correlate kernel (TMA loads from the owners' HBM over NVLink)",
+                    "nvlink_bytes_in_per_gpu_per_step": nv_bytes, "achieved_gbs_in_per_gpu": nv_gbs, "peak_gbs": 900.0,
+                    "peak_source": "NVLink 5 nominal, per direction and GPU", "frac": nv_gbs / 900.0,
+                    "note": "weak scaling over satellites needs every block on every GPU: at 1 satellite per GPU the step is bound by "
+                            "NVLink ingress (900 GB/s) instead of HBM (6.5 TB/s); `roofline` keeps the HBM figure for continuity"}
+        roofline["bound_multi_gpu"] = "nvlink-ingress"
+    line = {
+        "metric": "correlations/sec", "value": value, "unit": "correlations/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(P, world, {"launch": {k: info[k] for k in ("grid", "block", "smem_bytes", "stages", "tile_len", "consumer_warps")},
+                                          "signal_residency": ("every block resident on the one GPU" if world == 1 else
+                                                               f"every block scattered over the {world} GPUs' HBM by sample range; each kernel "
+                                                               "gathers its tiles over NVLink inside the timed region")}),
+        "roofline": roofline,
+        "exchange": exchange,
+        "parity_max_rel": parity,
+        "parity_pairs_per_rank": len(pairs),
+        "cpu_baseline": None,
+        "e2e": {"value": e2e_value, "unit": "correlations/s", "h2d_bytes_per_step": P * 8 * N_SAMPLES * N_ANTS,
+                "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps, "path": e2e_path,
+                "h2d_gb_per_s_per_gpu": P * 8 * N_SAMPLES * N_ANTS / world / (e2e_ms * 1e-3) / 1e9,
+                "bound": "PCIe host->device copy (the kernel needs %.2f ms of the %.1f ms step)" % (ms_per_step, e2e_ms)},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "cmacs_per_s": value * N_SAMPLES,
+        "realtime_channels": world * P / ms_per_step,      # 1 ms periods finished per ms of wall clock (K = 1 per block)
+    }
+    em.line = line        # from here on the contract line exists; everything below only adds keys
+
+    # ---- CPU baseline (N = 1, rank 0): before any optional GPU leg ----
+    if world == 1 and not args.no_cpu_baseline:
+        log("cpu baseline, all cores")
+        v, ms, used, kind, sample = cpu_arm(P, 1000, 1, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": "correlations/s", "cores": used, "kind": kind, "sample": sample}
+        log("cpu baseline, 1 thread")
+        v1, ms1, used1, _, sample1 = cpu_arm(8, 1000, 1, threads=1, budget_s=min(4.0, args.cpu_seconds))
+        line["cpu_baseline"]["single_thread"] = {"value": v1, "unit": "correlations/s", "cores": used1, "sample": sample1,
+                                                 "note": "Tracking.jl's CPU path is single-threaded (src/benchmarks.jl:63)"}
+    if args.no_side:
+        return
+
+    def side(name, fn):
+        """An optional leg: its result or its error goes into the line; a sticky CUDA error stops the side legs."""
+        if line.get("side_errors") and any("CUDA" in e or "launch failure" in e for e in line["side_errors"]):
+            return
+        log(f"side leg: {name}")
+        try:
+            out = fn()
+            torch.cuda.synchronize()
+            if rank == 0 and out is not None:
+                line.update(out)
+        except Exception as exc:      # noqa: BLE001
+            log(f"side leg {name} FAILED: {exc}")
+            line.setdefault("side_errors", []).append(f"{name}: {type(exc).__name__}: {str(exc)[:160]}")
+
+    side("c5", lambda: _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream))
+    if world == 1:
+        side("realtime_shared_block", lambda: _leg_realtime(eng, g, l1, shifts, dev, torch))
+        side("int16", lambda: _leg_int16(args, g, l1, shifts, local, dev, torch, work_stream, re, im, chan_list, slots, o_re, corr_per_step))
+        side("e2e_shared_block", lambda: _leg_shared_block(eng, g, l1, shifts, dev, torch, h_re, h_im))
+        side("single_call", lambda: _leg_single_call(eng, g, l1, shifts, dev, torch))
+    else:
+        side("kernel_only_replicated", lambda: _leg_replicated(eng, world, rank, P, FULL, chans, shifts, dev, torch, dist, corr_per_step))
+    if world > 1:
+        dist.barrier()
+
+
+def _leg_replicated(eng, world, rank, P, FULL, chans, shifts, dev, torch, dist, corr_per_step):
+    """Round 1's N-GPU figure, for continuity: every rank reads its OWN full copy of the blocks (no exchange at all)."""
+    slots = np.arange(FULL, FULL + P, dtype=np.int32)
+    for _ in range(3):
+        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+        eng.gather_wait()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(10):
+        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+        eng.gather_wait()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / 10], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"kernel_only_replicated": {"value": corr_per_step / (t.item() * 1e-3), "unit": "correlations/s", "ms_per_step": t.item(),
+                                       "note": "signal blocks replicated in every GPU's HBM beforehand: no exchange in the timed region "
+                                               "(round 1's definition of the N-GPU value; NOT the north_star data flow)"}}
+
+
+def _leg_realtime(eng, g, l1, shifts, dev, torch):
+    """The metric's second half: real-time (1 ms) satellite channels per GPU.  K channels share ONE 1 ms block (the receiver
+    case: every visible satellite of every constellation over the same antenna array); channels/ms = K / launch time."""
+    K_RT = 264
+    mk = lambda K: eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, DOPPLER + 3.0 * k, 0.001 * k) for k in range(K)]])
+    rt_chans = mk(K_RT)
+    rt_out = (torch.zeros(1, K_RT, N_TAPS, N_ANTS, device=dev), torch.zeros(1, K_RT, N_TAPS, N_ANTS, device=dev))
+    slot = np.array([20000], np.int32)
+
+    def timed(ch, out, reps, **kw):
+        for _ in range(5):
+            eng.correlate_batch(slot, ch, FS, shifts, N_ANTS, 0, N_SAMPLES, out=out, **kw)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            eng.correlate_batch(slot, ch, FS, shifts, N_ANTS, 0, N_SAMPLES, out=out, **kw)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    rt_ms = timed(rt_chans, rt_out, 20)
+    rt_info = eng.launch_info()
+    res = {"realtime_shared_block": {
+        "channels_per_launch": K_RT, "ms_per_launch": rt_ms, "realtime_channels_per_gpu": K_RT / rt_ms,
+        "fp32_tflops": K_RT * N_SAMPLES * N_ANTS * (6 + 4 * N_TAPS) / (rt_ms * 1e-3) / 1e12,
+        "sats_per_cta": rt_info["sats_per_cta"], "sat_groups": rt_info["sat_groups"], "tensor": rt_info["tensor"]}}
+    # the same launch on the tensor-core path (tcgen05 kind::tf32, csrc/gat_correlate_tc.cu)
+    rtt_ms = timed(rt_chans, rt_out, 20, tensor=True)
+    if eng.launch_info()["tensor"] == 1:
+        K_BIG = 1024
+        big_out = (torch.zeros(1, K_BIG, N_TAPS, N_ANTS, device=dev), torch.zeros(1, K_BIG, N_TAPS, N_ANTS, device=dev))
+        big_ms = timed(mk(K_BIG), big_out, 10, tensor=True)
+        res["realtime_shared_block_tensor"] = {
+            "channels_per_launch": K_RT, "ms_per_launch": rtt_ms, "realtime_channels_per_gpu": K_RT / rtt_ms,
+            "path": "tcgen05.mma kind::tf32 (GAT_TENSOR_TF32)",
+            "k1024": {"channels_per_launch": K_BIG, "ms_per_launch": big_ms, "realtime_channels_per_gpu": K_BIG / big_ms}}
+    return res
+
+
+def _leg_int16(args, g, l1, shifts, local, dev, torch, work_stream, re, im, chan_list, slots, o_re, corr_per_step):
+    """The same step fed with interleaved complex int16 samples (SDR wire format): half the PCIe and HBM bytes."""
+    P = len(chan_list)
+    eng_i = g.Engine(local)
+    eng_i.set_stream(work_stream.cuda_stream)
+    h_iq = torch.empty(P, N_ANTS, N_SAMPLES, 2, dtype=torch.int16, pin_memory=True)
+    for c0 in range(0, P, 32):
+        blk = torch.stack([re[c0:c0 + 32], im[c0:c0 + 32]], dim=-1)
+        h_iq[c0:c0 + 32].copy_((blk * 1024.0).round().clamp_(-32768, 32767).to(torch.int16))
+    blocks_np = [h_iq[p].numpy() for p in range(P)]
+    oi_re, oi_im = torch.zeros_like(o_re), torch.zeros_like(o_re)
+    h_out = torch.empty(2, P, 1, N_TAPS, N_ANTS, pin_memory=True)
+    chans_i = eng_i.marshal(chan_list)
+    islots = np.arange(P, dtype=np.int32)
+
+    def sc16_step():
+        for p in range(P):
+            eng_i.upload_signal_int(p, blocks_np[p], 1.0 / 1024.0)
+        eng_i.correlate_batch(islots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
+        h_out.copy_(torch.stack([oi_re, oi_im]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sc16_step()
+    assert oi_re[:, 0, 1, :].mean().item() > 0.9 * N_SAMPLES
+    w0 = time.perf_counter()
+    for _ in range(3):
+        sc16_step()
+    sc16_ms = (time.perf_counter() - w0) * 1e3 / 3
+    res = {"e2e_sc16": {"value": corr_per_step / (sc16_ms * 1e-3), "unit": "correlations/s", "ms_per_step": sc16_ms,
+                        "h2d_bytes_per_step": P * 4 * N_SAMPLES * N_ANTS,
+                        "path": "pinned host int16 I/Q -> H2D -> gat_correlate_batch reading the raw words (no FP32 expansion) -> D2H"}}
+    for _ in range(3):
+        eng_i.correlate_batch(islots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(10):
+        eng_i.correlate_batch(islots, chans_i, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(oi_re, oi_im))
+    i1.record()
+    torch.cuda.current_stream().synchronize()
+    i_ms = i0.elapsed_time(i1) / 10
+    res["int16_resident"] = {"value": corr_per_step / (i_ms * 1e-3), "unit": "correlations/s", "ms_per_step": i_ms,
+                             "hbm_bytes_per_step": P * 4 * N_SAMPLES * N_ANTS, "raw_int16_kernel": eng_i.launch_info()["sc16"],
+                             "hbm_gbs": P * 4 * N_SAMPLES * N_ANTS / (i_ms * 1e-3) / 1e9,
+                             "note": "device time, blocks resident as interleaved int16 I/Q (gat_upload_signal_sc16)"}
+    eng_i.close()
+    return res
+
+
+def _leg_shared_block(eng, g, l1, shifts, dev, torch, h_re, h_im):
+    """e2e when 32 satellites share each uploaded block (the receiver case: the PCIe transfer of a block is paid once)."""
+    PB, KB = 32, 32
+    sb_chans = eng.marshal([[g.Channel(l1, k % 32 + 1, 7.0 * k, DOPPLER + 3.0 * k, 0.001 * k) for k in range(KB)] for _ in range(PB)])
+    out = np.empty((2, PB, KB, N_TAPS, N_ANTS), np.float32)
+    step = lambda: eng.ingest_correlate(h_re[:PB], h_im[:PB], sb_chans, FS, shifts, 0, N_SAMPLES, out=out)
+    step()
+    w0 = time.perf_counter()
+    for _ in range(5):
+        step()
+    sb_ms = (time.perf_counter() - w0) * 1e3 / 5
+    return {"e2e_shared_block": {"value": PB * KB * N_TAPS * N_ANTS / (sb_ms * 1e-3), "unit": "correlations/s", "ms_per_step": sb_ms,
+                                 "blocks_per_step": PB, "sats_per_block": KB, "h2d_bytes_per_step": PB * 8 * N_SAMPLES * N_ANTS,
+                                 "channel_periods_per_s": PB * KB / (sb_ms * 1e-3),
+                                 "path": "pinned host -> gat_ingest_correlate (32 satellites per block) -> host"}}
+
+
+def _leg_single_call(eng, g, l1, shifts, dev, torch):
+    """The reference's own granularity (src/benchmarks.jl:872): ONE call over one 1 ms block + synchronisation."""
+    ch = eng.marshal([[g.Channel(l1, 1, 0.0, DOPPLER, 0.0)]])
+    out = (torch.zeros(1, 1, N_TAPS, N_ANTS, device=dev), torch.zeros(1, 1, N_TAPS, N_ANTS, device=dev))
+    slot = np.array([20000], np.int32)
+    for _ in range(50):
+        eng.correlate_batch(slot, ch, FS, shifts, N_ANTS, 0, N_SAMPLES, out=out)
+    eng.sync()
+    best, ts = 1e9, []
+    for _ in range(300):
+        t0 = time.perf_counter()
+        eng.correlate_batch(slot, ch, FS, shifts, N_ANTS, 0, N_SAMPLES, out=out)
+        eng.sync()
+        ts.append(time.perf_counter() - t0)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(300):
+        eng.correlate_batch(slot, ch, FS, shifts, N_ANTS, 0, N_SAMPLES, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    return {"single_call": {"sync_call_us_min": min(ts) * 1e6, "sync_call_us_median": float(np.median(ts)) * 1e6,
+                            "back_to_back_us": a.elapsed_time(b) / 300 * 1e3, "hbm_roofline_us": 8 * N_SAMPLES * N_ANTS / 6548.8e3,
+                            "note": "one gat_correlate_batch over one 50 000 x 16 block through the Python mirror, + gat_sync"}}
+
+
+def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
+    """BASELINE.json configs[4] ("C5"): GPS L1 + L5 mixed, 32 satellites x 16 antennas x 3 correlators over 50 000-sample blocks of
+    both bands, the satellites sharded over the GPUs.  A step = B one-ms periods (one launch per rank).  The blocks of both
+    bands live scattered over the ranks' HBM (the signal ring); each rank's kernel gathers what its shard needs over NVLink.
+      strong : 32 satellites in total (the config as written); bands are kept together, so from 2 GPUs on a rank reads ONE band
+      weak   : 32 satellites PER GPU (16 L1 + 16 L5 on every rank)
+    Device-timed, max over ranks, microseconds per 1 ms period."""
+    from gpuacceleratedtracking_b200.multigpu import gather_setup, ring_setup, shard_channels
+    B = 8
+    l1, l5 = g.GPSL1(), g.GPSL5()
+    systems = {0: l1, 1: l5}
+    shifts = g.get_correlator_sample_shifts(l1, g.EarlyPromptLateCorrelator(g.NumAnts(N_ANTS), g.NumAccumulators(N_TAPS)), FS, 0.5)
+    eng = g.Engine(local)
+    eng.set_stream(work_stream.cuda_stream)
+    slot = lambda b, j: b * B + j
+    tmp = torch.empty(2, N_ANTS, N_SAMPLES, device=dev)
+    if world > 1:
+        ring_setup(eng, 2 * B, N_SAMPLES, N_ANTS)
+    else:
+        eng.ring_connect([eng.ring_create(1, 0, 2 * B, N_SAMPLES, N_ANTS)])
+    eng.bind_signal(30000, tmp[0], tmp[1])
+    for b in (0, 1):
+        for j in range(B):
+            # distinct blocks: one strong satellite of the band + unit noise (same seeds on every rank)
+            eng.gen_signal(30000, systems[b], 1 + j % 16, 1500.0, FS, N_SAMPLES, N_ANTS, noise_sigma=1.0, seed=17 * j + b)
+            eng.sync()
+            eng.ring_upload(slot(b, j), tmp[0], tmp[1])
+            eng.sync()
+    gen = eng.ring_publish()
+    eng.ring_wait(gen)
+    eng.ring_release()
+    out = {}
+    for mode in ("strong", "weak"):
+        if mode == "strong":
+            all_ch = [g.Channel(l1 if k < 16 else l5, k % 16 + 1, 37.0 * k, 1500.0 + 40.0 * k, 0.01 * k) for k in range(32)]
+            _, mine = shard_channels(all_ch, world, rank)
+        else:
+            mine = [g.Channel(l1 if k < 16 else l5, (k + rank) % 16 + 1, 37.0 * k + rank, 1500.0 + 40.0 * k - 7.0 * rank, 0.01 * k)
+                    for k in range(32)]
+        bands = sorted({c.system.system_id for c in mine})
+        per_band = [[c for c in mine if c.system.system_id == b] for b in bands]
+        K = len(per_band[0])
+        assert all(len(x) == K for x in per_band)
+        P5 = len(bands) * B
+        slots = np.array([slot(b, j) for b in bands for j in range(B)], np.int32)
+        chans = eng.marshal([per_band[bi] for bi in range(len(bands)) for _ in range(B)])
+        elems = P5 * K * N_TAPS * N_ANTS
+        if world > 1:
+            gather_setup(eng, elems)
+            o = None
+        else:
+            o = (torch.zeros(P5, K, N_TAPS, N_ANTS, device=dev), torch.zeros(P5, K, N_TAPS, N_ANTS, device=dev))
+
+        def step():
+            if world > 1:
+                eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+                eng.gather_wait()
+            else:
+                eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=o)
+
+        for _ in range(5):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_steps = 40
+        a.record()
+        for _ in range(n_steps):
+            step()
+        b_.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b_) / n_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = t.item() * 1e3 / B
+        total = 32 if mode == "strong" else 32 * world
+        lo, ln = eng.ring_part()
+        out[mode] = {"satellites_total": total, "satellites_per_gpu": len(mine), "bands_per_gpu": len(bands), "us_per_period": us,
+                     "realtime_factor": 1000.0 / us, "realtime_channels": total * 1000.0 / us,
+                     "nvlink_bytes_in_per_gpu_per_period": len(bands) * 8 * N_SAMPLES * N_ANTS * (N_SAMPLES - ln) / N_SAMPLES if world > 1 else 0,
+                     "periods_per_step": B}
+    eng.close()
+    return {"c5": dict(out, workload="GPS L1 + L5 mixed, 32 satellites x 16 antennas x 3 correlators, 50000 samples/ms per band "
+                                     "(BASELINE configs[4]); blocks scattered over the GPUs' HBM, gathered by the kernels over NVLink")}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -661,7 +935,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--periods", type=int, default=256, help="1 ms signal blocks per step (batch)")
-    ap.add_argument("--ref-periods", type=int, default=0, help="periods per CPU step (default 2 x cores)")
+    ap.add_argument("--ref-periods", type=int, default=0, help="periods per CPU step of --impl reference (default: --periods)")
+    ap.add_argument("--no-side", action="store_true", help="skip the optional legs (c5, real-time channels, int16, ...)")
+    ap.add_argument("--deadline", type=float, default=420.0, help="seconds after which the line is emitted with what has been measured")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

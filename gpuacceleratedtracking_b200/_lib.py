@@ -60,11 +60,13 @@ SYMBOLS = {
     "gat_use_own_stream": (_i, [_vp]),
     "gat_gen_code": (_i, [_i, _i, _i8p, _i]),
     "gat_set_codes": (_i, [_vp, _i, _i8p, _i, _i]),
+    "gat_set_code_frequency": (_i, [_vp, _i, _d]),
     "gat_upload_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i]),
     "gat_upload_signal_sc16": (_i, [_vp, _i, _vp, _i, _i, _i, C.c_float, _i]),
     "gat_upload_signal_sc8": (_i, [_vp, _i, _vp, _i, _i, _i, C.c_float, _i]),
     "gat_bind_signal": (_i, [_vp, _i, _vp, _vp, _i, _i, _i]),
     "gat_gen_signal": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _i, _i, _d, _d, C.c_uint64, _i]),
+    "gat_slot_shape": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "gat_download_signal": (_i, [_vp, _i, _vp, _vp]),
     "gat_slot_export": (_i, [_vp, _i, C.POINTER(C.c_ubyte)]),
     "gat_slot_import": (_i, [_vp, _i, C.POINTER(C.c_ubyte)]),

@@ -948,6 +948,18 @@ int gat_set_codes(gat_ctx *ctx, int system_id, const int8_t *chips, int code_len
     t.code_len = code_len;
     t.n_prn = n_prn;
     t.col_stride = stride;
+    // the built-in ids carry their ICD chip rates; any other table needs gat_set_code_frequency before gat_gen_signal
+    t.code_freq_hz = (system_id == GAT_GPSL1 && code_len == 1023) ? 1.023e6 : (system_id == GAT_GPSL5 && code_len == 10230) ? 10.23e6 : 0.0;
+    return GAT_OK;
+}
+
+int gat_set_code_frequency(gat_ctx *ctx, int system_id, double code_freq_hz)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    if (system_id < 0 || system_id >= GAT_MAX_SYSTEMS || !ctx->codes[system_id].d_chips)
+        return fail(ctx, GAT_ERR_NO_CODES, "no chip table set for this system");
+    if (!(code_freq_hz > 0.0) || !std::isfinite(code_freq_hz)) return fail(ctx, GAT_ERR_INVALID, "code frequency must be positive");
+    ctx->codes[system_id].code_freq_hz = code_freq_hz;
     return GAT_OK;
 }
 
@@ -1166,7 +1178,7 @@ int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrie
         rc = ensure_planes(ctx, *s);
         if (rc) return rc;
     } else if (!(s->planes_valid && s->re && s->n_samples == n_samples && s->n_ants == n_ants)) {
-        // (a bound or owned slot of the right shape is generated into in place)
+        // (an owned slot, or caller planes bound with gat_bind_signal, of the right shape is generated into in place)
         if (!s->owned && s->re) {
             rc = free_planes(ctx, *s);
             if (rc) return rc;
@@ -1174,9 +1186,13 @@ int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrie
         rc = own_slot(ctx, *s, n_samples, n_ants, (static_cast<int64_t>(n_samples) + 3) & ~3LL);
         if (rc) return rc;
     }
+    // another process's memory (gat_slot_import) and the ring's shares are inputs only: never written from here
+    if (s->peer_base || !s->parts.empty())
+        return fail(ctx, GAT_ERR_INVALID, "gat_gen_signal cannot write into an imported or ring slot");
     s->raw_valid = false;   // the planes are about to change
-    // code frequency of the system: the built-ins carry theirs; caller tables pass it via prn-independent ratio
-    const double code_freq = (system_id == GAT_GPSL5) ? 10.23e6 : 1.023e6;
+    const double code_freq = t.code_freq_hz;
+    if (!(code_freq > 0.0))
+        return fail(ctx, GAT_ERR_INVALID, "no chip rate known for this table: call gat_set_code_frequency first");
     cudaError_t e = launch_gen_signal(s->re, s->im, s->ld, t.d_chips + static_cast<size_t>(prn - 1) * t.col_stride, t.code_len,
                                       code_freq / fs_hz, carrier_freq_hz, fs_hz, start_code_phase, start_carrier_phase_rad,
                                       n_samples, n_ants, ant_phase_step_rad, noise_sigma, seed, superpose, ctx->stream);
@@ -1311,6 +1327,16 @@ int gat_host_unregister(void *ptr)
         cudaGetLastError();
         return GAT_ERR_CUDA;
     }
+    return GAT_OK;
+}
+
+int gat_slot_shape(gat_ctx *ctx, int slot, int *n_samples_out, int *n_ants_out)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    const SignalSlot *s = find_slot(ctx, slot);
+    if (!slot_has_signal(s)) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(slot) + " has no signal");
+    if (n_samples_out) *n_samples_out = s->n_samples;
+    if (n_ants_out) *n_ants_out = s->n_ants;
     return GAT_OK;
 }
 

@@ -66,6 +66,7 @@ constexpr int kIngestDepth = 3, kIngestChunk = 16, kIngestSlotBase = 65000;   //
 struct CodeTable {
     int8_t *d_chips = nullptr;   // [n_prn][col_stride], columns zero-padded to kCodeColAlign bytes
     int code_len = 0, n_prn = 0, col_stride = 0;
+    double code_freq_hz = 0.0;   // nominal chip rate (gat_gen_signal); 0 = unknown (caller table without gat_set_code_frequency)
 };
 
 struct Staging {

@@ -129,6 +129,7 @@ class Engine:
         tab = np.ascontiguousarray(system.codes, np.int8)
         self._check(self._lib.gat_set_codes(self._h, system.system_id,
                                             tab.ctypes.data_as(C.POINTER(C.c_int8)), tab.shape[1], tab.shape[0]))
+        self._check(self._lib.gat_set_code_frequency(self._h, system.system_id, float(system.code_frequency)))
         self._systems[system.system_id] = system
 
     # -- signals ----------------------------------------------------------------------------
@@ -233,6 +234,11 @@ class Engine:
         sl = slots if isinstance(slots, np.ndarray) and slots.dtype == np.int32 else np.ascontiguousarray(slots, np.int32)
         if n_samples is None:
             raise ValueError("n_samples is required")
+        # libgat sizes its output by the SLOT's antenna count: a wrong n_ants here would overflow or under-fill `out`
+        m_slot = C.c_int()
+        self._check(self._lib.gat_slot_shape(self._h, int(sl[0]), None, C.byref(m_slot)))
+        if m_slot.value != n_ants:
+            raise ValueError(f"n_ants = {n_ants}, but slot {int(sl[0])} holds {m_slot.value} antennas")
         flags = ((_lib.GAT_ACCUMULATE if accumulate else 0) | (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0) |
                  (_lib.GAT_TENSOR_TF32 if tensor else 0) | (_lib.GAT_DEBUG_STALL_CONSUMERS if debug_stall else 0))
         i32p = C.POINTER(C.c_int32)
@@ -298,7 +304,7 @@ class Engine:
         """Host blocks in, host accumulators out, ONE C call for a whole batch of periods (gat_ingest_correlate): the
         library pipelines the H2D copies of chunk i + 1 under the kernel of chunk i.  re / im: host arrays
         [P, n_ants, ld] (numpy, or CPU torch tensors -- pinned ones copy asynchronously at full PCIe rate);
-        channels[p][k] or a ChannelArray.  Returns complex64 [P, K, L, M]."""
+        channels[p][k] or a ChannelArray.  Returns float32 [2 (re, im), P, K, L, M] (`out` if given)."""
         if _is_torch(re):
             assert not re.is_cuda and re.dtype == torch.float32 and re.is_contiguous() and im.is_contiguous()
             base_re, base_im, shape = re.data_ptr(), im.data_ptr(), tuple(re.shape)
@@ -375,9 +381,15 @@ class Engine:
     def gather_wait(self):
         self._check(self._lib.gat_gather_wait(self._h))
 
-    def gather_read(self) -> np.ndarray:
-        """complex64 [world, elems_per_rank(padded)] of the local gather buffer (synchronises)."""
+    def gather_read(self, out=None):
+        """complex64 [world, elems_per_rank(padded)] of the local gather buffer (synchronises).  With out=(re, im) float32
+        arrays of that shape the planes are copied into them instead (no allocation, returns None)."""
         world, elems = self._gather_shape
+        if out is not None:
+            re, im = out
+            assert re.shape == (world, elems) and im.shape == (world, elems) and re.dtype == np.float32 and im.dtype == np.float32
+            self._check(self._lib.gat_gather_read(self._h, C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data)))
+            return None
         re = np.empty((world, elems), np.float32)
         im = np.empty_like(re)
         self._check(self._lib.gat_gather_read(self._h, C.c_void_p(re.ctypes.data), C.c_void_p(im.ctypes.data)))

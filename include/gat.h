@@ -119,6 +119,11 @@ int gat_use_own_stream(gat_ctx *ctx);
 int gat_gen_code(int system_id, int prn, int8_t *out, int cap);
 /* Upload a table; chips is HOST memory, column-major [code_len x n_prn]. */
 int gat_set_codes(gat_ctx *ctx, int system_id, const int8_t *chips, int code_len, int n_prn);
+/* Nominal chip rate of a table, used ONLY by gat_gen_signal (a channel carries its own code_freq_hz).  The built-in
+ * ids get 1.023 MHz / 10.23 MHz when gat_set_codes installs a table of the ICD length; every other table (other ids,
+ * BOC / tiered codes, a custom table under id 0 or 1) has no rate until this is called -- gat_gen_signal then
+ * returns GAT_ERR_INVALID instead of silently assuming 1.023 MHz. */
+int gat_set_code_frequency(gat_ctx *ctx, int system_id, double code_freq_hz);
 
 /* ---- signal blocks --------------------------------------------------------------------- */
 /* A ctx holds a ring of signal slots (one 1 ms block each).  Upload copies (H2D or D2D,
@@ -143,11 +148,15 @@ int gat_upload_signal_sc8(gat_ctx *ctx, int slot, const int8_t *iq, int n_sample
 /* Device-side synthetic generator with gen_signal semantics (src/gen_signal.jl:135-152):
  * code phase Float64 -> floor/mod, carrier phase Float64 -> Float32 -> cos/sin, every antenna
  * identical.  Extensions (off when zero): per-antenna phase step [rad], AWGN sigma (seeded),
- * additive superposition onto the existing slot contents. */
+ * additive superposition onto the existing slot contents.  This call WRITES the slot: a ctx-owned slot, or caller
+ * planes registered with gat_bind_signal (then the caller's memory is generated into in place -- that is the point of
+ * binding writable planes); imported (gat_slot_import) and ring slots are refused. */
 int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrier_freq_hz,
                    double fs_hz, double start_code_phase, double start_carrier_phase_rad,
                    int n_samples, int n_ants, double ant_phase_step_rad, double noise_sigma,
                    uint64_t seed, int superpose);
+/* Shape of the block a slot holds (what the output size of a correlate call over it depends on). */
+int gat_slot_shape(gat_ctx *ctx, int slot, int *n_samples_out, int *n_ants_out);
 /* Copy a slot's planes back (tests): host column-major [n_samples x n_ants], ld = n_samples. */
 int gat_download_signal(gat_ctx *ctx, int slot, float *re, float *im);
 

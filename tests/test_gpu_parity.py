@@ -419,6 +419,51 @@ def test_device_gen_signal_matches_oracle(gat, orc, engine):
         assert np.array_equal(np.sign(re[0] ** 2 + im[0] ** 2), np.ones(n))
 
 
+def test_gen_signal_uses_the_tables_own_chip_rate(gat, orc):
+    """A caller table is generated at ITS chip rate (BOC / tiered / custom tables: round 1 assumed 1.023 MHz for every id
+    but GPS L5); a table whose rate is unknown is refused instead of guessed; imported / ring slots are never written."""
+    import ctypes as C
+    from gpuacceleratedtracking_b200 import _lib
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    boc = gat.boc(l1, 4, 1)                                  # sub-chip table: 2046 entries at 2.046 MHz
+    assert boc.code_frequency == 2 * l1.code_frequency
+    n, m = 8000, 2
+    fs = n / 1e-3
+    eng.gen_signal(3, boc, 7, 900.0, fs, n, m, 10.25, 0.3)
+    re, im = eng.download_signal(3, n, m)
+    r0, i0 = orc.gen_signal(boc.codes[6], boc.code_frequency, 900.0, fs, n, m, 10.25, 0.3)
+    assert np.abs(re - r0).max() < 5e-6 and np.abs(im - i0).max() < 5e-6
+    # a custom table installed under the GPS L1 id, with its own rate
+    custom = np.where(np.random.default_rng(1).integers(0, 2, (3, 511)) > 0, 1, -1).astype(np.int8)
+    sys_c = gat.GNSSSystem("custom511", 0, 511, 0.511e6, 0.0, 1, True, custom)
+    eng.gen_signal(4, sys_c, 2, 0.0, fs, n, m)
+    re, _ = eng.download_signal(4, n, m)
+    r0, _ = orc.gen_signal(custom[1], 0.511e6, 0.0, fs, n, m)
+    assert np.abs(re - r0).max() < 5e-6
+    # straight through the C ABI without a rate: refused
+    lib = _lib.load()
+    tab = np.ascontiguousarray(custom)
+    assert lib.gat_set_codes(eng._h, 5, tab.ctypes.data_as(C.POINTER(C.c_int8)), 511, 3) == 0
+    assert lib.gat_gen_signal(eng._h, 5, 5, 1, 0.0, fs, 0.0, 0.0, n, m, 0.0, 0.0, 0, 0) == _lib.GAT_ERR_INVALID
+    assert lib.gat_set_code_frequency(eng._h, 5, 0.511e6) == 0
+    assert lib.gat_gen_signal(eng._h, 5, 5, 1, 0.0, fs, 0.0, 0.0, n, m, 0.0, 0.0, 0, 0) == 0
+    assert lib.gat_set_code_frequency(eng._h, 6, 1e6) == _lib.GAT_ERR_NO_CODES
+    # ring slots are inputs only
+    eng.ring_connect([eng.ring_create(1, 0, 1, n, m)])
+    with pytest.raises(gat.GatError):
+        eng.gen_signal(0, l1, 1, 0.0, fs, n, m)
+    eng.close()
+
+
+def test_correlate_batch_checks_the_antenna_count(gat, engine):
+    l1 = gat.GPSL1()
+    z = np.zeros((4, 3000), np.float32)
+    engine.upload_signal(11, z, z)
+    with pytest.raises(ValueError):
+        engine.correlate(11, [gat.Channel(l1, 1)], 3e6, np.array([-1, 0, 1], np.int32), 2, 0, 3000)
+
+
 def test_gen_signal_extensions(gat, engine):
     l1 = gat.GPSL1()
     n, m, fs = 20000, 4, 2.0e7
