@@ -440,6 +440,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
                    double fs_hz, const int32_t *shifts, int n_taps, int start_sample, int n_samples,
                    float *out_re, float *out_im, int out_is_device, unsigned flags)
 {
+    NvtxRange nvtx_call("gat_correlate");
     int rc = check_ctx(ctx);
     if (rc) return rc;
     if (!slots || !channels || !shifts || ((!out_re || !out_im) && !(flags & GAT_GATHER)))
@@ -604,6 +605,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
             ta.win_ok = (static_cast<double>(kTileCap + span + 64) * shape.max_ratio + 2.0 < 32.0 && !env_int("GAT_TC_NO_WINDOW", 0)) ? 1 : 0;
             ta.debug = env_int("GAT_TC_DEBUG", 0);
             if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+            NvtxRange nvtx_launch("correlate_tc_kernel + tc_finalize_kernel");
             cudaError_t e = launch_correlate_tc(ta, grid, jobs, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "tensor-core correlate launch");
             GAT_CUDA(ctx, cudaEventRecord(stg->consumed, ctx->stream));
@@ -744,7 +746,11 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         ctx->timeline_ctas = plan.grid;
     }
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = launch_correlate(plan, args, ctx->stream);
+    cudaError_t e;
+    {
+        NvtxRange nvtx_launch("correlate_kernel");
+        e = launch_correlate(plan, args, ctx->stream);
+    }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "correlate kernel launch");
     ctx->barrier_count = barrier_target;
     if (gather) ctx->g_seq = args.gather_seq;
@@ -1002,6 +1008,7 @@ int upload_planes(gat_ctx *ctx, int slot, const float *re, const float *im, int 
 int gat_upload_signal(gat_ctx *ctx, int slot, const float *re, const float *im, int n_samples, int n_ants, int ld,
                       int src_is_device)
 {
+    NvtxRange nvtx_call("gat_upload_signal");
     int rc = check_ctx(ctx);
     if (rc) return rc;
     return upload_planes(ctx, slot, re, im, n_samples, n_ants, ld, src_is_device, ctx->stream);
@@ -1163,6 +1170,7 @@ int gat_gen_signal(gat_ctx *ctx, int slot, int system_id, int prn, double carrie
                    double start_code_phase, double start_carrier_phase_rad, int n_samples, int n_ants,
                    double ant_phase_step_rad, double noise_sigma, uint64_t seed, int superpose)
 {
+    NvtxRange nvtx_call("gat_gen_signal");
     int rc = check_ctx(ctx);
     if (rc) return rc;
     if (system_id < 0 || system_id >= GAT_MAX_SYSTEMS || !ctx->codes[system_id].d_chips)
@@ -1256,6 +1264,7 @@ int gat_ingest_correlate(gat_ctx *ctx, int n_periods, const float *const *h_re, 
                          int n_sats, const gat_channel *channels, double fs_hz, const int32_t *sample_shifts, int n_taps,
                          int start_sample, int n_samples, float *h_out_re, float *h_out_im, unsigned flags)
 {
+    NvtxRange nvtx_call("gat_ingest_correlate");
     int rc = check_ctx(ctx);
     if (rc) return rc;
     if (!h_re || !h_im || !channels || !sample_shifts || !h_out_re || !h_out_im || n_periods < 1 || n_sats < 1)

@@ -10,10 +10,21 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/gat.h"
 #include "gat_internal.h"
 
 namespace gat {
+
+// NVTX range around every host-side stage (the reference wraps each launch in `NVTX.@range`,
+// src/algorithms.jl:953, :973, :1015 ... :1526, and profiles with scripts/nsys.jl:100): free when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // One owner's share of a sharded slot (gat_ring_*): samples [start, start + len) of every antenna, in that owner's
 // HBM -- local memory, or a peer mapping (CUDA IPC / direct peer access) the kernel TMA-loads from over NVLink.

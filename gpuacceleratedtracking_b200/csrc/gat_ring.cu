@@ -243,6 +243,7 @@ int gat_ring_part(gat_ctx *ctx, int rank, int *start_out, int *len_out)
 
 int gat_ring_upload_part(gat_ctx *ctx, int slot, const float *re_part, const float *im_part, int ld, int src_is_device)
 {
+    NvtxRange nvtx_call("gat_ring_upload");
     int rc = ring_check(ctx, false);
     if (rc) return rc;
     Ring &r = ctx->ring;
