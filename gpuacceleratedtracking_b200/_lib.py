@@ -98,7 +98,20 @@ SYMBOLS = {
     "gat_ring_wait": (_i, [_vp, _i]),
     "gat_ring_release": (_i, [_vp]),
     "gat_ring_acquire": (_i, [_vp, _i]),
+    "gat_ring_enable_mirror": (_i, [_vp]),
+    "gat_ring_prefetch": (_i, [_vp, _i, _i, _i, _i]),
+    "gat_ring_mirror_wait": (_i, [_vp, _i]),
     "gat_ring_destroy": (_i, [_vp]),
+    "gat_mg_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_i)]),
+    "gat_mg_destroy": (_i, [_vp]),
+    "gat_mg_last_error": (C.c_char_p, [_vp]),
+    "gat_mg_device_count": (_i, [_vp]),
+    "gat_mg_ctx": (_vp, [_vp, _i]),
+    "gat_mg_set_codes": (_i, [_vp, _i, _i8p, _i, _i]),
+    "gat_mg_configure": (_i, [_vp, _i, _i, _i]),
+    "gat_mg_upload_signal": (_i, [_vp, _i, _vp, _vp, _i]),
+    "gat_mg_correlate": (_i, [_vp, _i, _i32p, _i, _chp, _d, _i32p, _i, _i, _i, _vp, _vp, _u]),
+    "gat_mg_sync": (_i, [_vp]),
     "gat_set_timeline": (_i, [_vp, _i]),
     "gat_get_timeline": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "gat_debug_chip_indices": (_i, [_vp, _chp, _d, _i, _i, _u, _i32p]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgat.so")
-SOURCES = ["gat_correlate.cu", "gat_correlate_tc.cu", "gat_api.cu", "gat_ring.cu", "gat_postcorr.cu", "gat_codes.cpp"]
+SOURCES = ["gat_correlate.cu", "gat_correlate_tc.cu", "gat_api.cu", "gat_ring.cu", "gat_mg.cu", "gat_postcorr.cu", "gat_codes.cpp"]
 HEADERS = [os.path.join(CSRC, "gat_internal.h"), os.path.join(CSRC, "gat_ctx.h"), os.path.join(HERE, "..", "include", "gat.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -60,6 +60,7 @@ struct SignalSlot {
 
 // The signal ring of gat_ring_*: `n_slots` blocks whose samples are spread over the `world` ranks' HBM.  Rank r's
 // allocation = [256 B of flags: pub[8] | rel[8]] [slot 0: re plane, im plane] [slot 1] ..., plane = n_ants x part_ld[r].
+constexpr int kRingEvents = 16;
 struct Ring {
     int world = 0, rank = 0, n_slots = 0, n_samples = 0, n_ants = 0;
     int part_tiles = 0, n_parts = 0;            // parts that hold samples (the leading ranks when the block is short)
@@ -70,6 +71,11 @@ struct Ring {
     unsigned char *local = nullptr;
     unsigned int pub_seq = 0, rel_seq = 0;      // generations published / released by this rank so far
     bool connected = false;
+    // mirror view (gat_ring_enable_mirror): local copies of the peers' shares, refreshed by copy-engine prefetches
+    unsigned char *mirror[kMaxPeers] = {};
+    cudaEvent_t rel_ev[kRingEvents] = {}, pf_ev[kRingEvents] = {};
+    int pf_tickets = 0;
+    bool mirrored = false;
 };
 constexpr size_t kRingFlagBytes = 256;
 constexpr int kIngestDepth = 3, kIngestChunk = 16, kIngestSlotBase = 65000;   // gat_ingest_correlate staging

@@ -74,14 +74,20 @@ float *ring_plane(const Ring &r, int j, int slot, int plane)
 
 unsigned int *ring_flags(const Ring &r, int j, int which) { return reinterpret_cast<unsigned int *>(r.base[j]) + 16 * which; }
 
-// all mappings are in place: turn ctx slots 0 .. n_slots-1 into sharded slots
-int ring_build_slots(gat_ctx *ctx)
+float *view_plane(const Ring &r, unsigned char *const *bases, int j, int slot, int plane)
+{
+    return reinterpret_cast<float *>(bases[j] + kRingFlagBytes + static_cast<size_t>(slot) * ring_slot_bytes(r, j)) +
+           static_cast<size_t>(plane) * r.n_ants * r.part_ld[j];
+}
+
+// turn ctx slots slot_base .. slot_base + n_slots-1 into sharded slots whose part j lives at bases[j]
+int ring_build_view(gat_ctx *ctx, int slot_base, unsigned char *const *bases)
 {
     Ring &r = ctx->ring;
     EncodeTiledFn enc = ring_encode_fn();
     if (!enc) return fail(ctx, GAT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     for (int s = 0; s < r.n_slots; ++s) {
-        SignalSlot &sl = ctx->slots[s];
+        SignalSlot &sl = ctx->slots[slot_base + s];
         if ((sl.owned && sl.re) || sl.raw || sl.peer_base) {
             GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (sl.owned && sl.re) GAT_CUDA(ctx, cudaFree(sl.re));
@@ -95,8 +101,8 @@ int ring_build_slots(gat_ctx *ctx)
         sl.parts.resize(r.n_parts);
         for (int j = 0; j < r.n_parts; ++j) {
             SlotPart &pt = sl.parts[j];
-            pt.re = ring_plane(r, j, s, 0);
-            pt.im = ring_plane(r, j, s, 1);
+            pt.re = view_plane(r, bases, j, s, 0);
+            pt.im = view_plane(r, bases, j, s, 1);
             pt.ld = r.part_ld[j];
             pt.start = r.part_start[j];
             pt.len = r.part_len[j];
@@ -114,7 +120,15 @@ int ring_build_slots(gat_ctx *ctx)
             }
         }
     }
-    r.connected = true;
+    return GAT_OK;
+}
+
+// all mappings are in place: ctx slots 0 .. n_slots-1 become the ring's blocks (parts read where they live)
+int ring_build_slots(gat_ctx *ctx)
+{
+    int rc = ring_build_view(ctx, 0, ctx->ring.base);
+    if (rc) return rc;
+    ctx->ring.connected = true;
     return GAT_OK;
 }
 
@@ -151,12 +165,18 @@ int gat_ring_destroy(gat_ctx *ctx)
     if (!r.local) return GAT_OK;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    for (int s = 0; s < r.n_slots; ++s) {
+    for (int s = 0; s < 2 * r.n_slots; ++s) {
         auto it = ctx->slots.find(s);
         if (it != ctx->slots.end() && !it->second.parts.empty()) ctx->slots.erase(it);
     }
-    for (int j = 0; j < kMaxPeers; ++j)
+    for (int j = 0; j < kMaxPeers; ++j) {
         if (r.opened[j]) cudaIpcCloseMemHandle(r.opened[j]);
+        if (r.mirror[j] && r.mirror[j] != r.local) cudaFree(r.mirror[j]);
+    }
+    for (int i = 0; i < kRingEvents; ++i) {
+        if (r.rel_ev[i]) cudaEventDestroy(r.rel_ev[i]);
+        if (r.pf_ev[i]) cudaEventDestroy(r.pf_ev[i]);
+    }
     cudaFree(r.local);
     r = Ring{};
     return GAT_OK;
@@ -297,7 +317,73 @@ int gat_ring_release(gat_ctx *ctx)
     if (rc) return rc;
     rc = ring_signal(ctx, 1, ctx->ring.rel_seq + 1, ctx->stream);
     if (rc) return rc;
-    return static_cast<int>(++ctx->ring.rel_seq);
+    ++ctx->ring.rel_seq;
+    if (ctx->ring.mirrored) GAT_CUDA(ctx, cudaEventRecord(ctx->ring.rel_ev[ctx->ring.rel_seq % kRingEvents], ctx->stream));
+    return static_cast<int>(ctx->ring.rel_seq);
+}
+
+// ---- mirror view: for shapes whose kernel is compute-bound (many satellites per GPU and block) ----
+// The fused pull fetches a remote tile once per satellite GROUP of the reading CTA set (remote lines are not cached in
+// the reader's L2), and its NVLink time sits on the kernel's critical path.  With the mirror the copy engines bring the
+// peers' shares into local HBM one generation ahead (no SM involved, fully under the previous generation's kernel);
+// slots n_slots .. 2 n_slots-1 are the same blocks read from those local copies.
+int gat_ring_enable_mirror(gat_ctx *ctx)
+{
+    int rc = ring_check(ctx, true);
+    if (rc) return rc;
+    Ring &r = ctx->ring;
+    if (r.mirrored) return GAT_OK;
+    for (int j = 0; j < r.n_parts; ++j) {
+        if (j == r.rank) {
+            r.mirror[j] = r.local;
+            continue;
+        }
+        const size_t bytes = kRingFlagBytes + static_cast<size_t>(r.n_slots) * ring_slot_bytes(r, j);
+        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&r.mirror[j]), bytes));
+        GAT_CUDA(ctx, cudaMemset(r.mirror[j], 0, bytes));
+    }
+    for (int i = 0; i < kRingEvents; ++i) {
+        GAT_CUDA(ctx, cudaEventCreateWithFlags(&r.rel_ev[i], cudaEventDisableTiming));
+        GAT_CUDA(ctx, cudaEventCreateWithFlags(&r.pf_ev[i], cudaEventDisableTiming));
+    }
+    rc = ring_build_view(ctx, r.n_slots, r.mirror);
+    if (rc) return rc;
+    r.mirrored = true;
+    return GAT_OK;
+}
+
+int gat_ring_prefetch(gat_ctx *ctx, int first_slot, int n_slots, int generation, int releases)
+{
+    NvtxRange nvtx_call("gat_ring_prefetch");
+    int rc = ring_check(ctx, true);
+    if (rc) return rc;
+    Ring &r = ctx->ring;
+    if (!r.mirrored) return fail(ctx, GAT_ERR_INVALID, "gat_ring_enable_mirror first");
+    if (first_slot < 0 || n_slots < 1 || first_slot + n_slots > r.n_slots) return fail(ctx, GAT_ERR_INVALID, "ring slot range out of bounds");
+    rc = ring_wait_flags(ctx, 0, generation, ctx->copy_stream);         // every owner's share of that generation is in place
+    if (rc) return rc;
+    if (releases > 0 && static_cast<unsigned int>(releases) <= r.rel_seq)     // this rank's own kernels are done with the mirror slots
+        GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, r.rel_ev[releases % kRingEvents], 0));
+    for (int j = 0; j < r.n_parts; ++j) {
+        if (j == r.rank || r.part_len[j] == 0) continue;
+        const size_t off = kRingFlagBytes + static_cast<size_t>(first_slot) * ring_slot_bytes(r, j);
+        GAT_CUDA(ctx, cudaMemcpyAsync(r.mirror[j] + off, r.base[j] + off, static_cast<size_t>(n_slots) * ring_slot_bytes(r, j),
+                                      cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    }
+    const int ticket = ++r.pf_tickets;
+    GAT_CUDA(ctx, cudaEventRecord(r.pf_ev[ticket % kRingEvents], ctx->copy_stream));
+    return ticket;
+}
+
+int gat_ring_mirror_wait(gat_ctx *ctx, int ticket)
+{
+    int rc = ring_check(ctx, true);
+    if (rc) return rc;
+    Ring &r = ctx->ring;
+    if (!r.mirrored || ticket < 1 || ticket > r.pf_tickets) return fail(ctx, GAT_ERR_INVALID, "no such prefetch ticket");
+    if (r.pf_tickets - ticket >= kRingEvents) return GAT_OK;            // long done: its event has been re-used since
+    GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, r.pf_ev[ticket % kRingEvents], 0));
+    return GAT_OK;
 }
 
 int gat_ring_acquire(gat_ctx *ctx, int releases)

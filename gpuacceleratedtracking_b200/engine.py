@@ -442,6 +442,16 @@ class Engine:
     def ring_acquire(self, releases: int):
         self._check(self._lib.gat_ring_acquire(self._h, int(releases)))
 
+    def ring_enable_mirror(self):
+        """Slots n_slots .. 2 n_slots-1 become the ring's blocks read from LOCAL copies (see ring_prefetch)."""
+        self._check(self._lib.gat_ring_enable_mirror(self._h))
+
+    def ring_prefetch(self, first_slot: int, n_slots: int, generation: int, releases: int = 0) -> int:
+        return self._count(self._lib.gat_ring_prefetch(self._h, first_slot, n_slots, int(generation), int(releases)))
+
+    def ring_mirror_wait(self, ticket: int):
+        self._check(self._lib.gat_ring_mirror_wait(self._h, int(ticket)))
+
     def ring_destroy(self):
         self._check(self._lib.gat_ring_destroy(self._h))
 
@@ -453,6 +463,87 @@ class Engine:
                                                      _lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0,
                                                      out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
+
+
+class MultiEngine:
+    """One host process driving several GPUs through gat_mg_* (include/gat.h): channels sharded over the devices, the
+    signal blocks scattered by sample range and gathered over NVLink inside the kernels, results in channel order."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self._lib.gat_mg_create(C.byref(h), len(devices), arr)
+        if rc != 0:
+            raise GatError(rc, self._lib.gat_status_string(rc).decode() + " (gat_mg_create)")
+        self._h = h
+        self.devices = list(devices)
+        self._systems: dict[int, GNSSSystem] = {}
+        self._shape = None
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GatError(rc, self._lib.gat_mg_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gat_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_codes(self, system: GNSSSystem):
+        if self._systems.get(system.system_id) is system:
+            return
+        tab = np.ascontiguousarray(system.codes, np.int8)
+        self._check(self._lib.gat_mg_set_codes(self._h, system.system_id, tab.ctypes.data_as(C.POINTER(C.c_int8)),
+                                               tab.shape[1], tab.shape[0]))
+        self._systems[system.system_id] = system
+
+    def configure(self, n_slots: int, n_samples: int, n_ants: int):
+        self._check(self._lib.gat_mg_configure(self._h, n_slots, n_samples, n_ants))
+        self._shape = (n_slots, n_samples, n_ants)
+
+    def upload_signal(self, slot: int, re, im):
+        """Host planes [n_ants, ld] (numpy or CPU torch; pinned memory copies asynchronously).  Keep them alive until the
+        next correlate call on this slot has returned."""
+        if _is_torch(re):
+            assert not re.is_cuda
+            m, ld = re.shape
+            pr, pi = re.data_ptr(), im.data_ptr()
+        else:
+            assert re.dtype == np.float32 and re.flags.c_contiguous and im.flags.c_contiguous
+            m, ld = re.shape
+            pr, pi = re.ctypes.data, im.ctypes.data
+        assert m == self._shape[2] and ld >= self._shape[1]
+        self._check(self._lib.gat_mg_upload_signal(self._h, slot, C.c_void_p(pr), C.c_void_p(pi), ld))
+
+    def correlate_batch(self, slots: Sequence[int], channels: Sequence[Sequence[Channel]], fs: float, shifts: Sequence[int],
+                        start_sample: int = 0, n_samples: int | None = None, code_phase_f64: bool = False) -> np.ndarray:
+        """channels[p][k] -> complex64 [P, K, L, M] in the caller's channel order."""
+        P, K = len(slots), len(channels[0])
+        for row in channels:
+            for ch in row:
+                self.set_codes(ch.system)
+        arr = (GatChannel * (P * K))(*[ch.to_c() for row in channels for ch in row])
+        sh = np.ascontiguousarray(shifts, np.int32)
+        sl = np.ascontiguousarray(slots, np.int32)
+        n_samples = self._shape[1] - start_sample if n_samples is None else n_samples
+        M = self._shape[2]
+        o_re = np.empty((P, K, sh.size, M), np.float32)
+        o_im = np.empty_like(o_re)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._lib.gat_mg_correlate(self._h, P, sl.ctypes.data_as(i32p), K, arr, fs, sh.ctypes.data_as(i32p), sh.size,
+                                               start_sample, n_samples, C.c_void_p(o_re.ctypes.data), C.c_void_p(o_im.ctypes.data),
+                                               _lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0))
+        return (o_re + 1j * o_im).astype(np.complex64)
+
+    def sync(self):
+        self._check(self._lib.gat_mg_sync(self._h))
 
 
 _default: dict[int, Engine] = {}

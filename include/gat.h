@@ -272,7 +272,41 @@ int gat_ring_publish(gat_ctx *ctx);                 /* returns this rank's gener
 int gat_ring_wait(gat_ctx *ctx, int generation);
 int gat_ring_release(gat_ctx *ctx);                 /* returns this rank's release count (>= 1), or < 0 */
 int gat_ring_acquire(gat_ctx *ctx, int releases);
+/* Mirror view, for kernels that are compute-bound (many satellites per block and GPU): the copy engines bring the peers'
+ * shares into local HBM one generation ahead, under the previous generation's kernel and without using an SM.  After
+ * gat_ring_enable_mirror the ctx's slots n_slots .. 2 n_slots-1 are the SAME blocks read from those local copies.
+ *   ingest stream : t = gat_ring_prefetch(first_slot, n, generation, releases)  -- waits until every rank published
+ *                   `generation` and until this rank's own release number `releases` has run (<= 0: nothing), then copies
+ *                   the peers' shares of ring slots first_slot .. first_slot + n-1 (one contiguous copy per peer)
+ *   ctx stream    : gat_ring_mirror_wait(t) -> gat_correlate*(slots n_slots + ...) -> gat_ring_release() */
+int gat_ring_enable_mirror(gat_ctx *ctx);
+int gat_ring_prefetch(gat_ctx *ctx, int first_slot, int n_slots, int generation, int releases);   /* returns a ticket >= 1 */
+int gat_ring_mirror_wait(gat_ctx *ctx, int ticket);
 int gat_ring_destroy(gat_ctx *ctx);
+
+/* ---- one host process, all GPUs of the box -----------------------------------------------------
+ * The call a single tracking-loop process makes (Julia: one `ccall` per integration period or batch): the satellite
+ * channels are partitioned over the devices, every device reads the same signal blocks, the accumulators come back in
+ * the caller's channel order.  Built on the signal ring above: gat_mg_upload_signal sends each device ITS sample range
+ * of the block through that device's own PCIe link (asynchronous, n_dev links in parallel) and the correlate kernels
+ * gather the other ranges over NVLink.  `devices` may name one device several times (logical shards; used by the
+ * single-GPU tests).  Typical loop: upload block t+1 into slot (t+1) % n_slots, THEN gat_mg_correlate on slot t % n_slots:
+ * the upload of the next block overlaps the kernels of the current one; a slot is not overwritten before every
+ * device has finished reading it (tracked per slot).
+ *   out: [n_ants x n_taps x n_sats x n_periods] host arrays; gat_mg_correlate is synchronous. */
+typedef struct gat_mg gat_mg;
+int gat_mg_create(gat_mg **out, int n_dev, const int *devices);
+int gat_mg_destroy(gat_mg *mg);
+const char *gat_mg_last_error(gat_mg *mg);
+int gat_mg_device_count(gat_mg *mg);
+gat_ctx *gat_mg_ctx(gat_mg *mg, int i);            /* device i's context (borrowed) for per-device calls, e.g. gat_last_launch_info */
+int gat_mg_set_codes(gat_mg *mg, int system_id, const int8_t *chips, int code_len, int n_prn);   /* on every device */
+int gat_mg_configure(gat_mg *mg, int n_slots, int n_samples, int n_ants);                          /* (re)builds the ring */
+int gat_mg_upload_signal(gat_mg *mg, int slot, const float *h_re, const float *h_im, int ld);     /* host planes [n_ants x ld] */
+int gat_mg_correlate(gat_mg *mg, int n_periods, const int32_t *slots, int n_sats, const gat_channel *channels,
+                     double fs_hz, const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples,
+                     float *h_out_re, float *h_out_im, unsigned flags);
+int gat_mg_sync(gat_mg *mg);
 
 /* ---- introspection (bench / tests) ----------------------------------------------------- */
 typedef struct gat_launch_info {

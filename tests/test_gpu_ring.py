@@ -112,6 +112,53 @@ def test_ring_generations_and_flags(gat, orc):
     _close(engs)
 
 
+def test_ring_mirror_prefetch(gat, orc):
+    """The mirror view: copy-engine prefetch of the peers' shares one generation ahead, kernels read local copies.
+    Same protocol as above plus prefetch tickets; results must equal the pull view's bit for bit."""
+    import torch
+    world, n, m, B, depth, gens = 3, 20000, 4, 2, 2, 5
+    rng = np.random.default_rng(6)
+    l1 = gat.GPSL1()
+    fs = n / 1e-3
+    shifts = orc.sample_shifts(1.023e6, fs, 0.5, 3)
+    n_slots = depth * B
+    engs = _make_ring(gat, world, n_slots, n, m)
+    for e in engs:
+        e.ring_enable_mirror()
+    data = torch.from_numpy(rng.normal(size=(gens, B, 2, m, n)).astype(np.float32)).pin_memory()
+    chans = [[gat.Channel(l1, 3 + r, 50.0 * r + 1.5, 1100.0 * r - 900.0, 0.05 * r)] for r in range(world)]
+    mk = lambda: (torch.zeros(B, 1, 3, m, device="cuda"), torch.zeros(B, 1, 3, m, device="cuda"))
+    out_m = [[mk() for _ in range(gens)] for _ in range(world)]
+    out_p = [[mk() for _ in range(gens)] for _ in range(world)]
+    for g in range(gens):
+        slots = [(g % depth) * B + b for b in range(B)]
+        for e in engs:
+            e.ring_acquire(g - depth + 1)
+            for b in range(B):
+                e.ring_upload(slots[b], data[g, b, 0].numpy(), data[g, b, 1].numpy())
+            assert e.ring_publish() == g + 1
+        tickets = [e.ring_prefetch(slots[0], B, g + 1, g - depth + 1) for e in engs]
+        for r, e in enumerate(engs):
+            e.ring_mirror_wait(tickets[r])
+            e.correlate_batch([n_slots + s for s in slots], [chans[r]] * B, fs, shifts, m, 0, n, out=out_m[r][g])   # local copies
+            e.ring_wait(g + 1)
+            e.correlate_batch(slots, [chans[r]] * B, fs, shifts, m, 0, n, out=out_p[r][g])                       # pulled
+            assert e.ring_release() == g + 1
+    for e in engs:
+        e.sync()
+    for r in range(world):
+        for g in range(gens):
+            assert torch.equal(out_m[r][g][0], out_p[r][g][0]) and torch.equal(out_m[r][g][1], out_p[r][g][1]), (r, g)
+            got = (out_m[r][g][0] + 1j * out_m[r][g][1]).cpu().numpy()
+            c = chans[r][0]
+            ref = orc.correlate_direct(data[g, 1, 0].numpy(), data[g, 1, 1].numpy(), l1.codes[c.prn - 1], 1.023e6, c.code_phase,
+                                       c.carrier_frequency, c.carrier_phase, fs, shifts)
+            assert np.abs(got[1, 0] - ref).max() <= TOL * np.sqrt(n) * 4, (r, g)
+    with pytest.raises(gat.GatError):
+        engs[0].ring_mirror_wait(10 ** 6)
+    _close(engs)
+
+
 def test_ring_errors(gat, orc):
     engs = _make_ring(gat, 2, 2, 5000, 2)
     e = engs[0]
