@@ -28,6 +28,52 @@ def test_library_exports_every_declared_symbol(gat):
     assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
 
 
+def _split_top_level(args: str):
+    out, depth, cur = [], 0, ""
+    for ch in args:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_binding_matches_the_header(gat):
+    """julia/GATB200.jl cannot run here (no Julia): check mechanically that every `ccall` names a symbol of include/gat.h
+    and passes as many arguments as the C prototype takes, and that INTEGRATION.md quotes the file's own two methods."""
+    from gpuacceleratedtracking_b200 import _lib
+    text = open(os.path.join(ROOT, "julia", "GATB200.jl")).read()
+    calls = list(re.finditer(r"ccall\(\(:(gat_[a-z0-9_]+),\s*(?:GATB200\.)?libgat\),\s*\w+,\s*\(", text))
+    assert len(calls) >= 15
+    seen = set()
+    for m in calls:
+        name = m.group(1)
+        assert name in _lib.SYMBOLS, f"GATB200.jl calls {name}, which include/gat.h does not declare"
+        i, depth = m.end(), 1                      # inside the argument-type tuple
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[i], 0)
+            i += 1
+        types = [t for t in _split_top_level(text[m.end():i - 1]) if t]
+        assert len(types) == len(_lib.SYMBOLS[name][1]), f"{name}: {len(types)} Julia argument types vs {len(_lib.SYMBOLS[name][1])} in C"
+        seen.add(name)
+    for needed in ("gat_create", "gat_set_codes", "gat_bind_signal", "gat_correlate", "gat_downconvert_and_correlate",
+                   "gat_ingest_correlate", "gat_mg_create", "gat_mg_correlate", "gat_mg_upload_signal"):
+        assert needed in seen
+    # one binding, quoted verbatim: the two reference-facing methods in INTEGRATION.md are the file's own text
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for start in ("function kernel_algorithm(", "function downconvert_and_correlate!(::B200"):
+        a = text.index(start)
+        body = text[a:text.index("\nend\n", a) + 5]
+        assert body in doc, f"INTEGRATION.md does not quote `{start}...` as it stands in julia/GATB200.jl"
+
+
 def test_version_and_status_strings(gat):
     lib = gat.load()
     assert lib.gat_version() == 100
