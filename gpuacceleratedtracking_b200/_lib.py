@@ -115,6 +115,8 @@ SYMBOLS = {
     "gat_set_timeline": (_i, [_vp, _i]),
     "gat_get_timeline": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "gat_debug_chip_indices": (_i, [_vp, _chp, _d, _i, _i, _u, _i32p]),
+    "gat_debug_replica_indices": (_i, [_vp, _chp, _d, _i32p, _i, _i, _i, _i, _u, _i32p]),
+    "gat_debug_tc_replica_bits": (_i, [_vp, _i, _i, _chp, _d, _i32p, _i, _i, _i, C.POINTER(C.c_uint8)]),
 }
 
 _lib = None

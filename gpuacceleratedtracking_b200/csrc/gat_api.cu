@@ -604,6 +604,16 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
             ta.total_units = total_units;
             ta.win_ok = (static_cast<double>(kTileCap + span + 64) * shape.max_ratio + 2.0 < 32.0 && !env_int("GAT_TC_NO_WINDOW", 0)) ? 1 : 0;
             ta.debug = env_int("GAT_TC_DEBUG", 0);
+            ta.dump = nullptr;
+            if (flags & kFlagDumpReplica) {
+                const size_t n_dump = static_cast<size_t>(total_units) * 32 * 20;
+                rc = ensure_device(ctx, ctx->d_dbg, ctx->d_dbg_cap, n_dump, false);
+                if (rc) return rc;
+                GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg, 0, n_dump * sizeof(int32_t), ctx->stream));
+                ta.dump = reinterpret_cast<uint32_t *>(ctx->d_dbg);
+                ctx->dump_tiles = tiles_per_job;
+                ctx->dump_aligned_start = aligned_start;
+            }
             if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
             NvtxRange nvtx_launch("correlate_tc_kernel + tc_finalize_kernel");
             cudaError_t e = launch_correlate_tc(ta, grid, jobs, ctx->stream);
@@ -636,6 +646,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
             return GAT_OK;
         }
         // otherwise: the shape is outside the tensor-core path's envelope -> the FP32 kernel below
+        if (flags & kFlagDumpReplica) return fail(ctx, GAT_ERR_UNSUPPORTED, "shape outside the tensor-core path's envelope");
     }
 
     LaunchPlan plan{};
@@ -737,6 +748,23 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         if (flags & GAT_ACCUMULATE) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_ACCUMULATE with an even tap count");
     }
 
+    args.dump = nullptr;
+    plan.dump = false;
+    if (flags & kFlagDumpReplica) {
+        // debug: the DUMP instantiation of the hot kernel records the chip-table index of every replica entry
+        if (n_periods != 1 || n_sats != 1 || use_raw || !dump_kernel_available(plan.A, plan.L))
+            return fail(ctx, GAT_ERR_UNSUPPORTED, "replica dump: one period, one channel, FP32 planes, antenna x tap class (1,3) (16,3) (8,5) (4,11)");
+        const size_t n_dump = static_cast<size_t>(args.tiles_per_job) * args.rep_stride;
+        rc = ensure_device(ctx, ctx->d_dbg, ctx->d_dbg_cap, n_dump, false);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg, 0xFF, n_dump * sizeof(int32_t), ctx->stream));
+        args.dump = reinterpret_cast<uint32_t *>(ctx->d_dbg);
+        plan.dump = true;
+        ctx->dump_tiles = args.tiles_per_job;
+        ctx->dump_stride = args.rep_stride;
+        ctx->dump_tile_len = args.tile_len;
+        ctx->dump_aligned_start = args.aligned_start;
+    }
     args.timeline = nullptr;
     if (ctx->timeline_on) {
         rc = ensure_device(ctx, ctx->d_timeline, ctx->timeline_cap, static_cast<size_t>(plan.grid) * 16, false);
@@ -1528,25 +1556,90 @@ int gat_eigen_weights(gat_ctx *ctx, int n_ch, int n_taps, int n_ants, const floa
     return GAT_OK;
 }
 
-int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift, int n_samples, unsigned flags,
-                           int32_t *out)
+// The replica chip-table indices of a correlate call, as the HOT kernel itself computed them: the call is really made
+// (DUMP instantiation of correlate_kernel over an all-zero block of n_ants antennas) and the index of every replica entry
+// it generated -- first tile from scratch, the following ones by the per-tile NCO advance, through whichever wrap branch
+// the launch plan selected -- is read back.  out[l * n_samples + i] = index used for tap l at sample start_sample + i.
+int gat_debug_replica_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, const int32_t *sample_shifts, int n_taps, int n_ants,
+                              int start_sample, int n_samples, unsigned flags, int32_t *out)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (!ch || !out || n_samples < 1 || !(fs_hz > 0.0)) return fail(ctx, GAT_ERR_INVALID, "bad arguments");
-    SatDev sd{};
-    rc = fill_sat(ctx, *ch, fs_hz, sd);
+    if (!ch || !out || !sample_shifts || n_samples < 1 || start_sample < 0 || !(fs_hz > 0.0) || n_taps < 1 || n_taps > GAT_MAX_TAPS ||
+        n_ants < 1 || n_ants > kMaxAnts || static_cast<int64_t>(start_sample) + n_samples > (1 << 26))
+        return fail(ctx, GAT_ERR_INVALID, "bad arguments");
+    const int dbg_slot = 65533;
+    SignalSlot *s = slot_for(ctx, dbg_slot);
+    const int n_total = start_sample + n_samples;
+    const int64_t ld = (static_cast<int64_t>(n_total) + 3) & ~3LL;
+    if (!s->owned && s->re) {
+        rc = free_planes(ctx, *s);
+        if (rc) return rc;
+    }
+    rc = own_slot(ctx, *s, n_total, n_ants, ld);
     if (rc) return rc;
-    rc = ensure_device(ctx, ctx->d_dbg, ctx->d_dbg_cap, static_cast<size_t>(n_samples), false);
+    GAT_CUDA(ctx, cudaMemsetAsync(s->re, 0, 2 * s->cap_floats * sizeof(float), ctx->stream));
+    std::vector<float> acc(2 * static_cast<size_t>(n_taps) * n_ants);
+    const int32_t slot_id = dbg_slot;
+    rc = correlate_impl(ctx, 1, &slot_id, 1, ch, fs_hz, sample_shifts, n_taps, start_sample, n_samples, acc.data(),
+                        acc.data() + acc.size() / 2, 0, (flags & GAT_CODE_PHASE_F64) | kFlagDumpReplica | (flags & GAT_DEBUG_STALL_CONSUMERS));
     if (rc) return rc;
-    // the tile base is taken at the latest tap, exactly as the hot kernel does with shifts[0]
-    const int shift_first = std::min(shift, 0) - 3;
-    cudaError_t e = launch_chip_indices(sd, shift_first, shift, n_samples, kTileCap, (flags & GAT_CODE_PHASE_F64) != 0,
-                                        ctx->d_dbg, ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "chip index launch");
-    ctx->launches += 1;
-    GAT_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_dbg, sizeof(int32_t) * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int32_t> dump(static_cast<size_t>(ctx->dump_tiles) * ctx->dump_stride);
+    GAT_CUDA(ctx, cudaMemcpyAsync(dump.data(), ctx->d_dbg, dump.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < n_taps; ++l) {
+        const int koff = sample_shifts[l] - sample_shifts[0];
+        for (int i = 0; i < n_samples; ++i) {
+            const int rel = start_sample + i - ctx->dump_aligned_start;
+            const int t = rel / ctx->dump_tile_len, tt = rel % ctx->dump_tile_len;
+            out[static_cast<size_t>(l) * n_samples + i] = dump[static_cast<size_t>(t) * ctx->dump_stride + tt + koff];
+        }
+    }
+    return GAT_OK;
+}
+
+int gat_debug_tc_replica_bits(gat_ctx *ctx, int slot, int n_sats, const gat_channel *channels, double fs_hz, const int32_t *sample_shifts,
+                              int n_taps, int start_sample, int n_samples, uint8_t *out)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!channels || !out || !sample_shifts || n_sats < 1 || n_taps < 1 || n_taps > 4 || n_samples < 1 || start_sample < 0)
+        return fail(ctx, GAT_ERR_INVALID, "bad arguments");
+    const SignalSlot *sl = find_slot(ctx, slot);
+    if (!slot_has_signal(sl)) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no signal");
+    std::vector<float> acc(2 * static_cast<size_t>(n_sats) * n_taps * sl->n_ants);
+    const int32_t slot_id = slot;
+    rc = correlate_impl(ctx, 1, &slot_id, n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples, acc.data(),
+                        acc.data() + acc.size() / 2, 0, GAT_TENSOR_TF32 | kFlagDumpReplica);
+    if (rc) return rc;
+    if (ctx->info.tensor != 1) return fail(ctx, GAT_ERR_UNSUPPORTED, "the call did not run on the tensor-core path");
+    const int G = (n_sats + 31) / 32, TJ = ctx->dump_tiles;
+    std::vector<uint32_t> dump(static_cast<size_t>(G) * TJ * 32 * 20);
+    GAT_CUDA(ctx, cudaMemcpyAsync(dump.data(), ctx->d_dbg, dump.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n_sats; ++k)
+        for (int l = 0; l < n_taps; ++l) {
+            const int koff = sample_shifts[l] - sample_shifts[0];
+            for (int i = 0; i < n_samples; ++i) {
+                const int rel = start_sample + i - ctx->dump_aligned_start;
+                const int t = rel / kTileCap, e = rel % kTileCap + koff;
+                const size_t row = ((static_cast<size_t>(k / 32) * TJ + t) * 32 + k % 32) * 20;
+                out[(static_cast<size_t>(k) * n_taps + l) * n_samples + i] = static_cast<uint8_t>((dump[row + (e >> 5)] >> (e & 31)) & 1u);
+            }
+        }
+    return GAT_OK;
+}
+
+// single-tap convenience kept from round 1 (then a look-alike kernel, now the hot kernel's own dump)
+int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift, int n_samples, unsigned flags,
+                           int32_t *out)
+{
+    if (!ctx || !out || n_samples < 1) return GAT_ERR_INVALID;
+    const int32_t shifts[3] = {shift - 1, shift, shift + 1};
+    std::vector<int32_t> all(3 * static_cast<size_t>(n_samples));
+    int rc = gat_debug_replica_indices(ctx, ch, fs_hz, shifts, 3, 1, 0, n_samples, flags, all.data());
+    if (rc) return rc;
+    std::memcpy(out, all.data() + n_samples, sizeof(int32_t) * n_samples);
     return GAT_OK;
 }
 

@@ -241,7 +241,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
 }
 
 // --------------------------------------------------------------------------------------
-// replica phase arithmetic (shared by the hot kernel and the debug chip-index kernel)
+// replica phase arithmetic
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t floormod64(int64_t a, int64_t m)
 {
@@ -259,16 +259,6 @@ __device__ __forceinline__ void nco_tile_base(const SatDev &sd, int64_t u0, uint
     const int64_t base = (int64_t)(tot >> sd.nco_fp);
     frac = (uint64_t)tot & ((1ull << sd.nco_fp) - 1ull);
     bmod = (uint32_t)floormod64(base, sd.code_len);
-}
-// advance the tile base by n samples (n * delta may exceed 64 bits when several tiles are skipped)
-__device__ __forceinline__ void nco_advance(uint64_t delta, int fp, uint32_t lc, uint32_t n, uint64_t &frac, uint32_t &bmod)
-{
-    const unsigned __int128 nf = (unsigned __int128)frac + (unsigned __int128)n * (unsigned __int128)delta;
-    const uint64_t carry = (uint64_t)(nf >> fp);
-    frac = (uint64_t)nf & ((1ull << fp) - 1ull);
-    uint64_t x = (uint64_t)bmod + carry;
-    if (x >= lc) x %= lc;
-    bmod = (uint32_t)x;
 }
 // chip-table index of replica entry u (u = sample offset in the tile + tap offset from the latest tap).
 // host guarantees (tile_len + span + 1) * delta + 2^fp < 2^64, so v = frac + u * delta is exact in 64 bits;
@@ -366,7 +356,10 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
 // --------------------------------------------------------------------------------------
 // SC16: the staged tile holds raw interleaved complex int16 samples (one 32-bit word = I | Q << 16 per
 // sample and antenna, a single plane) instead of two FP32 planes; they are converted in registers.
-template <int A, int L, bool F64, bool SC16>
+// DUMP: debug instantiation that also writes the chip-table index of every replica entry it generates to args.dump --
+// the bit-exactness tests read the HOT kernel's own index arithmetic (tile-to-tile NCO advance, both wrap branches, the
+// Float64 mode), not a look-alike.  Used with one period and one channel.
+template <int A, int L, bool F64, bool SC16, bool DUMP = false>
 __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -618,6 +611,8 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 int rows_per = rows_per_full;                         // (the buffer is padded to 128 entries)
                 if (len != tile_len) rows_per = (rows + gw - 1) / gw;
                 const int row0 = gr * rows_per, row1 = min(rows, row0 + rows_per);
+                [[maybe_unused]] uint32_t *dmp = nullptr;
+                if constexpr (DUMP) dmp = args.dump + (size_t)t * args.rep_stride;
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();   // previous tile's readers are done
                 if constexpr (F64) {
                     const int32_t u0 = n0 + args.shifts[0];
@@ -625,12 +620,22 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                     bmod = (uint32_t)floormod64(b, lc);
                     int r = row0;
                     for (; r + 1 < row1; r += 2) {
-                        const int c0 = tab[rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc)];
-                        const int c1 = tab[rep_index_f64(ratio, cphase, u0 + r * 32 + 32 + lane, b, bmod, lc)];
+                        const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
+                        const uint32_t i1 = rep_index_f64(ratio, cphase, u0 + r * 32 + 32 + lane, b, bmod, lc);
+                        const int c0 = tab[i0];
+                        const int c1 = tab[i1];
                         rep[r * 32 + lane] = chip_to_float(c0);
                         rep[r * 32 + 32 + lane] = chip_to_float(c1);
+                        if constexpr (DUMP) {
+                            dmp[r * 32 + lane] = i0;
+                            dmp[r * 32 + 32 + lane] = i1;
+                        }
                     }
-                    if (r < row1) rep[r * 32 + lane] = chip_to_float(tab[rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc)]);
+                    if (r < row1) {
+                        const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
+                        rep[r * 32 + lane] = chip_to_float(tab[i0]);
+                        if constexpr (DUMP) dmp[r * 32 + lane] = i0;
+                    }
                 } else {
                     if (!have_base) {
                         SatDev tmp;
@@ -657,6 +662,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
                                 c[j] = lds_s8_at(tab_s + min(idx, idx - lc));   // unsigned: idx - lc wraps high when idx < lc
+                                if constexpr (DUMP) dmp[(r + j) * 32 + lane] = min(idx, idx - lc);
                                 v += v32;
                             }
 #pragma unroll
@@ -665,19 +671,26 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                         for (; r < row1; ++r, v += v32, wa += 128u) {
                             const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
                             sts_b32_at(wa, 0x3f800000u | ((uint32_t)lds_s8_at(tab_s + min(idx, idx - lc)) & 0x80000000u));
+                            if constexpr (DUMP) dmp[r * 32 + lane] = min(idx, idx - lc);
                         }
                     } else {
                         for (; r + 3 < row1; r += 4) {
                             int c[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                c[j] = tab[rep_index_nco(v, sh, bmod, lc)];
+                                const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
+                                c[j] = tab[idx];
+                                if constexpr (DUMP) dmp[(r + j) * 32 + lane] = idx;
                                 v += v32;
                             }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) rep[(r + j) * 32 + lane] = chip_to_float(c[j]);
                         }
-                        for (; r < row1; ++r, v += v32) rep[r * 32 + lane] = chip_to_float(tab[rep_index_nco(v, sh, bmod, lc)]);
+                        for (; r < row1; ++r, v += v32) {
+                            const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
+                            rep[r * 32 + lane] = chip_to_float(tab[idx]);
+                            if constexpr (DUMP) dmp[r * 32 + lane] = idx;
+                        }
                     }
                 }
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
@@ -908,6 +921,18 @@ static KernelFn pick_mode(bool f64, bool sc16)
     return f64 ? (KernelFn)correlate_kernel<A, L, true, false> : (KernelFn)correlate_kernel<A, L, false, false>;
 }
 
+// the replica-index dump exists for one shape of every (accumulator class, generation pattern): one antenna per thread,
+// 16 antennas x 3 taps (the headline loop), 8 x 5 and 4 x 11
+static KernelFn pick_dump_kernel(int A, int L, bool f64)
+{
+#define GAT_DUMP_CASE(a, l) \
+    if (A == a && L == l) return f64 ? (KernelFn)correlate_kernel<a, l, true, false, true> : (KernelFn)correlate_kernel<a, l, false, false, true>;
+    GAT_DUMP_CASE(1, 3) GAT_DUMP_CASE(16, 3) GAT_DUMP_CASE(8, 5) GAT_DUMP_CASE(4, 11)
+#undef GAT_DUMP_CASE
+    return nullptr;
+}
+bool dump_kernel_available(int A, int L) { return pick_dump_kernel(A, L, false) != nullptr; }
+
 static KernelFn pick_kernel(int A, int L, bool f64, bool sc16)
 {
 #define GAT_CASE(a, l) \
@@ -935,13 +960,18 @@ cudaError_t configure_kernels()
                 if (!fn) continue;
                 cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 if (e != cudaSuccess) return e;
+                KernelFn dfn = f < 2 ? pick_dump_kernel(A, L, f == 1) : nullptr;
+                if (dfn) {
+                    e = cudaFuncSetAttribute((const void *)dfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                    if (e != cudaSuccess) return e;
+                }
             }
     return cudaSuccess;
 }
 
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream)
 {
-    KernelFn fn = pick_kernel(plan.A, plan.L, plan.f64, plan.sc16);
+    KernelFn fn = plan.dump ? pick_dump_kernel(plan.A, plan.L, plan.f64) : pick_kernel(plan.A, plan.L, plan.f64, plan.sc16);
     if (!fn) return cudaErrorInvalidValue;
     // Cooperative launch: the kernel ends with a grid-wide counting barrier, so all CTAs must be
     // co-resident.  grid <= #SMs with one CTA per SM satisfies that on an idle device; the cooperative
@@ -999,45 +1029,6 @@ cudaError_t launch_flag_wait(unsigned int *local_flags, int world, unsigned int 
 cudaError_t launch_gather_wait(unsigned int *const *, unsigned int *local_flags, int world, unsigned int seq, cudaStream_t stream)
 {
     gather_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, seq);
-    return cudaGetLastError();
-}
-
-// --------------------------------------------------------------------------------------
-// debug: replica chip indices through the very same tile-base / slot arithmetic
-// --------------------------------------------------------------------------------------
-__global__ void chip_index_kernel(const SatDev sd, int shift_first, int shift, int n_samples, int tile_len,
-                                  bool f64, int32_t *out)
-{
-    // walks the tiles exactly like a consumer warp of the hot kernel: base from scratch for the first
-    // tile, nco_advance afterwards, rep_index_* per entry
-    uint64_t frac = 0;
-    uint32_t bmod = 0;
-    const uint32_t lc = (uint32_t)sd.code_len;
-    const int tiles = (n_samples + tile_len - 1) / tile_len;
-    const int koff = shift - shift_first;
-    for (int t = 0; t < tiles; ++t) {
-        const int32_t u0 = t * tile_len + shift_first;
-        int32_t b = 0;
-        if (f64) {
-            b = f64_chip_floor(sd.code_ratio, sd.code_phase, u0);
-            bmod = (uint32_t)floormod64(b, lc);
-        } else if (t == 0) {
-            nco_tile_base(sd, u0, frac, bmod);
-        } else {
-            nco_advance((uint64_t)sd.nco_delta, sd.nco_fp, lc, (uint32_t)tile_len, frac, bmod);
-        }
-        for (int tt = threadIdx.x; tt < tile_len && t * tile_len + tt < n_samples; tt += blockDim.x) {
-            const int u = tt + koff;
-            out[t * tile_len + tt] = f64 ? (int32_t)rep_index_f64(sd.code_ratio, sd.code_phase, u0 + u, b, bmod, lc)
-                                         : (int32_t)rep_index_nco(frac + (uint64_t)u * (uint64_t)sd.nco_delta, sd.nco_fp - 32, bmod, lc);
-        }
-    }
-}
-
-cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples, int tile_len,
-                                bool f64, int32_t *d_out, cudaStream_t stream)
-{
-    chip_index_kernel<<<1, 256, 0, stream>>>(sat, shift_first, shift, n_samples, tile_len, f64, d_out);
     return cudaGetLastError();
 }
 

@@ -454,6 +454,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) correlate_tc_kernel(const __gri
             // the quarter's four warps exchange their replica rows.  The buffer alternates per tile: a warp that runs ahead
             // into tile t + 1 writes the other buffer, and it cannot reach tile t + 2 before everyone has left tile t.
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q4) : "memory");
+            if (args.dump && lane < kTcRepWords) {
+                // debug (gat_debug_tc_replica_bits): this tile's sign-bit rows of the warp's two channels, as the tap rows will read them
+                const int64_t ug = (int64_t)job * TJ + t;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int sat = 8 * q4 + 2 * sub + h;
+                    args.dump[(ug * kTcSats + sat) * kTcRepWords + lane] = rep_t[sat * kTcRepWords + lane];
+                }
+            }
             if (t == t_first) tc_trace(tr_ev, 6, 3 + 8 * seg);
 
             // ---- the signal tile: wait for the TMA, round to TF32, zero what lies outside [0, n_samples) ----

@@ -123,6 +123,7 @@ struct gat_ctx {
     size_t h_out_cap = 0;
     int32_t *d_dbg = nullptr;
     size_t d_dbg_cap = 0;
+    int dump_tiles = 0, dump_stride = 0, dump_tile_len = 0, dump_aligned_start = 0;   // geometry of the last replica-index dump
     unsigned char *d_raw = nullptr;      // raw integer samples awaiting expansion
     size_t d_raw_cap = 0;
     // fused multi-GPU gather

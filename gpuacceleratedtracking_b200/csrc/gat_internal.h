@@ -21,6 +21,7 @@ constexpr int kMaxPeers = 8;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
 constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256) + its back-pressure barrier (264)
 constexpr uint32_t kFlagStallConsumers = 0x100u;   // == GAT_DEBUG_STALL_CONSUMERS (include/gat.h)
+constexpr uint32_t kFlagDumpReplica = 0x200u;      // internal: run the DUMP instantiation (gat_debug_replica_indices)
 
 // One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
 struct SatDev {
@@ -86,6 +87,7 @@ struct alignas(64) CorrArgs {
     unsigned long long gather_off;     // this call's first element inside the slice (gat_gather_set_offset)
     unsigned int *done_counter;        // CTAs that finished their stores (self-cleaning)
     unsigned long long *timeline;      // debug: [grid][16] globaltimer stamps, or nullptr
+    uint32_t *dump;                    // debug (DUMP instantiations): [tiles_per_job][rep_stride] chip-table index of every replica entry
 };
 
 static_assert(sizeof(CorrArgs) <= 4096, "kernel parameter space");
@@ -95,6 +97,7 @@ struct LaunchPlan {
     int L;            // taps (template)
     bool f64;
     bool sc16;        // raw int16 I/Q tiles
+    bool dump;        // replica-index dump instantiation (debug)
     int grid, block;
     size_t smem;
     int RP;           // padded accumulators per role
@@ -122,6 +125,7 @@ struct alignas(64) TcArgs {
     int32_t tiles_per_job, G;
     int64_t total_units;
     int32_t win_ok;              // a tile's replica (tile + tap span + row padding) advances < 32 chips on every channel
+    uint32_t *dump;              // debug: [total_units][32 channels][kTcRepWords] replica sign-bit words of every tile, or nullptr
     int32_t debug;               // GAT_TC_DEBUG bit mask (experiments; results are wrong with 2..128 set): 2 skip MMAs, 16 skip TMA,
                                  // 64 skip replica rows, 128 hand-over skeleton only, 4096 record the hand-over timeline of CTA 0
 };
@@ -131,6 +135,7 @@ cudaError_t launch_correlate_tc(const TcArgs &args, int grid, int jobs, cudaStre
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream);
 cudaError_t configure_kernels();   // opt-in to > 48 KB dynamic smem for every instantiation
 bool kernel_available(int A, int L);
+bool dump_kernel_available(int A, int L);
 
 cudaError_t launch_gather_wait(unsigned int *const *flags_unused, unsigned int *local_flags, int world, unsigned int seq,
                                cudaStream_t stream);
@@ -139,8 +144,6 @@ struct FlagPtrs { unsigned int *p[kMaxPeers]; };
 cudaError_t launch_flag_signal(const FlagPtrs &dst, int world, int my_rank, unsigned int seq, cudaStream_t stream);
 cudaError_t launch_flag_wait(unsigned int *local_flags, int world, unsigned int seq, cudaStream_t stream);
 
-cudaError_t launch_chip_indices(const SatDev &sat, int shift_first, int shift, int n_samples,
-                                int tile_len, bool f64, int32_t *d_out, cudaStream_t stream);
 
 // expand interleaved complex integer samples [n_ants][ld_in][2] into FP32 planes [n_ants][ld_out]
 cudaError_t launch_beamform(const float *acc_re, const float *acc_im, const float *w_re, const float *w_im, float *y_re, float *y_im,

@@ -455,6 +455,32 @@ class Engine:
     def ring_destroy(self):
         self._check(self._lib.gat_ring_destroy(self._h))
 
+    def replica_indices(self, channel: Channel, fs: float, shifts: Sequence[int], n_ants: int, n_samples: int, start_sample: int = 0,
+                        code_phase_f64: bool = False, debug_stall: bool = False) -> np.ndarray:
+        """int32 [n_taps, n_samples]: the chip-table index the HOT kernel used for every (tap, sample) of such a call
+        (include/gat.h gat_debug_replica_indices)."""
+        self.set_codes(channel.system)
+        sh = np.ascontiguousarray(shifts, np.int32)
+        out = np.empty((sh.size, n_samples), np.int32)
+        c = channel.to_c()
+        flags = (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0) | (_lib.GAT_DEBUG_STALL_CONSUMERS if debug_stall else 0)
+        self._check(self._lib.gat_debug_replica_indices(self._h, C.byref(c), fs, sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size, n_ants,
+                                                        start_sample, n_samples, flags, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def tc_replica_bits(self, slot: int, channels: Sequence[Channel], fs: float, shifts: Sequence[int], n_samples: int,
+                        start_sample: int = 0) -> np.ndarray:
+        """uint8 [K, n_taps, n_samples]: the tensor-core kernel's replica sign bits (1 = chip -1) of such a call."""
+        for ch in channels:
+            self.set_codes(ch.system)
+        K = len(channels)
+        arr = (GatChannel * K)(*[ch.to_c() for ch in channels])
+        sh = np.ascontiguousarray(shifts, np.int32)
+        out = np.empty((K, sh.size, n_samples), np.uint8)
+        self._check(self._lib.gat_debug_tc_replica_bits(self._h, slot, K, arr, fs, sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size,
+                                                        start_sample, n_samples, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
     def chip_indices(self, channel: Channel, fs: float, shift: int, n_samples: int, code_phase_f64: bool = False):
         self.set_codes(channel.system)
         out = np.empty(n_samples, np.int32)

@@ -333,10 +333,22 @@ uint64_t gat_kernel_launch_count(gat_ctx *ctx); /* total kernels of ours launche
  * gat_get_timeline syncs and copies [n_ctas x 16] stamps of the LAST launch; returns n_ctas or <0. */
 int gat_set_timeline(gat_ctx *ctx, int enable);
 int gat_get_timeline(gat_ctx *ctx, uint64_t *out, int cap_ctas);
-/* Replica chip indices exactly as the kernel's code path computes them (device kernel),
- * for the bit-exactness tests: out[n_samples] (host), sample i, one tap shift. */
+/* Replica chip-table indices exactly as the HOT kernel computes them, for the bit-exactness tests: the correlate call
+ * is really made (a debug instantiation of the same kernel over an all-zero block of n_ants antennas) and the index of
+ * every replica entry it generated is read back -- the first tile's base from scratch, the following tiles through the
+ * per-tile NCO advance, through whichever wrap branch the launch plan selected, or the Float64 formula with
+ * GAT_CODE_PHASE_F64.  out[l * n_samples + i] = index used for tap l at sample start_sample + i (host memory).
+ * Shapes: (n_ants, n_taps) classes (1, 3) (16, 3) (8..16, 5) (4..16, 11) -- one per accumulator class of the kernel family. */
+int gat_debug_replica_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, const int32_t *sample_shifts,
+                              int n_taps, int n_ants, int start_sample, int n_samples, unsigned flags, int32_t *out);
+/* one tap, one antenna: out[n_samples] */
 int gat_debug_chip_indices(gat_ctx *ctx, const gat_channel *ch, double fs_hz, int shift,
                            int n_samples, unsigned flags, int32_t *out);
+/* The tensor-core kernel's replica SIGN BITS (it keeps no indices): 1 = chip -1.  out[(k * n_taps + l) * n_samples + i]
+ * for channel k, tap l, sample start_sample + i of a gat_correlate call with GAT_TENSOR_TF32 over slot `slot`; both
+ * generators (32-chip window / table lookup per entry; force the latter with the environment variable GAT_TC_NO_WINDOW=1). */
+int gat_debug_tc_replica_bits(gat_ctx *ctx, int slot, int n_sats, const gat_channel *channels, double fs_hz,
+                              const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples, uint8_t *out);
 
 #ifdef __cplusplus
 }
