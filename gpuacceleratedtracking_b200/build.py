@@ -14,13 +14,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libgat.so")
+# GAT_BUILD_TAG / GAT_EXTRA_NVCC_FLAGS: A/B builds of the same sources (e.g. -DGAT_PIPE_MODE=1) into libgat_<tag>.so,
+# selected at run time with GAT_LIB_PATH (scripts/dbg/ab.sh); the default build is untouched
+_TAG = os.environ.get("GAT_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libgat" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["gat_correlate.cu", "gat_correlate_tc.cu", "gat_api.cu", "gat_ring.cu", "gat_mg.cu", "gat_postcorr.cu", "gat_codes.cpp"]
 HEADERS = [os.path.join(CSRC, "gat_internal.h"), os.path.join(CSRC, "gat_ctx.h"), os.path.join(HERE, "..", "include", "gat.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-Wall", "-ccbin", "g++"]
+         "-Xcompiler", "-fPIC,-Wall", "-ccbin", "g++"] + os.environ.get("GAT_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _stale(target: str, deps: list[str]) -> bool:

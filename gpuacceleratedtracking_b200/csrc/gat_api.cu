@@ -101,31 +101,40 @@ struct Shape {
     bool sc16;
     int min_code_len = 1 << 30;
     int n_parts = 1, part_tiles = 0;   // sharded slots (signal ring)
+    int A = 1;                         // antennas per thread (template)
+    int n_taps = 0;                    // the caller's tap count (output layout); L = taps per warp (template), TG * L >= n_taps
+    int TG = 1;
+    bool dump = false;                 // replica-index dump requested (debug instantiations)
 };
 
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
 int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
 {
-    const int L = sh.L, M = sh.M, K = sh.K;
-    // antennas per thread: as many as ~96 accumulator registers allow -- the carrier and the tap loads
-    // are per THREAD, so fewer antennas per thread means more redundant work.  Measured on B200 (batch of
-    // 64 periods, 16 antennas): 11 taps A=4 130 us vs A=2 (19 warps) 150 us; 3 taps x 32 sats A=16
-    // 143 us vs A=8 168 us vs A=4 247 us.  These shapes are issue-bound, not latency-bound.
-    int A = (L <= 3) ? 16 : (L <= 5 ? 8 : 4);
-    A = std::min(A, pow2_ceil(M));
-    A = std::max(1, std::min(A, env_int("GAT_TUNE_A", A)));
+    const int L = sh.L, M = sh.M, K = sh.K, TG = sh.TG;   // L = taps per warp (template), TG warps split the call's taps
+    const int A = sh.A;
     if (!kernel_available(A, L)) return fail(ctx, GAT_ERR_UNSUPPORTED, "no kernel for this (antennas, taps) shape");
     const int AG = (M + A - 1) / A;
-    const int w_cap = max_consumer_warps(A, L);
-    if (AG > w_cap) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
+    // Replica warp (HELP instantiation): with few satellites per CTA and several antenna / tap groups sharing each tile, one
+    // extra warp generates all code replicas and the consumers only read them (gat_correlate.cu).  Needs two ring buffers per
+    // (slice, satellite) group inside the W per-warp buffers, i.e. >= 2 warps per group.
+    bool help = env_int("GAT_TUNE_REPHELPER", 1) != 0 && !sh.sc16 && AG * TG >= 2 && help_kernel_available(A, L, sh.f64, sh.dump);
+    int w_cap = help ? block_threads_help(A, L) / 32 - 2 : max_consumer_warps(A, L);
+    if (help && std::min(K, std::max(1, w_cap / (AG * TG))) > kHelperMaxSats) {
+        help = false;
+        w_cap = max_consumer_warps(A, L);
+    }
+    if (AG * TG > w_cap) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
 
     const int w_target_multi = std::min(w_cap, env_int("GAT_TUNE_WMAX", w_cap));
     const int w_target_single = std::min(w_cap, env_int("GAT_TUNE_W", w_cap == 11 ? 8 : 16));
     const int cache_stride = (sh.max_code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign;
     const size_t smem_budget = 227 * 1024;
-    int S = std::max(1, std::min(K, w_target_multi / AG));
+    const int RW = AG * TG;            // warps per satellite and sample slice
+    int S = std::max(1, std::min(K, w_target_multi / RW));
     S = std::max(1, std::min(S, env_int("GAT_TUNE_S", S)));
-    const int span = sh.shifts[L - 1] - sh.shifts[0];
+    // replica entries a tile needs beyond its own samples (with two tap groups the pad tap may reach one spacing further)
+    int span = sh.shifts[sh.n_taps - 1] - sh.shifts[0];
+    if (TG == 2) span = std::max(span, (sh.shifts[L] - sh.shifts[0]) + (sh.shifts[L - 1] - sh.shifts[0]));
     // every satellite batched on a CTA keeps its chip table in smem: leave room for >= 2 stages,
     // the per-warp code replicas and the flush buffer
     {
@@ -178,24 +187,41 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     stages = std::min(stages, std::min(kMaxStages, env_int("GAT_TUNE_STAGES", 12)));
     stages = std::max(1, static_cast<int>(std::min<int64_t>(stages, std::max<int64_t>(1, total_tiles))));
     // sample slices take whole tiles round-robin, so more slices than stages cannot all be fed
-    int SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
+    int SL = std::max(1, std::min(stages, w_target_single / (S * RW)));
     // few tiles per CTA: let every slice work on every tile instead of taking turns ("split").  Then the slices
     // stride through the tile together, 32 * SL samples per step, so SL is a power of two <= 8 (it divides the
     // 256-sample tile: every warp gets the same number of samples) and is no longer bounded by the stage count.
     const int grid_est = static_cast<int>(std::min<int64_t>(total_tiles, ctx->max_ctas > 0 ? std::min(ctx->n_sm, ctx->max_ctas) : ctx->n_sm));
-    int split_tiles = (w_target_single / (S * AG) > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid_est) ? 1 : 0;
+    int split_tiles = (w_target_single / (S * RW) > 1 && total_tiles < static_cast<int64_t>(2) * SL * grid_est) ? 1 : 0;
     split_tiles = env_int("GAT_TUNE_SPLIT", split_tiles);
     // warps sharing a code replica meet at named barriers 2..15: at most 14 such groups
     if (split_tiles && S > 14) split_tiles = 0;
     if (split_tiles) {
-        int cap = std::min(8, std::min(w_cap, w_target_single) / (S * AG));
+        int cap = std::min(8, std::min(w_cap, w_target_single) / (S * RW));
         SL = 1;
         while (2 * SL <= cap && (tile_len % (64 * SL)) == 0) SL *= 2;
         if (SL == 1) split_tiles = 0;
     }
-    if (!split_tiles) SL = std::max(1, std::min(stages, w_target_single / (S * AG)));
+    if (!split_tiles) SL = std::max(1, std::min(stages, w_target_single / (S * RW)));
     SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
-    const int W = S * AG * SL;
+    if (!split_tiles) {
+        // Whole tiles go round-robin over the slices AND over the ring stages.  The slice count must DIVIDE the stage count:
+        // then a stage is always read by the same slice, and a consumer's parity wait on its `full` barrier can only be one
+        // phase ahead.  Otherwise the stage's previous tile belongs to another slice; if that tile's TMA load is still in
+        // flight when a faster slice comes back to the stage, the parity wait sees the phase before it as "complete", the
+        // slice reads a tile that is not there and releases a stage it never owned -- wrong sums and, once the arrival
+        // counts are off, a dead CTA.  (Found in round 2: 4 or 5 slices over 6 stages hung reliably under back-to-back
+        // launches, and round 1's int16 plan had 8 slices over 12 stages; a protocol simulation reproduces the stale read.)
+        // Either fewer slices (the largest divisor) or a shorter ring (the largest multiple of the slice count): the ring is
+        // shortened only if it stays >= 8 stages deep -- small int16 tiles: 8 slices over 8 stages 170 us against 6 over 12
+        // 195 us; 32 KB FP32 tiles: 3 slices over 6 stages 76 us against 4 over 4 84 us (5 taps x 16 antennas, 64 periods).
+        if (SL > 1 && stages % SL != 0) {
+            if (stages / SL * SL >= 8) stages = stages / SL * SL;
+            else
+                while (SL > 1 && stages % SL != 0) --SL;
+        }
+    }
+    const int W = S * RW * SL;
     if (W > w_cap || S > 32) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: role count exceeds CTA size");
 
 
@@ -209,18 +235,25 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     plan.f64 = sh.f64;
     plan.sc16 = sh.sc16;
     plan.grid = grid;
-    plan.block = 32 * (W + 1);
+    plan.block = 32 * (W + 1 + (help ? 1 : 0));
+    plan.help = help;
+    plan.dump = sh.dump;
+    a.rep_helper = help ? 1 : 0;
     plan.smem = kSmemHeaderBytes + stages * tile_bytes + static_cast<size_t>(W) * (RP + rep_stride) * sizeof(float) +
                 static_cast<size_t>(S) * cache_stride;
     plan.RP = RP;
     plan.jobs = jobs;
 
-    for (int l = 0; l < kMaxTaps; ++l) a.shifts[l] = l < L ? sh.shifts[l] : 0;
-    for (int l = 0; l < kMaxTaps; ++l) a.koff4[l] = l < L ? 4 * (sh.shifts[l] - sh.shifts[0]) : 0;
+    // taps beyond the caller's count (TG * L > n_taps) are computed and dropped by emit_output: one group repeats the last
+    // shift; with two groups the pad tap continues the second group's spacing (the kernel reads group offset + koff4[l])
+    for (int l = 0; l < kMaxTaps; ++l) a.shifts[l] = sh.shifts[std::min(l, sh.n_taps - 1)];
+    for (int l = 0; l <= kMaxTaps; ++l) a.koff4[l] = 4 * (sh.shifts[std::min(l, sh.n_taps - 1)] - sh.shifts[0]);
+    a.span = span;
+    a.TG = TG;
     a.n_periods = sh.P;
     a.n_sats = K;
     a.n_ants = M;
-    a.n_taps = L;
+    a.n_taps = sh.n_taps;
     a.start_sample = sh.start;
     a.n_samples = sh.n;
     a.aligned_start = aligned_start;
@@ -455,11 +488,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         if (shifts[l] < shifts[l - 1]) return fail(ctx, GAT_ERR_INVALID, "sample shifts must be ascending");
     if (static_cast<int64_t>(shifts[n_taps - 1]) - shifts[0] > 4096) return fail(ctx, GAT_ERR_UNSUPPORTED, "tap span > 4096 samples");
 
-    // even tap counts run on the next odd instantiation with the last shift repeated
-    int L = n_taps;
-    if (L > 1 && (L % 2) == 0) ++L;
-    int32_t sh_pad[kMaxTaps];
-    for (int l = 0; l < L; ++l) sh_pad[l] = shifts[std::min(l, n_taps - 1)];
+    const int32_t *sh_pad = shifts;      // (the tensor-core path below reads the caller's taps as they are)
 
     // signal slots
     int M = -1;
@@ -526,9 +555,44 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     // channels
     const size_t n_ch = static_cast<size_t>(n_periods) * n_sats;
     std::vector<SatDev> sats(n_ch);
-    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, sh_pad, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1, use_raw};
+    // Kernel shape.  Antennas per thread: as many as ~96 accumulator registers allow -- the carrier and the tap loads are per
+    // THREAD, so fewer antennas per thread means more redundant work (measured, 64 periods x 16 antennas: 3 taps x 32
+    // satellites A=16 143 us, A=8 168 us, A=4 247 us).  Taps per warp L: the instantiated counts are 1, 3, 5, 7, 9, 11 (and
+    // 4, 6 with 4 antennas); a call with fewer taps than its instantiation repeats the last shift and the extra taps are
+    // dropped when the accumulators are written.  From 8 taps on (4 antennas per thread) the taps are split over TWO warps
+    // ("tap groups"): 2 x 4 x 6 accumulators instead of 88 put the shape into the 19-warp class; the wipe-off is repeated by
+    // both, which costs 23 % more FMAs and wins through occupancy (C4: see DESIGN.md).
+    int A, L, TG = 1;
+    if (n_taps <= 3) {
+        A = 16;
+        L = n_taps == 2 ? 3 : n_taps;
+    } else if (n_taps <= 5) {
+        A = 8;
+        L = 5;
+    } else {
+        A = 4;
+        L = n_taps | 1;
+    }
+    A = std::min(A, pow2_ceil(M));
+    A = std::max(1, std::min(A, env_int("GAT_TUNE_A", A)));
+    if (A == 4 && n_taps >= env_int("GAT_TUNE_TG_MIN_TAPS", 99) && !use_raw) {
+        // the second group's taps must sit at the first group's offsets shifted by one constant (the kernel addresses a
+        // group's taps relative to its first tap): true for the equally spaced sets get_correlator_sample_shifts makes
+        const int Lh = (n_taps + 1) / 2;   // 4, 5, 6
+        bool same = true;
+        for (int l = 0; l < Lh && Lh + l < n_taps; ++l) same = same && (shifts[Lh + l] - shifts[Lh] == shifts[l] - shifts[0]);
+        if (same) {
+            TG = 2;
+            L = Lh;
+        }
+    }
+    Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, shifts, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1, use_raw};
     shape.n_parts = n_parts;
     shape.part_tiles = part_tiles;
+    shape.A = A;
+    shape.TG = TG;
+    shape.n_taps = n_taps;
+    shape.dump = (flags & kFlagDumpReplica) != 0;
     for (size_t i = 0; i < n_ch; ++i) {
         rc = fill_sat(ctx, channels[i], fs_hz, sats[i]);
         if (rc) return rc;
@@ -681,7 +745,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     }
 
     // scratch
-    const size_t roles_rp = static_cast<size_t>(args.S) * args.AG * plan.RP;
+    const size_t roles_rp = static_cast<size_t>(args.S) * args.AG * args.TG * plan.RP;
     rc = ensure_device(ctx, ctx->d_partials, ctx->partials_cap, (static_cast<size_t>(plan.jobs) + plan.grid) * roles_rp, false);
     if (rc) return rc;
     if (!ctx->d_barrier) {
@@ -699,16 +763,16 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     const bool gather = (flags & GAT_GATHER) != 0;
     if (gather) {
         if (!ctx->g_connected) return fail(ctx, GAT_ERR_INVALID, "GAT_GATHER needs gat_gather_create + gat_gather_connect");
-        if (L != n_taps || (flags & GAT_ACCUMULATE)) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_GATHER needs an odd tap count and no GAT_ACCUMULATE");
+        if (flags & GAT_ACCUMULATE) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_GATHER cannot be combined with GAT_ACCUMULATE");
         if (ctx->g_off + n_ch * static_cast<size_t>(n_taps) * M > ctx->g_elems)
             return fail(ctx, GAT_ERR_INVALID, "gather buffer too small for this call (elements + gat_gather_set_offset)");
     }
-    const size_t out_elems = n_ch * n_taps * M;          // caller-visible
-    const size_t out_elems_k = n_ch * static_cast<size_t>(L) * M;  // kernel layout (padded taps)
-    const bool direct = gather || (out_is_device && L == n_taps);
-    // host results without padded taps: the kernel epilogue stores straight into pinned, device-mapped host
-    // memory (posted writes over PCIe), so the call needs no D2H copies -- just the stream synchronisation
-    const bool host_direct = !gather && !out_is_device && L == n_taps;
+    const size_t out_elems = n_ch * n_taps * M;
+    // the kernel writes the caller's [n_ants x n_taps x n_sats x n_periods] layout itself (padded taps are dropped at the
+    // store), to the device pointers given, or -- host results -- straight into pinned, device-mapped host memory (posted
+    // writes over PCIe), so the call needs no D2H copy, just the stream synchronisation
+    const bool direct = gather || out_is_device;
+    const bool host_direct = !direct;
     if (host_direct && 2 * out_elems > ctx->h_out_cap) {
         if (ctx->h_out) {
             GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -737,29 +801,21 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     } else if (direct) {
         args.out_re = out_re;
         args.out_im = out_im;
-    } else if (host_direct) {
+    } else {
         args.out_re = ctx->h_out;
         args.out_im = ctx->h_out + out_elems;
-    } else {
-        rc = ensure_device(ctx, ctx->d_out, ctx->d_out_cap, 2 * out_elems_k, false);
-        if (rc) return rc;
-        args.out_re = ctx->d_out;
-        args.out_im = ctx->d_out + out_elems_k;
-        if (flags & GAT_ACCUMULATE) return fail(ctx, GAT_ERR_UNSUPPORTED, "GAT_ACCUMULATE with an even tap count");
     }
 
     args.dump = nullptr;
-    plan.dump = false;
     if (flags & kFlagDumpReplica) {
         // debug: the DUMP instantiation of the hot kernel records the chip-table index of every replica entry
-        if (n_periods != 1 || n_sats != 1 || use_raw || !dump_kernel_available(plan.A, plan.L))
+        if (n_periods != 1 || n_sats != 1 || use_raw || !(plan.help || dump_kernel_available(plan.A, plan.L)))
             return fail(ctx, GAT_ERR_UNSUPPORTED, "replica dump: one period, one channel, FP32 planes, antenna x tap class (1,3) (16,3) (8,5) (4,11)");
         const size_t n_dump = static_cast<size_t>(args.tiles_per_job) * args.rep_stride;
         rc = ensure_device(ctx, ctx->d_dbg, ctx->d_dbg_cap, n_dump, false);
         if (rc) return rc;
         GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg, 0xFF, n_dump * sizeof(int32_t), ctx->stream));
         args.dump = reinterpret_cast<uint32_t *>(ctx->d_dbg);
-        plan.dump = true;
         ctx->dump_tiles = args.tiles_per_job;
         ctx->dump_stride = args.rep_stride;
         ctx->dump_tile_len = args.tile_len;
@@ -791,26 +847,6 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::memcpy(out_re, ctx->h_out, out_elems * sizeof(float));
         std::memcpy(out_im, ctx->h_out + out_elems, out_elems * sizeof(float));
-    } else if (!direct) {
-        // strip padded taps / move to the caller: rows of L*M floats -> n_taps*M floats per channel
-        const size_t row_k = static_cast<size_t>(L) * M * sizeof(float), row_u = static_cast<size_t>(n_taps) * M * sizeof(float);
-        if (out_is_device) {
-            GAT_CUDA(ctx, cudaMemcpy2DAsync(out_re, row_u, args.out_re, row_k, row_u, n_ch, cudaMemcpyDeviceToDevice, ctx->stream));
-            GAT_CUDA(ctx, cudaMemcpy2DAsync(out_im, row_u, args.out_im, row_k, row_u, n_ch, cudaMemcpyDeviceToDevice, ctx->stream));
-        } else {
-            if (2 * out_elems > ctx->h_out_cap) {
-                if (ctx->h_out) GAT_CUDA(ctx, cudaFreeHost(ctx->h_out));
-                ctx->h_out = nullptr;
-                ctx->h_out_cap = 0;
-                GAT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), 4 * out_elems * sizeof(float), cudaHostAllocMapped));
-                ctx->h_out_cap = 4 * out_elems;
-            }
-            GAT_CUDA(ctx, cudaMemcpy2DAsync(ctx->h_out, row_u, args.out_re, row_k, row_u, n_ch, cudaMemcpyDeviceToHost, ctx->stream));
-            GAT_CUDA(ctx, cudaMemcpy2DAsync(ctx->h_out + out_elems, row_u, args.out_im, row_k, row_u, n_ch, cudaMemcpyDeviceToHost, ctx->stream));
-            GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            std::memcpy(out_re, ctx->h_out, out_elems * sizeof(float));
-            std::memcpy(out_im, ctx->h_out + out_elems, out_elems * sizeof(float));
-        }
     }
     if (ctx->timing) {
         GAT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));

@@ -307,6 +307,84 @@ __device__ __forceinline__ void reduce_scatter(float *v, int lane)
     if constexpr (MASK > 1) reduce_scatter<N / 2, MASK / 2>(v, lane);
 }
 
+// --------------------------------------------------------------------------------------
+// rows [row0, row1) of one tile's code replica: rep[u] = +-1.0f chip under (tile sample 0 + latest tap + u), 32 entries
+// per row.  Called by the consumer warps that share a replica (each its share of the rows) or by the replica warp
+// (all rows).  NCO mode: (frac, bmod) = phase state under entry 0; F64 mode: u0 = absolute index of entry 0.
+// --------------------------------------------------------------------------------------
+template <bool F64, bool DUMP>
+__device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane, int row0, int row1, float *rep, uint32_t rep_s,
+                                                 const int8_t *tab, uint32_t tab_s, uint64_t frac, uint32_t bmod, uint64_t delta, int sh,
+                                                 uint32_t lc, double ratio, double cphase, int32_t u0, [[maybe_unused]] uint32_t *dmp)
+{
+    if constexpr (F64) {
+        const int32_t b = f64_chip_floor(ratio, cphase, u0);
+        bmod = (uint32_t)floormod64(b, lc);
+        int r = row0;
+        for (; r + 1 < row1; r += 2) {
+            const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
+            const uint32_t i1 = rep_index_f64(ratio, cphase, u0 + r * 32 + 32 + lane, b, bmod, lc);
+            const int c0 = tab[i0];
+            const int c1 = tab[i1];
+            rep[r * 32 + lane] = chip_to_float(c0);
+            rep[r * 32 + 32 + lane] = chip_to_float(c1);
+            if constexpr (DUMP) {
+                dmp[r * 32 + lane] = i0;
+                dmp[r * 32 + 32 + lane] = i1;
+            }
+        }
+        if (r < row1) {
+            const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
+            rep[r * 32 + lane] = chip_to_float(tab[i0]);
+            if constexpr (DUMP) dmp[r * 32 + lane] = i0;
+        }
+    } else {
+        uint64_t v = frac + (uint64_t)(uint32_t)(row0 * 32 + lane) * delta;
+        const uint64_t v32 = 32ull * delta;
+        int r = row0;
+        if (args.rep_single_wrap) {
+            // the tile advances the code by less than one period (host-checked): one branch-free wrap per
+            // entry, table and replica addressed through 32-bit shared-memory addresses
+            uint32_t wa = rep_s + 4u * (uint32_t)(row0 * 32 + lane);
+            for (; r + 3 < row1; r += 4, wa += 512u) {   // 4 independent table lookups in flight per lane
+                int c[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
+                    c[j] = lds_s8_at(tab_s + min(idx, idx - lc));   // unsigned: idx - lc wraps high when idx < lc
+                    if constexpr (DUMP) dmp[(r + j) * 32 + lane] = min(idx, idx - lc);
+                    v += v32;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sts_b32_at(wa + 128u * j, 0x3f800000u | ((uint32_t)c[j] & 0x80000000u));
+            }
+            for (; r < row1; ++r, v += v32, wa += 128u) {
+                const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
+                sts_b32_at(wa, 0x3f800000u | ((uint32_t)lds_s8_at(tab_s + min(idx, idx - lc)) & 0x80000000u));
+                if constexpr (DUMP) dmp[r * 32 + lane] = min(idx, idx - lc);
+            }
+        } else {
+            for (; r + 3 < row1; r += 4) {
+                int c[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
+                    c[j] = tab[idx];
+                    if constexpr (DUMP) dmp[(r + j) * 32 + lane] = idx;
+                    v += v32;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rep[(r + j) * 32 + lane] = chip_to_float(c[j]);
+            }
+            for (; r < row1; ++r, v += v32) {
+                const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
+                rep[r * 32 + lane] = chip_to_float(tab[idx]);
+                if constexpr (DUMP) dmp[r * 32 + lane] = idx;
+            }
+        }
+    }
+}
+
 // stream-K ownership: CTA b owns global tiles [b*TT/grid, (b+1)*TT/grid)
 __device__ __forceinline__ int tile_owner(int64_t x, int grid, int64_t total)
 {
@@ -324,7 +402,7 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
     if (e >= R) return;
     const int S = args.S, K = args.n_sats, M = args.n_ants;
     const int p = job / args.G, grp = job % args.G;
-    const int s2 = r % S, ag2 = r / S;
+    const int s2 = r % S, ag2 = (r / S) % args.AG, tg2 = r / (S * args.AG);
     int ml, l, c;
     if constexpr (A >= 2) {
         ml = 2 * ((e >> 2) / L) + (e & 1);
@@ -336,8 +414,9 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
         c = e & 1;
     }
     const int kk = grp * S + s2, m = ag2 * A + ml;
-    if (kk >= K || m >= M) return;
-    const size_t idx = (((size_t)p * K + kk) * L + l) * M + m;
+    l += tg2 * L;                      // tap groups: this role holds taps tg2 * L .. of the call's n_taps
+    if (kk >= K || m >= M || l >= args.n_taps) return;
+    const size_t idx = (((size_t)p * K + kk) * args.n_taps + l) * M + m;
     float *dst = (c ? args.out_im : args.out_re) + idx;
     val *= args.out_scale;             // raw integer tiles: the (power-of-two) sample scale is applied once, here
     if (args.flags & 1u) val += *dst;  // GAT_ACCUMULATE
@@ -359,8 +438,13 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
 // DUMP: debug instantiation that also writes the chip-table index of every replica entry it generates to args.dump --
 // the bit-exactness tests read the HOT kernel's own index arithmetic (tile-to-tile NCO advance, both wrap branches, the
 // Float64 mode), not a look-alike.  Used with one period and one channel.
-template <int A, int L, bool F64, bool SC16, bool DUMP = false>
-__global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
+// HELP: one more warp (index W + 1, the "replica warp") generates the code replica of every tile into a double-buffered ring, one
+// or two tiles ahead of the consumers, which then neither carry the code-NCO state nor meet at named barriers twice per tile.
+// For shapes with few satellites per CTA (one channel per block: 4 consumer warps share a tile, so the per-tile work of a
+// warp -- replica rows, two group barriers, bookkeeping -- was as long as its 8 FMA iterations: ncu source view of C4, only
+// 50 % of the warp samples inside the FMA loop).
+template <int A, int L, bool F64, bool SC16, bool DUMP = false, bool HELP = false>
+__global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int AP = (A >= 2) ? A / 2 : 1;
@@ -370,7 +454,8 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = args.W, S = args.S, AG = args.AG, SL = args.SL, G = args.G;
-    const int NR = S * AG;
+    const int TG = args.TG;                    // tap groups: warps that split the taps of one (satellite, antenna group)
+    const int NR = S * AG * TG;
     const int MP = AG * A;
     const int M = args.n_ants, K = args.n_sats;
     const int stages = args.stages;
@@ -395,7 +480,17 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             mbar_init(&empty_bar[s], (uint32_t)(split ? W : NR));  // one arrival per consumer warp that reads the stage
         }
         mbar_init(code_bar, 1);
-        mbar_init(code_free, (uint32_t)W);
+        mbar_init(code_free, (uint32_t)(W + (HELP ? 1 : 0)));
+        if constexpr (HELP) {
+            // replica ring: two buffers per (slice, satellite) group; full = the replica warp's arrival, empty = one arrival
+            // per consumer warp of the group
+            const int groups = (split ? 1 : SL) * S;
+            const uint32_t readers = (uint32_t)((split ? AG * SL : AG) * TG);
+            for (int i = 0; i < 2 * groups; ++i) {
+                mbar_init(reinterpret_cast<uint64_t *>(smem + kRepBarOff) + i, 1);
+                mbar_init(reinterpret_cast<uint64_t *>(smem + 2 * kRepBarOff) + i, readers);
+            }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // antenna rows that pad M up to AG*A are never written by the copies: keep them zero
@@ -496,18 +591,109 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
         return;
     }
 
+    if constexpr (HELP) {
+        if (warp == W + 1) {
+            // ============================ replica warp ============================
+            // Walks the CTA's tiles in order and writes each tile's code replica for every satellite of the group into the
+            // ring buffer (slice, satellite, tile parity) its consumers will read: (frac, bmod) advance tile by tile, exactly
+            // the arithmetic the consumer warps use when they generate their own rows.
+            const int span = args.span;
+            uint32_t qh = 0, segh = 0;
+            for (int64_t g = r0; g < r1; ++segh) {
+                const int job = (int)(g / TJ);
+                const int t_first = (int)(g - (int64_t)job * TJ);
+                const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
+                const int p = job / G, grp = job % G;
+                uint64_t delta[kHelperMaxSats], frac[kHelperMaxSats], adv_frac[kHelperMaxSats];
+                int64_t nco_start[kHelperMaxSats];
+                uint32_t bmod[kHelperMaxSats], adv_chips[kHelperMaxSats], lc[kHelperMaxSats];
+                int fp[kHelperMaxSats];
+                double ratio[kHelperMaxSats], cphase[kHelperMaxSats];
+                bool act[kHelperMaxSats];
+#pragma unroll
+                for (int s = 0; s < kHelperMaxSats; ++s) {
+                    act[s] = s < S && grp * S + s < K;
+                    delta[s] = frac[s] = adv_frac[s] = 0;
+                    nco_start[s] = 0;
+                    bmod[s] = adv_chips[s] = 0;
+                    lc[s] = 1;
+                    fp[s] = 32;
+                    ratio[s] = cphase[s] = 0.0;
+                    if (act[s]) {
+                        const SatDev *sd = &sats[(size_t)p * K + grp * S + s];
+                        delta[s] = (uint64_t)sd->nco_delta;
+                        nco_start[s] = sd->nco_start;
+                        fp[s] = sd->nco_fp;
+                        lc[s] = (uint32_t)sd->code_len;
+                        ratio[s] = sd->code_ratio;
+                        cphase[s] = sd->code_phase;
+                        if constexpr (!F64) {
+                            const unsigned __int128 adv = (unsigned __int128)(uint32_t)tile_len * (unsigned __int128)delta[s];
+                            adv_frac[s] = (uint64_t)adv & ((1ull << fp[s]) - 1ull);
+                            adv_chips[s] = (uint32_t)((uint64_t)(adv >> fp[s]) % lc[s]);
+                        }
+                    }
+                }
+                mbar_wait(code_bar, segh & 1u);      // this segment's chip tables are in shared memory
+                __syncwarp();
+                if (lane == 0) mbar_arrive(code_free);
+                for (int t = t_first; t < t_last; ++t, ++qh) {
+                    const int ts_rel = t * tile_len;
+                    const int len = min(tile_len, args.aligned_len - ts_rel);
+                    const int n0 = args.aligned_start + ts_rel - args.start_sample;
+                    const int rows = (((len + span + 31) >> 5) + 3) & ~3;          // whole groups of four rows (the buffer is padded)
+                    const uint32_t use = split ? qh : qh / (uint32_t)SL;           // how often this tile's group has been served before
+                    const int slice = split ? 0 : (int)(qh % (uint32_t)SL);
+                    [[maybe_unused]] uint32_t *dmp = nullptr;
+                    if constexpr (DUMP) dmp = args.dump + (size_t)t * args.rep_stride;
+#pragma unroll
+                    for (int s = 0; s < kHelperMaxSats; ++s) {
+                        if (!act[s]) continue;
+                        if constexpr (!F64) {
+                            if (t == t_first) {
+                                SatDev tmp;
+                                tmp.nco_delta = (int64_t)delta[s]; tmp.nco_start = nco_start[s]; tmp.nco_fp = fp[s]; tmp.code_len = (int32_t)lc[s];
+                                nco_tile_base(tmp, (int64_t)n0 + args.shifts[0], frac[s], bmod[s]);
+                            } else {
+                                frac[s] += adv_frac[s];
+                                bmod[s] += adv_chips[s] + (uint32_t)(frac[s] >> fp[s]);
+                                frac[s] &= (1ull << fp[s]) - 1ull;
+                                if (bmod[s] >= lc[s]) bmod[s] -= lc[s];
+                                if (bmod[s] >= lc[s]) bmod[s] -= lc[s];
+                            }
+                        }
+                        const int buf = 2 * (slice * S + s) + (int)(use & 1u);
+                        float *rep = rep_all + (size_t)buf * args.rep_stride;
+                        const int8_t *tab = code_cache + (size_t)s * args.cache_stride;
+                        mbar_wait(reinterpret_cast<uint64_t *>(smem + 2 * kRepBarOff) + buf, ((use >> 1) & 1u) ^ 1u);   // its previous readers are done
+                        gen_replica_rows<F64, DUMP>(args, lane, 0, rows, rep, smem_u32(rep), tab, smem_u32(tab), frac[s], bmod[s], delta[s],
+                                                    fp[s] - 32, lc[s], ratio[s], cphase[s], n0 + args.shifts[0], dmp);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t *>(smem + kRepBarOff) + buf);
+                    }
+                }
+                g += t_last - t_first;
+            }
+            return;
+        }
+    }
+
     // ============================== consumer warps ==============================
     const int role = warp % NR;
-    const int s_idx = role % S, ag = role / S;
+    const int s_idx = role % S, ag = (role / S) % AG, tg = role / (S * AG);
     const int sl = warp / NR;
     const int consumer_threads = 32 * W;
     const int roles_rp = NR * RP;
-    const int span = args.shifts[L - 1] - args.shifts[0];
+    const int span = args.span;
     // warps that work on the same satellite and the same tile share one code replica
-    const int gw = split ? AG * SL : AG;                    // warps per group
+    const int gw = (split ? AG * SL : AG) * TG;             // warps per group
     const int gid = split ? s_idx : sl * S + s_idx;         // group id (< W)
-    const int gr = split ? sl * AG + ag : ag;               // this warp's rank in its group
-    float *rep = rep_all + (size_t)gid * args.rep_stride;
+    const int gr = (split ? sl * AG + ag : ag) * TG + tg;   // this warp's rank in its group
+    // tap group tg holds taps tg * L ..: the host guarantees that their offsets RELATIVE to the group's first tap equal
+    // koff4[0 .. L-1] (equally spaced taps), so the group offset goes into the lane's replica address once per tile and
+    // the loop keeps addressing its taps through uniform registers
+    const uint32_t tg_off = (uint32_t)args.koff4[tg * L];
+    float *rep = rep_all + (size_t)(HELP ? 2 * gid : gid) * args.rep_stride;     // HELP: two ring buffers per group
     const int8_t *tab = code_cache + (size_t)s_idx * args.cache_stride;
     // 32-bit shared-memory addresses of everything the per-tile path touches, derived once (generic pointers make
     // ptxas re-derive the shared window base -- S2R CgaCtaId, LDC ... -- at every use) and pinned in registers
@@ -594,6 +780,11 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             const uint32_t qq = q + (uint32_t)(t - t_first);
             sp = 2 * (int)(qq % (uint32_t)stages) + (int)((qq / (uint32_t)stages) & 1u);
         }
+        [[maybe_unused]] uint32_t use = 0;                 // HELP: how often this warp's group has been served before tile t
+        if constexpr (HELP) {
+            const uint32_t qq = q + (uint32_t)(t - t_first);
+            use = split ? qq : qq / (uint32_t)SL;
+        }
         const bool stamp_first = (q == 0);
         q += (uint32_t)(t_last - t_first);                 // every tile of the segment counts, ours or not
         for (; t < t_last; t += step) {
@@ -602,7 +793,13 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
             const int ts_rel = t * tile_len;
             const int len = min(tile_len, args.aligned_len - ts_rel);
             const int n0 = args.aligned_start + ts_rel - args.start_sample;  // relative index of tile sample 0
-            if (active) {
+            [[maybe_unused]] uint32_t rep_tile_s = rep_s;
+            if constexpr (HELP) {
+                // the replica warp wrote this tile's replica into ring buffer (use & 1) of the group
+                rep_tile_s = rep_s + (use & 1u) * 4u * (uint32_t)args.rep_stride;
+                if (active) mbar_wait_s(smem_u32(smem + kRepBarOff) + 8u * (uint32_t)(2 * gid + (int)(use & 1u)), (use >> 1) & 1u);
+            }
+            if (!HELP && active) {
                 // ---- code replica of this tile, generated while the signal tile is still in flight ----
                 // rep[u] = chip under (tile sample 0 + latest tap + u); tap l of sample tt reads rep[tt + koff[l]]
                 // (the reference writes the same array to global memory, src/algorithms.jl:100-119, :1513-1525)
@@ -614,29 +811,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 [[maybe_unused]] uint32_t *dmp = nullptr;
                 if constexpr (DUMP) dmp = args.dump + (size_t)t * args.rep_stride;
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();   // previous tile's readers are done
-                if constexpr (F64) {
-                    const int32_t u0 = n0 + args.shifts[0];
-                    const int32_t b = f64_chip_floor(ratio, cphase, u0);
-                    bmod = (uint32_t)floormod64(b, lc);
-                    int r = row0;
-                    for (; r + 1 < row1; r += 2) {
-                        const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
-                        const uint32_t i1 = rep_index_f64(ratio, cphase, u0 + r * 32 + 32 + lane, b, bmod, lc);
-                        const int c0 = tab[i0];
-                        const int c1 = tab[i1];
-                        rep[r * 32 + lane] = chip_to_float(c0);
-                        rep[r * 32 + 32 + lane] = chip_to_float(c1);
-                        if constexpr (DUMP) {
-                            dmp[r * 32 + lane] = i0;
-                            dmp[r * 32 + 32 + lane] = i1;
-                        }
-                    }
-                    if (r < row1) {
-                        const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
-                        rep[r * 32 + lane] = chip_to_float(tab[i0]);
-                        if constexpr (DUMP) dmp[r * 32 + lane] = i0;
-                    }
-                } else {
+                if constexpr (!F64) {
                     if (!have_base) {
                         SatDev tmp;
                         tmp.nco_delta = (int64_t)delta; tmp.nco_start = nco_start; tmp.nco_fp = fp; tmp.code_len = (int32_t)lc;
@@ -649,50 +824,9 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                         if (bmod >= lc) bmod -= lc;
                         if (bmod >= lc) bmod -= lc;
                     }
-                    uint64_t v = frac + (uint64_t)(uint32_t)(row0 * 32 + lane) * delta;
-                    const uint64_t v32 = 32ull * delta;
-                    int r = row0;
-                    if (args.rep_single_wrap) {
-                        // the tile advances the code by less than one period (host-checked): one branch-free wrap per
-                        // entry, table and replica addressed through 32-bit shared-memory addresses
-                        uint32_t wa = rep_s + 4u * (uint32_t)(row0 * 32 + lane);
-                        for (; r + 3 < row1; r += 4, wa += 512u) {   // 4 independent table lookups in flight per lane
-                            int c[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
-                                c[j] = lds_s8_at(tab_s + min(idx, idx - lc));   // unsigned: idx - lc wraps high when idx < lc
-                                if constexpr (DUMP) dmp[(r + j) * 32 + lane] = min(idx, idx - lc);
-                                v += v32;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) sts_b32_at(wa + 128u * j, 0x3f800000u | ((uint32_t)c[j] & 0x80000000u));
-                        }
-                        for (; r < row1; ++r, v += v32, wa += 128u) {
-                            const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
-                            sts_b32_at(wa, 0x3f800000u | ((uint32_t)lds_s8_at(tab_s + min(idx, idx - lc)) & 0x80000000u));
-                            if constexpr (DUMP) dmp[r * 32 + lane] = min(idx, idx - lc);
-                        }
-                    } else {
-                        for (; r + 3 < row1; r += 4) {
-                            int c[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
-                                c[j] = tab[idx];
-                                if constexpr (DUMP) dmp[(r + j) * 32 + lane] = idx;
-                                v += v32;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) rep[(r + j) * 32 + lane] = chip_to_float(c[j]);
-                        }
-                        for (; r < row1; ++r, v += v32) {
-                            const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
-                            rep[r * 32 + lane] = chip_to_float(tab[idx]);
-                            if constexpr (DUMP) dmp[r * 32 + lane] = idx;
-                        }
-                    }
                 }
+                gen_replica_rows<F64, DUMP>(args, lane, row0, row1, rep, rep_s, tab, tab_s, frac, bmod, delta, sh, lc, ratio, cphase,
+                                            n0 + args.shifts[0], dmp);
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
             }
             mbar_wait_s(bars_s + 8u * (uint32_t)stage, par);
@@ -710,7 +844,7 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 // the phase step from the kernel arguments in every iteration
                 uint32_t ta_re = tre_s + 4u * (uint32_t)tt0;
                 uint32_t ta_im = ta_re + im_off;
-                uint32_t ra = rep_s + 4u * (uint32_t)tt0;
+                uint32_t ra = rep_tile_s + 4u * (uint32_t)tt0 + tg_off;
                 const uint32_t ta_end = tre_s + 4u * (uint32_t)len;
                 uint32_t astep = 4u * (uint32_t)tt_stride, pstep = ph_step32;
                 asm volatile("" : "+r"(astep), "+r"(pstep));        // opaque: keep them in registers
@@ -783,7 +917,12 @@ __global__ void __launch_bounds__(block_threads_max(A, L), 1) correlate_kernel(c
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_s(bars_s + 8u * (uint32_t)(kMaxStages + stage));
+            if (lane == 0) {
+                mbar_arrive_s(bars_s + 8u * (uint32_t)(kMaxStages + stage));
+                if constexpr (HELP)
+                    if (active) mbar_arrive_s(smem_u32(smem + 2 * kRepBarOff) + 8u * (uint32_t)(2 * gid + (int)(use & 1u)));
+            }
+            if constexpr (HELP) ++use;
             sp += 2 * step;                                  // step <= stages: at most one wrap, which flips the parity
             if (sp >= 2 * stages) sp = (sp - 2 * stages) ^ 1;
         }
@@ -922,16 +1061,30 @@ static KernelFn pick_mode(bool f64, bool sc16)
 }
 
 // the replica-index dump exists for one shape of every (accumulator class, generation pattern): one antenna per thread,
-// 16 antennas x 3 taps (the headline loop), 8 x 5 and 4 x 11
+// 16 antennas x 3 taps (the headline loop), 8 x 5, 4 x 7 and the tap-group shape 4 x 6 (two warps share 11 taps)
 static KernelFn pick_dump_kernel(int A, int L, bool f64)
 {
 #define GAT_DUMP_CASE(a, l) \
     if (A == a && L == l) return f64 ? (KernelFn)correlate_kernel<a, l, true, false, true> : (KernelFn)correlate_kernel<a, l, false, false, true>;
-    GAT_DUMP_CASE(1, 3) GAT_DUMP_CASE(16, 3) GAT_DUMP_CASE(8, 5) GAT_DUMP_CASE(4, 11)
+    GAT_DUMP_CASE(1, 3) GAT_DUMP_CASE(16, 3) GAT_DUMP_CASE(8, 5) GAT_DUMP_CASE(4, 7) GAT_DUMP_CASE(4, 11) GAT_DUMP_CASE(4, 6)
 #undef GAT_DUMP_CASE
     return nullptr;
 }
 bool dump_kernel_available(int A, int L) { return pick_dump_kernel(A, L, false) != nullptr; }
+
+// replica-warp instantiations: the shapes where several antenna (or tap) groups share a tile with few satellites per CTA
+static KernelFn pick_help_kernel(int A, int L, bool f64, bool dump)
+{
+#define GAT_HELP_CASE(a, l)                                                                                                                  \
+    if (A == a && L == l) {                                                                                                                  \
+        if (dump) return f64 ? (KernelFn)correlate_kernel<a, l, true, false, true, true> : (KernelFn)correlate_kernel<a, l, false, false, true, true>; \
+        return f64 ? (KernelFn)correlate_kernel<a, l, true, false, false, true> : (KernelFn)correlate_kernel<a, l, false, false, false, true>;         \
+    }
+    GAT_HELP_CASE(4, 7) GAT_HELP_CASE(4, 9) GAT_HELP_CASE(8, 5)
+#undef GAT_HELP_CASE
+    return nullptr;
+}
+bool help_kernel_available(int A, int L, bool f64, bool dump) { return pick_help_kernel(A, L, f64, dump) != nullptr; }
 
 static KernelFn pick_kernel(int A, int L, bool f64, bool sc16)
 {
@@ -939,6 +1092,7 @@ static KernelFn pick_kernel(int A, int L, bool f64, bool sc16)
     if (A == a && L == l) return pick_mode<a, l>(f64, sc16);
     GAT_CASE(1, 1) GAT_CASE(2, 1) GAT_CASE(4, 1) GAT_CASE(8, 1) GAT_CASE(16, 1)
     GAT_CASE(1, 3) GAT_CASE(2, 3) GAT_CASE(4, 3) GAT_CASE(8, 3) GAT_CASE(16, 3)
+    GAT_CASE(4, 4) GAT_CASE(4, 6)                      // tap-group shapes (many taps split over two warps)
     GAT_CASE(1, 5) GAT_CASE(2, 5) GAT_CASE(4, 5) GAT_CASE(8, 5)
     GAT_CASE(1, 7) GAT_CASE(2, 7) GAT_CASE(4, 7)
     GAT_CASE(1, 9) GAT_CASE(2, 9) GAT_CASE(4, 9)
@@ -952,7 +1106,7 @@ bool kernel_available(int A, int L) { return pick_kernel(A, L, false, false) != 
 cudaError_t configure_kernels()
 {
     static const int As[] = {1, 2, 4, 8, 16};
-    static const int Ls[] = {1, 3, 5, 7, 9, 11};
+    static const int Ls[] = {1, 3, 4, 5, 6, 7, 9, 11};
     for (int A : As)
         for (int L : Ls)
             for (int f = 0; f < 3; ++f) {
@@ -960,18 +1114,21 @@ cudaError_t configure_kernels()
                 if (!fn) continue;
                 cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 if (e != cudaSuccess) return e;
-                KernelFn dfn = f < 2 ? pick_dump_kernel(A, L, f == 1) : nullptr;
-                if (dfn) {
-                    e = cudaFuncSetAttribute((const void *)dfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-                    if (e != cudaSuccess) return e;
-                }
+                KernelFn more[3] = {f < 2 ? pick_dump_kernel(A, L, f == 1) : nullptr, f < 2 ? pick_help_kernel(A, L, f == 1, false) : nullptr,
+                                    f < 2 ? pick_help_kernel(A, L, f == 1, true) : nullptr};
+                for (KernelFn mf : more)
+                    if (mf) {
+                        e = cudaFuncSetAttribute((const void *)mf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                        if (e != cudaSuccess) return e;
+                    }
             }
     return cudaSuccess;
 }
 
 cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaStream_t stream)
 {
-    KernelFn fn = plan.dump ? pick_dump_kernel(plan.A, plan.L, plan.f64) : pick_kernel(plan.A, plan.L, plan.f64, plan.sc16);
+    KernelFn fn = plan.help ? pick_help_kernel(plan.A, plan.L, plan.f64, plan.dump)
+                            : (plan.dump ? pick_dump_kernel(plan.A, plan.L, plan.f64) : pick_kernel(plan.A, plan.L, plan.f64, plan.sc16));
     if (!fn) return cudaErrorInvalidValue;
     // Cooperative launch: the kernel ends with a grid-wide counting barrier, so all CTAs must be
     // co-resident.  grid <= #SMs with one CTA per SM satisfies that on an idle device; the cooperative

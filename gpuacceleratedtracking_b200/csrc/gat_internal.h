@@ -14,12 +14,39 @@ constexpr int kMaxAnts = 32;       // rows per plane that fit the staging ring
 // Two CTA classes: shapes whose accumulators need <= 32 registers run up to 19 consumer warps
 // (+ 1 producer = 640 threads, <= 102 registers/thread); the others 11 (+ 1 = 384 threads, 168 registers).
 constexpr int kMaxConsumerWarps = 19;
-__host__ __device__ constexpr int block_threads_max(int A, int L) { return 2 * A * L <= 32 ? 640 : 384; }
+// Two CTA classes: shapes whose accumulators need <= 48 registers run up to 19 consumer warps (+ 1 producer = 640 threads,
+// <= 102 registers/thread); the others 11 (+ 1 = 384 threads, 168 registers: 12 warps are 3 per scheduler, and a 13th
+// warp would put 4 on one scheduler's 16 K registers = 128 per thread).
+// Many taps (>= 7 with 4 antennas per thread) are split over TWO warps ("tap groups", gat_api.cu make_plan): each holds half
+// the taps of the same 4 antennas (2 x 4 x 6 = 48 accumulators), repeats the cheap wipe-off, and lands in the 19-warp class.
+// Measured before that (64 periods x 16 antennas, one channel, same box): 11 taps 116 us = 0.54 of the HBM roof with 8 warps
+// of 168 registers; a 12-warp / 128-register class took 7 taps 105 -> 82 us but spilled at 9 / 11 taps (11 taps: 187 us;
+// with the chips loaded in two halves 148 us); a software-pipelined sample loop (next sample's loads between this sample's
+// FMAs) was slower as well (128 us at 168 registers): the loop is bound by warps per scheduler, not by a warp's load phase.
+#ifndef GAT_WIDE_MAX_TAPS
+#define GAT_WIDE_MAX_TAPS 0      // experiments: 4-antenna shapes with 7 .. this many taps run 12 consumer warps + 1 at 128 registers
+#endif
+#ifndef GAT_HELP11_THREADS
+#define GAT_HELP11_THREADS 448   // experiments: CTA class of the replica-warp instantiation of the 11-tap shape
+#endif
+__host__ __device__ constexpr int block_threads_max(int A, int L)
+{
+    return 2 * A * L <= 48 ? 640 : ((A == 4 && L >= 7 && L <= GAT_WIDE_MAX_TAPS) ? 416 : 384);
+}
+// HELP instantiations (replica warp, see correlate_kernel): the consumer warps carry no code-NCO state and generate nothing,
+// which lets the many-tap shapes (4 antennas per thread, >= 7 taps) fit 128 registers: 12 consumer warps + producer +
+// replica warp = 448 threads, 3 consumer warps per scheduler.
+__host__ __device__ constexpr int block_threads_help(int A, int L)
+{
+    return (A == 4 && L >= 7) ? (L >= 11 ? GAT_HELP11_THREADS : 448) : block_threads_max(A, L);
+}
+constexpr int kHelperMaxSats = 4;     // satellites per CTA the one replica warp keeps up with
+constexpr int kRepBarOff = 512;       // replica ring barriers in the shared-memory header: full[i] at 512 + 8 i, empty[i] at 1024 + 8 i
 __host__ __device__ constexpr int max_consumer_warps(int A, int L) { return block_threads_max(A, L) / 32 - 1; }
 constexpr int kMaxStages = 16;
 constexpr int kMaxPeers = 8;
 constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to this many bytes
-constexpr int kSmemHeaderBytes = 1024;  // full/empty barriers (0..255), chip-table barrier (256) + its back-pressure barrier (264)
+constexpr int kSmemHeaderBytes = 2048;  // full/empty barriers (0..255), chip-table barrier (256) + its back-pressure barrier (264)
 constexpr uint32_t kFlagStallConsumers = 0x100u;   // == GAT_DEBUG_STALL_CONSUMERS (include/gat.h)
 constexpr uint32_t kFlagDumpReplica = 0x200u;      // internal: run the DUMP instantiation (gat_debug_replica_indices)
 
@@ -57,7 +84,9 @@ struct alignas(64) CorrArgs {
     unsigned int *grid_barrier; // monotonically increasing arrival counter (never reset)
     unsigned int barrier_target;// value the counter reaches when every CTA of THIS launch arrived
     int32_t shifts[kMaxTaps];
-    int32_t koff4[kMaxTaps];           // 4 * (shifts[l] - shifts[0]): byte offset of tap l in the code replica
+    int32_t koff4[kMaxTaps + 1];       // 4 * (shifts[l] - shifts[0]): byte offset of tap l in the code replica (+ 1: tap-group padding)
+    int32_t span;                      // shifts[last] - shifts[0]
+    int32_t TG;                        // tap groups: warps splitting the taps of one (satellite, antenna group); template L = taps per warp
     int32_t tt_stride;                 // samples between two iterations of a lane: 32, or 32 * SL when tiles are split
     int32_t n_periods, n_sats, n_ants, n_taps;
     int32_t start_sample, n_samples;   // integrated range [start, start + n)
@@ -73,6 +102,7 @@ struct alignas(64) CorrArgs {
     int32_t cache_stride;              // bytes per satellite in the smem chip-table cache (multiple of 16)
     int32_t total_tiles;               // jobs * tiles_per_job
     float out_scale;
+    int32_t rep_helper;                // 1: warp W + 1 generates every tile's replicas (HELP instantiation), consumers only read them
     int32_t rep_single_wrap;   // a tile (+ tap span) advances every code by less than one period: branch-free index wrap                   // multiplies every accumulator at emit (1 unless raw integer tiles carry a scale)
     int32_t fin_group;                 // lanes cooperating on one output element in the finalize (pow2 <= 32)
     int32_t split_tiles;               // 1: every slice works on every tile (small problems); 0: whole tiles round-robin
@@ -98,6 +128,7 @@ struct LaunchPlan {
     bool f64;
     bool sc16;        // raw int16 I/Q tiles
     bool dump;        // replica-index dump instantiation (debug)
+    bool help;        // replica-warp instantiation
     int grid, block;
     size_t smem;
     int RP;           // padded accumulators per role
@@ -136,6 +167,7 @@ cudaError_t launch_correlate(const LaunchPlan &plan, const CorrArgs &args, cudaS
 cudaError_t configure_kernels();   // opt-in to > 48 KB dynamic smem for every instantiation
 bool kernel_available(int A, int L);
 bool dump_kernel_available(int A, int L);
+bool help_kernel_available(int A, int L, bool f64, bool dump);
 
 cudaError_t launch_gather_wait(unsigned int *const *flags_unused, unsigned int *local_flags, int world, unsigned int seq,
                                cudaStream_t stream);

@@ -15,7 +15,12 @@ HBM = peaks["hbm_gbs"] * 1e9
 FP32 = 73.0e12          # measured with scripts/microbench/fma_rate.cu (36.5 TFMA/s)
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]
+
+
 def run(name, systems, K, M, L, N, pref, P, reps=30):
+    if ONLY and not any(o in name for o in ONLY):
+        return
     fs = N / 1e-3
     re = torch.randn(P, M, N, device="cuda"); im = torch.randn(P, M, N, device="cuda")
     for p in range(P):
@@ -53,6 +58,11 @@ run("C3 L5 K1 M16 L3 N50000 (single call)", [l5], 1, 16, 3, 50000, 0.5, 1, reps=
 run("C3 batch of 64 periods", [l5], 1, 16, 3, 50000, 0.5, 64)
 run("C4 L1 K1 M16 L11 N50000 (single call)", [l1], 1, 16, 11, 50000, 0.1, 1, reps=100)
 run("C4 batch of 64 periods", [l1], 1, 16, 11, 50000, 0.1, 64)
+run("L7 L1 K1 M16 L7 N50000 batch of 64 periods", [l1], 1, 16, 7, 50000, 0.1, 64)
+run("L5 L1 K1 M16 L5 N50000 batch of 64 periods", [l1], 1, 16, 5, 50000, 0.1, 64)
+run("L9 L1 K1 M16 L9 N50000 batch of 64 periods", [l1], 1, 16, 9, 50000, 0.1, 64)
+run("L7 L1 K1 M4 L7 N262144 batch of 16 periods (reference sweep shape)", [l1], 1, 4, 7, 262144, 0.5, 16)
+run("C4 K8: 8 satellites x 11 taps, batch of 8 periods", [l1], 8, 16, 11, 50000, 0.1, 8)
 run("C5 L1+L5 K32 M16 L3 N50000 (single call, one band block)", [l1, l5], 32, 16, 3, 50000, 0.5, 1, reps=100)
 run("C5 batch of 8 periods", [l1, l5], 32, 16, 3, 50000, 0.5, 8)
 run("264 L1 channels over one block", [l1], 264, 16, 3, 50000, 0.5, 1)

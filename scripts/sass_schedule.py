@@ -1,12 +1,12 @@
 """Static issue schedule of the FFMA2 loop of one correlate_kernel instantiation: decodes the per-instruction
 control word (stall count, yield, scoreboard waits) from the SASS encodings.
     python scripts/sass_schedule.py 16 3 0 [sc16]"""
-import re, subprocess, sys
+import os, re, subprocess, sys
 pos = [a for a in sys.argv[1:] if not a.startswith("--")]
 A, L, F = pos[:3]
 SC = pos[3] if len(pos) > 3 else "0"
 tag = f"Li{A}ELi{L}ELb{F}ELb{SC}E"
-sass = subprocess.run(["cuobjdump", "-sass", "gpuacceleratedtracking_b200/libgat.so"], capture_output=True, text=True).stdout
+sass = subprocess.run(["cuobjdump", "-sass", os.environ.get("GAT_LIB_PATH", "gpuacceleratedtracking_b200/libgat.so")], capture_output=True, text=True).stdout
 lines, on = [], False
 for line in sass.split("\n"):
     if "Function :" in line:

@@ -128,3 +128,39 @@ def test_table_reloads_with_stalled_consumers(gat, orc):
         r = orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase, fs, shifts)
         assert np.abs(got[k] - r).max() <= TOL * np.abs(r[1]).max() + 2e-2
     eng.close()
+
+
+@pytest.mark.parametrize("taps,m,P", [(5, 16, 64), (3, 16, 64), (5, 12, 48), (7, 12, 48), (3, 4, 96)])
+def test_slices_divide_stages_and_back_to_back_launches_survive(gat, orc, taps, m, P, monkeypatch):
+    """Round 2: whole-tile slices must divide the stage count (tests/test_ring_protocol.py has the model).  The shapes below
+    used to plan 4 or 5 slices over 6 stages (or are pushed there with GAT_TUNE_W) and hung under back-to-back launches."""
+    import torch
+    l1 = gat.GPSL1()
+    n, fs = 50000, 5.0e7
+    re = torch.randn(4, m, n, device="cuda")
+    im = torch.randn(4, m, n, device="cuda")
+    shifts = orc.sample_shifts(1.023e6, fs, 0.1, taps)
+    chans_l = [[gat.Channel(l1, 1, 2.0 * p, 1500.0, 0.0)] for p in range(P)]
+    for w in ("", "4", "5", "8", "10"):
+        if w:
+            monkeypatch.setenv("GAT_TUNE_W", w)
+        eng = gat.Engine(0)
+        for b in range(4):
+            eng.bind_signal(b, re[b], im[b])
+        chans = eng.marshal(chans_l)
+        out = (torch.zeros(P, 1, taps, m, device="cuda"), torch.zeros(P, 1, taps, m, device="cuda"))
+        slots = np.array([p % 4 for p in range(P)], np.int32)
+        first = None
+        for i in range(25):                                   # no synchronisation in between
+            eng.correlate_batch(slots, chans, fs, shifts, m, 0, n, out=out)
+            if i == 0:
+                eng.sync()
+                first = (out[0].clone(), out[1].clone())
+        eng.sync()
+        info = eng.launch_info()
+        assert info["stages"] % info["sample_slices"] == 0, info
+        assert torch.equal(out[0], first[0]) and torch.equal(out[1], first[1])
+        got = (out[0] + 1j * out[1]).cpu().numpy()
+        ref = orc.correlate_direct(re[1].cpu().numpy(), im[1].cpu().numpy(), l1.codes[0], 1.023e6, 2.0, 1500.0, 0.0, fs, shifts)
+        assert np.abs(got[1, 0] - ref).max() <= TOL * np.sqrt(n) * 4
+        eng.close()
