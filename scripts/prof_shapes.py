@@ -40,6 +40,12 @@ if which in ("single32", "all"):
     run("single K=32 L=3", 1, 32, 3, 0.5)
 if which in ("c4", "all"):
     run("batch P=64 K=1 L=11", 64, 1, 11, 0.1)
+if which == "l7":
+    run("batch P=64 K=1 L=7 (replica-warp instantiation)", 64, 1, 7, 0.1)
+if which == "l9":
+    run("batch P=64 K=1 L=9 (replica-warp instantiation)", 64, 1, 9, 0.1)
+if which == "l5":
+    run("batch P=64 K=1 L=5", 64, 1, 5, 0.1)
 if which in ("c3", "all"):
     run("batch P=64 K=1 L=3 L5", 64, 1, 3, 0.5, l5)
 if which in ("k32batch", "all"):
