@@ -967,6 +967,8 @@ int gat_destroy(gat_ctx *ctx)
     if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_timeline) cudaFree(ctx->d_timeline);
     if (ctx->d_ing_out) cudaFree(ctx->d_ing_out);
+    for (int b = 0; b < kIngestDepth; ++b)
+        if (ctx->d_ing_stage[b]) cudaFree(ctx->d_ing_stage[b]);
     for (int b = 0; b < kIngestDepth; ++b) {
         if (ctx->ing_ready[b]) cudaEventDestroy(ctx->ing_ready[b]);
         if (ctx->ing_free[b]) cudaEventDestroy(ctx->ing_free[b]);
@@ -1348,20 +1350,70 @@ int gat_ingest_correlate(gat_ctx *ctx, int n_periods, const float *const *h_re, 
     if (rc) return rc;
     float *d_re = ctx->d_ing_out, *d_im = ctx->d_ing_out + out_elems;
     const int n_up = start_sample + n_samples;
+    if (n_ants < 1 || n_ants > kMaxAnts || ld < n_up) return fail(ctx, GAT_ERR_INVALID, "bad signal arguments");
+    // Staging: every ring buffer is ONE allocation holding a chunk's re planes followed by its im planes, and the chunk's
+    // slots are zero-copy views into it.  When the caller's blocks are contiguous too (an array [P][n_ants][ld], the usual
+    // case) a chunk crosses PCIe as two large copies instead of 32 small ones (54 instead of 51.7 GB/s from pinned memory).
+    const int64_t dld = (ld % 4 == 0) ? ld : ((static_cast<int64_t>(n_up) + 3) & ~3LL);
+    const size_t plane = static_cast<size_t>(dld) * n_ants;
+    const size_t need = 2 * static_cast<size_t>(kIngestChunk) * plane;
+    if (need > ctx->ing_stage_cap || ctx->ing_n != n_up || ctx->ing_m != n_ants || ctx->ing_ld != dld) {
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GAT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if (need > ctx->ing_stage_cap) {
+            for (int b = 0; b < kIngestDepth; ++b) {
+                if (ctx->d_ing_stage[b]) GAT_CUDA(ctx, cudaFree(ctx->d_ing_stage[b]));
+                ctx->d_ing_stage[b] = nullptr;
+            }
+            ctx->ing_stage_cap = 0;
+            for (int b = 0; b < kIngestDepth; ++b) GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_ing_stage[b]), need * sizeof(float)));
+            ctx->ing_stage_cap = need;
+        }
+        for (int b = 0; b < kIngestDepth; ++b)
+            for (int i = 0; i < kIngestChunk; ++i) {
+                SignalSlot *s = slot_for(ctx, kIngestSlotBase + b * kIngestChunk + i);
+                rc = release_slot(ctx, *s);
+                if (rc) return rc;
+                s->re = ctx->d_ing_stage[b] + static_cast<size_t>(i) * plane;
+                s->im = ctx->d_ing_stage[b] + (static_cast<size_t>(kIngestChunk) + i) * plane;
+                s->ld = dld;
+                s->n_samples = n_up;
+                s->n_ants = n_ants;
+                s->owned = false;
+                s->planes_valid = true;
+                rc = encode_slot_maps(ctx, *s);
+                if (rc) return rc;
+            }
+        ctx->ing_n = n_up;
+        ctx->ing_m = n_ants;
+        ctx->ing_ld = dld;
+    }
     int32_t slot_ids[kIngestChunk];
     // nothing queued earlier on the ctx stream may still be reading the staging slots
-    GAT_CUDA(ctx, cudaEventRecord(ctx->ing_free[0], ctx->stream));
-    for (int b = 1; b < kIngestDepth; ++b) GAT_CUDA(ctx, cudaEventRecord(ctx->ing_free[b], ctx->stream));
+    for (int b = 0; b < kIngestDepth; ++b) GAT_CUDA(ctx, cudaEventRecord(ctx->ing_free[b], ctx->stream));
+    const size_t host_plane = static_cast<size_t>(ld) * n_ants;
     int chunk = 0;
     for (int p0 = 0; p0 < n_periods; p0 += kIngestChunk, ++chunk) {
         const int b = chunk % kIngestDepth;
         const int cnt = std::min(kIngestChunk, n_periods - p0);
         GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ing_free[b], 0));      // the kernel that read buffer b is done
+        bool contiguous = (dld == ld);
         for (int i = 0; i < cnt; ++i) {
             slot_ids[i] = kIngestSlotBase + b * kIngestChunk + i;
             if (!h_re[p0 + i] || !h_im[p0 + i]) return fail(ctx, GAT_ERR_INVALID, "null signal pointer");
-            rc = upload_planes(ctx, slot_ids[i], h_re[p0 + i], h_im[p0 + i], n_up, n_ants, ld, 0, ctx->copy_stream);
-            if (rc) return rc;
+            contiguous = contiguous && h_re[p0 + i] == h_re[p0] + i * host_plane && h_im[p0 + i] == h_im[p0] + i * host_plane;
+        }
+        float *s_re = ctx->d_ing_stage[b], *s_im = ctx->d_ing_stage[b] + static_cast<size_t>(kIngestChunk) * plane;
+        if (contiguous) {
+            GAT_CUDA(ctx, cudaMemcpyAsync(s_re, h_re[p0], cnt * plane * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+            GAT_CUDA(ctx, cudaMemcpyAsync(s_im, h_im[p0], cnt * plane * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else {
+            for (int i = 0; i < cnt; ++i) {
+                GAT_CUDA(ctx, cudaMemcpy2DAsync(s_re + i * plane, dld * sizeof(float), h_re[p0 + i], static_cast<size_t>(ld) * sizeof(float),
+                                                static_cast<size_t>(n_up) * sizeof(float), n_ants, cudaMemcpyHostToDevice, ctx->copy_stream));
+                GAT_CUDA(ctx, cudaMemcpy2DAsync(s_im + i * plane, dld * sizeof(float), h_im[p0 + i], static_cast<size_t>(ld) * sizeof(float),
+                                                static_cast<size_t>(n_up) * sizeof(float), n_ants, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
         }
         GAT_CUDA(ctx, cudaEventRecord(ctx->ing_ready[b], ctx->copy_stream));
         GAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ing_ready[b], 0));

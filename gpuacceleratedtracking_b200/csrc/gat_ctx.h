@@ -148,6 +148,10 @@ struct gat_ctx {
     cudaEvent_t ing_ready[gat::kIngestDepth] = {}, ing_free[gat::kIngestDepth] = {};
     float *d_ing_out = nullptr;
     size_t ing_out_cap = 0;
+    float *d_ing_stage[gat::kIngestDepth] = {};      // per ring buffer: re planes of a chunk, then its im planes (contiguous)
+    size_t ing_stage_cap = 0;                        // floats per ring buffer
+    int ing_n = 0, ing_m = 0;                        // shape the staging slots are currently bound for
+    int64_t ing_ld = 0;
 };
 
 namespace gat {

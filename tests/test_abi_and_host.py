@@ -243,3 +243,18 @@ def test_c_caller_runs_the_sweep():
     assert r.returncode == 0, r.stderr
     rows = [json.loads(line) for line in r.stdout.splitlines()]
     assert len(rows) == 48 and all(0 < row["resident_call_ns"] < 1e6 for row in rows)   # every shape in real time
+
+
+def test_plot_sweep_tool_writes_the_papers_figure(tmp_path):
+    """scripts/plot_sweep.py (JSONL -> the paper's processing-time-vs-sampling-frequency panels, as hand-written
+    SVG + a Markdown table) on the committed sweep of round 1."""
+    import subprocess
+    import sys
+    import xml.dom.minidom
+    src = os.path.join(ROOT, "profiles", "r01_sweep_reference_shapes.jsonl")
+    svg, md = tmp_path / "sweep.svg", tmp_path / "sweep.md"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "plot_sweep.py"), src, str(svg), str(md)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    doc = xml.dom.minidom.parse(str(svg))
+    assert len(doc.getElementsByTagName("polyline")) >= 3 * 6            # three curves in every panel
+    assert "real time (1 ms)" in svg.read_text() and md.read_text().count("\n") > 40

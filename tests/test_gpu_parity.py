@@ -702,3 +702,38 @@ def test_headline_shape_keeps_its_launch_plan(gat):
     info = eng.launch_info()
     assert info["stages"] >= 6 and info["consumer_warps"] >= 6 and info["tile_len"] == 256 and info["ants_per_thread"] == 16
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,m,n,pad,K", [(40, 4, 6000, 0, 3), (7, 2, 2501, 2, 1), (33, 16, 50000, 0, 1)])
+def test_ingest_correlate_host_batches(gat, orc, P, m, n, pad, K):
+    """gat_ingest_correlate: host blocks in, host accumulators out, chunks pipelined inside the library -- contiguous arrays
+    (two large copies per chunk), a padded / odd leading dimension (row-wise copies), batches that are not a multiple of the
+    chunk, pinned and pageable memory.  Same numbers as resident slots + gat_correlate_batch."""
+    import torch
+    rng = np.random.default_rng(P + m)
+    l1 = gat.GPSL1()
+    fs = n / 1e-3
+    ld = n + pad
+    re = rng.normal(size=(P, m, ld)).astype(np.float32)
+    im = rng.normal(size=(P, m, ld)).astype(np.float32)
+    shifts = orc.sample_shifts(1.023e6, fs, 0.5, 3)
+    chans = [[gat.Channel(l1, 1 + (p + k) % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)), 0.1 * k) for k in range(K)]
+             for p in range(P)]
+    eng = gat.Engine(0)
+    got = eng.ingest_correlate(re, im, chans, fs, shifts, 0, n)
+    assert got.shape == (2, P, K, 3, m)
+    pinned = (torch.from_numpy(re).pin_memory(), torch.from_numpy(im).pin_memory())
+    again = eng.ingest_correlate(pinned[0], pinned[1], chans, fs, shifts, 0, n)
+    assert np.array_equal(got, again)
+    for p in range(P):
+        eng.upload_signal(p, re[p], im[p], n_samples=n)
+    ref = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, 0, n)
+    scale = np.sqrt(n) * 4
+    assert np.abs(got[0] + 1j * got[1] - ref).max() <= 1e-5 * scale        # other launch splits, same sums
+    for p, k in ((0, 0), (P - 1, K - 1)):
+        c = chans[p][k]
+        o = orc.correlate_direct(re[p][:, :n].copy(), im[p][:, :n].copy(), l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
+                                 c.carrier_phase, fs, shifts)
+        assert np.abs(got[0, p, k] + 1j * got[1, p, k] - o).max() <= TOL * scale
+    eng.close()
