@@ -118,8 +118,10 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // extra warp generates all code replicas and the consumers only read them (gat_correlate.cu).  Needs two ring buffers per
     // (slice, satellite) group inside the W per-warp buffers, i.e. >= 2 warps per group.
     bool help = env_int("GAT_TUNE_REPHELPER", 1) != 0 && !sh.sc16 && AG * TG >= 2 && help_kernel_available(A, L, sh.f64, sh.dump);
-    int w_cap = help ? block_threads_help(A, L) / 32 - 2 : max_consumer_warps(A, L);
-    if (help && std::min(K, std::max(1, w_cap / (AG * TG))) > kHelperMaxSats) {
+    // (the register-reallocation class -- 11 taps -- has fixed warp positions: 12 consumer warps, one satellite per CTA)
+    const bool realloc_class = help && help_realloc(A, L);
+    int w_cap = help ? (realloc_class ? kReallocConsumerWarps : block_threads_help(A, L) / 32 - 2) : max_consumer_warps(A, L);
+    if (help && std::min(K, std::max(1, w_cap / (AG * TG))) > (realloc_class ? 1 : kHelperMaxSats)) {
         help = false;
         w_cap = max_consumer_warps(A, L);
     }
@@ -235,7 +237,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     plan.f64 = sh.f64;
     plan.sc16 = sh.sc16;
     plan.grid = grid;
-    plan.block = 32 * (W + 1 + (help ? 1 : 0));
+    plan.block = (help && help_realloc(A, L)) ? 512 : 32 * (W + 1 + (help ? 1 : 0));
     plan.help = help;
     plan.dump = sh.dump;
     a.rep_helper = help ? 1 : 0;

@@ -149,7 +149,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // debug timeline: one thread per role stamps a slot (see gat_get_timeline in include/gat.h)
 #define GAT_STAMP(slot)                                                                        \
     do {                                                                                       \
-        if (args.timeline && lane == 0 && (warp == 0 || warp == W))                            \
+        if (args.timeline && lane == 0 && (warp == 0 || warp == PW))                            \
             args.timeline[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns();                \
     } while (0)
 
@@ -443,8 +443,12 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
 // For shapes with few satellites per CTA (one channel per block: 4 consumer warps share a tile, so the per-tile work of a
 // warp -- replica rows, two group barriers, bookkeeping -- was as long as its 8 FMA iterations: ncu source view of C4, only
 // 50 % of the warp samples inside the FMA loop).
-template <int A, int L, bool F64, bool SC16, bool DUMP = false, bool HELP = false>
-__global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
+// ROLE (register-reallocation class only): the kernel body is instantiated once per warpgroup kind, each copy behind its own
+// setmaxnreg, so that ptxas allocates the consumer code against 160 registers and the producer / replica-warp code against
+// 32 (one copy with a join after the setmaxnreg made every value that lives across it spill).  0 = all roles in one copy.
+enum { kRoleAll = 0, kRoleAux = 1, kRoleConsumer = 2 };
+template <int A, int L, bool F64, bool SC16, bool DUMP, bool HELP, int ROLE>
+__device__ __forceinline__ void correlate_body(const CorrArgs &args)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int AP = (A >= 2) ? A / 2 : 1;
@@ -461,6 +465,10 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
     const int stages = args.stages;
     const int tile_len = args.tile_len;
     const int TJ = args.tiles_per_job;
+    // register-reallocation class (gat_internal.h): fixed warp positions, producer and replica warp in the fourth warpgroup
+    constexpr bool REALLOC = HELP && help_realloc(A, L);
+    constexpr int HS = REALLOC ? 1 : kHelperMaxSats;    // satellites per CTA the replica warp serves
+    const int PW = REALLOC ? kReallocConsumerWarps : W;   // producer warp; the replica warp is PW + 1
 
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxStages;
@@ -473,7 +481,7 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
     float *rep_all = part + (size_t)W * RP;                                           // [W][rep_stride]
     int8_t *code_cache = reinterpret_cast<int8_t *>(rep_all + (size_t)W * args.rep_stride);  // [S][cache_stride]
 
-    GAT_STAMP(warp == W ? 8 : 0);
+    GAT_STAMP(warp == PW ? 8 : 0);
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);                            // producer's expect_tx arrival (+ TMA bytes)
@@ -506,6 +514,12 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
         }
     }
     __syncthreads();
+    if constexpr (ROLE == kRoleAux) {
+        if (warp >= PW + 2) return;                   // two idle warps fill the fourth warpgroup
+    }
+    if constexpr (ROLE == kRoleConsumer) {
+        if (warp >= W) return;                        // plans with fewer than 12 consumer warps
+    }
 
     // small calls carry their TMA descriptors and channel records in the kernel arguments
     const PeriodDev *periods = args.use_inline ? reinterpret_cast<const PeriodDev *>(args.inline_blk) : args.periods;
@@ -516,9 +530,9 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
     const int64_t r1 = (int64_t)(blockIdx.x + 1) * TT / grid;
     uint32_t q = 0;    // running tile counter of this CTA -> ring stage and parity
     uint32_t seg = 0;  // running segment counter -> code_bar parity
-    GAT_STAMP(warp == W ? 9 : 1);
+    GAT_STAMP(warp == PW ? 9 : 1);
 
-    if (warp == W) {
+    if (ROLE != kRoleConsumer && warp == PW) {
         // ============================ producer warp ============================
         // Moves signal tiles (two 2-D TMA loads per tile) and keeps the chip table of every
         // satellite batched on this CTA in shared memory (one bulk copy per table change).
@@ -591,8 +605,8 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
         return;
     }
 
-    if constexpr (HELP) {
-        if (warp == W + 1) {
+    if constexpr (HELP && ROLE != kRoleConsumer) {
+        if (warp == PW + 1) {
             // ============================ replica warp ============================
             // Walks the CTA's tiles in order and writes each tile's code replica for every satellite of the group into the
             // ring buffer (slice, satellite, tile parity) its consumers will read: (frac, bmod) advance tile by tile, exactly
@@ -604,14 +618,14 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
                 const int t_first = (int)(g - (int64_t)job * TJ);
                 const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
                 const int p = job / G, grp = job % G;
-                uint64_t delta[kHelperMaxSats], frac[kHelperMaxSats], adv_frac[kHelperMaxSats];
-                int64_t nco_start[kHelperMaxSats];
-                uint32_t bmod[kHelperMaxSats], adv_chips[kHelperMaxSats], lc[kHelperMaxSats];
-                int fp[kHelperMaxSats];
-                double ratio[kHelperMaxSats], cphase[kHelperMaxSats];
-                bool act[kHelperMaxSats];
+                uint64_t delta[HS], frac[HS], adv_frac[HS];
+                int64_t nco_start[HS];
+                uint32_t bmod[HS], adv_chips[HS], lc[HS];
+                int fp[HS];
+                double ratio[HS], cphase[HS];
+                bool act[HS];
 #pragma unroll
-                for (int s = 0; s < kHelperMaxSats; ++s) {
+                for (int s = 0; s < HS; ++s) {
                     act[s] = s < S && grp * S + s < K;
                     delta[s] = frac[s] = adv_frac[s] = 0;
                     nco_start[s] = 0;
@@ -647,7 +661,7 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
                     [[maybe_unused]] uint32_t *dmp = nullptr;
                     if constexpr (DUMP) dmp = args.dump + (size_t)t * args.rep_stride;
 #pragma unroll
-                    for (int s = 0; s < kHelperMaxSats; ++s) {
+                    for (int s = 0; s < HS; ++s) {
                         if (!act[s]) continue;
                         if constexpr (!F64) {
                             if (t == t_first) {
@@ -679,6 +693,7 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
     }
 
     // ============================== consumer warps ==============================
+    if constexpr (ROLE == kRoleAux) return;
     const int role = warp % NR;
     const int s_idx = role % S, ag = (role / S) % AG, tg = role / (S * AG);
     const int sl = warp / NR;
@@ -1048,6 +1063,23 @@ __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_thread
     GAT_STAMP(6);
 }
 
+template <int A, int L, bool F64, bool SC16, bool DUMP = false, bool HELP = false>
+__global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
+{
+    if constexpr (HELP && help_realloc(A, L)) {
+        // every warp of a warpgroup executes the same setmaxnreg; the consumers' increase waits for the fourth group's decrease
+        if ((threadIdx.x >> 5) >= kReallocConsumerWarps) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kReallocAuxRegs));
+            correlate_body<A, L, F64, SC16, DUMP, HELP, kRoleAux>(args);
+        } else {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kReallocConsumerRegs));
+            correlate_body<A, L, F64, SC16, DUMP, HELP, kRoleConsumer>(args);
+        }
+    } else {
+        correlate_body<A, L, F64, SC16, DUMP, HELP, kRoleAll>(args);
+    }
+}
+
 // --------------------------------------------------------------------------------------
 // instantiation table + launcher
 // --------------------------------------------------------------------------------------
@@ -1066,7 +1098,11 @@ static KernelFn pick_dump_kernel(int A, int L, bool f64)
 {
 #define GAT_DUMP_CASE(a, l) \
     if (A == a && L == l) return f64 ? (KernelFn)correlate_kernel<a, l, true, false, true> : (KernelFn)correlate_kernel<a, l, false, false, true>;
+#ifdef GAT_DEV_ONLY_4_11   // development builds: only the 11-tap instantiations (seconds instead of minutes of ptxas)
+    GAT_DUMP_CASE(4, 11)
+#else
     GAT_DUMP_CASE(1, 3) GAT_DUMP_CASE(16, 3) GAT_DUMP_CASE(8, 5) GAT_DUMP_CASE(4, 7) GAT_DUMP_CASE(4, 11) GAT_DUMP_CASE(4, 6)
+#endif
 #undef GAT_DUMP_CASE
     return nullptr;
 }
@@ -1080,7 +1116,11 @@ static KernelFn pick_help_kernel(int A, int L, bool f64, bool dump)
         if (dump) return f64 ? (KernelFn)correlate_kernel<a, l, true, false, true, true> : (KernelFn)correlate_kernel<a, l, false, false, true, true>; \
         return f64 ? (KernelFn)correlate_kernel<a, l, true, false, false, true> : (KernelFn)correlate_kernel<a, l, false, false, false, true>;         \
     }
-    GAT_HELP_CASE(4, 7) GAT_HELP_CASE(4, 9) GAT_HELP_CASE(8, 5)
+#ifdef GAT_DEV_ONLY_4_11
+    GAT_HELP_CASE(4, 11)
+#else
+    GAT_HELP_CASE(4, 7) GAT_HELP_CASE(4, 9) GAT_HELP_CASE(8, 5) GAT_HELP_CASE(4, 11)
+#endif
 #undef GAT_HELP_CASE
     return nullptr;
 }
@@ -1090,6 +1130,9 @@ static KernelFn pick_kernel(int A, int L, bool f64, bool sc16)
 {
 #define GAT_CASE(a, l) \
     if (A == a && L == l) return pick_mode<a, l>(f64, sc16);
+#ifdef GAT_DEV_ONLY_4_11
+    GAT_CASE(4, 11)
+#else
     GAT_CASE(1, 1) GAT_CASE(2, 1) GAT_CASE(4, 1) GAT_CASE(8, 1) GAT_CASE(16, 1)
     GAT_CASE(1, 3) GAT_CASE(2, 3) GAT_CASE(4, 3) GAT_CASE(8, 3) GAT_CASE(16, 3)
     GAT_CASE(4, 4) GAT_CASE(4, 6)                      // tap-group shapes (many taps split over two warps)
@@ -1097,6 +1140,7 @@ static KernelFn pick_kernel(int A, int L, bool f64, bool sc16)
     GAT_CASE(1, 7) GAT_CASE(2, 7) GAT_CASE(4, 7)
     GAT_CASE(1, 9) GAT_CASE(2, 9) GAT_CASE(4, 9)
     GAT_CASE(1, 11) GAT_CASE(2, 11) GAT_CASE(4, 11)
+#endif
 #undef GAT_CASE
     return nullptr;
 }

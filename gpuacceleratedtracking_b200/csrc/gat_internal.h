@@ -27,8 +27,21 @@ constexpr int kMaxConsumerWarps = 19;
 #define GAT_WIDE_MAX_TAPS 0      // experiments: 4-antenna shapes with 7 .. this many taps run 12 consumer warps + 1 at 128 registers
 #endif
 #ifndef GAT_HELP11_THREADS
-#define GAT_HELP11_THREADS 448   // experiments: CTA class of the replica-warp instantiation of the 11-tap shape
+#define GAT_HELP11_THREADS 512   // CTA class of the replica-warp instantiation of the 11-tap shape (512 = register reallocation)
 #endif
+// Register reallocation (setmaxnreg): a 512-thread CTA launches at 128 registers per thread; the three consumer warpgroups
+// (warps 0..11) then grow to kReallocConsumerRegs while the fourth (producer = warp 12, replica warp = warp 13, two idle
+// warps) shrinks to kReallocAuxRegs: 384 * 152 + 128 * 56 = 65 536 (160 + 32 makes the producer and the replica warp spill).  The 11-tap shape (88 accumulators) thereby runs
+// 3 consumer warps per scheduler without spilling; at a flat 168 registers only 8 warps (2 per scheduler) fit.
+#ifndef GAT_REALLOC_CONSUMER_REGS
+#define GAT_REALLOC_CONSUMER_REGS 152
+#endif
+#ifndef GAT_REALLOC_AUX_REGS
+#define GAT_REALLOC_AUX_REGS 56
+#endif
+constexpr int kReallocConsumerRegs = GAT_REALLOC_CONSUMER_REGS;
+constexpr int kReallocAuxRegs = GAT_REALLOC_AUX_REGS;
+constexpr int kReallocConsumerWarps = 12;
 __host__ __device__ constexpr int block_threads_max(int A, int L)
 {
     return 2 * A * L <= 48 ? 640 : ((A == 4 && L >= 7 && L <= GAT_WIDE_MAX_TAPS) ? 416 : 384);
@@ -40,7 +53,8 @@ __host__ __device__ constexpr int block_threads_help(int A, int L)
 {
     return (A == 4 && L >= 7) ? (L >= 11 ? GAT_HELP11_THREADS : 448) : block_threads_max(A, L);
 }
-constexpr int kHelperMaxSats = 4;     // satellites per CTA the one replica warp keeps up with
+__host__ __device__ constexpr bool help_realloc(int A, int L) { return block_threads_help(A, L) == 512; }
+constexpr int kHelperMaxSats = 4;     // satellites per CTA the one replica warp keeps up with (1 in the reallocation class)
 constexpr int kRepBarOff = 512;       // replica ring barriers in the shared-memory header: full[i] at 512 + 8 i, empty[i] at 1024 + 8 i
 __host__ __device__ constexpr int max_consumer_warps(int A, int L) { return block_threads_max(A, L) / 32 - 1; }
 constexpr int kMaxStages = 16;
