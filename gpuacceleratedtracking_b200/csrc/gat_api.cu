@@ -164,9 +164,14 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     if (tile_len < 32 || tile_len > kTileCap || tile_len % 32) return fail(ctx, GAT_ERR_INVALID, "bad GAT_TUNE_TILE");
     if (sh.n_parts > 1 && (tile_len != kTileCap || aligned_start % kTileCap))
         return fail(ctx, GAT_ERR_UNSUPPORTED, "sharded (ring) slots need start_sample to be a multiple of 256");
-    // per-tile relative NCO phase must fit 64 bits: (tile + span + 1) * delta + 2^fp < 2^64
+    // Reallocation class: a consumer warp works through TWO consecutive tiles per visit (one code replica of 2 * tile + span
+    // entries, one prologue, 16 loop iterations) unless the tiles are split among the slices.  Everything that is sized per
+    // replica uses the longer window.
+    const int visit_max = realloc_class ? std::max(1, std::min(2, env_int("GAT_TUNE_VISIT", 2))) : 1;
+    const int rep_len = visit_max * tile_len;
+    // per-replica relative NCO phase must fit 64 bits: (window + span + 1) * delta + 2^fp < 2^64
     if (!sh.f64) {
-        const long double need = static_cast<long double>(tile_len + span + 160) * static_cast<long double>(sh.max_delta) +
+        const long double need = static_cast<long double>(rep_len + span + 160) * static_cast<long double>(sh.max_delta) +
                                  std::ldexp(1.0L, sh.min_fp);
         if (need >= std::ldexp(1.0L, 64))
             return fail(ctx, GAT_ERR_UNSUPPORTED, "code rate too high for the fixed-point window (code_freq/fs * tile too large)");
@@ -174,10 +179,12 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         const double worst = sh.max_ratio * (static_cast<double>(sh.n) + std::abs(sh.shifts[0]) + std::abs(sh.shifts[L - 1]));
         if (!(worst < 1.0e9)) return fail(ctx, GAT_ERR_UNSUPPORTED, "code phase range exceeds the f64 window arithmetic");
     }
-    const int rep_stride = (tile_len + span + 127) & ~127;   // generated in rows of 32 entries, four rows at a time
-    // (per-warp buffers sized for the most consumer warps this instantiation's CTA can hold)
-    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(w_cap) * (RP + rep_stride) * sizeof(float) +
-                               static_cast<size_t>(S) * cache_stride;
+    const int rep_stride = (rep_len + span + 127) & ~127;   // generated in rows of 32 entries, four rows at a time
+    // (per-warp buffers sized for the most consumer warps this instantiation's CTA can hold; the reallocation class keeps two
+    // replica buffers per (slice, satellite) group, at most three groups)
+    const int rep_bufs_max = realloc_class ? 2 * std::min(3, std::max(1, w_cap / RW)) : w_cap;
+    const size_t fixed_bytes = kSmemHeaderBytes + static_cast<size_t>(w_cap) * RP * sizeof(float) +
+                               static_cast<size_t>(rep_bufs_max) * rep_stride * sizeof(float) + static_cast<size_t>(S) * cache_stride;
 
     const int tiles_per_job = (aligned_len + tile_len - 1) / tile_len;
     const int64_t total_tiles = static_cast<int64_t>(jobs) * tiles_per_job;
@@ -206,7 +213,17 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     }
     if (!split_tiles) SL = std::max(1, std::min(stages, w_target_single / (S * RW)));
     SL = std::max(1, std::min(SL, env_int("GAT_TUNE_SL", SL)));
-    if (!split_tiles) {
+    int visit_tiles = 1;
+    if (realloc_class && !split_tiles) {
+        // one replica warp per slice; tile PAIRS go round-robin over the slices, so a stage stays with its slice when
+        // 2 * SL divides the ring (see below)
+        SL = std::min(SL, 3);
+        if (visit_max == 2 && stages >= 2 * SL) {
+            visit_tiles = 2;
+            stages = stages / (2 * SL) * (2 * SL);
+        }
+    }
+    if (!split_tiles && visit_tiles == 1) {
         // Whole tiles go round-robin over the slices AND over the ring stages.  The slice count must DIVIDE the stage count:
         // then a stage is always read by the same slice, and a consumer's parity wait on its `full` barrier can only be one
         // phase ahead.  Otherwise the stage's previous tile belongs to another slice; if that tile's TMA load is still in
@@ -241,8 +258,12 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     plan.help = help;
     plan.dump = sh.dump;
     a.rep_helper = help ? 1 : 0;
-    plan.smem = kSmemHeaderBytes + stages * tile_bytes + static_cast<size_t>(W) * (RP + rep_stride) * sizeof(float) +
-                static_cast<size_t>(S) * cache_stride;
+    const int rep_bufs = realloc_class ? 2 * (split_tiles ? S : SL * S) : W;
+    plan.smem = kSmemHeaderBytes + stages * tile_bytes + static_cast<size_t>(W) * RP * sizeof(float) +
+                static_cast<size_t>(rep_bufs) * rep_stride * sizeof(float) + static_cast<size_t>(S) * cache_stride;
+    a.rep_bufs = rep_bufs;
+    a.visit_tiles = visit_tiles;
+    a.dump_stride = (tile_len + span + 127) & ~127;
     plan.RP = RP;
     plan.jobs = jobs;
 
@@ -272,7 +293,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     a.part_tiles = sh.part_tiles;
     a.rep_stride = rep_stride;
     // chips advanced across one replica (tile + tap span, + the 32-entry row granularity) < shortest code
-    a.rep_single_wrap = (static_cast<double>(tile_len + span + 160) * sh.max_ratio + 2.0 < static_cast<double>(sh.min_code_len)) ? 1 : 0;
+    a.rep_single_wrap = (static_cast<double>(rep_len + span + 160) * sh.max_ratio + 2.0 < static_cast<double>(sh.min_code_len)) ? 1 : 0;
     a.rep_single_wrap = env_int("GAT_TUNE_REPWRAP", a.rep_single_wrap) ? a.rep_single_wrap : 0;
     a.cache_stride = cache_stride;
     a.total_tiles = static_cast<int32_t>(total_tiles);
@@ -813,13 +834,13 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         // debug: the DUMP instantiation of the hot kernel records the chip-table index of every replica entry
         if (n_periods != 1 || n_sats != 1 || use_raw || !(plan.help || dump_kernel_available(plan.A, plan.L)))
             return fail(ctx, GAT_ERR_UNSUPPORTED, "replica dump: one period, one channel, FP32 planes, antenna x tap class (1,3) (16,3) (8,5) (4,11)");
-        const size_t n_dump = static_cast<size_t>(args.tiles_per_job) * args.rep_stride;
+        const size_t n_dump = static_cast<size_t>(args.tiles_per_job + 1) * args.dump_stride;
         rc = ensure_device(ctx, ctx->d_dbg, ctx->d_dbg_cap, n_dump, false);
         if (rc) return rc;
         GAT_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg, 0xFF, n_dump * sizeof(int32_t), ctx->stream));
         args.dump = reinterpret_cast<uint32_t *>(ctx->d_dbg);
         ctx->dump_tiles = args.tiles_per_job;
-        ctx->dump_stride = args.rep_stride;
+        ctx->dump_stride = args.dump_stride;
         ctx->dump_tile_len = args.tile_len;
         ctx->dump_aligned_start = args.aligned_start;
     }

@@ -210,6 +210,10 @@ __device__ __forceinline__ float lds_f32_at(uint32_t smem_addr)
     return v;
 }
 
+#ifndef GAT_LOOP_UNROLL
+#define GAT_LOOP_UNROLL 1          // A/B builds: unroll factor of the sample loop
+#endif
+constexpr int kLoopUnroll = GAT_LOOP_UNROLL;
 typedef unsigned long long f32x2;  // two packed floats: lo = even antenna, hi = odd antenna
 __device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
@@ -312,10 +316,23 @@ __device__ __forceinline__ void reduce_scatter(float *v, int lane)
 // per row.  Called by the consumer warps that share a replica (each its share of the rows) or by the replica warp
 // (all rows).  NCO mode: (frac, bmod) = phase state under entry 0; F64 mode: u0 = absolute index of entry 0.
 // --------------------------------------------------------------------------------------
+// DUMP layout: [tile][dump_stride] -- entry u of a tile's replica is the chip under (tile sample 0 + latest tap + u).  A visit
+// of two tiles generates ONE replica of 2 * tile_len + span entries: entries below dump_stride belong to the first tile's slot,
+// entries from tile_len on to the second tile's (shifted by tile_len); the overlap is written to both.
+struct DumpDst {
+    uint32_t *p;        // first tile's slot
+    int32_t stride;     // entries per tile slot
+    int32_t second_at;  // first entry that (also) belongs to the second tile's slot; INT_MAX for a one-tile visit
+    __device__ __forceinline__ void put(int u, uint32_t idx) const
+    {
+        if (u < stride) p[u] = idx;
+        if (u >= second_at && u - second_at < stride) p[stride + (u - second_at)] = idx;
+    }
+};
 template <bool F64, bool DUMP>
 __device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane, int row0, int row1, float *rep, uint32_t rep_s,
                                                  const int8_t *tab, uint32_t tab_s, uint64_t frac, uint32_t bmod, uint64_t delta, int sh,
-                                                 uint32_t lc, double ratio, double cphase, int32_t u0, [[maybe_unused]] uint32_t *dmp)
+                                                 uint32_t lc, double ratio, double cphase, int32_t u0, [[maybe_unused]] const DumpDst &dmp)
 {
     if constexpr (F64) {
         const int32_t b = f64_chip_floor(ratio, cphase, u0);
@@ -329,14 +346,14 @@ __device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane,
             rep[r * 32 + lane] = chip_to_float(c0);
             rep[r * 32 + 32 + lane] = chip_to_float(c1);
             if constexpr (DUMP) {
-                dmp[r * 32 + lane] = i0;
-                dmp[r * 32 + 32 + lane] = i1;
+                dmp.put(r * 32 + lane, i0);
+                dmp.put(r * 32 + 32 + lane, i1);
             }
         }
         if (r < row1) {
             const uint32_t i0 = rep_index_f64(ratio, cphase, u0 + r * 32 + lane, b, bmod, lc);
             rep[r * 32 + lane] = chip_to_float(tab[i0]);
-            if constexpr (DUMP) dmp[r * 32 + lane] = i0;
+            if constexpr (DUMP) dmp.put(r * 32 + lane, i0);
         }
     } else {
         uint64_t v = frac + (uint64_t)(uint32_t)(row0 * 32 + lane) * delta;
@@ -352,7 +369,7 @@ __device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane,
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
                     c[j] = lds_s8_at(tab_s + min(idx, idx - lc));   // unsigned: idx - lc wraps high when idx < lc
-                    if constexpr (DUMP) dmp[(r + j) * 32 + lane] = min(idx, idx - lc);
+                    if constexpr (DUMP) dmp.put((r + j) * 32 + lane, min(idx, idx - lc));
                     v += v32;
                 }
 #pragma unroll
@@ -361,7 +378,7 @@ __device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane,
             for (; r < row1; ++r, v += v32, wa += 128u) {
                 const uint32_t idx = bmod + ((uint32_t)(v >> 32) >> sh);
                 sts_b32_at(wa, 0x3f800000u | ((uint32_t)lds_s8_at(tab_s + min(idx, idx - lc)) & 0x80000000u));
-                if constexpr (DUMP) dmp[r * 32 + lane] = min(idx, idx - lc);
+                if constexpr (DUMP) dmp.put(r * 32 + lane, min(idx, idx - lc));
             }
         } else {
             for (; r + 3 < row1; r += 4) {
@@ -370,7 +387,7 @@ __device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane,
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
                     c[j] = tab[idx];
-                    if constexpr (DUMP) dmp[(r + j) * 32 + lane] = idx;
+                    if constexpr (DUMP) dmp.put((r + j) * 32 + lane, idx);
                     v += v32;
                 }
 #pragma unroll
@@ -379,7 +396,7 @@ __device__ __forceinline__ void gen_replica_rows(const CorrArgs &args, int lane,
             for (; r < row1; ++r, v += v32) {
                 const uint32_t idx = rep_index_nco(v, sh, bmod, lc);
                 rep[r * 32 + lane] = chip_to_float(tab[idx]);
-                if constexpr (DUMP) dmp[r * 32 + lane] = idx;
+                if constexpr (DUMP) dmp.put(r * 32 + lane, idx);
             }
         }
     }
@@ -443,6 +460,26 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
 // For shapes with few satellites per CTA (one channel per block: 4 consumer warps share a tile, so the per-tile work of a
 // warp -- replica rows, two group barriers, bookkeeping -- was as long as its 8 FMA iterations: ncu source view of C4, only
 // 50 % of the warp samples inside the FMA loop).
+// Visits (reallocation class): the CTA's tiles q = 0, 1, .. go to the sample slices in runs of V consecutive tiles (V = 1 or 2),
+// run i to slice i % SL; a consumer warp works through a whole run per visit.  A segment (the CTA's share of one job) may
+// cut a run: then each piece is a visit of its own.  first_visit() returns the offset (tiles from the segment's first) of the
+// RUN that holds slice sl's first visit in a segment starting at CTA tile q0 (-1 ... : a run may have begun in the previous
+// segment); the visit itself covers [max(o_run, 0), min(o_run + V, n_seg)), following runs start V * SL tiles apart.
+__device__ __forceinline__ int first_run_offset(uint32_t q0, int sl, int V, int SL)
+{
+    const int PV = V * SL;
+    int o_run = V * sl - (int)(q0 % (uint32_t)PV);
+    if (o_run <= -V) o_run += PV;
+    return o_run;
+}
+// ring stage / parity code (2 * stage + parity) advanced by n <= stages tiles
+__device__ __forceinline__ int sp_advance(int sp, int n, int stages)
+{
+    sp += 2 * n;
+    if (sp >= 2 * stages) sp = (sp - 2 * stages) ^ 1;
+    return sp;
+}
+
 // ROLE (register-reallocation class only): the kernel body is instantiated once per warpgroup kind, each copy behind its own
 // setmaxnreg, so that ptxas allocates the consumer code against 160 registers and the producer / replica-warp code against
 // 32 (one copy with a join after the setmaxnreg made every value that lives across it spill).  0 = all roles in one copy.
@@ -468,7 +505,11 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
     // register-reallocation class (gat_internal.h): fixed warp positions, producer and replica warp in the fourth warpgroup
     constexpr bool REALLOC = HELP && help_realloc(A, L);
     constexpr int HS = REALLOC ? 1 : kHelperMaxSats;    // satellites per CTA the replica warp serves
-    const int PW = REALLOC ? kReallocConsumerWarps : W;   // producer warp; the replica warp is PW + 1
+    const int PW = REALLOC ? kReallocConsumerWarps : W;   // producer warp; the replica warps are PW + 1 ..
+    // replica warps: the reallocation class fills its fourth warpgroup with three of them -- (slice, satellite) group g is
+    // served by replica warp g % NREP.  (One warp for all slices was 87 % busy on the 11-tap shape and the consumers waited
+    // for it: ncu source view, profiles/r03_ncu_c4_one_replica_warp.txt.)
+    constexpr int NREP = REALLOC ? 3 : 1;
 
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxStages;
@@ -478,8 +519,8 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
     float *tiles = reinterpret_cast<float *>(smem + kSmemHeaderBytes);
     const int tile_floats = (SC16 ? 1 : 2) * MP * kTileCap;   // 32-bit words per stage
     float *part = tiles + (size_t)stages * tile_floats;                               // [W][RP]
-    float *rep_all = part + (size_t)W * RP;                                           // [W][rep_stride]
-    int8_t *code_cache = reinterpret_cast<int8_t *>(rep_all + (size_t)W * args.rep_stride);  // [S][cache_stride]
+    float *rep_all = part + (size_t)W * RP;                                           // [rep_bufs][rep_stride]
+    int8_t *code_cache = reinterpret_cast<int8_t *>(rep_all + (size_t)args.rep_bufs * args.rep_stride);  // [S][cache_stride]
 
     GAT_STAMP(warp == PW ? 8 : 0);
     if (tid == 0) {
@@ -488,7 +529,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
             mbar_init(&empty_bar[s], (uint32_t)(split ? W : NR));  // one arrival per consumer warp that reads the stage
         }
         mbar_init(code_bar, 1);
-        mbar_init(code_free, (uint32_t)(W + (HELP ? 1 : 0)));
+        mbar_init(code_free, (uint32_t)(W + (HELP ? NREP : 0)));
         if constexpr (HELP) {
             // replica ring: two buffers per (slice, satellite) group; full = the replica warp's arrival, empty = one arrival
             // per consumer warp of the group
@@ -515,7 +556,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
     }
     __syncthreads();
     if constexpr (ROLE == kRoleAux) {
-        if (warp >= PW + 2) return;                   // two idle warps fill the fourth warpgroup
+        if (warp > PW + NREP) return;                 // (none with three replica warps)
     }
     if constexpr (ROLE == kRoleConsumer) {
         if (warp >= W) return;                        // plans with fewer than 12 consumer warps
@@ -606,13 +647,64 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
     }
 
     if constexpr (HELP && ROLE != kRoleConsumer) {
-        if (warp == PW + 1) {
+        if (warp > PW && warp <= PW + NREP) {
+            [[maybe_unused]] const int rj = warp - PW - 1;
             // ============================ replica warp ============================
             // Walks the CTA's tiles in order and writes each tile's code replica for every satellite of the group into the
             // ring buffer (slice, satellite, tile parity) its consumers will read: (frac, bmod) advance tile by tile, exactly
             // the arithmetic the consumer warps use when they generate their own rows.
             const int span = args.span;
             uint32_t qh = 0, segh = 0;
+            if constexpr (REALLOC) {
+                // One satellite per CTA; replica warp rj serves slice rj (split tiles: warp 0 serves the one group) and walks
+                // exactly the visits its consumers walk: one replica of (tiles of the visit) * tile_len + span entries each.
+                const int V = args.visit_tiles;
+                const bool serve = split ? (rj == 0) : (rj < SL);
+                const int grp_id = split ? 0 : rj;
+                uint32_t use = 0;                    // visits served so far -> ring buffer and phase
+                for (int64_t g = r0; g < r1; ++segh) {
+                    const int job = (int)(g / TJ);
+                    const int t_first = (int)(g - (int64_t)job * TJ);
+                    const int t_last = (int)min((int64_t)TJ, (int64_t)t_first + (r1 - g));
+                    const int p = job / G, grp = job % G;
+                    const int n_seg = t_last - t_first;
+                    const bool act = grp * S < K;
+                    SatDev sd{};
+                    if (act) sd = sats[(size_t)p * K + grp * S];
+                    mbar_wait(code_bar, segh & 1u);      // this segment's chip tables are in shared memory
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(code_free);
+                    if (serve) {
+                        const int stride_o = split ? 1 : V * SL;
+                        int o_run = split ? 0 : first_run_offset(qh, rj, V, SL);
+                        for (; o_run < n_seg; o_run += stride_o, ++use) {
+                            const int o = max(o_run, 0);
+                            const int nt = min(o_run + (split ? 1 : V), n_seg) - o;
+                            if (!act) continue;
+                            const int t = t_first + o;
+                            const int ts_rel = t * tile_len;
+                            const int len = min(nt * tile_len, args.aligned_len - ts_rel);
+                            const int n0 = args.aligned_start + ts_rel - args.start_sample;
+                            const int rows = (((len + span + 31) >> 5) + 3) & ~3;
+                            [[maybe_unused]] DumpDst dmp{nullptr, args.dump_stride, nt == 2 ? tile_len : 0x7fffffff};
+                            if constexpr (DUMP) dmp.p = args.dump + (size_t)t * args.dump_stride;
+                            uint64_t frac = 0;
+                            uint32_t bmod = 0;
+                            if constexpr (!F64) nco_tile_base(sd, (int64_t)n0 + args.shifts[0], frac, bmod);
+                            const int buf = 2 * grp_id + (int)(use & 1u);
+                            float *rep = rep_all + (size_t)buf * args.rep_stride;
+                            mbar_wait(reinterpret_cast<uint64_t *>(smem + 2 * kRepBarOff) + buf, ((use >> 1) & 1u) ^ 1u);   // its previous readers are done
+                            gen_replica_rows<F64, DUMP>(args, lane, 0, rows, rep, smem_u32(rep), code_cache, smem_u32(code_cache), frac, bmod,
+                                                        (uint64_t)sd.nco_delta, sd.nco_fp - 32, (uint32_t)sd.code_len, sd.code_ratio, sd.code_phase,
+                                                        n0 + args.shifts[0], dmp);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t *>(smem + kRepBarOff) + buf);
+                        }
+                    }
+                    qh += (uint32_t)n_seg;
+                    g += n_seg;
+                }
+            } else
             for (int64_t g = r0; g < r1; ++segh) {
                 const int job = (int)(g / TJ);
                 const int t_first = (int)(g - (int64_t)job * TJ);
@@ -658,8 +750,8 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                     const int rows = (((len + span + 31) >> 5) + 3) & ~3;          // whole groups of four rows (the buffer is padded)
                     const uint32_t use = split ? qh : qh / (uint32_t)SL;           // how often this tile's group has been served before
                     const int slice = split ? 0 : (int)(qh % (uint32_t)SL);
-                    [[maybe_unused]] uint32_t *dmp = nullptr;
-                    if constexpr (DUMP) dmp = args.dump + (size_t)t * args.rep_stride;
+                    [[maybe_unused]] DumpDst dmp{nullptr, args.dump_stride, 0x7fffffff};
+                    if constexpr (DUMP) dmp.p = args.dump + (size_t)t * args.dump_stride;
 #pragma unroll
                     for (int s = 0; s < HS; ++s) {
                         if (!act[s]) continue;
@@ -675,6 +767,9 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                                 if (bmod[s] >= lc[s]) bmod[s] -= lc[s];
                                 if (bmod[s] >= lc[s]) bmod[s] -= lc[s];
                             }
+                        }
+                        if constexpr (NREP > 1) {
+                            if ((slice * S + s) % NREP != rj) continue;    // another replica warp's group (the NCO state above still advanced)
                         }
                         const int buf = 2 * (slice * S + s) + (int)(use & 1u);
                         float *rep = rep_all + (size_t)buf * args.rep_stride;
@@ -729,6 +824,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
     const int rows_per_full = gw == 1 ? ((((tile_len + span + 31) >> 5) + 3) & ~3) : (((tile_len + span + 31) >> 5) + gw - 1) / gw;
     const int step = split ? 1 : SL;               // this warp works on every step-th tile of the CTA's sequence
 
+    [[maybe_unused]] uint32_t use_run = 0;   // reallocation class: visits of this warp so far -> replica ring buffer and phase
     for (int64_t g = r0; g < r1; ++seg) {
         const int job = (int)(g / TJ);
         const int t_first = (int)(g - (int64_t)job * TJ);
@@ -786,6 +882,88 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
         __syncwarp();                    // every lane is past the wait before the producer may flip the phase again
         if (lane == 0) mbar_arrive(code_free);
 
+        if constexpr (REALLOC) {
+            // ---- visits: runs of V consecutive tiles per slice (first_run_offset above); one replica, one prologue per visit ----
+            static_assert(!REALLOC || (A >= 2 && !SC16), "reallocation class: packed FP32 tiles");
+            const int V = split ? 1 : args.visit_tiles;
+            const int n_seg = t_last - t_first;
+            const int stride_o = split ? 1 : V * SL;
+            int o_run = split ? 0 : first_run_offset(q, sl, V, SL);
+            int o_prev = max(o_run, 0);
+            int sp = 0;                                        // 2 * ring stage + phase parity of the visit's first tile
+            if (o_run < n_seg) {
+                const uint32_t qq = q + (uint32_t)o_prev;
+                sp = 2 * (int)(qq % (uint32_t)stages) + (int)((qq / (uint32_t)stages) & 1u);
+            }
+            const bool stamp_first = (q == 0);
+            q += (uint32_t)n_seg;
+            const int lane_base = split ? sl * 32 + lane : lane;
+            for (; o_run < n_seg; o_run += stride_o, ++use_run) {
+                const int o = max(o_run, 0);
+                const int nt = min(o_run + V, n_seg) - o;
+                sp = sp_advance(sp, o - o_prev, stages);
+                o_prev = o;
+                const int ts_rel = (t_first + o) * tile_len;
+                const int n0 = args.aligned_start + ts_rel - args.start_sample;  // relative index of the visit's sample 0
+                const uint32_t rbuf = (uint32_t)(2 * gid) + (use_run & 1u);
+                if (active) mbar_wait_s(smem_u32(smem + kRepBarOff) + 8u * rbuf, (use_run >> 1) & 1u);   // the replica warp wrote this visit's replica
+                int tt0 = lane_base;
+                if (n0 + tt0 < 0) tt0 += tt_stride;           // samples staged before start_sample (first tile of a job)
+                uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
+                uint32_t ra = rep_s + (use_run & 1u) * 4u * (uint32_t)args.rep_stride + 4u * (uint32_t)tt0 + tg_off;
+                int spj = sp;
+#pragma unroll 1
+                for (int j = 0; j < nt; ++j) {
+                    const int stage = spj >> 1;
+                    const int len = min(tile_len, args.aligned_len - ts_rel - j * tile_len);
+                    mbar_wait_s(bars_s + 8u * (uint32_t)stage, (uint32_t)spj & 1u);
+                    if (stamp_first && o == 0 && j == 0) GAT_STAMP(2);
+                    if (active) {
+                        // the lane's phase and replica address run on from the first tile of the visit (every lane has done
+                        // its 8 x 32 samples there), only the staged tile changes
+                        const uint32_t tre_s = tile0_s + (uint32_t)stage * tile_bytes;
+                        uint32_t ta_re = tre_s + 4u * (uint32_t)(j == 0 ? tt0 : lane_base);
+                        uint32_t ta_im = ta_re + im_off;
+                        const uint32_t ta_end = tre_s + 4u * (uint32_t)len;
+                        uint32_t astep = 4u * (uint32_t)tt_stride, pstep = ph_step32;
+                        asm volatile("" : "+r"(astep), "+r"(pstep), "+r"(ra), "+r"(ph));        // opaque: keep them in registers
+#pragma unroll 1
+                        for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) {
+                            float cr, ci;
+                            const float x = (float)(int32_t)ph * 1.4629180792671596e-9f;  // 2 pi / 2^32
+                            __sincosf(x, &ci, &cr);
+                            ph += pstep;
+                            float chip[L];
+#pragma unroll
+                            for (int l = 0; l < L; ++l) chip[l] = lds_f32_at(ra + (uint32_t)args.koff4[l]);
+                            const f32x2 CR = pack2(cr, cr), CI = pack2(ci, ci), NCI = pack2(-ci, -ci);
+                            f32x2 X[AP], Y[AP];
+#pragma unroll
+                            for (int a = 0; a < AP; ++a) {
+                                X[a] = pack2(lds_f32_at(ta_re + 4u * (2 * a) * kTileCap), lds_f32_at(ta_re + 4u * (2 * a + 1) * kTileCap));
+                                Y[a] = pack2(lds_f32_at(ta_im + 4u * (2 * a) * kTileCap), lds_f32_at(ta_im + 4u * (2 * a + 1) * kTileCap));
+                            }
+#pragma unroll
+                            for (int a = 0; a < AP; ++a) {
+                                const f32x2 Dre = fma2(Y[a], CI, mul2(X[a], CR));
+                                const f32x2 Dim = fma2(X[a], NCI, mul2(Y[a], CR));
+#pragma unroll
+                                for (int l = 0; l < L; ++l) {
+                                    const f32x2 CH = pack2(chip[l], chip[l]);
+                                    accRe[a][l] = fma2(Dre, CH, accRe[a][l]);
+                                    accIm[a][l] = fma2(Dim, CH, accIm[a][l]);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_s(bars_s + 8u * (uint32_t)(kMaxStages + stage));
+                    spj = sp_advance(spj, 1, stages);
+                }
+                if (lane == 0 && active) mbar_arrive_s(smem_u32(smem + 2 * kRepBarOff) + 8u * rbuf);
+            }
+            g += n_seg;
+        } else {
         // whole tiles go round-robin over the sample slices (tile q of the CTA belongs to slice q % SL); the first
         // one of this segment that is ours, its ring stage and parity: once per segment
         int t = t_first;
@@ -823,8 +1001,8 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                 int rows_per = rows_per_full;                         // (the buffer is padded to 128 entries)
                 if (len != tile_len) rows_per = (rows + gw - 1) / gw;
                 const int row0 = gr * rows_per, row1 = min(rows, row0 + rows_per);
-                [[maybe_unused]] uint32_t *dmp = nullptr;
-                if constexpr (DUMP) dmp = args.dump + (size_t)t * args.rep_stride;
+                [[maybe_unused]] DumpDst dmp{nullptr, args.dump_stride, 0x7fffffff};
+                if constexpr (DUMP) dmp.p = args.dump + (size_t)t * args.dump_stride;
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();   // previous tile's readers are done
                 if constexpr (!F64) {
                     if (!have_base) {
@@ -865,7 +1043,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                 asm volatile("" : "+r"(astep), "+r"(pstep));        // opaque: keep them in registers
                 // (unrolling by two was measured slower on the 11-tap shape: occupancy, not per-warp ILP, is
                 // what hides the MUFU / shared-memory latencies here)
-#pragma unroll 1
+#pragma unroll kLoopUnroll
                 for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) {
                     // ---- carrier replica: exp(j 2 pi phase) ----
                     float cr, ci;
@@ -942,6 +1120,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
             if (sp >= 2 * stages) sp = (sp - 2 * stages) ^ 1;
         }
         g += t_last - t_first;
+        }   // !REALLOC
 
         if (g >= r1) GAT_STAMP(3);
         // ------------------------------ flush this segment ------------------------------

@@ -33,6 +33,9 @@ constexpr int kMaxConsumerWarps = 19;
 // (warps 0..11) then grow to kReallocConsumerRegs while the fourth (producer = warp 12, replica warp = warp 13, two idle
 // warps) shrinks to kReallocAuxRegs: 384 * 152 + 128 * 56 = 65 536 (160 + 32 makes the producer and the replica warp spill).  The 11-tap shape (88 accumulators) thereby runs
 // 3 consumer warps per scheduler without spilling; at a flat 168 registers only 8 warps (2 per scheduler) fit.
+#ifndef GAT_REALLOC_MIN_TAPS
+#define GAT_REALLOC_MIN_TAPS 7   // 4-antenna shapes with at least this many taps use the reallocation class
+#endif
 #ifndef GAT_REALLOC_CONSUMER_REGS
 #define GAT_REALLOC_CONSUMER_REGS 152
 #endif
@@ -51,7 +54,7 @@ __host__ __device__ constexpr int block_threads_max(int A, int L)
 // replica warp = 448 threads, 3 consumer warps per scheduler.
 __host__ __device__ constexpr int block_threads_help(int A, int L)
 {
-    return (A == 4 && L >= 7) ? (L >= 11 ? GAT_HELP11_THREADS : 448) : block_threads_max(A, L);
+    return (A == 4 && L >= 7) ? (L >= GAT_REALLOC_MIN_TAPS ? GAT_HELP11_THREADS : 448) : block_threads_max(A, L);
 }
 __host__ __device__ constexpr bool help_realloc(int A, int L) { return block_threads_help(A, L) == 512; }
 constexpr int kHelperMaxSats = 4;     // satellites per CTA the one replica warp keeps up with (1 in the reallocation class)
@@ -131,7 +134,10 @@ struct alignas(64) CorrArgs {
     unsigned long long gather_off;     // this call's first element inside the slice (gat_gather_set_offset)
     unsigned int *done_counter;        // CTAs that finished their stores (self-cleaning)
     unsigned long long *timeline;      // debug: [grid][16] globaltimer stamps, or nullptr
-    uint32_t *dump;                    // debug (DUMP instantiations): [tiles_per_job][rep_stride] chip-table index of every replica entry
+    uint32_t *dump;                    // debug (DUMP instantiations): [tiles_per_job][dump_stride] chip-table index of every replica entry
+    int32_t dump_stride;               // entries per tile in `dump` (the one-tile replica stride)
+    int32_t rep_bufs;                  // code-replica buffers of rep_stride floats in shared memory (W, or 2 per group with replica warps)
+    int32_t visit_tiles;               // reallocation class: consecutive tiles a consumer warp works through per visit (1 or 2)
 };
 
 static_assert(sizeof(CorrArgs) <= 4096, "kernel parameter space");

@@ -737,3 +737,41 @@ def test_ingest_correlate_host_batches(gat, orc, P, m, n, pad, K):
                                  c.carrier_phase, fs, shifts)
         assert np.abs(got[0, p, k] + 1j * got[1, p, k] - o).max() <= TOL * scale
     eng.close()
+
+
+@pytest.mark.parametrize("m,n,start,P,cap,mode", [(16, 6300, 0, 5, 7, "nco"), (16, 6300, 5, 3, 3, "f64"), (12, 9001, 2, 4, 5, "nco"),
+                                                  (8, 50000, 0, 3, 148, "nco"), (16, 2049, 0, 9, 2, "nco"), (16, 520, 1, 6, 1, "nco")])
+def test_eleven_tap_visits_of_two_tiles(gat, orc, m, n, start, P, cap, mode):
+    """The 11-tap class (register reallocation, three replica warps) walks its tiles in visits of two: batches whose jobs
+    hold an ODD number of tiles on few CTAs cut the pairs at segment boundaries (single-tile visits, a pair whose halves belong
+    to two segments), offsets stage samples before start_sample, 12 / 8 antennas change the warp roles."""
+    eng = gat.Engine(0)
+    eng.set_max_ctas(cap)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(n + m)
+    fs = n / 1e-3
+    shifts = (np.arange(11, dtype=np.int32) - 5) * 2
+    blocks, chans = [], []
+    for p in range(P):
+        re = rng.normal(size=(m, start + n + 3)).astype(np.float32)
+        im = rng.normal(size=(m, start + n + 3)).astype(np.float32)
+        eng.upload_signal(p, re, im)
+        blocks.append((re, im))
+        chans.append([gat.Channel(l1, int(rng.integers(1, 33)), float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)),
+                                  float(rng.uniform(-0.5, 0.5)))])
+    got = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, start, n, code_phase_f64=(mode == "f64"))
+    info = eng.launch_info()
+    assert info["block"] == 512 and info["grid"] <= cap
+    for p in range(P):
+        c = chans[p][0]
+        ref = orc.correlate_direct(*blocks[p], l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase, fs,
+                                   shifts, start_sample=start, n_samples=n, code_mode=mode)
+        assert np.abs(got[p, 0] - ref).max() <= 2e-5 * 3 * np.sqrt(n) + 1e-3, (p, np.abs(got[p, 0] - ref).max())
+    # the same batch with one-tile visits gives the same sums up to FP32 summation order of the carrier phase steps
+    os.environ["GAT_TUNE_VISIT"] = "1"
+    try:
+        got1 = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, start, n, code_phase_f64=(mode == "f64"))
+    finally:
+        del os.environ["GAT_TUNE_VISIT"]
+    assert np.abs(got1 - got).max() <= 1e-5 * 3 * np.sqrt(n) + 1e-3
+    eng.close()

@@ -115,3 +115,22 @@ def test_tensor_kernel_sign_bits(gat, orc, sysname, fs, window, monkeypatch):
             want = (system.codes[c.prn - 1][idx] < 0).astype(np.uint8)
             assert np.array_equal(bits[k], want), (sysname, fs, window, k, np.argwhere(bits[k] != want)[:3])
     eng.close()
+
+
+@pytest.mark.parametrize("mode", ["nco", "f64"])
+@pytest.mark.parametrize("cap", [1, 3, 5])
+def test_hot_kernel_indices_two_tile_visits(gat, orc, mode, cap):
+    """The 11-tap class generates ONE replica per visit of two tiles (three replica warps, one per sample slice).  Few CTAs
+    make every CTA walk many tiles, so the dump comes from pair visits, from the single-tile visits at an odd end and from
+    a start offset that stages samples before the range."""
+    l1 = gat.GPSL1()
+    shifts = [-25, -20, -15, -10, -5, 0, 5, 10, 15, 20, 25]
+    eng = gat.Engine(0)
+    eng.set_max_ctas(cap)
+    for fs, start, n in ((50e6, 0, 50000), (50e6, 5, 6300 - 5), (6e6, 3, 3333), (50e6, 0, 300)):
+        for cp in (0.0, 1022.6):
+            got = eng.replica_indices(gat.Channel(l1, 4, cp, 1000.0, 0.0), fs, shifts, 16, n, start_sample=start,
+                                      code_phase_f64=(mode == "f64"))
+            want = _oracle(orc, l1, fs, cp, shifts, n, mode)
+            assert np.array_equal(got, want), (fs, start, n, cp, mode, cap, np.argwhere(got != want)[:3])
+    eng.close()
