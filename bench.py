@@ -761,9 +761,29 @@ def _leg_single_call(eng, g, l1, shifts, dev, torch):
         eng.correlate_batch(slot, ch, FS, shifts, N_ANTS, 0, N_SAMPLES, out=out)
     b.record()
     torch.cuda.synchronize()
-    return {"single_call": {"sync_call_us_min": min(ts) * 1e6, "sync_call_us_median": float(np.median(ts)) * 1e6,
-                            "back_to_back_us": a.elapsed_time(b) / 300 * 1e3, "hbm_roofline_us": 8 * N_SAMPLES * N_ANTS / 6548.8e3,
-                            "note": "one gat_correlate_batch over one 50 000 x 16 block through the Python mirror, + gat_sync"}}
+    res = {"sync_call_us_min": min(ts) * 1e6, "sync_call_us_median": float(np.median(ts)) * 1e6,
+           "back_to_back_us": a.elapsed_time(b) / 300 * 1e3, "hbm_roofline_us": 8 * N_SAMPLES * N_ANTS / 6548.8e3,
+           "note": "one gat_correlate_batch over one 50 000 x 16 block through the Python mirror, + gat_sync; resident_* = the same "
+                   "synchronous call inside a resident session (gat_resident_correlate: the kernel stays on the device, no launch), "
+                   "host results included"}
+    # the same call inside a resident session (include/gat.h gat_resident_*)
+    from gpuacceleratedtracking_b200 import _lib
+    c1 = g.Channel(l1, 1, 0.0, DOPPLER, 0.0)
+    arr = (_lib.GatChannel * 1)(c1.to_c())
+    eng.resident_begin([20000], [c1], FS, shifts, N_ANTS, 0, N_SAMPLES)
+    try:
+        for _ in range(50):
+            eng.resident_correlate(0, arr)
+        rts = []
+        for _ in range(300):
+            t0 = time.perf_counter()
+            eng.resident_correlate(0, arr)
+            rts.append(time.perf_counter() - t0)
+        res["resident_call_us_min"] = min(rts) * 1e6
+        res["resident_call_us_median"] = float(np.median(rts)) * 1e6
+    finally:
+        eng.resident_end()
+    return {"single_call": res}
 
 
 def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
@@ -900,6 +920,8 @@ def run_sweep(args):
     and L5 N = 2^15..2^18, PRN 1, 1500 Hz.  Estimator: minimum of one whole call including the synchronisation
     (paper/paper.tex:150, src/benchmarks.jl:872).  Fields:
       GPU_sync_ns    gat_correlate_batch (device-resident signal and outputs) + gat_sync, host wall clock
+      GPU_resident_ns  the same synchronous call inside a resident session (gat_resident_correlate: the kernel stays on the
+                     device, accumulators land in host memory; 0 where the class has no resident instantiation)
       GPU_device_ns  device time per call over back-to-back launches (CUDA events)
       CPU_ns         the oracle's port of Tracking.downconvert_and_correlate!, one thread, timed inside C
                      (the cpu_baseline leg of this file; Julia is not available here)"""
@@ -955,13 +977,34 @@ def run_sweep(args):
         b.record()
         torch.cuda.synchronize()
         dev = a.elapsed_time(b) / reps * 1e-3
+        res_best = 0.0
+        try:
+            from gpuacceleratedtracking_b200 import _lib
+            c1 = g.Channel(system, 1, 0.0, DOPPLER, 0.0)
+            arr = (_lib.GatChannel * 1)(c1.to_c())
+            eng.resident_begin([0], [c1], fs, shifts, M, 0, N)
+            try:
+                for _ in range(20):
+                    acc = eng.resident_correlate(0, arr)
+                assert abs(float(acc[0, L // 2, 0].real) - N) < 1e-3 * N
+                res_best = 1e9
+                for _ in range(reps):
+                    t0 = time.perf_counter()
+                    eng.resident_correlate(0, arr)
+                    res_best = min(res_best, time.perf_counter() - t0)
+            finally:
+                eng.resident_end()
+        except g.GatError as e:
+            if e.status != _lib.GAT_ERR_UNSUPPORTED:
+                raise
         re, im = eng.download_signal(0, N, M)
         cpu_reps = max(5, min(200, int(0.2 / max(1e-6, 1.5e-9 * N * M * L))))
         cpu_ns, r = oracle.time_tracking(re, im, system.codes[0], system.code_frequency, 0.0, DOPPLER, 0.0, fs, shifts,
                                          reps=cpu_reps, native=native)
         assert abs(r[L // 2, 0].real - N) < 1e-3 * N
         print(json.dumps({"system": name, "num_samples": N, "num_ants": M, "num_correlators": L, "sampling_frequency_hz": fs,
-                          "GPU_sync_ns": round(best * 1e9), "GPU_device_ns": round(dev * 1e9), "CPU_ns": round(cpu_ns),
+                          "GPU_sync_ns": round(best * 1e9), "GPU_resident_ns": round(res_best * 1e9), "GPU_device_ns": round(dev * 1e9),
+                          "CPU_ns": round(cpu_ns),
                           "realtime": best < 1e-3, "cmacs_per_s_gpu_sync": round(N * M * L / best)}), flush=True)
 
     l1, l5 = g.GPSL1(), g.GPSL5()

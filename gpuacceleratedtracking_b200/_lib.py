@@ -102,6 +102,9 @@ SYMBOLS = {
     "gat_ring_prefetch": (_i, [_vp, _i, _i, _i, _i]),
     "gat_ring_mirror_wait": (_i, [_vp, _i]),
     "gat_ring_destroy": (_i, [_vp]),
+    "gat_resident_begin": (_i, [_vp, _i32p, _i, _i, _chp, _d, _i32p, _i, _i, _i]),
+    "gat_resident_correlate": (_i, [_vp, _i, _chp, _vp, _vp]),
+    "gat_resident_end": (_i, [_vp]),
     "gat_mg_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_i)]),
     "gat_mg_destroy": (_i, [_vp]),
     "gat_mg_last_error": (C.c_char_p, [_vp]),

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("GAT_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libgat" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["gat_correlate.cu", "gat_correlate_tc.cu", "gat_api.cu", "gat_ring.cu", "gat_mg.cu", "gat_postcorr.cu", "gat_codes.cpp"]
+SOURCES = ["gat_correlate.cu", "gat_resident.cu", "gat_correlate_tc.cu", "gat_api.cu", "gat_ring.cu", "gat_mg.cu", "gat_postcorr.cu", "gat_codes.cpp"]
 HEADERS = [os.path.join(CSRC, "gat_internal.h"), os.path.join(CSRC, "gat_ctx.h"), os.path.join(HERE, "..", "include", "gat.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -36,7 +36,9 @@ def _stale(target: str, deps: list[str]) -> bool:
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
     path = os.path.join(CSRC, src)
-    if _stale(obj, [path] + HEADERS):
+    # gat_resident.cu includes gat_correlate.cu (the kernel body is shared)
+    extra = [os.path.join(CSRC, "gat_correlate.cu")] if src == "gat_resident.cu" else []
+    if _stale(obj, [path] + HEADERS + extra):
         cmd = [NVCC, *FLAGS, "-c", path, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -3,6 +3,9 @@
 // gat_correlate.cu.  No CPU fallback exists: every entry point needs a live sm_100 device.
 #include <new>
 
+#include <atomic>
+#include <cstdio>
+#include <chrono>
 #include "gat_ctx.h"
 
 using namespace gat;
@@ -502,6 +505,8 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (!slots || !channels || !shifts || ((!out_re || !out_im) && !(flags & GAT_GATHER)))
         return fail(ctx, GAT_ERR_INVALID, "null pointer argument");
     if (n_periods < 1 || n_sats < 1) return fail(ctx, GAT_ERR_INVALID, "n_periods and n_sats must be >= 1");
+    if (ctx->res.active)
+        return fail(ctx, GAT_ERR_INVALID, "a resident session owns the device (gat_resident_correlate / gat_resident_end)");
     if (n_taps < 1 || n_taps > GAT_MAX_TAPS) return fail(ctx, GAT_ERR_UNSUPPORTED, "n_taps must be 1..11");
     if (!(fs_hz > 0.0) || !std::isfinite(fs_hz)) return fail(ctx, GAT_ERR_INVALID, "sampling frequency must be positive");
     if (start_sample < 0 || n_samples < 1) return fail(ctx, GAT_ERR_INVALID, "empty or negative sample range");
@@ -852,6 +857,14 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
         args.timeline = ctx->d_timeline;
         ctx->timeline_ctas = plan.grid;
     }
+    if (flags & kFlagResidentPlan) {
+        // gat_resident_begin: everything is validated, planned and marshalled -- the launch is the resident kernel's
+        if (use_raw || sharded || plan.dump) return fail(ctx, GAT_ERR_UNSUPPORTED, "resident sessions run on FP32 planes of plain slots");
+        ctx->res.plan = plan;
+        ctx->res.args = args;
+        ctx->res.n_ants = M;
+        return GAT_OK;
+    }
     if (ctx->timing) GAT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e;
     {
@@ -996,6 +1009,7 @@ int gat_destroy(gat_ctx *ctx)
         if (ctx->ing_ready[b]) cudaEventDestroy(ctx->ing_ready[b]);
         if (ctx->ing_free[b]) cudaEventDestroy(ctx->ing_free[b]);
     }
+    gat_resident_end(ctx);
     gat_gather_destroy(ctx);
     gat_ring_destroy(ctx);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1329,6 +1343,259 @@ int gat_correlate_batch(gat_ctx *ctx, int n_periods, const int32_t *slots, int n
 {
     return correlate_impl(ctx, n_periods, slots, n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples,
                           out_re, out_im, out_is_device, flags);
+}
+
+// ------------------------------------------------------------------------------------------
+// resident sessions (gat_resident.cu): one call + synchronisation per block without a kernel launch
+// ------------------------------------------------------------------------------------------
+namespace {
+
+int resident_launch(gat_ctx *ctx, uint32_t first_seq)
+{
+    Resident &r = ctx->res;
+    // the relay cells may hold the exit notice of an earlier launch under this very sequence number
+    GAT_CUDA(ctx, cudaMemsetAsync(r.d_relay, 0, kResMaxCells * 16, r.stream));
+    r.ctl.first_seq = first_seq;
+    r.args.barrier_target = ctx->barrier_count + static_cast<unsigned int>(r.plan.grid);
+    cudaError_t e = launch_resident(r.plan, r.args, r.ctl, r.smem, r.stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "resident kernel launch");
+    r.launched = true;
+    ctx->launches += 1;
+    return GAT_OK;
+}
+
+void resident_write_command(Resident &r, uint32_t seq, const uint32_t *words, int n_words)
+{
+    volatile uint32_t *cmd = r.h_cmd;
+    const int n_cells = r.ctl.n_cells;
+    for (int c = 0; c < n_cells; ++c)
+        for (int j = 0; j < 3; ++j) cmd[4 * c + j] = (3 * c + j < n_words) ? words[3 * c + j] : 0u;
+    // data before sequence words (x86 stores are observed in program order; the fence keeps the compiler honest)
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    for (int c = 0; c < n_cells; ++c) cmd[4 * c + 3] = seq;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
+}  // namespace
+
+int gat_resident_begin(gat_ctx *ctx, const int32_t *slots, int n_slots, int n_sats, const gat_channel *channels, double fs_hz,
+                       const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Resident &r = ctx->res;
+    if (r.active) return fail(ctx, GAT_ERR_INVALID, "a resident session is already open");
+    if (!slots || n_slots < 1 || n_slots > 4096 || !channels) return fail(ctx, GAT_ERR_INVALID, "bad arguments");
+    if (n_sats < 1 || n_sats > kResMaxSats)
+        return fail(ctx, GAT_ERR_UNSUPPORTED, "a resident command carries 1.." + std::to_string(kResMaxSats) + " channels");
+    // plan + marshal through the ordinary call path (validation, kernel class, shared-memory carve-up), no launch
+    std::vector<float> dummy(2 * static_cast<size_t>(n_sats) * n_taps * kMaxAnts);
+    rc = correlate_impl(ctx, 1, &slots[0], n_sats, channels, fs_hz, sample_shifts, n_taps, start_sample, n_samples, dummy.data(),
+                        dummy.data() + dummy.size() / 2, 0, kFlagResidentPlan);
+    if (rc) return rc;
+    if (!resident_kernel_available(r.plan.A, r.plan.L, r.plan.help))
+        return fail(ctx, GAT_ERR_UNSUPPORTED, "no resident instantiation for this (antennas, taps) class: 1 / 4 / 16 antennas with <= 3 or 7 taps, 16 with 11");
+    const int M = r.n_ants;
+    std::vector<PeriodDev> maps(n_slots);
+    for (int i = 0; i < n_slots; ++i) {
+        SignalSlot *sl = find_slot(ctx, slots[i]);
+        if (!slot_has_signal(sl) || !sl->parts.empty()) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot " + std::to_string(slots[i]) + " has no (plain) signal");
+        if (sl->n_ants != M || static_cast<int64_t>(start_sample) + n_samples > sl->n_samples)
+            return fail(ctx, GAT_ERR_INVALID, "all slots of a resident session must hold the range and the same antenna count");
+        rc = ensure_planes(ctx, *sl);
+        if (rc) return rc;
+        if (!sl->maps_valid) return fail(ctx, GAT_ERR_NO_SIGNAL, "slot has no TMA descriptor");
+        maps[i] = sl->maps;
+    }
+    GAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // uploads and expansions queued so far are done
+    if (!r.stream) GAT_CUDA(ctx, cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+    if (!r.h_cmd) {
+        GAT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&r.h_cmd), kResMaxCells * 16 + 64, cudaHostAllocMapped));
+        r.h_flag = r.h_cmd + kResMaxCells * 4;
+        GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&r.d_relay), kResMaxCells * 16 + 64));
+    }
+    std::memset(r.h_cmd, 0, kResMaxCells * 16 + 64);
+    GAT_CUDA(ctx, cudaMemset(r.d_relay, 0, kResMaxCells * 16 + 64));
+    if (r.d_maps) GAT_CUDA(ctx, cudaFree(r.d_maps));
+    r.d_maps = nullptr;
+    GAT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&r.d_maps), sizeof(PeriodDev) * n_slots));
+    GAT_CUDA(ctx, cudaMemcpy(r.d_maps, maps.data(), sizeof(PeriodDev) * n_slots, cudaMemcpyHostToDevice));
+    // results: one 8-byte word {value bits, sequence number} per accumulator, straight into mapped host memory
+    r.out_elems = static_cast<size_t>(n_sats) * n_taps * M;
+    if (r.h_res) GAT_CUDA(ctx, cudaFreeHost(r.h_res));
+    r.h_res = nullptr;
+    GAT_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&r.h_res), 2 * r.out_elems * sizeof(unsigned long long), cudaHostAllocMapped));
+    std::memset(r.h_res, 0, 2 * r.out_elems * sizeof(unsigned long long));
+    r.args.out_re = reinterpret_cast<float *>(r.h_res);
+    r.args.out_im = reinterpret_cast<float *>(r.h_res + r.out_elems);
+    r.args.n_peers = 0;
+    r.args.use_inline = 0;
+    r.args.periods = nullptr;
+    r.args.sats = nullptr;
+    r.args.flags = 0;
+    r.ctl.cmd_host = reinterpret_cast<const uint4 *>(r.h_cmd);
+    r.ctl.relay = r.d_relay;
+    r.ctl.slot_maps = r.d_maps;
+    r.ctl.n_cells = (4 + 16 * n_sats + 2) / 3;
+    r.ctl.cmd_off = static_cast<int32_t>((r.plan.smem + 127) & ~static_cast<size_t>(127));
+    r.ctl.idle_limit_ms = static_cast<uint32_t>(std::max(1, env_int("GAT_RESIDENT_IDLE_MS", 2000)));
+    r.debug = env_int("GAT_RESIDENT_DEBUG", 0) != 0;
+    r.ctl.stamps = r.debug ? reinterpret_cast<unsigned long long *>(r.h_flag + 4) : nullptr;
+    r.dbg_host_ns = r.dbg_seen_to_body_ns = r.dbg_body_ns = 0;
+    r.dbg_calls = 0;
+    r.args.timeline = nullptr;
+    if (r.debug) {
+        rc = ensure_device(ctx, ctx->d_timeline, ctx->timeline_cap, static_cast<size_t>(r.plan.grid) * 16, false);
+        if (rc) return rc;
+        GAT_CUDA(ctx, cudaMemset(ctx->d_timeline, 0, static_cast<size_t>(r.plan.grid) * 16 * sizeof(unsigned long long)));
+        r.args.timeline = ctx->d_timeline;
+    }
+    r.smem = static_cast<size_t>(r.ctl.cmd_off) + kResCmdSmemBytes;
+    if (r.smem > 227 * 1024) return fail(ctx, GAT_ERR_UNSUPPORTED, "shape leaves no shared memory for the command area");
+    static_assert(sizeof(SatDev) == 64, "command layout: 16 words per channel");
+    static_assert(4 + 16 * kResMaxSats <= 3 * kResMaxCells && (4 + 16 * kResMaxSats) * 4 <= kResCmdSmemBytes, "command size");
+    r.n_slots = n_slots;
+    r.n_sats = n_sats;
+    r.n_taps = n_taps;
+    r.fs_hz = fs_hz;
+    r.rep_len = 2 * r.args.tile_len;
+    r.seq = 0;
+    r.launched = false;
+    r.active = true;
+    rc = resident_launch(ctx, 1u);
+    if (rc) r.active = false;
+    return rc;
+}
+
+int gat_resident_correlate(gat_ctx *ctx, int slot_index, const gat_channel *channels, float *out_re, float *out_im)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    Resident &r = ctx->res;
+    if (!r.active) return fail(ctx, GAT_ERR_INVALID, "no resident session (gat_resident_begin)");
+    if (!channels || !out_re || !out_im || slot_index < 0 || slot_index >= r.n_slots) return fail(ctx, GAT_ERR_INVALID, "bad arguments");
+    uint32_t words[4 + 16 * kResMaxSats];
+    words[0] = kResOpCorrelate;
+    words[1] = static_cast<uint32_t>(slot_index);
+    words[2] = static_cast<uint32_t>(r.n_sats);
+    words[3] = 0u;
+    for (int k = 0; k < r.n_sats; ++k) {
+        SatDev sd{};
+        rc = fill_sat(ctx, channels[k], r.fs_hz, sd);
+        if (rc) return rc;
+        // the session's plan fixed the chip-table cache, the replica window and its wrap branch: a channel must fit them
+        const long double need = static_cast<long double>(r.rep_len + r.args.span + 160) * static_cast<long double>(sd.nco_delta) +
+                                 std::ldexp(1.0L, sd.nco_fp);
+        const bool wrap_ok = !r.args.rep_single_wrap ||
+                             static_cast<double>(r.rep_len + r.args.span + 160) * sd.code_ratio + 2.0 < static_cast<double>(sd.code_len);
+        if (((sd.code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign) > r.args.cache_stride || need >= std::ldexp(1.0L, 64) || !wrap_ok)
+            return fail(ctx, GAT_ERR_UNSUPPORTED, "channel outside the envelope the resident session was planned for (code length / code rate)");
+        std::memcpy(&words[4 + 16 * k], &sd, sizeof(sd));
+    }
+    const uint32_t seq = ++r.seq;
+    if (r.launched && cudaStreamQuery(r.stream) == cudaSuccess) r.launched = false;    // ended on its idle limit
+    if (!r.launched) {
+        rc = resident_launch(ctx, seq);
+        if (rc) return rc;
+        r.relaunches += 1;
+    }
+    resident_write_command(r, seq, words, 4 + 16 * r.n_sats);
+    // every accumulator arrives as {value, seq}: the command is complete when all of them carry this sequence number
+    const volatile unsigned long long *res = r.h_res;
+    const size_t n_res = 2 * r.out_elems;
+    size_t next = 0;                 // elements [0, next) have arrived
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t spins = 1;; ++spins) {
+        while (next < n_res && static_cast<uint32_t>(res[next] >> 32) == seq) ++next;
+        if (next == n_res) break;
+        if ((spins & 0xFFFu) == 0) {
+            const cudaError_t q = cudaStreamQuery(r.stream);
+            if (q == cudaSuccess && static_cast<uint32_t>(res[next] >> 32) != seq) {
+                // the kernel left on its idle limit just as this command was written: start it again for this command
+                r.launched = false;
+                rc = resident_launch(ctx, seq);
+                if (rc) return rc;
+                r.relaunches += 1;
+            } else if (q != cudaErrorNotReady && q != cudaSuccess) {
+                r.launched = false;
+                r.active = false;
+                return cuda_fail(ctx, q, "resident kernel");
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                r.active = false;
+                return fail(ctx, GAT_ERR_CUDA, "resident kernel did not answer within 20 s");
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (r.debug) {
+        const volatile unsigned long long *st = reinterpret_cast<const volatile unsigned long long *>(r.h_flag + 4);
+        r.dbg_host_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+        r.dbg_seen_to_body_ns += static_cast<double>(st[1] - st[0]);
+        r.dbg_body_ns += static_cast<double>(st[2] - st[1]);
+        r.dbg_calls += 1;
+    }
+    ctx->barrier_count += static_cast<unsigned int>(r.plan.grid);
+    for (size_t i = 0; i < r.out_elems; ++i) {
+        const uint32_t vr = static_cast<uint32_t>(res[i]), vi = static_cast<uint32_t>(res[r.out_elems + i]);
+        std::memcpy(&out_re[i], &vr, sizeof(float));
+        std::memcpy(&out_im[i], &vi, sizeof(float));
+    }
+    ctx->info.kernels_launched = 0;
+    return GAT_OK;
+}
+
+int gat_resident_end(gat_ctx *ctx)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    Resident &r = ctx->res;
+    int rc = GAT_OK;
+    if (r.debug && r.dbg_calls)
+        std::fprintf(stderr, "[gat resident] %llu calls: host write -> flag seen %.2f us; device: command seen -> body %.2f us, body (CTA 0) %.2f us\n",
+                     static_cast<unsigned long long>(r.dbg_calls), r.dbg_host_ns / r.dbg_calls * 1e-3, r.dbg_seen_to_body_ns / r.dbg_calls * 1e-3,
+                     r.dbg_body_ns / r.dbg_calls * 1e-3);
+    const bool dbg_timeline = r.debug && r.dbg_calls && r.args.timeline;
+    const unsigned long long dbg_t0 = (r.debug && r.h_flag) ? reinterpret_cast<const volatile unsigned long long *>(r.h_flag + 4)[0] : 0ull;
+    r.debug = false;
+    if (r.active && r.launched && cudaStreamQuery(r.stream) == cudaErrorNotReady) {
+        const uint32_t words[4] = {kResOpExit, 0u, 0u, 0u};
+        resident_write_command(r, ++r.seq, words, 4);
+    }
+    if (r.stream) {
+        const cudaError_t e = cudaStreamSynchronize(r.stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "resident kernel");
+    }
+    if (dbg_timeline && rc == GAT_OK) {
+        // per-CTA stamps of the LAST command (GAT_STAMP slots of correlate_body), relative to CTA 0 seeing the command
+        static const char *names[16] = {"c.entry", "c.setup", "c.first_tile", "c.last_tile", "c.published", "c.barrier", "c.exit", "",
+                                        "p.entry", "p.setup", "p.cached", "p.first_issued", "p.all_issued", "", "", ""};
+        const int G = r.plan.grid;
+        std::vector<unsigned long long> tl(static_cast<size_t>(G) * 16);
+        if (cudaMemcpy(tl.data(), ctx->d_timeline, tl.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int sl = 0; sl < 16; ++sl) {
+                std::vector<double> v;
+                for (int b = 0; b < G; ++b)
+                    if (tl[static_cast<size_t>(b) * 16 + sl]) v.push_back((static_cast<double>(tl[static_cast<size_t>(b) * 16 + sl]) - static_cast<double>(dbg_t0)) * 1e-3);
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                std::fprintf(stderr, "[gat resident]   %-14s min %6.2f  median %6.2f  max %6.2f us after the command was seen\n", names[sl], v.front(),
+                             v[v.size() / 2], v.back());
+            }
+    }
+    r.active = false;
+    r.launched = false;
+    if (r.d_maps) cudaFree(r.d_maps);
+    r.d_maps = nullptr;
+    if (r.d_relay) cudaFree(r.d_relay);
+    r.d_relay = nullptr;
+    if (r.h_res) cudaFreeHost(r.h_res);
+    r.h_res = nullptr;
+    if (r.h_cmd) cudaFreeHost(r.h_cmd);
+    r.h_cmd = nullptr;
+    r.h_flag = nullptr;
+    if (r.stream) cudaStreamDestroy(r.stream);
+    r.stream = nullptr;
+    return rc;
 }
 
 int gat_downconvert_and_correlate(gat_ctx *ctx, const float *h_re, const float *h_im, int ld, int n_ants, int n_sats,

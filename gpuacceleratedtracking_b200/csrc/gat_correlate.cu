@@ -44,6 +44,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -410,8 +414,11 @@ __device__ __forceinline__ int tile_owner(int64_t x, int grid, int64_t total)
 
 // accumulator slot x of a job -> output element.  Slot layout per role r = ag*S + s:
 //   A >= 2: e = ((antenna_pair * L + tap) * 2 + {re,im}) * 2 + {even,odd antenna};  A == 1: e = tap*2 + {re,im}
-template <int A, int L>
-__device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x, float val)
+// RES (resident kernel): the element goes to HOST memory as one 8-byte word {value bits, command sequence number} -- the host
+// knows an element has arrived when its sequence number matches, so a command needs no completion fence and no flag
+// (a system-scope fence after sysmem stores cost 2 - 11 us per CTA in the first version of the resident kernel).
+template <int A, int L, bool RES = false>
+__device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x, float val, [[maybe_unused]] uint32_t res_seq = 0u)
 {
     constexpr int R = 2 * A * L;
     constexpr int RP = (R + 31) / 32 * 32;
@@ -434,6 +441,11 @@ __device__ __forceinline__ void emit_output(const CorrArgs &args, int job, int x
     l += tg2 * L;                      // tap groups: this role holds taps tg2 * L .. of the call's n_taps
     if (kk >= K || m >= M || l >= args.n_taps) return;
     const size_t idx = (((size_t)p * K + kk) * args.n_taps + l) * M + m;
+    if constexpr (RES) {
+        uint2 *dst2 = reinterpret_cast<uint2 *>(c ? args.out_im : args.out_re) + idx;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst2), "r"(__float_as_uint(val * args.out_scale)), "r"(res_seq) : "memory");
+        return;
+    }
     float *dst = (c ? args.out_im : args.out_re) + idx;
     val *= args.out_scale;             // raw integer tiles: the (power-of-two) sample scale is applied once, here
     if (args.flags & 1u) val += *dst;  // GAT_ACCUMULATE
@@ -484,8 +496,18 @@ __device__ __forceinline__ int sp_advance(int sp, int n, int stages)
 // setmaxnreg, so that ptxas allocates the consumer code against 160 registers and the producer / replica-warp code against
 // 32 (one copy with a join after the setmaxnreg made every value that lives across it spill).  0 = all roles in one copy.
 enum { kRoleAll = 0, kRoleAux = 1, kRoleConsumer = 2 };
-template <int A, int L, bool F64, bool SC16, bool DUMP, bool HELP, int ROLE>
-__device__ __forceinline__ void correlate_body(const CorrArgs &args)
+// RES (resident kernel, gat_resident.cu): the body runs once per command inside a kernel that stays on the device; what changes
+// from call to call -- the block's descriptors, the channel records, the grid barrier's target and the completion sequence
+// number -- comes from `ro` instead of the kernel arguments.
+struct ResOverride {
+    const PeriodDev *periods;     // descriptors of the selected slot (device global memory)
+    const SatDev *sats;           // this command's channel records (shared memory)
+    unsigned int barrier_target;
+    uint32_t seq;
+    uint32_t reinit;              // not the launch's first command: the barriers hold the previous command's objects
+};
+template <int A, int L, bool F64, bool SC16, bool DUMP, bool HELP, int ROLE, bool RES = false>
+__device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unused]] const ResOverride &ro = ResOverride{})
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int AP = (A >= 2) ? A / 2 : 1;
@@ -524,6 +546,26 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
 
     GAT_STAMP(warp == PW ? 8 : 0);
     if (tid == 0) {
+        // (one thread, one barrier after the other: a lane-parallel version saved 0.3 us per small call and made the resident
+        // kernel hang under back-to-back commands -- not understood, reverted)
+        if constexpr (RES) {
+            // mbarrier.init on a live mbarrier object is undefined (and does hang): invalidate the previous command's first
+            if (ro.reinit) {
+                for (int s = 0; s < stages; ++s) {
+                    mbar_inval(&full_bar[s]);
+                    mbar_inval(&empty_bar[s]);
+                }
+                mbar_inval(code_bar);
+                mbar_inval(code_free);
+                if constexpr (HELP) {
+                    const int groups = (split ? 1 : SL) * S;
+                    for (int i = 0; i < 2 * groups; ++i) {
+                        mbar_inval(reinterpret_cast<uint64_t *>(smem + kRepBarOff) + i);
+                        mbar_inval(reinterpret_cast<uint64_t *>(smem + 2 * kRepBarOff) + i);
+                    }
+                }
+            }
+        }
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);                            // producer's expect_tx arrival (+ TMA bytes)
             mbar_init(&empty_bar[s], (uint32_t)(split ? W : NR));  // one arrival per consumer warp that reads the stage
@@ -563,8 +605,9 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
     }
 
     // small calls carry their TMA descriptors and channel records in the kernel arguments
-    const PeriodDev *periods = args.use_inline ? reinterpret_cast<const PeriodDev *>(args.inline_blk) : args.periods;
-    const SatDev *sats = args.use_inline ? reinterpret_cast<const SatDev *>(args.inline_blk + args.inline_sat_off) : args.sats;
+    const PeriodDev *periods = RES ? ro.periods : (args.use_inline ? reinterpret_cast<const PeriodDev *>(args.inline_blk) : args.periods);
+    const SatDev *sats = RES ? ro.sats : (args.use_inline ? reinterpret_cast<const SatDev *>(args.inline_blk + args.inline_sat_off) : args.sats);
+    const unsigned int barrier_target = RES ? ro.barrier_target : args.barrier_target;
     const int64_t TT = args.total_tiles;
     const int grid = gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * TT / grid;
@@ -1161,7 +1204,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                 float acc = 0.f;
                 for (int i = 0; i < SL; ++i) acc += part[(i * NR + r) * RP + e];
                 if (sole)
-                    emit_output<A, L>(args, job, x, acc);
+                    emit_output<A, L, RES>(args, job, x, acc, RES ? ro.seq : 0u);
                 else
                     __stcg(my_partial + x, acc);
             }
@@ -1180,8 +1223,8 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
         const uint64_t t0 = global_timer_ns();
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(args.grid_barrier) : "memory");
-            if ((int)(seen - args.barrier_target) < 0 && global_timer_ns() - t0 > 5 * kWaitLimitNs) __trap();
-        } while ((int)(seen - args.barrier_target) < 0);
+            if ((int)(seen - barrier_target) < 0 && global_timer_ns() - t0 > 5 * kWaitLimitNs) __trap();
+        } while ((int)(seen - barrier_target) < 0);
     }
     consumer_bar_sync(consumer_threads);
     GAT_STAMP(5);
@@ -1222,7 +1265,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                 }
             }
             for (int o = GS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (emit && gl == 0) emit_output<A, L>(args, job, x, acc);
+            if (emit && gl == 0) emit_output<A, L, RES>(args, job, x, acc, RES ? ro.seq : 0u);
         }
     }
     if (args.n_peers >= 1) {
@@ -1235,13 +1278,14 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args)
                 *args.done_counter = 0u;   // self-cleaning for the next launch
                 __threadfence_system();
                 for (int d = 0; d < args.n_peers; ++d)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(args.peer_flag[d] + args.my_rank), "r"(args.gather_seq) : "memory");
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(args.peer_flag[d] + args.my_rank), "r"(RES ? ro.seq : args.gather_seq) : "memory");
             }
         }
     }
     GAT_STAMP(6);
 }
 
+#ifndef GAT_RESIDENT_TU     // gat_resident.cu includes this file for the helpers and correlate_body above
 template <int A, int L, bool F64, bool SC16, bool DUMP = false, bool HELP = false>
 __global__ void __launch_bounds__(HELP ? block_threads_help(A, L) : block_threads_max(A, L), 1) correlate_kernel(const __grid_constant__ CorrArgs args)
 {
@@ -1523,5 +1567,7 @@ cudaError_t launch_gen_signal(float *re, float *im, int64_t ld, const int8_t *co
                                                       ant_phase_step_rad, noise_sigma, seed, superpose);
     return cudaGetLastError();
 }
+
+#endif  // GAT_RESIDENT_TU
 
 }  // namespace gat

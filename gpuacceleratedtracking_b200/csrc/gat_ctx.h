@@ -97,6 +97,31 @@ struct Staging {
 
 constexpr int kStagingRing = 8;
 
+// gat_resident_*: one session = one shape, a set of slots, a kernel that stays on the device (gat_resident.cu)
+struct Resident {
+    bool active = false;
+    cudaStream_t stream = nullptr;      // the resident kernel's own (non-blocking) stream
+    LaunchPlan plan{};
+    CorrArgs args{};
+    ResCtl ctl{};
+    size_t smem = 0;
+    uint32_t *h_cmd = nullptr;          // pinned, mapped: kResMaxCells cells of 4 words
+    uint32_t *h_flag = nullptr;         // pinned, mapped: debug stamps live behind it
+    uint4 *d_relay = nullptr;
+    unsigned long long *h_res = nullptr;   // pinned, mapped: [re block | im block] of {value bits, sequence number} words
+    PeriodDev *d_maps = nullptr;
+    uint32_t seq = 0;                   // last command issued
+    bool launched = false;              // a kernel was launched and has not been seen finished
+    int n_slots = 0, n_sats = 0, n_taps = 0, n_ants = 0, rep_len = 0;
+    double fs_hz = 0.0;
+    size_t out_elems = 0;
+    uint64_t relaunches = 0;
+    // GAT_RESIDENT_DEBUG: where a call's time goes (host clock around the call, device stamps inside it)
+    bool debug = false;
+    double dbg_host_ns = 0, dbg_seen_to_body_ns = 0, dbg_body_ns = 0;
+    uint64_t dbg_calls = 0;
+};
+
 }  // namespace gat
 
 struct gat_ctx {
@@ -152,6 +177,7 @@ struct gat_ctx {
     size_t ing_stage_cap = 0;                        // floats per ring buffer
     int ing_n = 0, ing_m = 0;                        // shape the staging slots are currently bound for
     int64_t ing_ld = 0;
+    gat::Resident res;
 };
 
 namespace gat {

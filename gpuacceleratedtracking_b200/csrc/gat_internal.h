@@ -66,6 +66,7 @@ constexpr int kCodeColAlign = 16;  // device chip-table columns are padded to th
 constexpr int kSmemHeaderBytes = 2048;  // full/empty barriers (0..255), chip-table barrier (256) + its back-pressure barrier (264)
 constexpr uint32_t kFlagStallConsumers = 0x100u;   // == GAT_DEBUG_STALL_CONSUMERS (include/gat.h)
 constexpr uint32_t kFlagDumpReplica = 0x200u;      // internal: run the DUMP instantiation (gat_debug_replica_indices)
+constexpr uint32_t kFlagResidentPlan = 0x400u;     // internal: plan and marshal only -- gat_resident_begin keeps (plan, args)
 
 // One satellite channel of one period, pre-digested on the host (gat_api.cu: fill_sat).
 struct SatDev {
@@ -188,6 +189,24 @@ cudaError_t configure_kernels();   // opt-in to > 48 KB dynamic smem for every i
 bool kernel_available(int A, int L);
 bool dump_kernel_available(int A, int L);
 bool help_kernel_available(int A, int L, bool f64, bool dump);
+
+// ---- resident kernel (gat_resident.cu, gat_resident_* in include/gat.h) ----
+constexpr int kResMaxCells = 32;              // command cells of 16 bytes {d0, d1, d2, seq}: one warp-wide load
+constexpr int kResMaxSats = 5;                // data words: [op, slot index, n_sats, 0][SatDev x n_sats] <= 3 * kResMaxCells
+constexpr uint32_t kResOpCorrelate = 1u, kResOpExit = 2u;
+constexpr int kResCmdSmemBytes = 512;         // the command's data words in shared memory, behind the plan's carve-up
+struct ResCtl {
+    const uint4 *cmd_host;        // the host's command cells (pinned, mapped: device pointer)
+    uint4 *relay;                 // device memory: the cells as CTA 0 received them (the other CTAs poll these)
+    const PeriodDev *slot_maps;   // device memory: descriptors of the session's slots
+    int32_t n_cells;
+    int32_t cmd_off;              // byte offset of the command area in dynamic shared memory
+    uint32_t idle_limit_ms;       // CTA 0 ends the kernel after this long without a command
+    uint32_t first_seq;           // sequence number of the first command this launch serves
+    unsigned long long *stamps;   // debug (GAT_RESIDENT_DEBUG): host-mapped [4] globaltimer stamps of the last command, or nullptr
+};
+bool resident_kernel_available(int A, int L, bool help);
+cudaError_t launch_resident(const LaunchPlan &plan, const CorrArgs &args, const ResCtl &ctl, size_t smem_bytes, cudaStream_t stream);
 
 cudaError_t launch_gather_wait(unsigned int *const *flags_unused, unsigned int *local_flags, int world, unsigned int seq,
                                cudaStream_t stream);

@@ -334,6 +334,36 @@ class Engine:
                                                    C.c_void_p(out[0].ctypes.data), C.c_void_p(out[1].ctypes.data), 0))
         return out
 
+    # ---- resident sessions (include/gat.h gat_resident_*): one call + sync per block without a kernel launch ----
+    def resident_begin(self, slots: Sequence[int], channels: Sequence[Channel], fs: float, shifts: Sequence[int], n_ants: int,
+                       start_sample: int, n_samples: int):
+        """Open a resident session over `slots` (blocks of one geometry) for len(channels) channels per call; `channels`
+        are representative (their systems' chip tables are installed)."""
+        for ch in channels:
+            self.set_codes(ch.system)
+        sl = np.ascontiguousarray(slots, np.int32)
+        sh = np.ascontiguousarray(shifts, np.int32)
+        K = len(channels)
+        arr = (GatChannel * K)(*[ch.to_c() for ch in channels])
+        self._check(self._lib.gat_resident_begin(self._h, sl.ctypes.data_as(C.POINTER(C.c_int32)), sl.size, K, arr, fs,
+                                                 sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size, start_sample, n_samples))
+        self._res_shape = (K, sh.size, n_ants)
+        self._res_out = np.empty((2,) + self._res_shape, np.float32)
+
+    def resident_correlate(self, slot_index: int, channels) -> np.ndarray:
+        """One synchronous correlation of the block in slots[slot_index]; complex64 [K, n_taps, n_ants].  `channels`: a
+        sequence of Channel, or a prepared ctypes array of GatChannel (the per-millisecond loop reuses one)."""
+        if isinstance(channels, C.Array):
+            arr = channels
+        else:
+            arr = (GatChannel * len(channels))(*[ch.to_c() for ch in channels])
+        o = self._res_out
+        self._check(self._lib.gat_resident_correlate(self._h, slot_index, arr, C.c_void_p(o[0].ctypes.data), C.c_void_p(o[1].ctypes.data)))
+        return (o[0] + 1j * o[1]).astype(np.complex64)
+
+    def resident_end(self):
+        self._check(self._lib.gat_resident_end(self._h))
+
     def gather_set_offset(self, elems: int):
         self._check(self._lib.gat_gather_set_offset(self._h, int(elems)))
 

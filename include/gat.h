@@ -284,6 +284,29 @@ int gat_ring_prefetch(gat_ctx *ctx, int first_slot, int n_slots, int generation,
 int gat_ring_mirror_wait(gat_ctx *ctx, int ticket);
 int gat_ring_destroy(gat_ctx *ctx);
 
+/* ---- resident sessions: one call + synchronisation per block WITHOUT a kernel launch --------------------------------
+ * The reference times one `CUDA.@sync kernel_algorithm(...)` per 1 ms block (src/benchmarks.jl:872, paper/paper.tex:150);
+ * a tracking loop makes exactly that call every millisecond.  Through a kernel launch it costs ~18 us on a B200, most of
+ * it launch, argument marshalling and completion latency.  A resident session launches the correlate kernel ONCE: it
+ * stays on the device, polls a command the host writes into pinned mapped memory, runs the same fused
+ * downconvert-and-correlate (same plan, bit-identical sums to gat_correlate), writes the accumulators straight into host
+ * memory and raises a flag the caller spins on.
+ *   gat_resident_begin     fixes the shape (slots that hold blocks of the same geometry, channel count <= 5, sampling
+ *                          rate, taps, sample range; `channels` = representative channels: systems / code rates) and
+ *                          launches the kernel.  Classes: 1 / 4 / 16 antennas with <= 3 or 7 taps, 16 antennas x 11 taps
+ *                          (GAT_ERR_UNSUPPORTED otherwise), integer-NCO code phase, FP32 planes.
+ *   gat_resident_correlate one command: the block in slots[slot_index], n_sats channels (any PRN / phases / Doppler of the
+ *                          planned systems) -> out [n_ants x n_taps x n_sats] host arrays.  Synchronous.
+ *   gat_resident_end       ends the kernel and frees the session (also done by gat_destroy).
+ * While a session is open the kernel owns every SM: gat_correlate* on this ctx return GAT_ERR_INVALID, kernels of OTHER
+ * contexts or libraries on the device wait; copies (gat_upload_signal of FP32 host data into the session's slots, on
+ * the ctx stream) run on the copy engines and are fine.  To bound that wait the kernel leaves by itself after
+ * GAT_RESIDENT_IDLE_MS (environment, default 2000) without a command; the next gat_resident_correlate starts it again. */
+int gat_resident_begin(gat_ctx *ctx, const int32_t *slots, int n_slots, int n_sats, const gat_channel *channels, double fs_hz,
+                       const int32_t *sample_shifts, int n_taps, int start_sample, int n_samples);
+int gat_resident_correlate(gat_ctx *ctx, int slot_index, const gat_channel *channels, float *out_re, float *out_im);
+int gat_resident_end(gat_ctx *ctx);
+
 /* ---- one host process, all GPUs of the box -----------------------------------------------------
  * The call a single tracking-loop process makes (Julia: one `ccall` per integration period or batch): the satellite
  * channels are partitioned over the devices, every device reads the same signal blocks, the accumulators come back in

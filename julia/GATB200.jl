@@ -134,6 +134,31 @@ end
 
 host_register!(a::Array) = ccall((:gat_host_register, libgat), Cint, (Ptr{Cvoid}, UInt64), a, sizeof(a))
 
+# ---- resident sessions (gat_resident_*): the per-millisecond call of a tracking loop without a kernel launch ------------
+"""
+`resident_begin!(ctx, slots, channels, shifts, fs, start_sample, num_samples)` launches the correlate kernel once; it stays on
+the device and `resident_correlate!(ctx, slot_index, channels, out_re, out_im)` then costs a PCIe round trip plus the
+correlation itself instead of a kernel launch and a stream synchronisation (the reference's measurement is exactly one such
+call per 1 ms block: src/benchmarks.jl:872).  `slots` hold blocks of one geometry (bind or upload them first); `channels`
+is a `Vector{GatChannel}` of at most 5 channels; `out_re`, `out_im` are host `Array{Float32,3}` [M x NCOR x K].
+`resident_end!(ctx)` frees the device again.
+"""
+function resident_begin!(ctx::Context, slots::Vector{<:Integer}, channels::Vector{GatChannel}, correlator_sample_shifts::SVector{NCOR, Int64},
+        sampling_frequency, start_sample::Integer, num_samples::Integer) where {NCOR}
+    shifts = Int32.(collect(correlator_sample_shifts))
+    check(ctx, ccall((:gat_resident_begin, libgat), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Cint, Cint, Ptr{GatChannel}, Cdouble, Ptr{Int32}, Cint, Cint, Cint),
+        ctx.handle, Int32.(slots), length(slots), length(channels), channels, hz(sampling_frequency), shifts, NCOR, start_sample, num_samples))
+end
+
+function resident_correlate!(ctx::Context, slot_index::Integer, channels::Vector{GatChannel}, out_re::Array{Float32, 3}, out_im::Array{Float32, 3})
+    check(ctx, ccall((:gat_resident_correlate, libgat), Cint, (Ptr{Cvoid}, Cint, Ptr{GatChannel}, Ptr{Cfloat}, Ptr{Cfloat}),
+        ctx.handle, slot_index, channels, out_re, out_im))
+    return out_re, out_im
+end
+
+resident_end!(ctx::Context) = check(ctx, ccall((:gat_resident_end, libgat), Cint, (Ptr{Cvoid},), ctx.handle))
+
 # ---- all GPUs of the box from this one process (gat_mg_*) -------------------------------------------------------
 mutable struct MultiContext
     handle::Ptr{Cvoid}

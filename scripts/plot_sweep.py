@@ -14,7 +14,7 @@ import math
 import sys
 
 CURVES = [("CPU_ns", "CPU port, 1 thread", "#d62728"), ("GPU_sync_ns", "B200 call + sync", "#1f77b4"),
-          ("GPU_device_ns", "B200 back-to-back", "#2ca02c")]
+          ("GPU_resident_ns", "B200 resident session", "#9467bd"), ("GPU_device_ns", "B200 back-to-back", "#2ca02c")]
 W, H, ML, MB, MT, MR = 330, 250, 52, 40, 26, 10
 
 
@@ -24,7 +24,7 @@ def log_ticks(lo, hi):
 
 def panel(rows, title, x0, y0):
     xs = [r["sampling_frequency_hz"] for r in rows]
-    ys = [r[k] * 1e-9 for r in rows for k, _, _ in CURVES if k in r]
+    ys = [r[k] * 1e-9 for r in rows for k, _, _ in CURVES if r.get(k, 0) > 0]
     xlo, xhi = min(xs) * 0.8, max(xs) * 1.25
     ylo, yhi = min(min(ys) * 0.7, 1e-6), max(max(ys) * 1.4, 2e-3)
     px = lambda x: x0 + ML + (math.log10(x) - math.log10(xlo)) / (math.log10(xhi) - math.log10(xlo)) * (W - ML - MR)
@@ -42,7 +42,9 @@ def panel(rows, title, x0, y0):
     out.append(f'<line x1="{x0 + ML}" y1="{py(1e-3):.1f}" x2="{x0 + W - MR}" y2="{py(1e-3):.1f}" stroke="#000" stroke-dasharray="5,3"/>')
     out.append(f'<text x="{x0 + W - MR - 3}" y="{py(1e-3) - 3:.1f}" text-anchor="end" font-size="9">real time (1 ms)</text>')
     for key, _, colour in CURVES:
-        pts = [(px(r["sampling_frequency_hz"]), py(r[key] * 1e-9)) for r in rows if key in r]
+        pts = [(px(r["sampling_frequency_hz"]), py(r[key] * 1e-9)) for r in rows if r.get(key, 0) > 0]   # (0 = not measured)
+        if not pts:
+            continue
         out.append('<polyline fill="none" stroke="%s" stroke-width="1.6" points="%s"/>' % (colour, " ".join(f"{a:.1f},{b:.1f}" for a, b in pts)))
         out += [f'<circle cx="{a:.1f}" cy="{b:.1f}" r="2.2" fill="{colour}"/>' for a, b in pts]
     out.append(f'<text x="{x0 + W / 2}" y="{y0 + H - 6}" text-anchor="middle" font-size="10">sampling frequency [Hz]</text>')
@@ -78,16 +80,17 @@ def main():
     for _, label, colour in CURVES:
         svg.append(f'<line x1="{lx}" y1="{n_rows * H + 18}" x2="{lx + 22}" y2="{n_rows * H + 18}" stroke="{colour}" stroke-width="2"/>')
         svg.append(f'<text x="{lx + 26}" y="{n_rows * H + 22}" font-size="11">{label}</text>')
-        lx += 190
+        lx += 175
     svg.append(f'<text x="{lx}" y="{n_rows * H + 22}" font-size="10" fill="#555">{meta.get("GPU_model", "")} / {meta.get("CPU_model", "")}; estimator: minimum</text>')
     svg.append("</svg>")
     open(dst, "w").write("\n".join(svg) + "\n")
     if len(sys.argv) > 3:
         with open(sys.argv[3], "w") as f:
-            f.write("| system | antennas | correlators | samples | CPU 1 thread [us] | GPU call + sync [us] | GPU back-to-back [us] | real time |\n|---|---|---|---|---|---|---|---|\n")
+            f.write("| system | antennas | correlators | samples | CPU 1 thread [us] | GPU call + sync [us] | GPU resident session [us] | GPU back-to-back [us] | real time |\n|---|---|---|---|---|---|---|---|---|\n")
             for k in keys:
                 for r in sorted(groups[k], key=lambda r: r["num_samples"]):
-                    f.write(f"| {k[0]} | {k[1]} | {k[2]} | {r['num_samples']} | {r['CPU_ns'] / 1e3:.1f} | {r['GPU_sync_ns'] / 1e3:.1f} | "
+                    res = f"{r['GPU_resident_ns'] / 1e3:.1f}" if r.get("GPU_resident_ns", 0) > 0 else "-"
+                    f.write(f"| {k[0]} | {k[1]} | {k[2]} | {r['num_samples']} | {r['CPU_ns'] / 1e3:.1f} | {r['GPU_sync_ns'] / 1e3:.1f} | {res} | "
                             f"{r['GPU_device_ns'] / 1e3:.1f} | {'yes' if r['realtime'] else 'no'} |\n")
     print(f"{len(rows)} points in {len(keys)} panels -> {dst}")
 
