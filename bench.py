@@ -773,11 +773,11 @@ def _leg_single_call(eng, g, l1, shifts, dev, torch):
     eng.resident_begin([20000], [c1], FS, shifts, N_ANTS, 0, N_SAMPLES)
     try:
         for _ in range(50):
-            eng.resident_correlate(0, arr)
+            eng.resident_correlate(0, arr, raw=True)
         rts = []
         for _ in range(300):
             t0 = time.perf_counter()
-            eng.resident_correlate(0, arr)
+            eng.resident_correlate(0, arr, raw=True)
             rts.append(time.perf_counter() - t0)
         res["resident_call_us_min"] = min(rts) * 1e6
         res["resident_call_us_median"] = float(np.median(rts)) * 1e6
@@ -990,7 +990,7 @@ def run_sweep(args):
                 res_best = 1e9
                 for _ in range(reps):
                     t0 = time.perf_counter()
-                    eng.resident_correlate(0, arr)
+                    eng.resident_correlate(0, arr, raw=True)
                     res_best = min(res_best, time.perf_counter() - t0)
             finally:
                 eng.resident_end()

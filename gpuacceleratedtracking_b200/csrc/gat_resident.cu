@@ -73,6 +73,12 @@ __device__ __forceinline__ void resident_loop(const CorrArgs &args, const ResCtl
         }
         __syncthreads();
         if (cmd_s[0] != kResOpCorrelate) return;    // exit command, or CTA 0 gave up waiting
+        if (threadIdx.x == 32) {
+            // the selected block's TMA descriptors on their way into the descriptor cache while the barriers are set up
+            const PeriodDev *pd = ctl.slot_maps + cmd_s[1];
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&pd->re) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&pd->im) : "memory");
+        }
         ResOverride ro;
         ro.periods = ctl.slot_maps + cmd_s[1];
         ro.sats = reinterpret_cast<const SatDev *>(cmd_s + 4);

@@ -349,16 +349,21 @@ class Engine:
                                                  sh.ctypes.data_as(C.POINTER(C.c_int32)), sh.size, start_sample, n_samples))
         self._res_shape = (K, sh.size, n_ants)
         self._res_out = np.empty((2,) + self._res_shape, np.float32)
+        self._res_ptrs = (C.c_void_p(self._res_out[0].ctypes.data), C.c_void_p(self._res_out[1].ctypes.data))
 
-    def resident_correlate(self, slot_index: int, channels) -> np.ndarray:
+    def resident_correlate(self, slot_index: int, channels, raw: bool = False) -> np.ndarray:
         """One synchronous correlation of the block in slots[slot_index]; complex64 [K, n_taps, n_ants].  `channels`: a
-        sequence of Channel, or a prepared ctypes array of GatChannel (the per-millisecond loop reuses one)."""
+        sequence of Channel, or a prepared ctypes array of GatChannel (the per-millisecond loop reuses one).  raw=True
+        returns the session's own float32 [2 (re, im), K, n_taps, n_ants] buffer (valid until the next call) and skips the
+        complex conversion, which costs more than the correlation."""
         if isinstance(channels, C.Array):
             arr = channels
         else:
             arr = (GatChannel * len(channels))(*[ch.to_c() for ch in channels])
         o = self._res_out
-        self._check(self._lib.gat_resident_correlate(self._h, slot_index, arr, C.c_void_p(o[0].ctypes.data), C.c_void_p(o[1].ctypes.data)))
+        self._check(self._lib.gat_resident_correlate(self._h, slot_index, arr, self._res_ptrs[0], self._res_ptrs[1]))
+        if raw:
+            return o
         return (o[0] + 1j * o[1]).astype(np.complex64)
 
     def resident_end(self):
