@@ -13,15 +13,19 @@ than the 126 MB L2, so every step streams from HBM) = ONE fused kernel launch pe
   e2e     same metric through the C ABI with HOST buffers.  N = 1: one gat_ingest_correlate call per step (the
           library copies 16-period chunks from pinned host memory on its ingest stream under the kernel of the
           previous chunk and returns host accumulators).
-  N > 1   one process per GPU (torchrun).  Satellite channels are independent given the signal block, so they
-          shard across ranks (rank r correlates its own satellite: weak scaling, per-GPU work fixed) and EVERY rank
-          needs EVERY block -- north_star's per-period signal exchange.  The blocks live scattered over the ranks'
-          HBM (rank r owns one sample range of every block: what its own PCIe link delivers) and each rank's correlate
-          kernel gathers its tiles over NVLink inside its own TMA pipeline (gat_ring_*: the all-gather fused into
-          the kernel; no NCCL call, no receive buffer).  That exchange is INSIDE the timed region of `value`.  The
-          accumulators go back through the gather fused into the kernel epilogue (peer stores).  Before timing, the
-          accumulators every rank sees are checked against the oracle (`parity_max_rel`, bar 1e-4).  The e2e leg adds
-          the H2D copy of every rank's share from its pinned host memory and the D2H read on rank 0.
+  N > 1   one process per GPU (torchrun), weak scaling: `world` satellites on `world` GPUs, the blocks scattered over the
+          GPUs' HBM by sample range (rank r owns one contiguous range of every block: what its own PCIe link delivers).
+          Two decompositions are measured on the same blocks, both parity-checked against the oracle (bar 1e-4):
+          * `value` -- SAMPLE-sharded (SURVEY 8e "alternative worth measuring: better for small K"): every rank correlates
+            ALL satellites over ITS OWN sample range (phases taken at the period's sample 0: gat_set_sample_origin, same
+            integer NCO / Q0.64 carrier arithmetic, bit-exact chip indices), the partial sums go into every rank's gather
+            buffer from the kernel epilogue (NVLink peer stores) and gat_gather_sum adds them.  No signal crosses NVLink;
+            the exchange of the partial sums and their addition are INSIDE the timed region.
+          * `satellite_sharded` -- north_star's data flow: rank r correlates its own satellite over the WHOLE block, which
+            its kernel gathers tile by tile over NVLink inside its TMA pipeline (gat_ring_*: all-gather fused into the
+            kernel).  With one channel per GPU this is bound by NVLink ingress (<= 0.9 TB/s against 6.5 TB/s of HBM), which
+            is why the engine shards samples for few channels per GPU and satellites for many (`c5`: 32 satellites).
+          The e2e leg adds the H2D copy of every rank's share from its pinned host memory and the D2H read on rank 0.
   c5      BASELINE configs[4] (32 L1 + L5 satellites, sharded) at the same N: strong and weak, us per 1 ms period.
 
   The contract line is assembled BEFORE the optional legs run and is printed no matter how they end (exception
@@ -201,7 +205,10 @@ def cpu_arm(periods: int, steps: int, warmup: int, threads: int = 0, budget_s: f
 def bench_config(P: int, world: int, extra: dict | None = None) -> dict:
     """The `config` object: identical keys (and, for the same --periods, values) in both arms."""
     cfg = {"workload": WORKLOAD, "periods_per_step": P, "n_sats_per_gpu": 1, "n_ants": N_ANTS, "n_taps": N_TAPS,
-           "n_samples": N_SAMPLES, "parallelism": f"satellite-sharded x{world}",
+           "n_samples": N_SAMPLES,
+           "parallelism": (f"satellite-sharded x{world}" if world == 1 else
+                           f"sample-sharded x{world}: every GPU correlates all {world} satellites over its own 1/{world} of each block, "
+                           "partial sums exchanged and added inside the timed region"),
            "l2_policy": f"inputs larger than L2 ({P * 8 * N_SAMPLES * N_ANTS / 1e6:.0f} MB of distinct signal blocks per step)"}
     if extra:
         cfg.update(extra)
@@ -304,7 +311,7 @@ def run_gpu(args):
 
 def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
     import oracle
-    from gpuacceleratedtracking_b200.multigpu import gather_setup, ring_setup, shard_channels
+    from gpuacceleratedtracking_b200.multigpu import gather_setup, ring_setup, shard_channels, shard_sample_ranges
 
     if args.c5_only:                                               # tuning aid: the C5 leg alone (not the contract line)
         ws = torch.cuda.Stream(device=dev)
@@ -364,18 +371,48 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
         gen = eng.ring_publish()
         eng.ring_wait(gen)
         eng.ring_release()
-        gather_setup(eng, elems)
+        # THE STEP AT N > 1 (`value`): with ONE channel per GPU that exchange is all a step would do (NVLink ingress <= 0.9 TB/s
+        # against 6.5 TB/s of HBM), so the engine shards the SAMPLES instead (SURVEY 8e "alternative": better for small K):
+        # every rank correlates ALL `world` satellites over the sample range its own PCIe link delivered -- no signal crosses
+        # NVLink -- with the channel phases taken at the period's sample 0 (gat_set_sample_origin: same integer NCO / Q0.64
+        # carrier arithmetic as a whole-block call), the partial sums go into every rank's gather buffer from the kernel
+        # epilogue (peer stores), and gat_gather_sum adds the `world` slices.  The satellite-sharded step (fused all-gather of
+        # the blocks) is measured right after it and reported as `satellite_sharded`.
+        elems_s = P * world * N_TAPS * N_ANTS
+        gather_setup(eng, max(elems, elems_s))
         slots = np.arange(P, dtype=np.int32)
+        smp_lo, smp_len = shard_sample_ranges(N_SAMPLES, world)[rank]
+        LOC = 40000
+        for p in range(P):
+            eng.bind_signal(LOC + p, re[p][:, smp_lo:smp_lo + smp_len], im[p][:, smp_lo:smp_lo + smp_len])
+        loc_slots = np.arange(LOC, LOC + P, dtype=np.int32)
+        chans_all = eng.marshal([[chan_of(r, p) for r in range(world)] for p in range(P)])
+        s_re = torch.zeros(P, world, N_TAPS, N_ANTS, device=dev)
+        s_im = torch.zeros_like(s_re)
     else:
         slots = np.arange(FULL, FULL + P, dtype=np.int32)
     barrier()
 
-    def step():
+    def launch_sat():
+        eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
+
+    def launch():
         if world > 1:
-            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
-            eng.gather_wait()          # stream-ordered: every rank's block of this step has landed here
+            eng.correlate_batch(loc_slots, chans_all, FS, shifts, N_ANTS, 0, smp_len, gather=True)
         else:
             eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
+
+    def finish():
+        if world > 1:
+            eng.gather_wait()          # stream-ordered: every rank's partial sums of this step have landed here
+            eng.gather_sum(elems_s, (s_re, s_im))
+
+    def step():
+        launch()
+        finish()
+
+    if world > 1:
+        eng.set_sample_origin(smp_lo)
 
     log("warm-up")
     for _ in range(warmup):
@@ -384,20 +421,24 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
 
     # ---- parity gate: the accumulators every rank sees against the oracle (double-precision direct formula) ----
     if world > 1:
-        seen = eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS)
+        seen = (s_re + 1j * s_im).cpu().numpy().transpose(1, 0, 2, 3).reshape(world, P, 1, N_TAPS, N_ANTS)   # [satellite, period, ...]
     else:
         seen = (o_re + 1j * o_im).cpu().numpy().reshape(1, P, 1, N_TAPS, N_ANTS)
     pairs = sorted({(0, 0), (world - 1, P - 1), (world // 2, P // 2), (rank, (7 * rank + 3) % P)})
-    parity = 0.0
-    for r, p in pairs:
-        c = chan_of(r, p)
-        ref = oracle.correlate_direct(re[p].cpu().numpy(), im[p].cpu().numpy(), l1.codes[c.prn - 1], CODE_FREQ, c.code_phase,
-                                      c.carrier_frequency, c.carrier_phase, FS, shifts)
-        parity = max(parity, float(np.abs(seen[r, p, 0] - ref).max() / np.abs(ref[N_TAPS // 2]).max()))
-    pt = torch.tensor([parity], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
-    parity = pt.item()
+
+    def parity_of(seen_):
+        worst = 0.0
+        for r, p in pairs:
+            c = chan_of(r, p)
+            ref = oracle.correlate_direct(re[p].cpu().numpy(), im[p].cpu().numpy(), l1.codes[c.prn - 1], CODE_FREQ, c.code_phase,
+                                          c.carrier_frequency, c.carrier_phase, FS, shifts)
+            worst = max(worst, float(np.abs(seen_[r, p, 0] - ref).max() / np.abs(ref[N_TAPS // 2]).max()))
+        pt = torch.tensor([worst], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        return pt.item()
+
+    parity = parity_of(seen)
     log(f"parity_max_rel {parity:.2e} over {len(pairs)} (rank, period) pairs per rank")
     assert parity < 1e-4, f"parity {parity}"
     assert float(np.abs(seen[:, :, 0, 1, :]).mean()) > 0.9 * N_SAMPLES
@@ -422,13 +463,9 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
     t0.record()
     for a, b in ev:
         a.record()
-        if world > 1:
-            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
-            b.record()
-            eng.gather_wait()
-        else:
-            eng.correlate_batch(slots, chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=(o_re, o_im))
-            b.record()
+        launch()
+        b.record()
+        finish()
     t1.record()
     barrier()
     gpu_launches = eng.kernel_launches - launches0
@@ -444,6 +481,36 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
     value = corr_per_step / (ms_per_step * 1e-3)
     info = eng.launch_info()
     log(f"value {value / 1e6:.2f} M corr/s, {ms_per_step:.4f} ms/step, kernel {kernel_ms:.4f} ms")
+
+    # ---- N > 1: the satellite-sharded step (north_star's data flow: every rank needs every block; the all-gather of the blocks
+    # is fused into the kernel's TMA pipeline) on the same blocks, same timing rules, parity-checked ----
+    sat = None
+    if world > 1:
+        eng.set_sample_origin(-1)
+        for _ in range(3):
+            launch_sat()
+            eng.gather_wait()
+        barrier()
+        sat_parity = parity_of(eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS))
+        assert sat_parity < 1e-4, f"satellite-sharded parity {sat_parity}"
+        n_sat = max(3, min(steps, 10))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_sat)]
+        ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ta.record()
+        for a, b in evs:
+            a.record()
+            launch_sat()
+            b.record()
+            eng.gather_wait()
+        tb.record()
+        barrier()
+        ts = torch.tensor([ta.elapsed_time(tb) / n_sat, float(np.mean([a.elapsed_time(b) for a, b in evs]))], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sat_ms, sat_kernel_ms = ts.tolist()
+        sat = {"ms_per_step": sat_ms, "kernel_ms": sat_kernel_ms, "value": corr_per_step / (sat_ms * 1e-3), "steps": n_sat, "parity_max_rel": sat_parity}
+        eng.set_sample_origin(smp_lo)
+        log(f"satellite-sharded: {sat['value'] / 1e6:.2f} M corr/s, {sat_ms:.4f} ms/step")
 
     # ---- e2e: host buffers -> H2D -> correlate -> D2H, through the C ABI ----
     e2e_steps = max(2, min(steps, args.e2e_steps))
@@ -462,44 +529,30 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
 
         e2e_path = "pinned host -> gat_ingest_correlate (H2D in 16-period chunks on the ingest stream, overlapped with the kernels) -> host"
     else:
-        # every rank holds ITS sample range of every block in pinned host memory (N PCIe links in parallel), uploads it into
-        # its share of the ring chunk by chunk and publishes; the kernels gather the other ranges over NVLink
-        part_ld = max(4, (part_len + 3) & ~3)
+        # every rank holds ITS sample range of every block in pinned host memory (N PCIe links in parallel): one
+        # gat_ingest_correlate call per rank and step (H2D chunks under the kernels, all `world` satellites over the rank's own
+        # samples, partial sums back on the host), then the partial sums are added on rank 0 (NCCL reduce of 1.5 MB) and read back
+        part_ld = max(4, (smp_len + 3) & ~3)
         hp_re = torch.zeros(P, N_ANTS, part_ld, pin_memory=True)
         hp_im = torch.zeros(P, N_ANTS, part_ld, pin_memory=True)
-        if part_len:
-            hp_re[:, :, :part_len].copy_(re[:, :, part_lo:part_lo + part_len])
-            hp_im[:, :, :part_len].copy_(im[:, :, part_lo:part_lo + part_len])
-        chunk_chans = [eng.marshal(chan_list[c0:c0 + CH]) for c0 in range(0, P, CH)]
-        n_chunks = P // CH
-        g_host = (np.empty((world, (elems + 63) & ~63), np.float32), np.empty((world, (elems + 63) & ~63), np.float32))
+        hp_re[:, :, :smp_len].copy_(re[:, :, smp_lo:smp_lo + smp_len])
+        hp_im[:, :, :smp_len].copy_(im[:, :, smp_lo:smp_lo + smp_len])
+        h_part = torch.empty(2, P, world, N_TAPS, N_ANTS, pin_memory=True)
+        h_part_np = h_part.numpy()
+        d_part = torch.empty(2, P, world, N_TAPS, N_ANTS, device=dev)
+        h_sum = torch.empty(2, P, world, N_TAPS, N_ANTS, pin_memory=True)
         torch.cuda.synchronize()
-        state = {"pub": 1, "rel": 1, "steps": 0}                       # the set-up above published and released once
 
         def e2e_step():
-            pub0, rel0 = state["pub"], state["rel"]
-            for ci in range(n_chunks):                               # ingest stream: runs ahead of the kernels
-                # the chunk's slots were last read by the same chunk of the previous step: wait for every rank's release of it
-                eng.ring_acquire(rel0 - n_chunks + ci + 1 if state["steps"] else 0)
-                if part_len:
-                    for p in range(ci * CH, (ci + 1) * CH):
-                        eng.ring_upload(p, hp_re[p], hp_im[p], part=True)
-                assert eng.ring_publish() == pub0 + ci + 1
-            for ci in range(n_chunks):                               # main stream
-                eng.ring_wait(pub0 + ci + 1)                         # every rank's share of the chunk is in place
-                eng.gather_set_offset(ci * CH * N_TAPS * N_ANTS)
-                eng.correlate_batch(slots[ci * CH:(ci + 1) * CH], chunk_chans[ci], FS, shifts, N_ANTS, 0, N_SAMPLES, gather=True)
-                eng.ring_release()
-            eng.gather_set_offset(0)
-            state.update(pub=pub0 + n_chunks, rel=rel0 + n_chunks, steps=state["steps"] + 1)
-            eng.gather_wait()
+            eng.ingest_correlate(hp_re, hp_im, chans_all, FS, shifts, 0, smp_len, out=h_part_np)
+            d_part.copy_(h_part, non_blocking=True)
+            dist.reduce(d_part, dst=0)
             if rank == 0:
-                eng.gather_read(out=g_host)                          # synchronises + D2H of every rank's accumulators
-            else:
-                eng.sync()
+                h_sum.copy_(d_part, non_blocking=True)
+            torch.cuda.synchronize()
 
-        e2e_path = (f"pinned host (1/{world} of every block per rank) -> gat_ring_upload_part over {world} PCIe links -> kernels gather the "
-                    "tiles over NVLink (fused all-gather) -> gather fused into the epilogue -> D2H on rank 0")
+        e2e_path = (f"pinned host (1/{world} of every block per rank, {world} PCIe links) -> gat_ingest_correlate on every rank (all {world} "
+                    "satellites over the rank's own samples) -> partial sums reduced onto rank 0 (NCCL, 1.5 MB) -> D2H")
     log("e2e leg")
     for _ in range(2):
         e2e_step()
@@ -514,11 +567,16 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = te.item()
     e2e_value = corr_per_step / (e2e_ms * 1e-3)
+    if world > 1 and rank == 0:
+        e2e_err = float((h_sum[0] - s_re.cpu()).abs().max())
+        assert e2e_err <= 1e-5 * N_SAMPLES, f"e2e accumulators differ from the resident run by {e2e_err}"
     if world == 1:
         e2e_err = float(np.abs(h_res[0].reshape(P, N_TAPS, N_ANTS) - o_re.cpu().numpy().reshape(P, N_TAPS, N_ANTS)).max())
         # (16-period launches split the tiles differently from the 256-period launch: same sums, another order)
         assert e2e_err <= 1e-5 * N_SAMPLES, f"e2e accumulators differ from the resident run by {e2e_err}"
     log(f"e2e {e2e_value / 1e6:.3f} M corr/s, {e2e_ms:.2f} ms/step")
+    if world > 1:
+        eng.set_sample_origin(-1)          # the side legs below work on whole blocks again
 
     if rank != 0 and world == 1:
         return
@@ -527,7 +585,8 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-    algo_bytes = P * (8 * N_SAMPLES * N_ANTS) + P * (8 * N_TAPS * N_ANTS) + 1023   # signal once + outputs + chip table
+    n_loc = smp_len if world > 1 else N_SAMPLES                  # samples of every block this GPU reads
+    algo_bytes = P * (8 * n_loc * N_ANTS) + P * world * (8 * N_TAPS * N_ANTS) + 1023 * world   # signal once + outputs + chip tables
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -538,35 +597,48 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
-    remote_frac = (N_SAMPLES - part_len) / N_SAMPLES if world > 1 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms}
     exchange = None
     if world > 1:
-        # the kernel's binding resource is now the NVLink ingress of every GPU: (world - 1) / world of every block is remote
-        nv_bytes = P * 8 * N_SAMPLES * N_ANTS * remote_frac
-        nv_gbs = nv_bytes / (kernel_ms * 1e-3) / 1e9
-        exchange = {"kind": "all-gather of the signal blocks fused into the correlate kernel (TMA loads from the owners' HBM over NVLink)",
-                    "nvlink_bytes_in_per_gpu_per_step": nv_bytes, "achieved_gbs_in_per_gpu": nv_gbs, "peak_gbs": 900.0,
-                    "peak_source": "NVLink 5 nominal, per direction and GPU", "frac": nv_gbs / 900.0,
-                    "note": "weak scaling over satellites needs every block on every GPU: at 1 satellite per GPU the step is bound by "
-                            "NVLink ingress (900 GB/s) instead of HBM (6.5 TB/s); `roofline` keeps the HBM figure for continuity"}
-        roofline["bound_multi_gpu"] = "nvlink-ingress"
+        # per GPU the kernel now reads 1 / world of every block for `world` satellites: FP32 work as at N = 1, HBM bytes / world
+        flops = P * world * n_loc * N_ANTS * (6 + 4 * N_TAPS)
+        fp32_peak = 73.0e12                                      # measured (scripts/microbench/fma_rate.cu), DESIGN.md section 5
+        t_hbm, t_fp = algo_bytes / (peak * 1e9), flops / fp32_peak
+        roofline["bound_multi_gpu"] = "fp32" if t_fp > t_hbm else "hbm"
+        roofline["fp32"] = {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak / 1e12,
+                            "frac": flops / (kernel_ms * 1e-3) / fp32_peak, "flops_per_launch": flops}
+        roofline["frac_of_binding"] = max(t_hbm, t_fp) / (kernel_ms * 1e-3)
+        ex_bytes = elems_s * 8 * (world - 1)
+        exchange = {"kind": "partial sums of every rank stored into every rank's gather buffer from the kernel epilogue (NVLink peer "
+                            "stores), slices added by gat_gather_sum",
+                    "nvlink_bytes_out_per_gpu_per_step": ex_bytes, "signal_bytes_over_nvlink": 0,
+                    "note": "sample-sharded: every GPU correlates all satellites over its own sample range; no signal block crosses NVLink"}
+        nv_bytes = P * 8 * N_SAMPLES * N_ANTS * (N_SAMPLES - part_len) / N_SAMPLES
+        sat["exchange"] = {"kind": "all-gather of the signal blocks fused into the correlate kernel (TMA loads from the owners' HBM over NVLink)",
+                           "nvlink_bytes_in_per_gpu_per_step": nv_bytes,
+                           "achieved_gbs_in_per_gpu": nv_bytes / (sat["kernel_ms"] * 1e-3) / 1e9, "peak_gbs": 900.0,
+                           "peak_source": "NVLink 5 nominal, per direction and GPU",
+                           "frac": nv_bytes / (sat["kernel_ms"] * 1e-3) / 1e9 / 900.0}
+        sat["note"] = ("north_star's data flow at ONE satellite per GPU: rank r correlates its own satellite over the whole block, which "
+                       "it gathers tile by tile over NVLink inside the kernel -- bound by NVLink ingress (<= 0.9 TB/s) instead of HBM "
+                       "(6.5 TB/s); the engine therefore shards samples for few channels per GPU (`value`) and satellites for many (`c5`)")
     line = {
         "metric": "correlations/sec", "value": value, "unit": "correlations/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(P, world, {"launch": {k: info[k] for k in ("grid", "block", "smem_bytes", "stages", "tile_len", "consumer_warps")},
                                           "signal_residency": ("every block resident on the one GPU" if world == 1 else
-                                                               f"every block scattered over the {world} GPUs' HBM by sample range; each kernel "
-                                                               "gathers its tiles over NVLink inside the timed region")}),
+                                                               f"every block scattered over the {world} GPUs' HBM by sample range (what each "
+                                                               "GPU's PCIe link delivers)")}),
         "roofline": roofline,
         "exchange": exchange,
+        "satellite_sharded": sat,
         "parity_max_rel": parity,
         "parity_pairs_per_rank": len(pairs),
         "cpu_baseline": None,
         "e2e": {"value": e2e_value, "unit": "correlations/s", "h2d_bytes_per_step": P * 8 * N_SAMPLES * N_ANTS,
-                "d2h_bytes_per_step": world * P * 8 * N_TAPS * N_ANTS, "ms_per_step": e2e_ms, "steps": e2e_steps, "path": e2e_path,
+                "d2h_bytes_per_step": (P * 8 * N_TAPS * N_ANTS if world == 1 else (world + 1) * P * world * 8 * N_TAPS * N_ANTS), "ms_per_step": e2e_ms, "steps": e2e_steps, "path": e2e_path,
                 "h2d_gb_per_s_per_gpu": P * 8 * N_SAMPLES * N_ANTS / world / (e2e_ms * 1e-3) / 1e9,
                 "bound": "PCIe host->device copy (the kernel needs %.2f ms of the %.1f ms step)" % (ms_per_step, e2e_ms)},
         "gpu_launches": int(gpu_launches),

@@ -102,6 +102,8 @@ SYMBOLS = {
     "gat_ring_prefetch": (_i, [_vp, _i, _i, _i, _i]),
     "gat_ring_mirror_wait": (_i, [_vp, _i]),
     "gat_ring_destroy": (_i, [_vp]),
+    "gat_set_sample_origin": (_i, [_vp, _i]),
+    "gat_gather_sum": (_i, [_vp, C.c_uint64, _vp, _vp]),
     "gat_resident_begin": (_i, [_vp, _i32p, _i, _i, _chp, _d, _i32p, _i, _i, _i]),
     "gat_resident_correlate": (_i, [_vp, _i, _chp, _vp, _vp]),
     "gat_resident_end": (_i, [_vp]),

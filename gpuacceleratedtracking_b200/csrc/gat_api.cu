@@ -131,7 +131,10 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     if (AG * TG > w_cap) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
 
     const int w_target_multi = std::min(w_cap, env_int("GAT_TUNE_WMAX", w_cap));
-    const int w_target_single = std::min(w_cap, env_int("GAT_TUNE_W", w_cap == 11 ? 8 : 16));
+    // (two channels per block of 16 antennas -- the per-GPU step of the 2-GPU sample-sharded run: 5 slices x 2 channels = 10 warps over
+    // a 5-stage ring, 0.185 -> 0.156 ms per 256 half-blocks against 3 slices over 6 stages)
+    const bool two_channels = K == 2 && AG * TG == 1 && w_cap == 11;
+    const int w_target_single = std::min(w_cap, env_int("GAT_TUNE_W", w_cap == 11 ? (two_channels ? 10 : 8) : 16));
     const int cache_stride = (sh.max_code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign;
     const size_t smem_budget = 227 * 1024;
     const int RW = AG * TG;            // warps per satellite and sample slice
@@ -238,7 +241,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
         // shortened only if it stays >= 8 stages deep -- small int16 tiles: 8 slices over 8 stages 170 us against 6 over 12
         // 195 us; 32 KB FP32 tiles: 3 slices over 6 stages 76 us against 4 over 4 84 us (5 taps x 16 antennas, 64 periods).
         if (SL > 1 && stages % SL != 0) {
-            if (stages / SL * SL >= 8) stages = stages / SL * SL;
+            if (stages / SL * SL >= 8 || (two_channels && SL == 5 && stages > SL)) stages = stages / SL * SL;
             else
                 while (SL > 1 && stages % SL != 0) --SL;
         }
@@ -633,6 +636,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
 
     // ---- tensor-core path (opt-in): many channels over the same block(s), see gat_correlate_tc.cu ----
     ctx->info.tensor = 0;
+    if (ctx->sample_origin >= 0) flags &= ~static_cast<unsigned>(GAT_TENSOR_TF32);   // sample ranges run on the FP32 kernel
     if (flags & GAT_TENSOR_TF32) {
         const int span = sh_pad[n_taps - 1] - sh_pad[0];
         bool ok = !(flags & (GAT_CODE_PHASE_F64 | GAT_ACCUMULATE | GAT_GATHER)) && n_taps <= 4 && M <= 16 && span <= 224 &&
@@ -747,6 +751,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (rc) return rc;
     args.flags = flags;
     args.out_scale = use_raw ? raw_scale : 1.f;
+    args.phase_off = ctx->sample_origin >= 0 ? ctx->sample_origin + start_sample : 0;
 
     // parameter block: [PeriodDev x P][SatDev x P*K]
     const size_t per_bytes = sizeof(PeriodDev) * periods.size();
@@ -1860,6 +1865,27 @@ int gat_gather_set_offset(gat_ctx *ctx, uint64_t elem_offset)
     if (!ctx) return GAT_ERR_INVALID;
     if (elem_offset >= ctx->g_elems && ctx->g_elems) return fail(ctx, GAT_ERR_INVALID, "gather offset beyond the slice");
     ctx->g_off = elem_offset;
+    return GAT_OK;
+}
+
+int gat_set_sample_origin(gat_ctx *ctx, int origin)
+{
+    if (!ctx) return GAT_ERR_INVALID;
+    if (ctx->res.active) return fail(ctx, GAT_ERR_INVALID, "a resident session is open");
+    ctx->sample_origin = origin < 0 ? -1 : origin;
+    return GAT_OK;
+}
+
+int gat_gather_sum(gat_ctx *ctx, uint64_t n_elems, float *d_out_re, float *d_out_im)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!ctx->g_connected || !d_out_re || !d_out_im) return fail(ctx, GAT_ERR_INVALID, "gather not connected, or null outputs");
+    if (n_elems < 1 || n_elems > ctx->g_elems) return fail(ctx, GAT_ERR_INVALID, "more elements than a gather slice holds");
+    const cudaError_t e = launch_sum_slices(ctx->g_re[ctx->g_rank], ctx->g_im[ctx->g_rank], ctx->g_elems, ctx->g_world, n_elems, d_out_re,
+                                            d_out_im, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "sum_slices_kernel");
+    ctx->launches += 1;
     return GAT_OK;
 }
 

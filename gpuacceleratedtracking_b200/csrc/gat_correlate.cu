@@ -733,13 +733,13 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                             if constexpr (DUMP) dmp.p = args.dump + (size_t)t * args.dump_stride;
                             uint64_t frac = 0;
                             uint32_t bmod = 0;
-                            if constexpr (!F64) nco_tile_base(sd, (int64_t)n0 + args.shifts[0], frac, bmod);
+                            if constexpr (!F64) nco_tile_base(sd, (int64_t)n0 + args.phase_off + args.shifts[0], frac, bmod);
                             const int buf = 2 * grp_id + (int)(use & 1u);
                             float *rep = rep_all + (size_t)buf * args.rep_stride;
                             mbar_wait(reinterpret_cast<uint64_t *>(smem + 2 * kRepBarOff) + buf, ((use >> 1) & 1u) ^ 1u);   // its previous readers are done
                             gen_replica_rows<F64, DUMP>(args, lane, 0, rows, rep, smem_u32(rep), code_cache, smem_u32(code_cache), frac, bmod,
                                                         (uint64_t)sd.nco_delta, sd.nco_fp - 32, (uint32_t)sd.code_len, sd.code_ratio, sd.code_phase,
-                                                        n0 + args.shifts[0], dmp);
+                                                        n0 + args.phase_off + args.shifts[0], dmp);
                             __syncwarp();
                             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t *>(smem + kRepBarOff) + buf);
                         }
@@ -802,7 +802,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                             if (t == t_first) {
                                 SatDev tmp;
                                 tmp.nco_delta = (int64_t)delta[s]; tmp.nco_start = nco_start[s]; tmp.nco_fp = fp[s]; tmp.code_len = (int32_t)lc[s];
-                                nco_tile_base(tmp, (int64_t)n0 + args.shifts[0], frac[s], bmod[s]);
+                                nco_tile_base(tmp, (int64_t)n0 + args.phase_off + args.shifts[0], frac[s], bmod[s]);
                             } else {
                                 frac[s] += adv_frac[s];
                                 bmod[s] += adv_chips[s] + (uint32_t)(frac[s] >> fp[s]);
@@ -819,7 +819,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                         const int8_t *tab = code_cache + (size_t)s * args.cache_stride;
                         mbar_wait(reinterpret_cast<uint64_t *>(smem + 2 * kRepBarOff) + buf, ((use >> 1) & 1u) ^ 1u);   // its previous readers are done
                         gen_replica_rows<F64, DUMP>(args, lane, 0, rows, rep, smem_u32(rep), tab, smem_u32(tab), frac[s], bmod[s], delta[s],
-                                                    fp[s] - 32, lc[s], ratio[s], cphase[s], n0 + args.shifts[0], dmp);
+                                                    fp[s] - 32, lc[s], ratio[s], cphase[s], n0 + args.phase_off + args.shifts[0], dmp);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t *>(smem + kRepBarOff) + buf);
                     }
@@ -952,7 +952,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                 if (active) mbar_wait_s(smem_u32(smem + kRepBarOff) + 8u * rbuf, (use_run >> 1) & 1u);   // the replica warp wrote this visit's replica
                 int tt0 = lane_base;
                 if (n0 + tt0 < 0) tt0 += tt_stride;           // samples staged before start_sample (first tile of a job)
-                uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
+                uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + args.phase_off + tt0) * car_delta) >> 32);
                 uint32_t ra = rep_s + (use_run & 1u) * 4u * (uint32_t)args.rep_stride + 4u * (uint32_t)tt0 + tg_off;
                 int spj = sp;
 #pragma unroll 1
@@ -1051,7 +1051,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                     if (!have_base) {
                         SatDev tmp;
                         tmp.nco_delta = (int64_t)delta; tmp.nco_start = nco_start; tmp.nco_fp = fp; tmp.code_len = (int32_t)lc;
-                        nco_tile_base(tmp, (int64_t)n0 + args.shifts[0], frac, bmod);
+                        nco_tile_base(tmp, (int64_t)n0 + args.phase_off + args.shifts[0], frac, bmod);
                         have_base = true;
                     } else {
                         frac += adv_frac;
@@ -1062,7 +1062,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                     }
                 }
                 gen_replica_rows<F64, DUMP>(args, lane, row0, row1, rep, rep_s, tab, tab_s, frac, bmod, delta, sh, lc, ratio, cphase,
-                                            n0 + args.shifts[0], dmp);
+                                            n0 + args.phase_off + args.shifts[0], dmp);
                 if (gw > 1) group_bar_sync(2 + gid, 32 * gw); else __syncwarp();
             }
             mbar_wait_s(bars_s + 8u * (uint32_t)stage, par);
@@ -1074,7 +1074,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                 // past the end never reach the loop (tt < len).  The loop itself stays branch-free.
                 int tt0 = split ? sl * 32 + lane : lane;
                 if (n0 + tt0 < 0) tt0 += tt_stride;
-                uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + tt0) * car_delta) >> 32);
+                uint32_t ph = (uint32_t)((car_phase + (uint64_t)(int64_t)(n0 + args.phase_off + tt0) * car_delta) >> 32);
                 // running shared-memory addresses of this lane's sample in the re / im planes and in the replica;
                 // the loop carries nothing else (no sample counter): ptxas otherwise re-derives the tile base and
                 // the phase step from the kernel arguments in every iteration

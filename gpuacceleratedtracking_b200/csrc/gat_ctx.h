@@ -178,6 +178,7 @@ struct gat_ctx {
     int ing_n = 0, ing_m = 0;                        // shape the staging slots are currently bound for
     int64_t ing_ld = 0;
     gat::Resident res;
+    int sample_origin = -1;   // gat_set_sample_origin: >= 0 = the slots hold samples [origin, ..) of the period the phases refer to
 };
 
 namespace gat {

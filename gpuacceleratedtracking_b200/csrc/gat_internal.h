@@ -139,6 +139,8 @@ struct alignas(64) CorrArgs {
     int32_t dump_stride;               // entries per tile in `dump` (the one-tile replica stride)
     int32_t rep_bufs;                  // code-replica buffers of rep_stride floats in shared memory (W, or 2 per group with replica warps)
     int32_t visit_tiles;               // reallocation class: consecutive tiles a consumer warp works through per visit (1 or 2)
+    int32_t phase_off;                 // sample index, in the channel phases' frame, of start_sample (0: the phases refer to start_sample;
+                                       // gat_set_sample_origin: the phases refer to sample 0 of the integration period this slot is a range of)
 };
 
 static_assert(sizeof(CorrArgs) <= 4096, "kernel parameter space");
@@ -217,6 +219,8 @@ cudaError_t launch_flag_wait(unsigned int *local_flags, int world, unsigned int 
 
 
 // expand interleaved complex integer samples [n_ants][ld_in][2] into FP32 planes [n_ants][ld_out]
+cudaError_t launch_sum_slices(const float *in_re, const float *in_im, size_t slice_stride, int n_slices, size_t n, float *out_re,
+                              float *out_im, cudaStream_t stream);
 cudaError_t launch_beamform(const float *acc_re, const float *acc_im, const float *w_re, const float *w_im, float *y_re, float *y_im,
                             int n_ch, int n_taps, int n_ants, cudaStream_t stream);
 cudaError_t launch_eigen_weights(const float *acc_re, const float *acc_im, int n_ch, int n_taps, int n_ants, int tap, float forget, int iters,

@@ -8,6 +8,7 @@
 // the ctx stream right behind the correlate kernel.  PARITY UNPINNED: the reference ships no post-correlation
 // filter of its own; the tests check these kernels against numpy (float64) restatements of the formulas above.
 #include "gat_internal.h"
+#include <algorithm>
 
 namespace gat {
 
@@ -90,6 +91,31 @@ __global__ void eigen_weights_kernel(const float *__restrict__ acc_re, const flo
         w_re[(size_t)k * n_ants + lane] = wr;
         w_im[(size_t)k * n_ants + lane] = wi;
     }
+}
+
+// out[i] = sum over the `n_slices` slices of a gather buffer, in slice order (fixed order: bit-reproducible) -- the
+// cross-GPU reduction of sample-sharded correlation (every rank holds partial sums over its own sample range)
+__global__ void sum_slices_kernel(const float *__restrict__ in_re, const float *__restrict__ in_im, size_t slice_stride, int n_slices,
+                                  size_t n, float *__restrict__ out_re, float *__restrict__ out_im)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float ar = 0.f, ai = 0.f;
+        for (int r = 0; r < n_slices; ++r) {
+            ar += __ldcg(in_re + (size_t)r * slice_stride + i);     // written by peers' stores: bypass L1
+            ai += __ldcg(in_im + (size_t)r * slice_stride + i);
+        }
+        out_re[i] = ar;
+        out_im[i] = ai;
+    }
+}
+
+cudaError_t launch_sum_slices(const float *in_re, const float *in_im, size_t slice_stride, int n_slices, size_t n, float *out_re,
+                              float *out_im, cudaStream_t stream)
+{
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 8);
+    sum_slices_kernel<<<std::max(1, blocks), threads, 0, stream>>>(in_re, in_im, slice_stride, n_slices, n, out_re, out_im);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_beamform(const float *acc_re, const float *acc_im, const float *w_re, const float *w_im, float *y_re, float *y_im,

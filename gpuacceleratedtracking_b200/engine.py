@@ -416,6 +416,17 @@ class Engine:
     def gather_wait(self):
         self._check(self._lib.gat_gather_wait(self._h))
 
+    # ---- sample sharding (include/gat.h gat_set_sample_origin / gat_gather_sum) ----
+    def set_sample_origin(self, origin: int):
+        """The ctx's slots hold samples [origin, ...) of the period the channel phases refer to (-1: off)."""
+        self._check(self._lib.gat_set_sample_origin(self._h, int(origin)))
+
+    def gather_sum(self, n_elems: int, out):
+        """Add the `world` slices of the local gather buffer (first n_elems elements) into out = (re, im) device tensors."""
+        o_re, o_im = out
+        assert o_re.is_cuda and o_re.dtype == torch.float32 and o_re.numel() >= n_elems and o_im.numel() >= n_elems
+        self._check(self._lib.gat_gather_sum(self._h, int(n_elems), C.c_void_p(o_re.data_ptr()), C.c_void_p(o_im.data_ptr())))
+
     def gather_read(self, out=None):
         """complex64 [world, elems_per_rank(padded)] of the local gather buffer (synchronises).  With out=(re, im) float32
         arrays of that shape the planes are copied into them instead (no allocation, returns None)."""

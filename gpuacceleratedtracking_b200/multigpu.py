@@ -27,6 +27,14 @@ def shard_bounds(n_items: int, world_size: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def shard_sample_ranges(n_samples: int, world_size: int, align: int = 4) -> list[tuple[int, int]]:
+    """Sample sharding (include/gat.h gat_set_sample_origin): [(first sample, length)] of every rank's contiguous range of
+    a block, balanced, every start a multiple of `align` samples (16-byte aligned rows for the TMA descriptors when the
+    range is bound in place).  The decomposition for few channels per GPU: no signal crosses NVLink, the partial sums do."""
+    cuts = [min(n_samples, (n_samples * r // world_size) // align * align) for r in range(world_size)] + [n_samples]
+    return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world_size)]
+
+
 def shard_channels(channels: Sequence, world_size: int, rank: int, keep_bands_together: bool = True):
     """Returns (indices, shard).  With keep_bands_together, channels are first ordered by
     system id so a GPU tends to need only one band's signal (SURVEY 8e 'Partitioning')."""

@@ -237,6 +237,20 @@ int gat_gather_connect(gat_ctx *ctx, const unsigned char *handles /* [world][GAT
 int gat_gather_set_offset(gat_ctx *ctx, uint64_t elem_offset);
 int gat_gather_wait(gat_ctx *ctx);
 int gat_gather_read(gat_ctx *ctx, float *h_re, float *h_im); /* sync + D2H of [world x elems_per_rank] */
+/* ---- sample sharding: the decomposition for FEW channels per GPU (SURVEY 8e "alternative worth measuring") ----
+ * Sharding the satellites means every GPU needs every block (the signal exchange above); with one or two channels per GPU
+ * that exchange (NVLink, <= 0.9 TB/s) is all the step does.  The accumulators are SUMS over samples, so the samples can be
+ * sharded instead: every GPU correlates ALL channels over the sample range its own PCIe link delivered -- no signal crosses
+ * NVLink -- and the partial sums are added across the GPUs:
+ *   gat_set_sample_origin(ctx, o)  (sticky; -1 = off)  the ctx's slots hold samples [o, o + n) of the integration period the
+ *       channel phases refer to: the code / carrier phase of slot sample s is taken at period sample o + s, with the same
+ *       integer NCO and Q0.64 carrier arithmetic as a whole-block call (bit-exact chip indices), so the partial sums of the
+ *       ranges add up to the whole block's accumulators up to FP32 summation order;
+ *   gat_correlate*(... GAT_GATHER) puts this rank's partial sums into slice `rank` of every rank's gather buffer;
+ *   gat_gather_wait; gat_gather_sum(n, out_re, out_im) adds the `world` slices in rank order into device outputs
+ *       (stream-ordered; identical on every rank). */
+int gat_set_sample_origin(gat_ctx *ctx, int origin);
+int gat_gather_sum(gat_ctx *ctx, uint64_t n_elems, float *d_out_re, float *d_out_im);
 int gat_gather_destroy(gat_ctx *ctx);
 
 /* ---- signal ring: the all-gather of the signal blocks fused into the correlate kernel ----------

@@ -159,6 +159,11 @@ end
 
 resident_end!(ctx::Context) = check(ctx, ccall((:gat_resident_end, libgat), Cint, (Ptr{Cvoid},), ctx.handle))
 
+# ---- sample sharding: a ctx that holds samples [origin, ...) of every period (gat_set_sample_origin / gat_gather_sum) ----
+set_sample_origin!(ctx::Context, origin::Integer) = check(ctx, ccall((:gat_set_sample_origin, libgat), Cint, (Ptr{Cvoid}, Cint), ctx.handle, origin))
+gather_sum!(ctx::Context, out_re::CuArray{Float32}, out_im::CuArray{Float32}) =
+    check(ctx, ccall((:gat_gather_sum, libgat), Cint, (Ptr{Cvoid}, UInt64, CuPtr{Cfloat}, CuPtr{Cfloat}), ctx.handle, length(out_re), out_re, out_im))
+
 # ---- all GPUs of the box from this one process (gat_mg_*) -------------------------------------------------------
 mutable struct MultiContext
     handle::Ptr{Cvoid}

@@ -258,3 +258,16 @@ def test_plot_sweep_tool_writes_the_papers_figure(tmp_path):
     doc = xml.dom.minidom.parse(str(svg))
     assert len(doc.getElementsByTagName("polyline")) >= 3 * 6            # three curves in every panel
     assert "real time (1 ms)" in svg.read_text() and md.read_text().count("\n") > 40
+
+
+def test_sample_ranges_cover_the_block():
+    """multigpu.shard_sample_ranges: contiguous, 4-aligned starts, balanced within one alignment unit."""
+    from gpuacceleratedtracking_b200.multigpu import shard_sample_ranges
+    for n in (50000, 2500, 262144, 7, 4):
+        for world in (1, 2, 3, 4, 8):
+            r = shard_sample_ranges(n, world)
+            assert len(r) == world and r[0][0] == 0 and sum(ln for _, ln in r) == n
+            assert all(lo % 4 == 0 and ln >= 0 for lo, ln in r)
+            assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(world - 1))
+            if n >= 8 * world:
+                assert max(ln for _, ln in r) - min(ln for _, ln in r) <= 8

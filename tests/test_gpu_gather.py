@@ -62,8 +62,25 @@ def _worker(rank, world, port, q):
         ref = np.stack([orc.correlate_direct(re, im, c.system.codes[c.prn - 1], c.system.code_frequency, c.code_phase,
                                              c.carrier_frequency, c.carrier_phase, fs, shifts) for c in chans])
         err = np.abs(got - ref).max() / np.abs(ref[:, 1]).max()
+        # the other decomposition: every rank correlates ALL channels over its own sample range, partial sums gathered + added
+        from gpuacceleratedtracking_b200.multigpu import shard_sample_ranges
+        eng2 = gat.Engine(rank)
+        lo, ln = shard_sample_ranges(n, world)[rank]
+        eng2.upload_signal(0, np.ascontiguousarray(re[:, lo:lo + ln]), np.ascontiguousarray(im[:, lo:lo + ln]))
+        all_elems = len(chans) * 3 * m
+        gather_setup(eng2, all_elems)
+        eng2.set_sample_origin(lo)
+        o_re, o_im = torch.zeros(all_elems, device="cuda"), torch.zeros(all_elems, device="cuda")
+        for _ in range(2):
+            eng2.correlate_batch([0], [chans], fs, shifts, m, 0, ln, gather=True)
+            eng2.gather_wait()
+            eng2.gather_sum(all_elems, (o_re, o_im))
+        eng2.sync()
+        summed = (o_re.cpu().numpy() + 1j * o_im.cpu().numpy()).reshape(len(chans), 3, m)
+        err = max(err, np.abs(summed - ref).max() / np.abs(ref[:, 1]).max())
         q.put((rank, float(err)))
         dist.barrier()
+        eng2.close()
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -131,4 +148,63 @@ def test_slot_export_import_across_processes(gat, orc):
         eng.export_slot(1)
     with pytest.raises(gat.GatError):
         eng.import_slot(2, bytes(96))
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", ["nco", "f64"])
+def test_sample_sharded_partial_sums_add_up(gat, orc, mode):
+    """Sample sharding (gat_set_sample_origin): every "rank" correlates ALL channels over its own sample range with the phases
+    taken at the period's sample 0; the partial sums of the ranges add up to the whole block's accumulators (FP32 summation
+    order aside), the chip indices of a range are bit-exactly the whole block's, and gat_gather_sum adds gather slices."""
+    import torch
+    from gpuacceleratedtracking_b200.multigpu import shard_sample_ranges
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(3)
+    n, m, fs = 50000, 16, 5.0e7
+    re = rng.normal(size=(m, n)).astype(np.float32)
+    im = rng.normal(size=(m, n)).astype(np.float32)
+    chans = [gat.Channel(l1, prn, float(rng.uniform(0, 1023)), float(rng.uniform(-4e3, 4e3)), float(rng.uniform(-.5, .5))) for prn in (3, 8, 22)]
+    shifts = np.array([-24, 0, 24], np.int32)
+    f64 = mode == "f64"
+    eng.upload_signal(0, re, im)
+    whole = eng.correlate(0, chans, fs, shifts, m, n_samples=n, code_phase_f64=f64).astype(np.complex128)
+    ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase, fs, shifts,
+                                         code_mode=mode) for c in chans])
+    scale = 3 * np.sqrt(n)
+    for world in (2, 3, 8):
+        ranges = shard_sample_ranges(n, world)
+        assert sum(ln for _, ln in ranges) == n and all(lo % 4 == 0 for lo, _ in ranges)
+        total = np.zeros_like(whole)
+        for r, (lo, ln) in enumerate(ranges):
+            eng.upload_signal(10 + r, np.ascontiguousarray(re[:, lo:lo + ln]), np.ascontiguousarray(im[:, lo:lo + ln]))
+            eng.set_sample_origin(lo)
+            total += eng.correlate(10 + r, chans, fs, shifts, m, n_samples=ln, code_phase_f64=f64)
+        eng.set_sample_origin(-1)
+        assert np.abs(total - whole).max() <= 2e-6 * scale, (world, np.abs(total - whole).max())
+        assert np.abs(total - ref).max() <= 2e-5 * scale
+    # a sub-range that starts inside the slot: origin + start_sample
+    lo, ln = 12344, 7001
+    eng.upload_signal(20, np.ascontiguousarray(re[:, lo - 8:lo + ln]), np.ascontiguousarray(im[:, lo - 8:lo + ln]))
+    eng.set_sample_origin(lo - 8)
+    part = eng.correlate(20, chans, fs, shifts, m, start_sample=8, n_samples=ln, code_phase_f64=f64).astype(np.complex128)
+    idx = eng.replica_indices(chans[0], fs, shifts, m, ln, start_sample=8, code_phase_f64=f64)
+    # ... and the ranges before and after it from the whole block's slot (origin 0): the three pieces add up to the whole
+    eng.set_sample_origin(0)
+    head = eng.correlate(0, chans, fs, shifts, m, start_sample=0, n_samples=lo, code_phase_f64=f64)
+    tail = eng.correlate(0, chans, fs, shifts, m, start_sample=lo + ln, n_samples=n - lo - ln, code_phase_f64=f64)
+    eng.set_sample_origin(-1)
+    assert np.abs(head + part + tail - whole).max() <= 2e-6 * scale
+    full_idx = np.stack([orc.chip_index(1.023e6, fs, chans[0].code_phase, 1023, int(sft), lo + ln, mode) for sft in shifts])
+    assert np.array_equal(idx, full_idx[:, lo:lo + ln])
+    # gat_gather_sum over a one-rank gather buffer is a copy of slice 0
+    elems = len(chans) * 3 * m
+    eng.gather_connect([eng.gather_create(1, 0, elems)])
+    eng.correlate_batch([0], [chans], fs, shifts, m, 0, n, gather=True, code_phase_f64=f64)
+    eng.gather_wait()
+    o_re, o_im = torch.zeros(elems, device="cuda"), torch.zeros(elems, device="cuda")
+    eng.gather_sum(elems, (o_re, o_im))
+    eng.sync()
+    got = (o_re.cpu().numpy() + 1j * o_im.cpu().numpy()).reshape(len(chans), 3, m)
+    assert np.array_equal(got.astype(np.complex64), whole.astype(np.complex64))
     eng.close()
