@@ -487,9 +487,14 @@ def _gpu_legs(args, em, world, rank, local, dev, torch, dist, g):
     sat = None
     if world > 1:
         eng.set_sample_origin(-1)
-        for _ in range(3):
-            launch_sat()
-            eng.gather_wait()
+        # (0.3 s of this step first: the NVLink links idle during the sample-sharded step and come back to full rate only
+        # after some tens of milliseconds of traffic -- three warm-up steps measured 326 GB/s per GPU at N = 8 instead of 611)
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.3:
+            for _ in range(5):
+                launch_sat()
+                eng.gather_wait()
+            torch.cuda.synchronize()
         barrier()
         sat_parity = parity_of(eng.gather_read()[:, :elems].reshape(world, P, 1, N_TAPS, N_ANTS))
         assert sat_parity < 1e-4, f"satellite-sharded parity {sat_parity}"

@@ -14,9 +14,9 @@ for n in (1, 2, 4, 8):
     except Exception as e:
         print(n, "no line", e); continue
     c5 = d.get("c5") or {}
-    print("N=%d value %.2f M/s  ms/step %.4f  e2e %.3f M/s  parity %.1e  exch %s  c5 strong %s weak %s  errs %s" % (
+    print("N=%d value %.2f M/s  ms/step %.4f  e2e %.3f M/s  parity %.1e  sat-sharded %.1f M/s  c5 strong %s weak %s  errs %s" % (
         n, d["value"] / 1e6, d["ms_per_step"], d["e2e"]["value"] / 1e6, d["parity_max_rel"],
-        (d.get("exchange") or {}).get("achieved_gbs_in_per_gpu"),
+        ((d.get("satellite_sharded") or {}).get("value") or 0) / 1e6,
         {k: round(v["us_per_period"], 2) for k, v in (c5.get("strong") or {}).items() if isinstance(v, dict)},
         {k: round(v["us_per_period"], 2) for k, v in (c5.get("weak") or {}).items() if isinstance(v, dict)}, d.get("side_errors")))
 PY
