@@ -173,12 +173,16 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // Reallocation class: a consumer warp works through TWO consecutive tiles per visit (one code replica of 2 * tile + span
     // entries, one prologue, 16 loop iterations) unless the tiles are split among the slices.  Everything that is sized per
     // replica uses the longer window.
-    const int visit_max = realloc_class ? std::max(1, std::min(2, env_int("GAT_TUNE_VISIT", 2))) : 1;
+    int visit_max = realloc_class ? std::max(1, std::min(2, env_int("GAT_TUNE_VISIT", 2))) : 1;
+    // per-replica relative NCO phase must fit 64 bits: (window + span + 1) * delta + 2^fp < 2^64 -- at very low sampling rates
+    // (several chips per sample) only a one-tile window does
+    auto window_need = [&](int len) {
+        return static_cast<long double>(len + span + 160) * static_cast<long double>(sh.max_delta) + std::ldexp(1.0L, sh.min_fp);
+    };
+    if (!sh.f64 && visit_max == 2 && window_need(2 * tile_len) >= std::ldexp(1.0L, 64)) visit_max = 1;
     const int rep_len = visit_max * tile_len;
-    // per-replica relative NCO phase must fit 64 bits: (window + span + 1) * delta + 2^fp < 2^64
     if (!sh.f64) {
-        const long double need = static_cast<long double>(rep_len + span + 160) * static_cast<long double>(sh.max_delta) +
-                                 std::ldexp(1.0L, sh.min_fp);
+        const long double need = window_need(rep_len);
         if (need >= std::ldexp(1.0L, 64))
             return fail(ctx, GAT_ERR_UNSUPPORTED, "code rate too high for the fixed-point window (code_freq/fs * tile too large)");
     } else {
@@ -1463,7 +1467,7 @@ int gat_resident_begin(gat_ctx *ctx, const int32_t *slots, int n_slots, int n_sa
     r.n_sats = n_sats;
     r.n_taps = n_taps;
     r.fs_hz = fs_hz;
-    r.rep_len = 2 * r.args.tile_len;
+    r.rep_len = std::max(1, r.args.visit_tiles) * r.args.tile_len;
     r.seq = 0;
     r.launched = false;
     r.active = true;

@@ -139,6 +139,15 @@ __device__ __forceinline__ float chip_to_float(int c)   // +-1 int8 -> +-1.0f wi
 {
     return __uint_as_float(0x3f800000u | ((uint32_t)c & 0x80000000u));
 }
+// CTA-wide barrier for code that exists in TWO copies (the reallocation class instantiates the kernel body once per warpgroup kind):
+// __syncthreads() is `barrier.sync.aligned`, which promises that every thread of the CTA executes the SAME instruction; the two
+// copies meet at different ones, so they use the non-aligned form on the same barrier resource (synccheck flags the aligned one).
+template <int ROLE>
+__device__ __forceinline__ void cta_sync()
+{
+    if constexpr (ROLE == 0) __syncthreads();
+    else asm volatile("barrier.sync 0;" ::: "memory");
+}
 __device__ __forceinline__ void consumer_bar_sync(int threads)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
@@ -596,7 +605,7 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
             tiles[(size_t)st * tile_floats + (size_t)(plane * MP + M + row) * kTileCap + col] = 0.f;
         }
     }
-    __syncthreads();
+    cta_sync<ROLE>();
     if constexpr (ROLE == kRoleAux) {
         if (warp > PW + NREP) return;                 // (none with three replica warps)
     }

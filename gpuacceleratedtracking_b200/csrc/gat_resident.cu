@@ -71,7 +71,7 @@ __device__ __forceinline__ void resident_loop(const CorrArgs &args, const ResCtl
                 cmd_s[3 * lane + 2] = c.z;
             }
         }
-        __syncthreads();
+        cta_sync<ROLE>();
         if (cmd_s[0] != kResOpCorrelate) return;    // exit command, or CTA 0 gave up waiting
         if (threadIdx.x == 32) {
             // the selected block's TMA descriptors on their way into the descriptor cache while the barriers are set up
@@ -88,7 +88,7 @@ __device__ __forceinline__ void resident_loop(const CorrArgs &args, const ResCtl
         if (ctl.stamps && blockIdx.x == 0 && threadIdx.x == 0) ctl.stamps[1] = global_timer_ns();   // debug: body entered
         correlate_body<A, L, false, false, false, HELP, ROLE, true>(args, ro);
         if (ctl.stamps && blockIdx.x == 0 && threadIdx.x == 0) ctl.stamps[2] = global_timer_ns();   // debug: CTA 0 through its finalize
-        __syncthreads();                             // every warp is out of the body before its barriers are set up again
+        cta_sync<ROLE>();                             // every warp is out of the body before its barriers are set up again
     }
 }
 
