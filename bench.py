@@ -871,6 +871,9 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
       mirror : every reader's copy engines pull the peers' shares of the NEXT step into local HBM under this step's kernel
                (an owner-push variant -- copy-engine WRITES into the readers' HBM -- was measured no faster: both directions
                run at ~300-330 GB/s per GPU on an 8 x B200 box, against 611 GB/s for the kernel's own TMA pull)
+      sample : no signal exchange at all -- every rank correlates ALL satellites of the job over ITS OWN sample range of both
+               bands' blocks (gat_set_sample_origin), the partial sums are exchanged through the fused gather and added
+               (gat_gather_sum): 8 K L M bytes per period cross NVLink instead of 8 N M
     Shardings:
       strong : 32 satellites in total (the config as written); bands are kept together, so from 2 GPUs on a rank reads ONE band
       weak   : 32 satellites PER GPU (16 L1 + 16 L5 on every rank)
@@ -904,6 +907,18 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
     eng.ring_wait(gen)
     rel = eng.ring_release()
     eng.sync()
+    # sample sharding reads this rank's own range of every block from plain local slots
+    s_lo, s_ln = eng.ring_part()
+    loc = torch.empty(2, B, 2, N_ANTS, max(s_ln, 4), device=dev) if world > 1 else None
+    if world > 1:
+        for b in (0, 1):
+            for j in range(B):
+                eng.gen_signal(30000, systems[b], 1 + j % 16, 1500.0, FS, N_SAMPLES, N_ANTS, noise_sigma=1.0, seed=17 * j + b)
+                eng.sync()
+                loc[b, j, 0].copy_(tmp[0][:, s_lo:s_lo + s_ln])
+                loc[b, j, 1].copy_(tmp[1][:, s_lo:s_lo + s_ln])
+                eng.bind_signal(31000 + b * B + j, loc[b, j, 0], loc[b, j, 1])
+        torch.cuda.synchronize()
     out = {}
     for mode in ("strong", "weak"):
         if mode == "strong":
@@ -920,7 +935,19 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
         chans = eng.marshal([per_band[bi] for bi in range(len(bands)) for _ in range(B)])
         elems = P5 * K * N_TAPS * N_ANTS
         if world > 1:
-            gather_setup(eng, elems)
+            # sample sharding: every rank works on ALL satellites of the job, both bands
+            if mode == "strong":
+                every = all_ch
+            else:
+                every = [g.Channel(l1 if k < 16 else l5, (k + r) % 16 + 1, 37.0 * k + r, 1500.0 + 40.0 * k - 7.0 * r, 0.01 * k)
+                         for r in range(world) for k in range(32)]
+            ev_band = [[c for c in every if c.system.system_id == b] for b in (0, 1)]
+            K_all = len(ev_band[0])
+            chans_all = eng.marshal([ev_band[b] for b in (0, 1) for _ in range(B)])
+            loc_slots = np.array([31000 + b * B + j for b in (0, 1) for j in range(B)], np.int32)
+            elems_all = 2 * B * K_all * N_TAPS * N_ANTS
+            s_out = (torch.zeros(elems_all, device=dev), torch.zeros(elems_all, device=dev))
+            gather_setup(eng, max(elems, elems_all))
             o = None
         else:
             o = (torch.zeros(P5, K, N_TAPS, N_ANTS, device=dev), torch.zeros(P5, K, N_TAPS, N_ANTS, device=dev))
@@ -928,7 +955,7 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
         lo, ln = eng.ring_part()
         res = {"satellites_total": total, "satellites_per_gpu": len(mine), "bands_per_gpu": len(bands), "periods_per_step": B,
                "nvlink_bytes_in_per_gpu_per_period": len(bands) * 8 * N_SAMPLES * N_ANTS * (N_SAMPLES - ln) / N_SAMPLES if world > 1 else 0}
-        for ingest in (("pull", "mirror") if world > 1 else ("resident",)):
+        for ingest in (("pull", "mirror", "sample") if world > 1 else ("resident",)):
             base = n_slots if ingest == "mirror" else 0
             slots = [np.array([base + slot(st, b, j) for b in bands for j in range(B)], np.int32) for st in range(SETS)]
             state = {"step": 0, "rel": rel, "tickets": {}}
@@ -943,6 +970,12 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
 
             def step():
                 s = state["step"]
+                if ingest == "sample":
+                    eng.correlate_batch(loc_slots, chans_all, FS, shifts, N_ANTS, 0, s_ln, gather=True)
+                    eng.gather_wait()
+                    eng.gather_sum(elems_all, s_out)
+                    state["step"] = s + 1
+                    return
                 if ingest == "mirror":
                     if s == 0:
                         prefetch(0)
@@ -956,6 +989,7 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
                     eng.correlate_batch(slots[s % SETS], chans, FS, shifts, N_ANTS, 0, N_SAMPLES, out=o)
                 state["step"] = s + 1
 
+            eng.set_sample_origin(s_lo if ingest == "sample" else -1)
             for _ in range(6):
                 step()
             if world > 1:
@@ -975,6 +1009,7 @@ def _leg_c5(args, world, rank, local, dev, torch, dist, g, work_stream):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             us = t.item() * 1e3 / B
             res[ingest] = {"us_per_period": us, "realtime_factor": 1000.0 / us, "realtime_channels": total * 1000.0 / us}
+            eng.set_sample_origin(-1)
         best = min((v["us_per_period"], k) for k, v in res.items() if isinstance(v, dict))
         res["us_per_period"], res["best_ingest"] = best
         res["realtime_channels"] = total * 1000.0 / best[0]

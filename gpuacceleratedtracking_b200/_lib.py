@@ -109,6 +109,7 @@ SYMBOLS = {
     "gat_resident_end": (_i, [_vp]),
     "gat_mg_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_i)]),
     "gat_mg_destroy": (_i, [_vp]),
+    "gat_mg_set_sharding": (_i, [_vp, _i]),
     "gat_mg_last_error": (C.c_char_p, [_vp]),
     "gat_mg_device_count": (_i, [_vp]),
     "gat_mg_ctx": (_vp, [_vp, _i]),

@@ -640,7 +640,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
 
     // ---- tensor-core path (opt-in): many channels over the same block(s), see gat_correlate_tc.cu ----
     ctx->info.tensor = 0;
-    if (ctx->sample_origin >= 0) flags &= ~static_cast<unsigned>(GAT_TENSOR_TF32);   // sample ranges run on the FP32 kernel
+    if (ctx->sample_origin_on) flags &= ~static_cast<unsigned>(GAT_TENSOR_TF32);   // sample ranges run on the FP32 kernel
     if (flags & GAT_TENSOR_TF32) {
         const int span = sh_pad[n_taps - 1] - sh_pad[0];
         bool ok = !(flags & (GAT_CODE_PHASE_F64 | GAT_ACCUMULATE | GAT_GATHER)) && n_taps <= 4 && M <= 16 && span <= 224 &&
@@ -755,7 +755,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     if (rc) return rc;
     args.flags = flags;
     args.out_scale = use_raw ? raw_scale : 1.f;
-    args.phase_off = ctx->sample_origin >= 0 ? ctx->sample_origin + start_sample : 0;
+    args.phase_off = ctx->sample_origin_on ? ctx->sample_origin + start_sample : 0;
 
     // parameter block: [PeriodDev x P][SatDev x P*K]
     const size_t per_bytes = sizeof(PeriodDev) * periods.size();
@@ -1876,7 +1876,8 @@ int gat_set_sample_origin(gat_ctx *ctx, int origin)
 {
     if (!ctx) return GAT_ERR_INVALID;
     if (ctx->res.active) return fail(ctx, GAT_ERR_INVALID, "a resident session is open");
-    ctx->sample_origin = origin < 0 ? -1 : origin;
+    ctx->sample_origin_on = origin >= 0;
+    ctx->sample_origin = origin >= 0 ? origin : 0;
     return GAT_OK;
 }
 

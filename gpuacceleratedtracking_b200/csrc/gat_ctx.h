@@ -178,7 +178,8 @@ struct gat_ctx {
     int ing_n = 0, ing_m = 0;                        // shape the staging slots are currently bound for
     int64_t ing_ld = 0;
     gat::Resident res;
-    int sample_origin = -1;   // gat_set_sample_origin: >= 0 = the slots hold samples [origin, ..) of the period the phases refer to
+    bool sample_origin_on = false;   // gat_set_sample_origin: slot sample s is sample origin + s of the period the phases refer to
+    int sample_origin = 0;           // (gat_mg sets a signed value: its callers' phases refer to start_sample, not to sample 0)
 };
 
 namespace gat {

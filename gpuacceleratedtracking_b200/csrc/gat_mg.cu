@@ -9,6 +9,12 @@
 //   * channels are sorted by system id (bands stay together) and cut into contiguous, balanced shards;
 //   * every device's launch is queued before any result is awaited, so the GPUs run concurrently from one host thread;
 //     the accumulators land in the caller's arrays in the ORIGINAL channel order.
+//   * DEFAULT since round 2's second session: SAMPLE sharding (gat_mg_set_sharding).  The accumulators are sums over samples,
+//     so every device correlates ALL channels over the sample range it already holds (its share of the ring) and the host adds
+//     the devices' partial sums in device order: no signal crosses NVLink at all, 8 K L M bytes of partial sums per period
+//     come back per device.  Measured on 8 x B200 (bench.py c5 leg): C5 weak 35 us -> see DESIGN.md section 6.  The phases are
+//     taken with the whole-block call's integer arithmetic (gat_set_sample_origin's mechanism), so the chip indices are
+//     bit-exact; the sums differ from a single-device call in FP32 summation order only.
 #include <new>
 #include <numeric>
 
@@ -27,7 +33,9 @@ struct gat_mg {
     std::vector<float *> d_out;            // per device: re | im accumulators of its shard
     std::vector<size_t> d_out_cap;
     std::vector<float> h_tmp;
+    int sharding = 0;                      // 0 = samples (default), 1 = satellites (signal exchange over NVLink)
 };
+constexpr int kMgLocalSlotBase = 60000;    // plain slots bound to each device's own share of the ring slots
 
 namespace {
 
@@ -126,6 +134,24 @@ int gat_mg_configure(gat_mg *mg, int n_slots, int n_samples, int n_ants)
     mg->generation = 0;
     mg->releases = 0;
     mg->slot_release.assign(n_slots, 0);
+    // sample sharding reads every device's OWN share of a ring slot through a plain slot bound to that memory
+    for (int i = 0; i < world; ++i) {
+        gat_ctx *c = mg->ctx[i];
+        for (int s = 0; s < n_slots; ++s) {
+            const SignalSlot *rs = find_slot(c, s);
+            if (!rs || static_cast<int>(rs->parts.size()) <= i || rs->parts[i].len < 1) continue;
+            const SlotPart &lp = rs->parts[i];
+            int rc = gat_bind_signal(c, kMgLocalSlotBase + s, lp.re, lp.im, lp.len, n_ants, static_cast<int>(lp.ld));
+            if (rc) return mg_ctx_fail(mg, i, rc);
+        }
+    }
+    return GAT_OK;
+}
+
+int gat_mg_set_sharding(gat_mg *mg, int mode)
+{
+    if (!mg || mode < 0 || mode > 1) return GAT_ERR_INVALID;
+    mg->sharding = mode;
     return GAT_OK;
 }
 
@@ -159,6 +185,72 @@ int gat_mg_correlate(gat_mg *mg, int n_periods, const int32_t *slots, int n_sats
         if (slots[p] < 0 || slots[p] >= mg->n_slots) return mg_fail(mg, GAT_ERR_INVALID, "slot outside the configured ring");
     const int world = static_cast<int>(mg->ctx.size());
     const int M = mg->n_ants;
+    if (mg->sharding == 0) {
+        // ---- sample sharding: every device, all channels, its own sample range; the host adds the partial sums ----
+        if (start_sample < 0 || n_samples < 1 || static_cast<int64_t>(start_sample) + n_samples > mg->n_samples)
+            return mg_fail(mg, GAT_ERR_INVALID, "sample range outside the configured blocks");
+        if (mg->dirty) {
+            for (int i = 0; i < world; ++i) {
+                int g = gat_ring_publish(mg->ctx[i]);
+                if (g < 0) return mg_ctx_fail(mg, i, g);
+                mg->generation = g;
+            }
+            mg->dirty = false;
+        }
+        const size_t elems = static_cast<size_t>(n_periods) * n_sats * n_taps * M;
+        std::vector<int32_t> loc(n_periods);
+        for (int p = 0; p < n_periods; ++p) loc[p] = kMgLocalSlotBase + slots[p];
+        std::vector<char> active(world, 0);
+        for (int i = 0; i < world; ++i) {
+            gat_ctx *c = mg->ctx[i];
+            const Ring &rg = c->ring;
+            const int ps = rg.part_start[i], pl = rg.part_len[i];
+            const int a0 = std::max(start_sample, ps), a1 = std::min(start_sample + n_samples, ps + pl);
+            MG_CUDA(mg, i, cudaSetDevice(c->device));
+            int rc = gat_ring_wait(c, mg->generation);          // this device's share of the block has landed (ingest stream)
+            if (rc) return mg_ctx_fail(mg, i, rc);
+            if (a1 <= a0) continue;                             // the range does not touch this device's share
+            if (2 * elems > mg->d_out_cap[i]) {
+                MG_CUDA(mg, i, cudaStreamSynchronize(c->stream));
+                if (mg->d_out[i]) MG_CUDA(mg, i, cudaFree(mg->d_out[i]));
+                mg->d_out[i] = nullptr;
+                mg->d_out_cap[i] = 0;
+                MG_CUDA(mg, i, cudaMalloc(reinterpret_cast<void **>(&mg->d_out[i]), 4 * elems * sizeof(float)));
+                mg->d_out_cap[i] = 4 * elems;
+            }
+            // the caller's phases refer to start_sample: slot sample s of this share is sample ps + s - start_sample of that frame
+            c->sample_origin_on = true;
+            c->sample_origin = ps - start_sample;
+            rc = gat_correlate_batch(c, n_periods, loc.data(), n_sats, channels, fs_hz, sample_shifts, n_taps, a0 - ps, a1 - a0, mg->d_out[i],
+                                     mg->d_out[i] + elems, 1, flags);
+            c->sample_origin_on = false;
+            c->sample_origin = 0;
+            if (rc) return mg_ctx_fail(mg, i, rc);
+            active[i] = 1;
+        }
+        for (int i = 0; i < world; ++i) {
+            int r = gat_ring_release(mg->ctx[i]);
+            if (r < 0) return mg_ctx_fail(mg, i, r);
+            mg->releases = r;
+        }
+        for (int p = 0; p < n_periods; ++p) mg->slot_release[slots[p]] = mg->releases;
+        std::fill(h_out_re, h_out_re + elems, 0.f);
+        std::fill(h_out_im, h_out_im + elems, 0.f);
+        mg->h_tmp.resize(2 * elems);
+        for (int i = 0; i < world; ++i) {                       // fixed device order: bit-reproducible sums
+            if (!active[i]) continue;
+            gat_ctx *c = mg->ctx[i];
+            MG_CUDA(mg, i, cudaSetDevice(c->device));
+            MG_CUDA(mg, i, cudaMemcpyAsync(mg->h_tmp.data(), mg->d_out[i], 2 * elems * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            MG_CUDA(mg, i, cudaStreamSynchronize(c->stream));
+            for (size_t e = 0; e < elems; ++e) {
+                h_out_re[e] += mg->h_tmp[e];
+                h_out_im[e] += mg->h_tmp[elems + e];
+            }
+        }
+        return GAT_OK;
+    }
+    // ---- satellite sharding ----
     // shard the channel axis: stable order by system id (a device then tends to need one band's tables), contiguous and balanced
     std::vector<int> order(n_sats);
     std::iota(order.begin(), order.end(), 0);

@@ -580,6 +580,11 @@ class MultiEngine:
         self._check(self._lib.gat_mg_configure(self._h, n_slots, n_samples, n_ants))
         self._shape = (n_slots, n_samples, n_ants)
 
+    def set_sharding(self, mode: str):
+        """"samples" (default: every device correlates all channels over its own sample range, the host adds the partial
+        sums) or "satellites" (channels partitioned, the blocks' other ranges read over NVLink inside the kernel)."""
+        self._check(self._lib.gat_mg_set_sharding(self._h, {"samples": 0, "satellites": 1}[mode]))
+
     def upload_signal(self, slot: int, re, im):
         """Host planes [n_ants, ld] (numpy or CPU torch; pinned memory copies asynchronously).  Keep them alive until the
         next correlate call on this slot has returned."""

@@ -333,6 +333,11 @@ int gat_resident_end(gat_ctx *ctx);
  *   out: [n_ants x n_taps x n_sats x n_periods] host arrays; gat_mg_correlate is synchronous. */
 typedef struct gat_mg gat_mg;
 int gat_mg_create(gat_mg **out, int n_dev, const int *devices);
+/* How gat_mg_correlate splits a call over the devices.  0 (default) = SAMPLES: every device correlates all channels over the
+ * sample range of the block it already holds and the host adds the devices' partial sums -- no signal crosses NVLink
+ * (bit-exact chip indices; FP32 summation order differs from a one-device call).  1 = SATELLITES: the channels are
+ * partitioned, every device reads the whole block, the other devices' ranges over NVLink inside the kernel. */
+int gat_mg_set_sharding(gat_mg *mg, int mode);
 int gat_mg_destroy(gat_mg *mg);
 const char *gat_mg_last_error(gat_mg *mg);
 int gat_mg_device_count(gat_mg *mg);

@@ -193,6 +193,10 @@ upload_signal!(mg::MultiContext, slot::Integer, re::Matrix{Float32}, im::Matrix{
     mgcheck(mg, ccall((:gat_mg_upload_signal, libgat), Cint, (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint), mg.handle, slot, re, im, size(re, 1)))
 
 "Channels [K x P] sharded over the devices, blocks gathered over NVLink inside the kernels; `Array{ComplexF32,4}` [M x NCOR x K x P] back."
+# :samples (default) or :satellites -- how a call is split over the devices (gat_mg_set_sharding)
+set_sharding!(mg::MultiContext, mode::Symbol) =
+    mgcheck(mg, ccall((:gat_mg_set_sharding, libgat), Cint, (Ptr{Cvoid}, Cint), mg.handle, mode === :satellites ? 1 : 0))
+
 function correlate(mg::MultiContext, slots::Vector{<:Integer}, channels::Matrix{GatChannel}, correlator_sample_shifts::SVector{NCOR, Int64},
         sampling_frequency, num_samples::Integer, num_ants::Integer; start_sample::Integer = 0) where {NCOR}
     K, P = size(channels)

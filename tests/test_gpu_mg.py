@@ -20,8 +20,9 @@ def _devices():
     return cases
 
 
+@pytest.mark.parametrize("sharding", ["samples", "satellites"])
 @pytest.mark.parametrize("devices", _devices(), ids=lambda d: "dev" + "".join(map(str, d)))
-def test_mg_correlate_mixed_bands(gat, orc, devices):
+def test_mg_correlate_mixed_bands(gat, orc, devices, sharding):
     rng = np.random.default_rng(len(devices) * 7 + 1)
     l1, l5 = gat.GPSL1(), gat.GPSL5()
     n, m, P = 50000, 4, 2
@@ -35,6 +36,7 @@ def test_mg_correlate_mixed_bands(gat, orc, devices):
                           float(rng.uniform(-0.5, 0.5))) for s in systems] for _ in range(P)]
     mg = gat.MultiEngine(devices)
     mg.configure(P, n, m)
+    mg.set_sharding(sharding)
     for p in range(P):
         mg.upload_signal(p, re[p], im[p])
     got = mg.correlate_batch(list(range(P)), chans, fs, shifts)
@@ -46,6 +48,13 @@ def test_mg_correlate_mixed_bands(gat, orc, devices):
             ref = orc.correlate_direct(re[p], im[p], c.system.codes[c.prn - 1], c.system.code_frequency, c.code_phase,
                                        c.carrier_frequency, c.carrier_phase, fs, shifts)
             assert np.abs(got[p, k] - ref).max() <= TOL * np.sqrt(n) * 4, (p, k)
+    # a range inside the block (start in one device's share, end in another's): both shardings agree with the oracle
+    start = 12345 if sharding == "samples" else 12288        # (ring slots read in place need a start on a 256-sample tile)
+    part = mg.correlate_batch([0], [chans[0]], fs, shifts, start_sample=start, n_samples=30001)
+    for k, c in enumerate(chans[0]):
+        ref = orc.correlate_direct(re[0], im[0], c.system.codes[c.prn - 1], c.system.code_frequency, c.code_phase, c.carrier_frequency,
+                                   c.carrier_phase, fs, shifts, start_sample=start, n_samples=30001)
+        assert np.abs(part[0, k] - ref).max() <= TOL * np.sqrt(n) * 4, k
     mg.close()
 
 
