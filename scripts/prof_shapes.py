@@ -12,7 +12,7 @@ l1, l5 = g.GPSL1(), g.GPSL5()
 N, M = 50000, 16
 fs = N / 1e-3
 torch.cuda.set_device(0)
-P = 256 if which in ("batch256", "int16") else 64
+P = 256 if which in ("batch256", "int16", "ss8") else 64
 re = torch.randn(P, M, N, device="cuda"); im = torch.randn(P, M, N, device="cuda")
 torch.cuda.synchronize()
 for p in range(P):
@@ -52,6 +52,20 @@ if which in ("k32batch", "all"):
     run("batch P=8 K=32 L=3", 8, 32, 3, 0.5)
 if which == "rt264":
     run("single K=264 L=3 (realtime_shared_block)", 1, 264, 3, 0.5)
+if which == "ss8":
+    # the per-GPU kernel of the 8-GPU sample-sharded bench step: 8 satellites over 1/8 of each of 256 blocks
+    n8 = N // 8 // 4 * 4
+    for p in range(P):
+        eng.bind_signal(10 + p, re[p][:, :n8], im[p][:, :n8])
+    c = g.EarlyPromptLateCorrelator(g.NumAnts(M), g.NumAccumulators(3))
+    shifts = g.get_correlator_sample_shifts(l1, c, fs, 0.5)
+    chans = eng.marshal([[g.Channel(l1, k + 1, 3.0 * p, 1500.0 + 10 * k, 0.0) for k in range(8)] for p in range(P)])
+    out = (torch.zeros(P, 8, 3, M, device="cuda"), torch.zeros(P, 8, 3, M, device="cuda"))
+    eng.set_sample_origin(n8)
+    for _ in range(reps):
+        eng.correlate_batch(list(range(10, 10 + P)), chans, fs, shifts, M, 0, n8, out=out)
+    eng.sync()
+    print("sample-sharded per-GPU step, 8 GPUs: P=256 K=8 n=%d" % n8, eng.launch_info())
 if which == "int16":
     # bench.py's int16_resident figure: 256 blocks kept as raw int16 I/Q, one channel each
     iq = torch.randint(-2047, 2048, (P, M, N, 2), device="cuda", dtype=torch.int16)
