@@ -739,9 +739,11 @@ def test_ingest_correlate_host_batches(gat, orc, P, m, n, pad, K):
     eng.close()
 
 
+@pytest.mark.parametrize("taps", [11, 7])
 @pytest.mark.parametrize("m,n,start,P,cap,mode", [(16, 6300, 0, 5, 7, "nco"), (16, 6300, 5, 3, 3, "f64"), (12, 9001, 2, 4, 5, "nco"),
-                                                  (8, 50000, 0, 3, 148, "nco"), (16, 2049, 0, 9, 2, "nco"), (16, 520, 1, 6, 1, "nco")])
-def test_eleven_tap_visits_of_two_tiles(gat, orc, m, n, start, P, cap, mode):
+                                                  (8, 50000, 0, 3, 148, "nco"), (16, 2049, 0, 9, 2, "nco"), (16, 520, 1, 6, 1, "nco"),
+                                                  (32, 4000, 3, 2, 4, "nco"), (5, 7000, 0, 3, 6, "f64")])
+def test_eleven_tap_visits_of_two_tiles(gat, orc, m, n, start, P, cap, mode, taps):
     """The 11-tap class (register reallocation, three replica warps) walks its tiles in visits of two: batches whose jobs
     hold an ODD number of tiles on few CTAs cut the pairs at segment boundaries (single-tile visits, a pair whose halves belong
     to two segments), offsets stage samples before start_sample, 12 / 8 antennas change the warp roles."""
@@ -750,7 +752,7 @@ def test_eleven_tap_visits_of_two_tiles(gat, orc, m, n, start, P, cap, mode):
     l1 = gat.GPSL1()
     rng = np.random.default_rng(n + m)
     fs = n / 1e-3
-    shifts = (np.arange(11, dtype=np.int32) - 5) * 2
+    shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
     blocks, chans = [], []
     for p in range(P):
         re = rng.normal(size=(m, start + n + 3)).astype(np.float32)
