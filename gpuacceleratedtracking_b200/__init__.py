@@ -13,6 +13,6 @@ from .api import (ALGODICT, EarlyPromptLateCorrelator, KernelAlgorithm, NumAccum
                   downconvert_and_correlate, gen_signal, get_accumulators, get_correlator_sample_shifts,
                   get_early, get_late, get_prompt, kernel_algorithm)
 
-from .tracking import TrackingState, track, engine_correlator, pll_disc, dll_disc
+from .tracking import TrackingState, track, engine_correlator, resident_correlator, pll_disc, dll_disc
 
 __all__ = [n for n in dir() if not n.startswith("_")]

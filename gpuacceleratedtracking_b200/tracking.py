@@ -143,3 +143,17 @@ def engine_correlator(engine: Engine, block_source: Callable[[int], tuple], samp
         return engine.correlate(slot, chans, sampling_frequency, shifts, n_ants, start, num_samples,
                                 code_phase_f64=code_phase_f64)
     return fn
+
+
+def resident_correlator(engine: Engine, slots: Sequence[int], channels: Sequence[Channel], sampling_frequency: float,
+                        shifts: Sequence[int], n_ants: int, num_samples: int, start_sample: int = 0) -> CorrelateFn:
+    """A CorrelateFn inside a resident session (include/gat.h gat_resident_*): the per-millisecond call of the loop costs a PCIe
+    round trip plus the correlation instead of a kernel launch and a stream synchronisation.  Block b lives in
+    slots[b % len(slots)] (a ring the caller keeps filled); `channels` are representative channels (one per tracked satellite,
+    at most 5).  Call engine.resident_end() when the loop is done."""
+    engine.resident_begin(list(slots), list(channels), sampling_frequency, shifts, n_ants, start_sample, num_samples)
+    n = len(slots)
+
+    def fn(block: int, chans: Sequence[Channel]) -> np.ndarray:
+        return engine.resident_correlate(block % n, chans)
+    return fn

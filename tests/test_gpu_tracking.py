@@ -57,3 +57,32 @@ def test_tracking_with_f64_code_phase_mode(gat, orc, engine):
     traj = gat.track([gat.TrackingState(9, l1, -853.0, 400.05)], corr, blocks, n, fs, shifts)
     assert abs(traj["carrier_doppler"][-60:, 0].mean() + 850.0) < 1.5
     assert np.abs(traj["prompt_re"][-60:, 0]).mean() > 0.8
+
+
+def test_tracking_loop_inside_a_resident_session(gat, orc):
+    """The closed loop with one resident command per millisecond (gat_resident_*): bit for bit the trajectories of the loop that
+    launches a kernel per block -- same plan, same kernel body -- and locked on the true Dopplers."""
+    l1 = gat.GPSL1()
+    n, m, fs, blocks = 4000, 4, 4.0e6, 300
+    truth = [dict(prn=9, doppler=-850.0, code_phase=400.0, carrier_phase=0.1), dict(prn=21, doppler=1999.0, code_phase=3.5, carrier_phase=-0.2)]
+    re, im = make_record(orc, l1, truth, blocks, n, m, fs, noise=0.3, seed=9)
+    shifts = orc.sample_shifts(1.023e6, fs, 0.5, 3)
+    eng = gat.Engine(0)
+    for b in range(blocks):                                          # one slot per 1 ms block (a receiver would keep a short ring filled)
+        eng.upload_signal(b, np.ascontiguousarray(re[:, b * n:(b + 1) * n]), np.ascontiguousarray(im[:, b * n:(b + 1) * n]))
+
+    def fresh():
+        return [gat.TrackingState(9, l1, -853.0, 400.05), gat.TrackingState(21, l1, 2003.0, 3.45)]
+
+    launched = gat.track(fresh(), lambda b, ch: eng.correlate(b, ch, fs, shifts, m, n_samples=n), blocks, n, fs, shifts)
+    states = fresh()
+    corr = gat.resident_correlator(eng, range(blocks), [s.channel() for s in states], fs, shifts, m, n)
+    try:
+        resident = gat.track(states, corr, blocks, n, fs, shifts)
+    finally:
+        eng.resident_end()
+    for key in launched:
+        assert np.array_equal(launched[key], resident[key]), key
+    for k, t in enumerate(truth):
+        assert abs(resident["carrier_doppler"][-60:, k].mean() - t["doppler"]) < 1.5
+    eng.close()
