@@ -303,8 +303,8 @@ int gat_ring_destroy(gat_ctx *ctx);
  * a tracking loop makes exactly that call every millisecond.  Through a kernel launch it costs ~18 us on a B200, most of
  * it launch, argument marshalling and completion latency.  A resident session launches the correlate kernel ONCE: it
  * stays on the device, polls a command the host writes into pinned mapped memory, runs the same fused
- * downconvert-and-correlate (same plan, bit-identical sums to gat_correlate), writes the accumulators straight into host
- * memory and raises a flag the caller spins on.
+ * downconvert-and-correlate (same plan, bit-identical sums to gat_correlate) and stores every accumulator straight into
+ * host memory together with the command's sequence number; the caller spins until all of them carry it.
  *   gat_resident_begin     fixes the shape (slots that hold blocks of the same geometry, channel count <= 5, sampling
  *                          rate, taps, sample range; `channels` = representative channels: systems / code rates) and
  *                          launches the kernel.  Classes: 1 / 4 / 16 antennas with <= 3 or 7 taps, 16 antennas x 11 taps
@@ -322,11 +322,11 @@ int gat_resident_correlate(gat_ctx *ctx, int slot_index, const gat_channel *chan
 int gat_resident_end(gat_ctx *ctx);
 
 /* ---- one host process, all GPUs of the box -----------------------------------------------------
- * The call a single tracking-loop process makes (Julia: one `ccall` per integration period or batch): the satellite
- * channels are partitioned over the devices, every device reads the same signal blocks, the accumulators come back in
- * the caller's channel order.  Built on the signal ring above: gat_mg_upload_signal sends each device ITS sample range
- * of the block through that device's own PCIe link (asynchronous, n_dev links in parallel) and the correlate kernels
- * gather the other ranges over NVLink.  `devices` may name one device several times (logical shards; used by the
+ * The call a single tracking-loop process makes (Julia: one `ccall` per integration period or batch); the accumulators
+ * come back in the caller's channel order.  gat_mg_upload_signal sends each device ITS sample range of the block through
+ * that device's own PCIe link (asynchronous, n_dev links in parallel).  By default (gat_mg_set_sharding) every device then
+ * correlates ALL channels over that range and the host adds the devices' partial sums -- no signal crosses NVLink; in
+ * satellite mode the channels are partitioned and the correlate kernels gather the other ranges over NVLink (signal ring).  `devices` may name one device several times (logical shards; used by the
  * single-GPU tests).  Typical loop: upload block t+1 into slot (t+1) % n_slots, THEN gat_mg_correlate on slot t % n_slots:
  * the upload of the next block overlaps the kernels of the current one; a slot is not overwritten before every
  * device has finished reading it (tracked per slot).
