@@ -108,6 +108,7 @@ struct Shape {
     int n_taps = 0;                    // the caller's tap count (output layout); L = taps per warp (template), TG * L >= n_taps
     int TG = 1;
     bool dump = false;                 // replica-index dump requested (debug instantiations)
+    int reserve_smem = 0;              // bytes of dynamic shared memory kept free behind the plan (resident sessions: the command area)
 };
 
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
@@ -136,7 +137,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     const bool two_channels = K == 2 && AG * TG == 1 && w_cap == 11;
     const int w_target_single = std::min(w_cap, env_int("GAT_TUNE_W", w_cap == 11 ? (two_channels ? 10 : 8) : 16));
     const int cache_stride = (sh.max_code_len + kCodeColAlign - 1) / kCodeColAlign * kCodeColAlign;
-    const size_t smem_budget = 227 * 1024;
+    const size_t smem_budget = 227 * 1024 - static_cast<size_t>(sh.reserve_smem);
     const int RW = AG * TG;            // warps per satellite and sample slice
     int S = std::max(1, std::min(K, w_target_multi / RW));
     S = std::max(1, std::min(S, env_int("GAT_TUNE_S", S)));
@@ -628,6 +629,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     shape.TG = TG;
     shape.n_taps = n_taps;
     shape.dump = (flags & kFlagDumpReplica) != 0;
+    shape.reserve_smem = (flags & kFlagResidentPlan) ? kResCmdSmemBytes + 128 : 0;
     for (size_t i = 0; i < n_ch; ++i) {
         rc = fill_sat(ctx, channels[i], fs_hz, sats[i]);
         if (rc) return rc;

@@ -193,10 +193,11 @@ bool dump_kernel_available(int A, int L);
 bool help_kernel_available(int A, int L, bool f64, bool dump);
 
 // ---- resident kernel (gat_resident.cu, gat_resident_* in include/gat.h) ----
-constexpr int kResMaxCells = 32;              // command cells of 16 bytes {d0, d1, d2, seq}: one warp-wide load
-constexpr int kResMaxSats = 5;                // data words: [op, slot index, n_sats, 0][SatDev x n_sats] <= 3 * kResMaxCells
+constexpr int kResChunks = 6;                 // a command is up to kResChunks warp-wide loads of 32 cells of 16 bytes {d0, d1, d2, seq}
+constexpr int kResMaxCells = 32 * kResChunks;
+constexpr int kResMaxSats = 32;               // data words: [op, slot index, n_sats, 0][SatDev x n_sats] <= 3 * kResMaxCells
 constexpr uint32_t kResOpCorrelate = 1u, kResOpExit = 2u;
-constexpr int kResCmdSmemBytes = 512;         // the command's data words in shared memory, behind the plan's carve-up
+constexpr int kResCmdSmemBytes = 2304;        // the command's data words in shared memory, behind the plan's carve-up
 struct ResCtl {
     const uint4 *cmd_host;        // the host's command cells (pinned, mapped: device pointer)
     uint4 *relay;                 // device memory: the cells as CTA 0 received them (the other CTAs poll these)

@@ -8,8 +8,8 @@
 // call: host write -> PCIe -> poll -> correlate -> posted result writes + flag -> host poll.
 //
 // Protocol (one command in flight, sequence numbers 1, 2, ..):
-//   host    writes the command as 16-byte cells {d0, d1, d2, seq} into pinned mapped memory: the data words first, then
-//           the sequence words.  A cell is read by ONE 16-byte load, so a cell whose seq matches carries this
+//   host    writes the command (slot index + up to 32 channel records) as 16-byte cells {d0, d1, d2, seq} into pinned mapped
+//           memory: the data words first, then the sequence words.  A cell is read by ONE 16-byte load, so a cell whose seq matches carries this
 //           command's data whatever order the PCIe reads of different cells complete in.
 //   CTA 0   warp 0 polls the cells over PCIe (one warp-wide load per try), then relays them, sequence words included,
 //           through device memory; the other CTAs poll those cells in L2 -- 147 CTAs polling host memory would put
@@ -40,36 +40,53 @@ __device__ __forceinline__ void resident_loop(const CorrArgs &args, const ResCtl
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t seq = ctl.first_seq;; ++seq) {
         if (warp == 0) {
-            uint4 c = make_uint4(0u, 0u, 0u, 0u);
+            // a command is n_cells cells = up to kResChunks warp-wide 16-byte loads, all in flight together (one PCIe round trip)
+            uint4 c[kResChunks];
+            const int n_cells = ctl.n_cells;
+            auto load_all = [&](const uint4 *base) {
+                bool ok = true;
+#pragma unroll
+                for (int k = 0; k < kResChunks; ++k) {
+                    c[k] = make_uint4(0u, 0u, 0u, seq);
+                    if (32 * k + lane < n_cells) c[k] = ld_sys_v4(base + 32 * k + lane);
+                }
+#pragma unroll
+                for (int k = 0; k < kResChunks; ++k) ok = ok && c[k].w == seq;
+                return __all_sync(0xffffffffu, ok);
+            };
             if (blockIdx.x == 0) {
                 const uint64_t t0 = global_timer_ns();
                 bool idle = false;
-                while (true) {
-                    if (lane < ctl.n_cells) c = ld_sys_v4(ctl.cmd_host + lane);
-                    if (__all_sync(0xffffffffu, lane >= ctl.n_cells || c.w == seq)) break;
+                while (!load_all(ctl.cmd_host)) {
                     if (global_timer_ns() - t0 > (uint64_t)ctl.idle_limit_ms * 1000000ull) {
                         idle = true;
                         break;
                     }
                 }
-                if (idle) c = make_uint4(lane == 0 ? kResOpExit : 0u, 0u, 0u, seq);
+                if (idle) {
+#pragma unroll
+                    for (int k = 0; k < kResChunks; ++k) c[k] = make_uint4((k == 0 && lane == 0) ? kResOpExit : 0u, 0u, 0u, seq);
+                }
                 if (ctl.stamps && lane == 0) ctl.stamps[0] = global_timer_ns();     // debug: command seen
                 // relay: the same cells (each one 16-byte store, its sequence word included) through device memory
-                if (lane < ctl.n_cells)
-                    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ctl.relay + lane), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+#pragma unroll
+                for (int k = 0; k < kResChunks; ++k)
+                    if (32 * k + lane < n_cells)
+                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ctl.relay + 32 * k + lane), "r"(c[k].x), "r"(c[k].y),
+                                     "r"(c[k].z), "r"(c[k].w)
+                                     : "memory");
             } else {
                 unsigned int tries = 0;
-                while (true) {
-                    if (lane < ctl.n_cells) c = ld_sys_v4(ctl.relay + lane);
-                    if (__all_sync(0xffffffffu, lane >= ctl.n_cells || c.w == seq)) break;
+                while (!load_all(ctl.relay))
                     if (++tries > 4096u) __nanosleep(200);   // long idle: stop hammering L2
+            }
+#pragma unroll
+            for (int k = 0; k < kResChunks; ++k)
+                if (32 * k + lane < n_cells) {
+                    cmd_s[3 * (32 * k + lane) + 0] = c[k].x;
+                    cmd_s[3 * (32 * k + lane) + 1] = c[k].y;
+                    cmd_s[3 * (32 * k + lane) + 2] = c[k].z;
                 }
-            }
-            if (lane < ctl.n_cells) {
-                cmd_s[3 * lane + 0] = c.x;
-                cmd_s[3 * lane + 1] = c.y;
-                cmd_s[3 * lane + 2] = c.z;
-            }
         }
         cta_sync<ROLE>();
         if (cmd_s[0] != kResOpCorrelate) return;    // exit command, or CTA 0 gave up waiting

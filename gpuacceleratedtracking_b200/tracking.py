@@ -150,7 +150,7 @@ def resident_correlator(engine: Engine, slots: Sequence[int], channels: Sequence
     """A CorrelateFn inside a resident session (include/gat.h gat_resident_*): the per-millisecond call of the loop costs a PCIe
     round trip plus the correlation instead of a kernel launch and a stream synchronisation.  Block b lives in
     slots[b % len(slots)] (a ring the caller keeps filled); `channels` are representative channels (one per tracked satellite,
-    at most 5).  Call engine.resident_end() when the loop is done."""
+    at most 32).  Call engine.resident_end() when the loop is done."""
     engine.resident_begin(list(slots), list(channels), sampling_frequency, shifts, n_ants, start_sample, num_samples)
     n = len(slots)
 

@@ -305,7 +305,7 @@ int gat_ring_destroy(gat_ctx *ctx);
  * stays on the device, polls a command the host writes into pinned mapped memory, runs the same fused
  * downconvert-and-correlate (same plan, bit-identical sums to gat_correlate) and stores every accumulator straight into
  * host memory together with the command's sequence number; the caller spins until all of them carry it.
- *   gat_resident_begin     fixes the shape (slots that hold blocks of the same geometry, channel count <= 5, sampling
+ *   gat_resident_begin     fixes the shape (slots that hold blocks of the same geometry, channel count <= 32, sampling
  *                          rate, taps, sample range; `channels` = representative channels: systems / code rates) and
  *                          launches the kernel.  Classes: 1 / 4 / 16 antennas with <= 3 or 7 taps, 16 antennas x 11 taps
  *                          (GAT_ERR_UNSUPPORTED otherwise), integer-NCO code phase, FP32 planes.

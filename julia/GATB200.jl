@@ -140,7 +140,7 @@ host_register!(a::Array) = ccall((:gat_host_register, libgat), Cint, (Ptr{Cvoid}
 the device and `resident_correlate!(ctx, slot_index, channels, out_re, out_im)` then costs a PCIe round trip plus the
 correlation itself instead of a kernel launch and a stream synchronisation (the reference's measurement is exactly one such
 call per 1 ms block: src/benchmarks.jl:872).  `slots` hold blocks of one geometry (bind or upload them first); `channels`
-is a `Vector{GatChannel}` of at most 5 channels; `out_re`, `out_im` are host `Array{Float32,3}` [M x NCOR x K].
+is a `Vector{GatChannel}` of at most 32 channels; `out_re`, `out_im` are host `Array{Float32,3}` [M x NCOR x K].
 `resident_end!(ctx)` frees the device again.
 """
 function resident_begin!(ctx::Context, slots::Vector{<:Integer}, channels::Vector{GatChannel}, correlator_sample_shifts::SVector{NCOR, Int64},

@@ -21,7 +21,7 @@ def _chan(gat, rng, system):
 
 
 @pytest.mark.parametrize("m,taps,n,k", [(1, 3, 2500, 1), (4, 3, 8192, 1), (16, 3, 50000, 1), (16, 3, 50000, 3), (4, 7, 16384, 1),
-                                        (16, 7, 50000, 1), (16, 11, 50000, 1), (1, 7, 4096, 2), (16, 2, 20000, 5)])
+                                        (16, 7, 50000, 1), (16, 11, 50000, 1), (1, 7, 4096, 2), (16, 2, 20000, 5), (16, 3, 50000, 32), (4, 3, 30000, 13)])
 def test_resident_equals_launched_call(gat, orc, m, taps, n, k):
     rng = np.random.default_rng(1000 * m + taps + n)
     l1 = gat.GPSL1()
