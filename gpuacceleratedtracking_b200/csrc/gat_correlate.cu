@@ -223,6 +223,9 @@ __device__ __forceinline__ float lds_f32_at(uint32_t smem_addr)
     return v;
 }
 
+#ifndef GAT_FULL_UNROLL
+#define GAT_FULL_UNROLL 1          // 1: straight-line code for full tiles in the reallocation class (7 / 9 / 11 taps); 2: in every class
+#endif
 #ifndef GAT_LOOP_UNROLL
 #define GAT_LOOP_UNROLL 1          // A/B builds: unroll factor of the sample loop
 #endif
@@ -979,21 +982,21 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                         const uint32_t ta_end = tre_s + 4u * (uint32_t)len;
                         uint32_t astep = 4u * (uint32_t)tt_stride, pstep = ph_step32;
                         asm volatile("" : "+r"(astep), "+r"(pstep), "+r"(ra), "+r"(ph));        // opaque: keep them in registers
-#pragma unroll 1
-                        for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) {
+                        // one sample of this lane: carrier, the L chips, A antennas' wipe-off and taps
+                        auto sample = [&](uint32_t a_re, uint32_t a_im, uint32_t a_rep) {
                             float cr, ci;
                             const float x = (float)(int32_t)ph * 1.4629180792671596e-9f;  // 2 pi / 2^32
                             __sincosf(x, &ci, &cr);
                             ph += pstep;
                             float chip[L];
 #pragma unroll
-                            for (int l = 0; l < L; ++l) chip[l] = lds_f32_at(ra + (uint32_t)args.koff4[l]);
+                            for (int l = 0; l < L; ++l) chip[l] = lds_f32_at(a_rep + (uint32_t)args.koff4[l]);
                             const f32x2 CR = pack2(cr, cr), CI = pack2(ci, ci), NCI = pack2(-ci, -ci);
                             f32x2 X[AP], Y[AP];
 #pragma unroll
                             for (int a = 0; a < AP; ++a) {
-                                X[a] = pack2(lds_f32_at(ta_re + 4u * (2 * a) * kTileCap), lds_f32_at(ta_re + 4u * (2 * a + 1) * kTileCap));
-                                Y[a] = pack2(lds_f32_at(ta_im + 4u * (2 * a) * kTileCap), lds_f32_at(ta_im + 4u * (2 * a + 1) * kTileCap));
+                                X[a] = pack2(lds_f32_at(a_re + 4u * (2 * a) * kTileCap), lds_f32_at(a_re + 4u * (2 * a + 1) * kTileCap));
+                                Y[a] = pack2(lds_f32_at(a_im + 4u * (2 * a) * kTileCap), lds_f32_at(a_im + 4u * (2 * a + 1) * kTileCap));
                             }
 #pragma unroll
                             for (int a = 0; a < AP; ++a) {
@@ -1006,6 +1009,19 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                                     accIm[a][l] = fma2(Dim, CH, accIm[a][l]);
                                 }
                             }
+                        };
+#if GAT_FULL_UNROLL
+                        // a full tile of a non-split plan is exactly 8 samples per lane, 128 bytes apart: straight-line code
+                        // with immediate offsets, no loop branch (the branch's resolve stall was 7 % of the warp samples)
+                        if (len == kTileCap && !split && ta_re == tre_s + 4u * (uint32_t)lane) {
+#pragma unroll
+                            for (int it = 0; it < kTileCap / 32; ++it) sample(ta_re + 128u * it, ta_im + 128u * it, ra + 128u * it);
+                            ra += 128u * (kTileCap / 32);
+                        } else
+#endif
+                        {
+#pragma unroll 1
+                            for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) sample(ta_re, ta_im, ra);
                         }
                     }
                     __syncwarp();
@@ -1095,8 +1111,8 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                 asm volatile("" : "+r"(astep), "+r"(pstep));        // opaque: keep them in registers
                 // (unrolling by two was measured slower on the 11-tap shape: occupancy, not per-warp ILP, is
                 // what hides the MUFU / shared-memory latencies here)
-#pragma unroll kLoopUnroll
-                for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) {
+                // one sample of this lane at the given shared-memory addresses (re plane, im plane, replica)
+                auto sample = [&](uint32_t ta_re, uint32_t ta_im, uint32_t ra) {
                     // ---- carrier replica: exp(j 2 pi phase) ----
                     float cr, ci;
                     const float x = (float)(int32_t)ph * 1.4629180792671596e-9f;  // 2 pi / 2^32
@@ -1159,6 +1175,19 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                             sIm[l] = fmaf(dim, chip[l], sIm[l]);
                         }
                     }
+                };
+                // a full tile walked with one warp per tile is exactly 8 samples per lane, 128 bytes apart: straight-line code
+                // for the many-tap shapes outside the reallocation class (8 satellites x 11 taps: 110 -> 97 us; slower at
+                // 5 taps, 74 -> 81 us, and neutral at 3, so only from 7 taps on)
+                constexpr bool kStraight = GAT_FULL_UNROLL >= 2 || (GAT_FULL_UNROLL == 1 && L >= 7);
+                bool straight = false;
+                if constexpr (kStraight) straight = (len == kTileCap && astep == 128u && tt0 == lane);
+                if (straight) {
+#pragma unroll
+                    for (int it = 0; it < kTileCap / 32; ++it) sample(ta_re + 128u * it, ta_im + 128u * it, ra + 128u * it);
+                } else {
+#pragma unroll kLoopUnroll
+                    for (; ta_re < ta_end; ta_re += astep, ta_im += astep, ra += astep) sample(ta_re, ta_im, ra);
                 }
             }
             __syncwarp();
