@@ -1178,7 +1178,8 @@ __device__ __forceinline__ void correlate_body(const CorrArgs &args, [[maybe_unu
                 };
                 // a full tile walked with one warp per tile is exactly 8 samples per lane, 128 bytes apart: straight-line code
                 // for the many-tap shapes outside the reallocation class (8 satellites x 11 taps: 110 -> 97 us; slower at
-                // 5 taps, 74 -> 81 us, and neutral at 3, so only from 7 taps on)
+                // 5 taps, 74 -> 81 us, and on raw int16 tiles, 169 -> 182 us, neutral at 3 taps: eight copies of a 16-antenna
+                // body no longer fit the instruction cache next to the prologue -- so only from 7 taps on)
                 constexpr bool kStraight = GAT_FULL_UNROLL >= 2 || (GAT_FULL_UNROLL == 1 && L >= 7);
                 bool straight = false;
                 if constexpr (kStraight) straight = (len == kTileCap && astep == 128u && tt0 == lane);
