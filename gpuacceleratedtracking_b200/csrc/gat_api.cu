@@ -123,10 +123,14 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // (slice, satellite) group inside the W per-warp buffers, i.e. >= 2 warps per group.
     bool help = env_int("GAT_TUNE_REPHELPER", 1) != 0 && !sh.sc16 && AG * TG >= 2 && help_kernel_available(A, L, sh.f64, sh.dump);
     // (the register-reallocation class -- 11 taps -- has fixed warp positions: 12 consumer warps, one satellite per CTA)
-    const bool realloc_class = help && help_realloc(A, L);
+    bool realloc_class = help && help_realloc(A, L);
     int w_cap = help ? (realloc_class ? kReallocConsumerWarps : block_threads_help(A, L) / 32 - 2) : max_consumer_warps(A, L);
     if (help && std::min(K, std::max(1, w_cap / (AG * TG))) > (realloc_class ? 1 : kHelperMaxSats)) {
+        // several satellites per CTA: the plain instantiation, and none of the reallocation class's sizing below (two-tile
+        // replicas, two buffers per group) -- with it still on, 5 satellites x 9 / 11 taps x 8 antennas asked for 233 216 B of
+        // shared memory and the cooperative launch was refused
         help = false;
+        realloc_class = false;
         w_cap = max_consumer_warps(A, L);
     }
     if (AG * TG > w_cap) return fail(ctx, GAT_ERR_UNSUPPORTED, "too many antennas for this tap count");
@@ -272,6 +276,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     const int rep_bufs = realloc_class ? 2 * (split_tiles ? S : SL * S) : W;
     plan.smem = kSmemHeaderBytes + stages * tile_bytes + static_cast<size_t>(W) * RP * sizeof(float) +
                 static_cast<size_t>(rep_bufs) * rep_stride * sizeof(float) + static_cast<size_t>(S) * cache_stride;
+    if (plan.smem > smem_budget) return fail(ctx, GAT_ERR_UNSUPPORTED, "internal: launch plan exceeds the shared-memory budget");
     a.rep_bufs = rep_bufs;
     a.visit_tiles = visit_tiles;
     a.dump_stride = (tile_len + span + 127) & ~127;

@@ -777,3 +777,74 @@ def test_eleven_tap_visits_of_two_tiles(gat, orc, m, n, start, P, cap, mode, tap
         del os.environ["GAT_TUNE_VISIT"]
     assert np.abs(got1 - got).max() <= 1e-5 * 3 * np.sqrt(n) + 1e-3
     eng.close()
+
+
+@pytest.mark.parametrize("K,taps,m,n,start,P,cap,mode", [(8, 11, 16, 6300, 0, 3, 148, "nco"), (8, 11, 16, 6300, 3, 2, 5, "nco"),
+                                                         (3, 7, 16, 5000, 2, 4, 7, "f64"), (5, 9, 8, 2049, 0, 3, 3, "nco"),
+                                                         (2, 11, 4, 9001, 1, 2, 148, "nco")])
+def test_many_taps_many_satellites_straight_line_tiles(gat, orc, K, taps, m, n, start, P, cap, mode):
+    """>= 7 taps with several satellites per block run OUTSIDE the reallocation class; their full 256-sample tiles are
+    straight-line code (8 samples per lane), ragged last tiles and first tiles that stage samples before start_sample take the
+    counted loop.  Both paths in one launch, few CTAs so that every CTA crosses segments, every channel against the oracle."""
+    eng = gat.Engine(0)
+    eng.set_max_ctas(cap)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(1000 * K + taps + n)
+    fs = n / 1e-3
+    shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+    blocks, chans = [], []
+    for p in range(P):
+        re = rng.normal(size=(m, start + n + 3)).astype(np.float32)
+        im = rng.normal(size=(m, start + n + 3)).astype(np.float32)
+        eng.upload_signal(p, re, im)
+        blocks.append((re, im))
+        chans.append([gat.Channel(l1, int(rng.integers(1, 33)), float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)),
+                                  float(rng.uniform(-0.5, 0.5))) for _ in range(K)])
+    got = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, start, n, code_phase_f64=(mode == "f64"))
+    info = eng.launch_info()
+    assert info["grid"] <= cap and info["tile_len"] == 256
+    again = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, start, n, code_phase_f64=(mode == "f64"))
+    assert np.array_equal(got, again)                     # fixed summation order: bit-reproducible
+    for p in range(P):
+        for k in (0, K - 1):
+            c = chans[p][k]
+            ref = orc.correlate_direct(*blocks[p], l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency, c.carrier_phase,
+                                       fs, shifts, start_sample=start, n_samples=n, code_mode=mode)
+            assert np.abs(got[p, k] - ref).max() <= 2e-5 * 3 * np.sqrt(n) + 1e-3, (p, k, np.abs(got[p, k] - ref).max())
+    eng.close()
+
+
+def test_planner_sweep_every_shape_launches_and_matches(gat, orc):
+    """Every (satellites, taps, antennas) combination of the supported ranges gets a launch plan that fits the SM (shared
+    memory, warps) and gives the oracle's sums -- the sweep that found the 5 satellites x 9 taps x 8 antennas plan asking for
+    233 216 B of shared memory.  One engine, two short periods per shape, first and last channel checked."""
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(5)
+    n, P = 1500, 2
+    fs = n / 1e-3
+    plans = set()
+    for m in (1, 2, 3, 4, 8, 12, 16):
+        blocks = []
+        for p in range(P):
+            re = rng.normal(size=(m, n + 2)).astype(np.float32)
+            im = rng.normal(size=(m, n + 2)).astype(np.float32)
+            eng.upload_signal(p, re, im)
+            blocks.append((re, im))
+        for taps in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
+            shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+            for K in (1, 2, 3, 4, 5, 6, 8, 11, 13):
+                chans = [[gat.Channel(l1, 1 + (3 * k + p) % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)),
+                                      float(rng.uniform(-0.5, 0.5))) for k in range(K)] for p in range(P)]
+                got = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, 1, n)
+                info = eng.launch_info()
+                assert info["smem_bytes"] <= 227 * 1024 and info["block"] <= 1024, (K, taps, m, info)
+                plans.add((info["block"], info["ants_per_thread"], info["sats_per_cta"], info["sample_slices"], info["stages"]))
+                for k in (0, K - 1):
+                    c = chans[P - 1][k]
+                    ref = orc.correlate_direct(*blocks[P - 1], l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
+                                               c.carrier_phase, fs, shifts, start_sample=1, n_samples=n)
+                    err = np.abs(got[P - 1, k] - ref).max()
+                    assert err <= 2e-5 * 3 * np.sqrt(n) + 1e-3, (K, taps, m, k, err, info)
+    assert len(plans) > 20          # the sweep really walks through different CTA classes and decompositions
+    eng.close()
