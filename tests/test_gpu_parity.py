@@ -848,3 +848,81 @@ def test_planner_sweep_every_shape_launches_and_matches(gat, orc):
                     assert err <= 2e-5 * 3 * np.sqrt(n) + 1e-3, (K, taps, m, k, err, info)
     assert len(plans) > 20          # the sweep really walks through different CTA classes and decompositions
     eng.close()
+
+
+@pytest.mark.parametrize("variant", ["l5", "l1+l5", "int16", "f64", "offset_cap"])
+def test_planner_sweep_variants(gat, orc, variant):
+    """The same sweep along the other axes the planner sizes shared memory by: 10 230-chip tables (the cache of a CTA's chip
+    tables bounds the satellites per CTA), mixed systems in one block, raw int16 tiles (half-size stages, 12-deep rings),
+    Float64 code phase, and a capped grid with a start offset (segments, tiles staged before start_sample)."""
+    eng = gat.Engine(0)
+    l1, l5 = gat.GPSL1(), gat.GPSL5()
+    rng = np.random.default_rng(len(variant))
+    n, P = 2100, 2
+    start = 3 if variant == "offset_cap" else 0
+    if variant == "offset_cap":
+        eng.set_max_ctas(2)
+    fs = 2.5e7 if "l5" in variant else n / 1e-3
+    mode = "f64" if variant == "f64" else "nco"
+    for m in (1, 2, 4, 8, 16):
+        blocks = []
+        for p in range(P):
+            if variant == "int16":
+                iq = rng.integers(-2047, 2048, size=(m, n + 5, 2)).astype(np.int16)
+                eng.upload_signal_int(p, iq, 1.0 / 512.0)
+                blocks.append((iq[..., 0].astype(np.float32) / 512.0, iq[..., 1].astype(np.float32) / 512.0))
+            else:
+                re = rng.normal(size=(m, n + 5)).astype(np.float32)
+                im = rng.normal(size=(m, n + 5)).astype(np.float32)
+                eng.upload_signal(p, re, im)
+                blocks.append((re, im))
+        for taps in (1, 3, 5, 7, 9, 11):
+            shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+            for K in (1, 2, 3, 5, 8, 13, 21):
+                def system(k):
+                    return l5 if variant == "l5" or (variant == "l1+l5" and k % 2) else l1
+                chans = [[gat.Channel(system(k), 1 + (3 * k + p) % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)),
+                                      float(rng.uniform(-0.5, 0.5))) for k in range(K)] for p in range(P)]
+                got = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, start, n, code_phase_f64=(mode == "f64"))
+                info = eng.launch_info()
+                assert info["smem_bytes"] <= 227 * 1024 and info["block"] <= 1024, (K, taps, m, info)
+                for k in (0, K - 1):
+                    c = chans[P - 1][k]
+                    ref = orc.correlate_direct(*blocks[P - 1], c.system.codes[c.prn - 1], c.system.code_frequency, c.code_phase,
+                                               c.carrier_frequency, c.carrier_phase, fs, shifts, start_sample=start, n_samples=n,
+                                               code_mode=mode)
+                    err = np.abs(got[P - 1, k] - ref).max()
+                    assert err <= 2e-5 * 4 * np.sqrt(n) + 1e-3, (variant, K, taps, m, k, err, info)
+    eng.close()
+
+
+def test_resident_sweep_plans_fit(gat):
+    """Resident sessions reserve shared memory for the command area on top of the launch plan: every supported shape opens,
+    answers one command bit-identically to the launched call and closes; an unsupported shape is refused with a status, never
+    with a failed launch."""
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(9)
+    n = 3000
+    fs = n / 1e-3
+    opened = 0
+    for m in (1, 4, 8, 16):
+        eng.upload_signal(0, rng.normal(size=(m, n + 4)).astype(np.float32), rng.normal(size=(m, n + 4)).astype(np.float32))
+        for taps in (1, 3, 5, 7, 9, 11):
+            shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+            for K in (1, 2, 5, 13, 32):
+                ch = [gat.Channel(l1, 1 + k % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)), 0.1) for k in range(K)]
+                want = eng.correlate(0, ch, fs, shifts, m, start_sample=1, n_samples=n)
+                try:
+                    eng.resident_begin([0], ch, fs, shifts, m, 1, n)
+                except gat.GatError as e:
+                    assert e.status == -3, (m, taps, K, str(e))          # GAT_ERR_UNSUPPORTED
+                    continue
+                try:
+                    got = eng.resident_correlate(0, ch).copy()
+                finally:
+                    eng.resident_end()
+                opened += 1
+                assert np.array_equal(got, want), (m, taps, K)
+    assert opened >= 40
+    eng.close()
