@@ -926,3 +926,35 @@ def test_resident_sweep_plans_fit(gat):
                 assert np.array_equal(got, want), (m, taps, K)
     assert opened >= 40
     eng.close()
+
+
+def test_many_tap_ragged_length_sweep(gat, orc):
+    """7 / 9 / 11 taps over block lengths around the tile and visit boundaries (1 sample ... two tiles + 1, four tiles + 1) with
+    start offsets 0-3: the straight-line path takes only full tiles, the counted loop the rest, and what lies outside the
+    integrated range (poisoned here) must not reach the sums."""
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(77)
+    fs = 5.0e6
+    for m in (4, 16):
+        for n in (1, 5, 31, 33, 255, 256, 257, 511, 512, 513, 767, 1025):
+            for start in (0, 1, 3):
+                re = rng.normal(size=(m, start + n + 4)).astype(np.float32)
+                im = rng.normal(size=(m, start + n + 4)).astype(np.float32)
+                re[:, :start] = 1e6
+                im[:, :start] = -1e6
+                re[:, start + n:] = -1e6
+                im[:, start + n:] = 1e6
+                eng.upload_signal(0, re, im)
+                for taps in (7, 9, 11):
+                    shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+                    for K in (1, 2):
+                        ch = [gat.Channel(l1, int(rng.integers(1, 33)), float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)),
+                                          float(rng.uniform(-0.5, 0.5))) for _ in range(K)]
+                        got = eng.correlate(0, ch, fs, shifts, m, start_sample=start, n_samples=n)
+                        for k, c in enumerate(ch):
+                            ref = orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
+                                                       c.carrier_phase, fs, shifts, start_sample=start, n_samples=n)
+                            err = np.abs(got[k] - ref).max()
+                            assert err <= 2e-5 * 4 * np.sqrt(n) + 1e-3, (m, n, start, taps, K, k, err)
+    eng.close()
