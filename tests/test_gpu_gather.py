@@ -208,3 +208,36 @@ def test_sample_sharded_partial_sums_add_up(gat, orc, mode):
     got = (o_re.cpu().numpy() + 1j * o_im.cpu().numpy()).reshape(len(chans), 3, m)
     assert np.array_equal(got.astype(np.complex64), whole.astype(np.complex64))
     eng.close()
+
+
+def test_sample_sharded_sweep_taps_antennas_ranks(gat, orc):
+    """Sample ranges with the phases taken at sample 0, over tap counts (incl. the reallocation class), antennas, channels and
+    rank counts that do not divide the block: the partial sums add up to the whole block's accumulators and to the oracle's."""
+    from gpuacceleratedtracking_b200.multigpu import shard_sample_ranges
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(31)
+    n, fs = 10007, 1.0007e7
+    for m in (4, 16):
+        re = rng.normal(size=(m, n)).astype(np.float32)
+        im = rng.normal(size=(m, n)).astype(np.float32)
+        eng.upload_signal(0, re, im)
+        for taps in (3, 7, 11):
+            shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 3
+            for K in (1, 3):
+                chans = [gat.Channel(l1, int(rng.integers(1, 33)), float(rng.uniform(0, 1023)), float(rng.uniform(-4e3, 4e3)),
+                                     float(rng.uniform(-.5, .5))) for _ in range(K)]
+                whole = eng.correlate(0, chans, fs, shifts, m, n_samples=n).astype(np.complex128)
+                ref = np.stack([orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
+                                                     c.carrier_phase, fs, shifts) for c in chans])
+                scale = 3 * np.sqrt(n)
+                assert np.abs(whole - ref).max() <= 2e-5 * scale
+                for world in (2, 5):
+                    total = np.zeros_like(whole)
+                    for r, (lo, ln) in enumerate(shard_sample_ranges(n, world)):
+                        eng.upload_signal(10 + r, np.ascontiguousarray(re[:, lo:lo + ln]), np.ascontiguousarray(im[:, lo:lo + ln]))
+                        eng.set_sample_origin(lo)
+                        total += eng.correlate(10 + r, chans, fs, shifts, m, n_samples=ln)
+                    eng.set_sample_origin(-1)
+                    assert np.abs(total - whole).max() <= 4e-6 * scale, (m, taps, K, world, np.abs(total - whole).max())
+    eng.close()

@@ -958,3 +958,29 @@ def test_many_tap_ragged_length_sweep(gat, orc):
                             err = np.abs(got[k] - ref).max()
                             assert err <= 2e-5 * 4 * np.sqrt(n) + 1e-3, (m, n, start, taps, K, k, err)
     eng.close()
+
+
+def test_ingest_correlate_sweep(gat):
+    """gat_ingest_correlate over period counts around the 16-period chunk, antennas, taps and channels: the same numbers as
+    resident slots + gat_correlate_batch (same launch plan per chunk or not: within FP32 summation order)."""
+    rng = np.random.default_rng(12)
+    l1 = gat.GPSL1()
+    n = 3000
+    fs = n / 1e-3
+    eng = gat.Engine(0)
+    for P in (1, 15, 17, 33):
+        for m in (1, 4, 16):
+            re = rng.normal(size=(P, m, n)).astype(np.float32)
+            im = rng.normal(size=(P, m, n)).astype(np.float32)
+            for p in range(P):
+                eng.upload_signal(p, re[p], im[p])
+            for taps in (3, 11):
+                shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+                for K in (1, 5):
+                    chans = [[gat.Channel(l1, 1 + (p + 2 * k) % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)), 0.1 * k)
+                              for k in range(K)] for p in range(P)]
+                    got = eng.ingest_correlate(re, im, chans, fs, shifts, 0, n)
+                    assert got.shape == (2, P, K, taps, m)
+                    ref = eng.correlate_batch(list(range(P)), chans, fs, shifts, m, 0, n)
+                    assert np.abs(got[0] + 1j * got[1] - ref).max() <= 1e-5 * 4 * np.sqrt(n), (P, m, taps, K)
+    eng.close()
