@@ -165,3 +165,34 @@ def test_tensor_path_gps_l5_codes(gat, orc, engine):
         assert abs(abs(got[0, 1, 0]) - 0.5 * n) < 0.05 * n                  # the present L5 signal is found at full strength
         fp32 = engine.correlate(46, chans, fs, shifts, m, n_samples=n)
         assert np.abs(got - fp32).max() <= 2e-5 * n * rms
+
+
+def test_tensor_path_sweep(gat, orc):
+    """Channel counts around the 16-channel MMA groups, 1-4 taps, 1-16 antennas, block lengths around the 256-sample tile, with a
+    start offset: the tensor-core path (or the FP32 kernel, where the planner declines it) stays inside the TF32 bar."""
+    eng = gat.Engine(0)
+    l1 = gat.GPSL1()
+    rng = np.random.default_rng(404)
+    fs = 8.0e6
+    took = 0
+    for m in (1, 3, 16):
+        for n, start in ((255, 0), (1025, 3), (4099, 1)):
+            re = rng.normal(size=(m, start + n + 5)).astype(np.float32)
+            im = rng.normal(size=(m, start + n + 5)).astype(np.float32)
+            eng.upload_signal(0, re, im)
+            rms = float(np.sqrt(np.mean(re.astype(np.float64) ** 2 + im.astype(np.float64) ** 2)))
+            for taps in (1, 2, 3, 4):
+                shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 3
+                for K in (1, 15, 16, 17, 33, 70):
+                    chans = [gat.Channel(l1, 1 + k % 32, float(rng.uniform(0, 1023)), float(rng.uniform(-5e3, 5e3)),
+                                         float(rng.uniform(-.5, .5))) for k in range(K)]
+                    got = eng.correlate(0, chans, fs, shifts, m, start_sample=start, n_samples=n, tensor=True)
+                    took += eng.launch_info()["tensor"]
+                    for k in (0, K - 1):
+                        c = chans[k]
+                        ref = orc.correlate_direct(re, im, l1.codes[c.prn - 1], 1.023e6, c.code_phase, c.carrier_frequency,
+                                                   c.carrier_phase, fs, shifts, start_sample=start, n_samples=n)
+                        # (short blocks: the TF32 rounding noise ~3e-4 * sqrt(N) * rms exceeds 2e-5 * N * rms below N ~ 225 -- three sigma of it)
+                        assert np.abs(got[k] - ref).max() <= max(2e-5 * n, 1e-3 * np.sqrt(n)) * rms + 1e-3, (m, n, taps, K, k, eng.launch_info()["tensor"])
+    assert took > 50
+    eng.close()
