@@ -125,7 +125,11 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // (the register-reallocation class -- 11 taps -- has fixed warp positions: 12 consumer warps, one satellite per CTA)
     bool realloc_class = help && help_realloc(A, L);
     int w_cap = help ? (realloc_class ? kReallocConsumerWarps : block_threads_help(A, L) / 32 - 2) : max_consumer_warps(A, L);
-    if (help && std::min(K, std::max(1, w_cap / (AG * TG))) > (realloc_class ? 1 : kHelperMaxSats)) {
+    // Several satellites over 13..16 antennas with >= 7 taps stay in the reallocation class, ONE satellite per CTA pass (G = K
+    // groups): consecutive jobs re-read the period's block out of L2, and 12 consumer warps at 152 registers beat the plain
+    // instantiation's 8 at 168 by more than the re-reads cost (8 satellites x 11 taps x 8 periods: 97 us -> see DESIGN 5)
+    const bool realloc_multi = realloc_class && K > 1 && AG * TG == 4 && env_int("GAT_TUNE_REALLOC_MULTI", 1) != 0;
+    if (help && !realloc_multi && std::min(K, std::max(1, w_cap / (AG * TG))) > (realloc_class ? 1 : kHelperMaxSats)) {
         // several satellites per CTA: the plain instantiation, and none of the reallocation class's sizing below (two-tile
         // replicas, two buffers per group) -- with it still on, 5 satellites x 9 / 11 taps x 8 antennas asked for 233 216 B of
         // shared memory and the cooperative launch was refused
@@ -145,6 +149,7 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     const int RW = AG * TG;            // warps per satellite and sample slice
     int S = std::max(1, std::min(K, w_target_multi / RW));
     S = std::max(1, std::min(S, env_int("GAT_TUNE_S", S)));
+    if (realloc_class) S = 1;
     // replica entries a tile needs beyond its own samples (with two tap groups the pad tap may reach one spacing further)
     int span = sh.shifts[sh.n_taps - 1] - sh.shifts[0];
     if (TG == 2) span = std::max(span, (sh.shifts[L] - sh.shifts[0]) + (sh.shifts[L - 1] - sh.shifts[0]));
