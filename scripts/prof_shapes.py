@@ -40,6 +40,8 @@ if which in ("single32", "all"):
     run("single K=32 L=3", 1, 32, 3, 0.5)
 if which in ("c4", "all"):
     run("batch P=64 K=1 L=11", 64, 1, 11, 0.1)
+if which == "c4k8":
+    run("batch P=8 K=8 L=11 (one satellite per pass in the reallocation class)", 8, 8, 11, 0.1)
 if which == "l7":
     run("batch P=64 K=1 L=7 (replica-warp instantiation)", 64, 1, 7, 0.1)
 if which == "l9":
