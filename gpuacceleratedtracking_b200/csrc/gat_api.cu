@@ -125,10 +125,11 @@ int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
     // (the register-reallocation class -- 11 taps -- has fixed warp positions: 12 consumer warps, one satellite per CTA)
     bool realloc_class = help && help_realloc(A, L);
     int w_cap = help ? (realloc_class ? kReallocConsumerWarps : block_threads_help(A, L) / 32 - 2) : max_consumer_warps(A, L);
-    // Several satellites over 13..16 antennas with >= 7 taps stay in the reallocation class, ONE satellite per CTA pass (G = K
-    // groups): consecutive jobs re-read the period's block out of L2, and 12 consumer warps at 152 registers beat the plain
-    // instantiation's 8 at 168 by more than the re-reads cost (8 satellites x 11 taps x 8 periods: 97 us -> see DESIGN 5)
-    const bool realloc_multi = realloc_class && K > 1 && AG * TG == 4 && env_int("GAT_TUNE_REALLOC_MULTI", 1) != 0;
+    // Several satellites with >= 7 taps stay in the reallocation class, ONE satellite per CTA pass (G = K groups): consecutive
+    // jobs re-read the period's block out of L2, and 12 consumer warps at 152 registers beat the plain instantiation's 8-10 at
+    // 168 by more than the re-reads cost (8 satellites x 11 taps x 8 periods, same-box A/B: 16 antennas 97.4 -> 76.9 us,
+    // 12 antennas 89.9 -> 76.9, 8 antennas 66.9 -> 62.9; 5 satellites x 9 taps x 8 antennas x 16 periods 71.1 -> 67.1)
+    const bool realloc_multi = realloc_class && K > 1 && env_int("GAT_TUNE_REALLOC_MULTI", 1) != 0;
     if (help && !realloc_multi && std::min(K, std::max(1, w_cap / (AG * TG))) > (realloc_class ? 1 : kHelperMaxSats)) {
         // several satellites per CTA: the plain instantiation, and none of the reallocation class's sizing below (two-tile
         // replicas, two buffers per group) -- with it still on, 5 satellites x 9 / 11 taps x 8 antennas asked for 233 216 B of

@@ -66,3 +66,6 @@ run("C4 K8: 8 satellites x 11 taps, batch of 8 periods", [l1], 8, 16, 11, 50000,
 run("C5 L1+L5 K32 M16 L3 N50000 (single call, one band block)", [l1, l5], 32, 16, 3, 50000, 0.5, 1, reps=100)
 run("C5 batch of 8 periods", [l1, l5], 32, 16, 3, 50000, 0.5, 8)
 run("264 L1 channels over one block", [l1], 264, 16, 3, 50000, 0.5, 1)
+run("M12 K8 L11: 8 satellites x 11 taps x 12 antennas, batch of 8 periods", [l1], 8, 12, 11, 50000, 0.1, 8)
+run("M8 K8 L11: 8 satellites x 11 taps x 8 antennas, batch of 8 periods", [l1], 8, 8, 11, 50000, 0.1, 8)
+run("M8 K5 L9: 5 satellites x 9 taps x 8 antennas, batch of 16 periods", [l1], 5, 8, 9, 50000, 0.1, 16)
