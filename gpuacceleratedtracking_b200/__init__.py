@@ -8,7 +8,7 @@ fallback and raises if the library or the GPU is missing.
 from ._lib import (GAT_ACCUMULATE, GAT_CODE_PHASE_F64, GAT_GPSL1, GAT_GPSL5, GatError, LIB_PATH, load)
 from .gnss import (GNSSDICT, GNSSSystem, GPSL1, GPSL5, NH10, boc, get_center_frequency, get_code_frequency, get_code_length,
                    with_secondary_code)
-from .engine import Channel, Engine, MultiEngine, default_engine
+from .engine import Channel, Engine, MultiEngine, default_engine, plan_probe
 from .api import (ALGODICT, EarlyPromptLateCorrelator, KernelAlgorithm, NumAccumulators, NumAnts, Signal,
                   downconvert_and_correlate, gen_signal, get_accumulators, get_correlator_sample_shifts,
                   get_early, get_late, get_prompt, kernel_algorithm)

@@ -17,6 +17,7 @@ GAT_CODE_PHASE_F64 = 2
 GAT_GATHER = 4
 GAT_TENSOR_TF32 = 8
 GAT_DEBUG_STALL_CONSUMERS = 0x100
+GAT_PROBE_INT16, GAT_PROBE_RESIDENT = 0x10000, 0x20000
 GAT_IPC_HANDLE_BYTES = 64
 GAT_SLOT_DESC_BYTES = 96
 GAT_GPSL1, GAT_GPSL5 = 0, 1
@@ -77,6 +78,7 @@ SYMBOLS = {
     "gat_host_register": (_i, [_vp, C.c_uint64]),
     "gat_host_unregister": (_i, [_vp]),
     "gat_last_launch_info": (_i, [_vp, C.POINTER(GatLaunchInfo)]),
+    "gat_plan_probe": (_i, [_i, _i, _i, _i, _i, _i, _i32p, _i, _i, _d, _d, _i, _u, C.POINTER(GatLaunchInfo), C.c_char_p, _i]),
     "gat_set_max_ctas": (_i, [_vp, _i]),
     "gat_beamform": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gat_eigen_weights": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, C.c_float, _i, _vp, _vp, _vp, _vp]),

@@ -111,6 +111,36 @@ struct Shape {
     int reserve_smem = 0;              // bytes of dynamic shared memory kept free behind the plan (resident sessions: the command area)
 };
 
+// Antennas per thread A, taps per warp L (template arguments) and tap groups TG for a call's tap count -- see the comment
+// where correlate_impl calls it.
+static void choose_instantiation(int n_taps, int M, bool use_raw, const int32_t *shifts, int &A, int &L, int &TG)
+{
+    TG = 1;
+    if (n_taps <= 3) {
+        A = 16;
+        L = n_taps == 2 ? 3 : n_taps;
+    } else if (n_taps <= 5) {
+        A = 8;
+        L = 5;
+    } else {
+        A = 4;
+        L = n_taps | 1;
+    }
+    A = std::min(A, pow2_ceil(M));
+    A = std::max(1, std::min(A, env_int("GAT_TUNE_A", A)));
+    if (A == 4 && n_taps >= env_int("GAT_TUNE_TG_MIN_TAPS", 99) && !use_raw) {
+        // the second group's taps must sit at the first group's offsets shifted by one constant (the kernel addresses a
+        // group's taps relative to its first tap): true for the equally spaced sets get_correlator_sample_shifts makes
+        const int Lh = (n_taps + 1) / 2;   // 4, 5, 6
+        bool same = true;
+        for (int l = 0; l < Lh && Lh + l < n_taps; ++l) same = same && (shifts[Lh + l] - shifts[Lh] == shifts[l] - shifts[0]);
+        if (same) {
+            TG = 2;
+            L = Lh;
+        }
+    }
+}
+
 // Choose the kernel instantiation and the CTA decomposition (DESIGN.md "Launch planning").
 int make_plan(gat_ctx *ctx, const Shape &sh, LaunchPlan &plan, CorrArgs &a)
 {
@@ -610,29 +640,7 @@ int correlate_impl(gat_ctx *ctx, int n_periods, const int32_t *slots, int n_sats
     // ("tap groups"): 2 x 4 x 6 accumulators instead of 88 put the shape into the 19-warp class; the wipe-off is repeated by
     // both, which costs 23 % more FMAs and wins through occupancy (C4: see DESIGN.md).
     int A, L, TG = 1;
-    if (n_taps <= 3) {
-        A = 16;
-        L = n_taps == 2 ? 3 : n_taps;
-    } else if (n_taps <= 5) {
-        A = 8;
-        L = 5;
-    } else {
-        A = 4;
-        L = n_taps | 1;
-    }
-    A = std::min(A, pow2_ceil(M));
-    A = std::max(1, std::min(A, env_int("GAT_TUNE_A", A)));
-    if (A == 4 && n_taps >= env_int("GAT_TUNE_TG_MIN_TAPS", 99) && !use_raw) {
-        // the second group's taps must sit at the first group's offsets shifted by one constant (the kernel addresses a
-        // group's taps relative to its first tap): true for the equally spaced sets get_correlator_sample_shifts makes
-        const int Lh = (n_taps + 1) / 2;   // 4, 5, 6
-        bool same = true;
-        for (int l = 0; l < Lh && Lh + l < n_taps; ++l) same = same && (shifts[Lh + l] - shifts[Lh] == shifts[l] - shifts[0]);
-        if (same) {
-            TG = 2;
-            L = Lh;
-        }
-    }
+    choose_instantiation(n_taps, M, use_raw, shifts, A, L, TG);
     Shape shape{n_periods, n_sats, M, L, start_sample, n_samples, shifts, 0.0, 63, 0, (flags & GAT_CODE_PHASE_F64) != 0, 1, use_raw};
     shape.n_parts = n_parts;
     shape.part_tiles = part_tiles;
@@ -1782,6 +1790,51 @@ int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out)
     if (!ctx || !out) return GAT_ERR_INVALID;
     *out = ctx->info;
     return GAT_OK;
+}
+
+int gat_plan_probe(int n_sm, int max_ctas, int n_periods, int n_sats, int n_ants, int n_taps, const int32_t *sample_shifts,
+                   int start_sample, int n_samples, double fs_hz, double code_freq_hz, int code_len, unsigned flags,
+                   gat_launch_info *out, char *err, int err_cap)
+{
+    // the planner on a context that never touches CUDA: the same checks, instantiation choice and make_plan as correlate_impl
+    gat_ctx probe;
+    probe.n_sm = n_sm;
+    probe.max_ctas = max_ctas;
+    auto finish = [&](int rc) {
+        if (err && err_cap > 0) {
+            std::strncpy(err, probe.err.c_str(), static_cast<size_t>(err_cap) - 1);
+            err[err_cap - 1] = 0;
+        }
+        return rc;
+    };
+    if (!sample_shifts || !out || n_sm < 1) return finish(fail(&probe, GAT_ERR_INVALID, "null pointer argument or n_sm < 1"));
+    if (n_periods < 1 || n_sats < 1) return finish(fail(&probe, GAT_ERR_INVALID, "n_periods and n_sats must be >= 1"));
+    if (n_taps < 1 || n_taps > GAT_MAX_TAPS) return finish(fail(&probe, GAT_ERR_UNSUPPORTED, "n_taps must be 1..11"));
+    if (n_ants < 1 || n_ants > kMaxAnts) return finish(fail(&probe, GAT_ERR_UNSUPPORTED, "antenna count must be 1..32"));
+    if (!(fs_hz > 0.0) || !(code_freq_hz > 0.0) || code_len < 1) return finish(fail(&probe, GAT_ERR_INVALID, "frequencies and code length must be positive"));
+    if (start_sample < 0 || n_samples < 1) return finish(fail(&probe, GAT_ERR_INVALID, "empty or negative sample range"));
+    for (int l = 1; l < n_taps; ++l)
+        if (sample_shifts[l] < sample_shifts[l - 1]) return finish(fail(&probe, GAT_ERR_INVALID, "sample shifts must be ascending"));
+    if (static_cast<int64_t>(sample_shifts[n_taps - 1]) - sample_shifts[0] > 4096)
+        return finish(fail(&probe, GAT_ERR_UNSUPPORTED, "tap span > 4096 samples"));
+    const bool f64 = (flags & GAT_CODE_PHASE_F64) != 0;
+    const bool raw = (flags & GAT_PROBE_INT16) != 0 && !f64;
+    int A, L, TG;
+    choose_instantiation(n_taps, n_ants, raw, sample_shifts, A, L, TG);
+    Shape shape{n_periods, n_sats, n_ants, L, start_sample, n_samples, sample_shifts, 0.0, 63, 0, f64, 1, raw};
+    shape.A = A;
+    shape.TG = TG;
+    shape.n_taps = n_taps;
+    shape.reserve_smem = (flags & GAT_PROBE_RESIDENT) ? kResCmdSmemBytes + 128 : 0;
+    shape.max_ratio = code_freq_hz / fs_hz;
+    shape.min_fp = nco_fixed_point(code_len);
+    shape.max_delta = static_cast<int64_t>(std::floor(code_freq_hz * std::ldexp(1.0, shape.min_fp) / fs_hz));
+    shape.max_code_len = shape.min_code_len = code_len;
+    LaunchPlan plan{};
+    CorrArgs args{};
+    const int rc = make_plan(&probe, shape, plan, args);
+    if (rc == GAT_OK) *out = probe.info;
+    return finish(rc);
 }
 
 int gat_set_timing(gat_ctx *ctx, int enable)

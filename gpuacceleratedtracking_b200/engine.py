@@ -53,6 +53,23 @@ def _ptr(x) -> int:
     return x.data_ptr() if _is_torch(x) else x.ctypes.data
 
 
+def plan_probe(n_periods: int, n_sats: int, n_ants: int, shifts: Sequence[int], n_samples: int, fs: float, *, start_sample: int = 0,
+               code_frequency: float = 1.023e6, code_length: int = 1023, n_sm: int = 148, max_ctas: int = 0,
+               code_phase_f64: bool = False, int16: bool = False, resident: bool = False) -> dict:
+    """The launch plan libgat would choose for a shape (gat_plan_probe): host-only, no device needed.  Raises GatError with
+    the status and message gat_correlate_batch would return for a shape it cannot plan."""
+    lib = _lib.load()
+    sh = np.ascontiguousarray(shifts, dtype=np.int32)
+    li = GatLaunchInfo()
+    err = C.create_string_buffer(256)
+    flags = (_lib.GAT_CODE_PHASE_F64 if code_phase_f64 else 0) | (_lib.GAT_PROBE_INT16 if int16 else 0) | (_lib.GAT_PROBE_RESIDENT if resident else 0)
+    rc = lib.gat_plan_probe(n_sm, max_ctas, n_periods, n_sats, n_ants, len(sh), sh.ctypes.data_as(C.POINTER(C.c_int32)), start_sample,
+                            n_samples, float(fs), float(code_frequency), int(code_length), flags, C.byref(li), err, len(err))
+    if rc != 0:
+        raise GatError(rc, err.value.decode())
+    return {n: getattr(li, n) for n, _ in li._fields_}
+
+
 class Engine:
     def __init__(self, device: int = 0, stream: int | None = None):
         self._lib = _lib.load()

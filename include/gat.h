@@ -361,6 +361,19 @@ typedef struct gat_launch_info {
     float last_kernel_ms;       /* device time of the last correlate kernel if timing enabled */
 } gat_launch_info;
 int gat_last_launch_info(gat_ctx *ctx, gat_launch_info *out);
+/* Host-only planner probe: NO CUDA call, works without a device.  The launch plan gat_correlate_batch would choose for
+ * n_periods blocks x n_sats channels (all of one code length and chip rate) on a device with n_sm SMs and the given
+ * gat_set_max_ctas value: grid, CTA size, dynamic shared memory, antennas per thread, satellites per CTA, sample slices,
+ * ring stages.  flags: GAT_CODE_PHASE_F64, GAT_PROBE_INT16 (the slots hold raw int16 words and the kernel reads them),
+ * GAT_PROBE_RESIDENT (plan of a resident session).  Returns GAT_OK, or the status gat_correlate_batch would return for
+ * a shape it cannot plan, with the message copied into err (may be NULL).  Used by the CPU test tier to sweep the
+ * planner's invariants (shared-memory budget, warps per CTA, slice / stage divisibility) over the supported shapes, and
+ * by hosts that size their channel batches before a device is attached. */
+#define GAT_PROBE_INT16 0x10000u
+#define GAT_PROBE_RESIDENT 0x20000u
+int gat_plan_probe(int n_sm, int max_ctas, int n_periods, int n_sats, int n_ants, int n_taps, const int32_t *sample_shifts,
+                   int start_sample, int n_samples, double fs_hz, double code_freq_hz, int code_len, unsigned flags,
+                   gat_launch_info *out, char *err, int err_cap);
 /* The correlate kernel is persistent: one CTA per SM, all SMs.  A communication kernel that should run
  * CONCURRENTLY (an NCCL broadcast of the next signal blocks, ...) then finds no free SM and the two serialise.
  * max_ctas > 0 caps the grid so that the remaining SMs stay free (measured, 2 GPUs, NCCL broadcast of the next

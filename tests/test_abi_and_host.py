@@ -271,3 +271,53 @@ def test_sample_ranges_cover_the_block():
             assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(world - 1))
             if n >= 8 * world:
                 assert max(ln for _, ln in r) - min(ln for _, ln in r) <= 8
+
+
+def _probe_sweep(gat, **kw):
+    import itertools
+    import numpy as np
+    seen, refused = set(), {}
+    for K, taps, m, (n, P), code_len in itertools.product((1, 2, 3, 4, 5, 6, 8, 11, 13, 21, 32, 40), range(1, 12),
+                                                          (1, 2, 3, 4, 5, 8, 12, 16, 17, 24, 32),
+                                                          ((100, 1), (2049, 3), (50000, 64), (262144, 2)), (1023, 10230)):
+        shifts = (np.arange(taps, dtype=np.int32) - taps // 2) * 2
+        fc = 1.023e6 * code_len / 1023
+        try:
+            info = gat.plan_probe(P, K, m, shifts, n, max(n / 1e-3, 2.5 * fc), code_frequency=fc, code_length=code_len, **kw)
+        except gat.GatError as e:
+            assert e.status == -3 and "internal" not in str(e), (K, taps, m, n, P, code_len, str(e))
+            refused.setdefault(str(e), (K, taps, m, n, P, code_len))
+            continue
+        budget = 227 * 1024 - (2304 + 128 if kw.get("resident") else 0)
+        where = (K, taps, m, n, P, code_len, info)
+        assert 0 < info["smem_bytes"] <= budget, where
+        assert info["block"] % 32 == 0 and 64 <= info["block"] <= 1024, where
+        assert 1 <= info["consumer_warps"] <= info["block"] // 32 - 1, where
+        cap = kw.get("max_ctas") or kw.get("n_sm", 148)
+        assert 1 <= info["grid"] <= min(cap, max(1, info["items"])), where
+        assert 1 <= info["stages"] <= 16 and info["tile_len"] == 256, where
+        assert info["sats_per_cta"] * info["sat_groups"] >= K and info["ants_per_thread"] * info["ant_groups"] >= m, where
+        assert info["consumer_warps"] % (info["sats_per_cta"] * info["ant_groups"]) == 0, where
+        seen.add((info["block"], info["ants_per_thread"], info["sats_per_cta"], info["sample_slices"], info["stages"]))
+    return seen, refused
+
+
+def test_planner_invariants_over_the_shape_space(gat, monkeypatch):
+    """gat_plan_probe (host-only) over ~11 600 shapes per variant: every plan fits the SM (dynamic shared memory <= 227 KB, <= 1024
+    threads, warps = roles x slices), covers all satellites and antennas, keeps the grid inside the device; a shape the planner
+    refuses is refused with GAT_ERR_UNSUPPORTED and a caller-facing reason, never an internal one.  The sweep that would have
+    caught the 233 216-byte plan of 5 satellites x 9 taps x 8 antennas (found on the GPU in round 2) without a GPU."""
+    seen, refused = _probe_sweep(gat)
+    assert len(seen) > 40, len(seen)
+    for variant in (dict(code_phase_f64=True), dict(int16=True), dict(resident=True), dict(max_ctas=3), dict(n_sm=132)):
+        _probe_sweep(gat, **variant)
+    # the fall-back planner path (several satellites per CTA outside the reallocation class) stays healthy too
+    monkeypatch.setenv("GAT_TUNE_REALLOC_MULTI", "0")
+    _probe_sweep(gat)
+    info = gat.plan_probe(3, 5, 8, [-8, -6, -4, -2, 0, 2, 4, 6, 8], 2049, 2.049e6)
+    assert info["block"] == 352 and info["sats_per_cta"] == 5 and info["smem_bytes"] <= 227 * 1024
+    monkeypatch.delenv("GAT_TUNE_REALLOC_MULTI")
+    info = gat.plan_probe(8, 8, 16, list(range(-10, 12, 2)), 50000, 5e7)
+    assert info["block"] == 512 and info["sats_per_cta"] == 1 and info["sat_groups"] == 8      # one satellite per pass
+    # messages a caller can act on
+    print(sorted(refused))
